@@ -1,0 +1,171 @@
+/*
+ * sddm_b200.h — C ABI of the B200-native reverse-diffusion speech-enhancement hot path.
+ *
+ * The reference (yangye1098/Speech-Denoising-Diffusion-Model-2) is pure Python/PyTorch and has no FFI;
+ * each entry point below names the reference function(s) (file:line under /root/reference) whose device
+ * work it replaces.  Plain pointers and sizes only: no torch types cross this boundary.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative SDDM_E_* code otherwise; the message is available
+ *     through sddm_last_error() (thread-local).  No exceptions cross the ABI, and there is NO CPU fallback:
+ *     unsupported shapes / missing device => error.
+ *   - all device pointers are fp32, contiguous, on the current CUDA device; work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*), no hidden synchronisation (CUDA-graph capturable) unless stated.
+ *   - the caller owns every buffer including the workspace; the plan owns only packed weights + tables.
+ *   - a plan is not thread-safe; use one plan per (process, device).
+ *   - waveforms are [B, 1, L] (L = num_samples, 16448 for config_unet.json); one row = one chunk.
+ */
+#ifndef SDDM_B200_H
+#define SDDM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(SDDM_BUILD) && defined(__GNUC__)
+#define SDDM_API __attribute__((visibility("default")))
+#else
+#define SDDM_API
+#endif
+
+#define SDDM_OK 0
+#define SDDM_E_INVALID (-1)     /* bad argument / unsupported configuration */
+#define SDDM_E_STATE (-2)       /* call order: weights / schedule missing, plan not finalised */
+#define SDDM_E_CUDA (-3)        /* a CUDA runtime call failed */
+#define SDDM_E_WORKSPACE (-4)   /* workspace too small */
+
+/* precision modes for the denoiser convolutions */
+#define SDDM_PREC_FP32 0        /* CUDA-core fp32 FMA (parity mode: eps_hat error ~1e-6) */
+#define SDDM_PREC_BF16 1        /* tcgen05 / TMEM implicit GEMM, bf16 operands, fp32 accumulate */
+
+/* posterior-update variants: SDDM.p_transition argument, model/model.py:17-26 */
+#define SDDM_VAR_ORIGINAL 0     /* diffusion.py:177-190, x_T = pure noise               */
+#define SDDM_VAR_CONDITION_IN 1 /* diffusion.py:177-190, x_T = get_x_T (diffusion.py:281) */
+#define SDDM_VAR_SR3 2          /* diffusion.py:164-175 */
+#define SDDM_VAR_SUPPORTIVE 3   /* diffusion.py:192-209 */
+#define SDDM_VAR_CONDITIONAL 4  /* diffusion.py:211-222, x_T = get_x_T_conditional (:302) */
+
+typedef struct sddm_plan sddm_plan;
+
+/* Mirrors the kwargs of UNetModified2.__init__ (model/UNetModified2.py:146-160) + GaussianDiffusion.n_timestep. */
+typedef struct sddm_config {
+    int32_t n_timestep;       /* T (config_unet.json: 100) */
+    int32_t num_samples;      /* L, samples per chunk (16448) */
+    int32_t segment_len;      /* frame length F (128) */
+    int32_t segment_stride;   /* hop (64); (L - F) % hop must be 0 (UNetModified2.py:13) */
+    int32_t in_channel;       /* must be 2 */
+    int32_t out_channel;      /* must be 1 */
+    int32_t inner_channel;    /* 32 */
+    int32_t norm_groups;      /* 32 */
+    int32_t n_mults;          /* len(channel_mults) <= 8 */
+    int32_t channel_mults[8]; /* (1,2,3,4,5) */
+    int32_t res_blocks;       /* 1 */
+    int32_t precision;        /* SDDM_PREC_* */
+    int32_t reserved[4];
+} sddm_config;
+
+/* The 12 per-timestep coefficient tables, each of length n_timestep + 1 (host pointers, fp32).
+ * = the registered buffers of GaussianDiffusion (model/diffusion.py:87-161). */
+typedef struct sddm_schedule {
+    const float* betas;
+    const float* alphas;
+    const float* sqrt_alpha_bar;
+    const float* predicted_noise_coeff;
+    const float* sigma;
+    const float* supportive_gamma;
+    const float* supportive_sigma_hat;
+    const float* sqrt_delta;
+    const float* c_xt;
+    const float* c_yt;
+    const float* c_epst;
+    const float* sqrt_delta_estimated;
+} sddm_schedule;
+
+SDDM_API const char* sddm_last_error(void);
+SDDM_API int sddm_version(void);
+/* number of kernels this library has launched in this process (monotonic). */
+SDDM_API uint64_t sddm_launch_count(void);
+
+/* ---- plan lifecycle ------------------------------------------------------------------------------- */
+/* replaces: UNetModified2.__init__ (UNetModified2.py:146-235) as far as shapes go. */
+SDDM_API int sddm_plan_create(const sddm_config* cfg, sddm_plan** out);
+SDDM_API void sddm_plan_destroy(sddm_plan* plan);
+
+/* replaces: model.load_state_dict (infer.py:51).  `name` is the reference state_dict key WITHOUT the
+ * 'noise_estimate_model.' prefix (e.g. "downs.1.block1.block.3.weight"); data is fp32, host or device
+ * (copied immediately, the pointer is not retained).  Shape is checked against the config. */
+SDDM_API int sddm_plan_load_weight(sddm_plan* plan, const char* name, const void* data, const int64_t* shape, int ndim);
+
+/* replaces: GaussianDiffusion.__init__ buffers (diffusion.py:87-161); n must equal n_timestep + 1. */
+SDDM_API int sddm_plan_set_schedule(sddm_plan* plan, const sddm_schedule* sch, int n);
+
+/* Packs weights into kernel layouts and precomputes the per-timestep noise-embedding table
+ * E[t] = concat_i Linear_i(noise_level_mlp(sqrt_alpha_bar[t]))  (UNetModified2.py:49-89,168-174,249).
+ * Must be called after all weights + the schedule are loaded; synchronises the device once. */
+SDDM_API int sddm_plan_finalize(sddm_plan* plan);
+
+/* bytes of device workspace needed by sddm_eps / sddm_sample for a batch of B chunks. */
+SDDM_API size_t sddm_workspace_bytes(const sddm_plan* plan, int B);
+
+/* ---- hot path ------------------------------------------------------------------------------------- */
+/* replaces: UNetModified2.forward (UNetModified2.py:237-269) = framing + cat + UNet + overlap-add.
+ * noise_level: device [B] (per-row, as the module API allows) or NULL, in which case row t of the
+ * precomputed table is used for every row (what SDDM.infer does, model.py:108-110). */
+SDDM_API int sddm_eps(sddm_plan* plan, const float* cond, const float* x_t, const float* noise_level, int t,
+             float* eps_out, int B, void* ws, size_t ws_bytes, void* stream);
+
+/* replaces: GaussianDiffusion.get_x_T / get_x_T_conditional (diffusion.py:281-320).
+ * z: injected N(0,1) noise [B,1,L] or NULL => Philox4x32-10 keyed (seed, row0 + row, draw 0). */
+SDDM_API int sddm_x_T(sddm_plan* plan, int variant, const float* cond, const float* z, uint64_t seed, int64_t row0,
+             float* x_out, int B, void* stream);
+
+/* replaces: GaussianDiffusion.p_transition{,_sr3,_supportive,_conditional} (diffusion.py:164-222),
+ * in place on x_t, including the clamp to [-1,1].  z as above (draw index T + 1 - t); ignored for t == 1. */
+SDDM_API int sddm_p_step(sddm_plan* plan, int variant, float* x_t, const float* eps, const float* cond, const float* z,
+                uint64_t seed, int64_t row0, int t, int B, void* stream);
+
+/* Plan-less forms of the two calls above for callers that hold only the GaussianDiffusion tables
+ * (diffusion.p_transition / get_x_T invoked directly, as trainer code may): the step scalars are passed by value.
+ *   x_T:   x = a * cond + b * z           (a = sqrt_alpha_bar[T]; b = sqrt(1 - a^2) or sqrt_delta[T])
+ *   step:  k8 = {predicted_noise_coeff[t], sqrt(alphas[t]), noise std, gamma, 1 - gamma, c_xt, c_yt, c_epst}[t] */
+SDDM_API int sddm_x_T_raw(int variant, float a, float b, const float* cond, const float* z, uint64_t seed, int64_t row0,
+                 float* x_out, int B, int L, void* stream);
+SDDM_API int sddm_p_step_raw(int variant, const float* k8, float* x_t, const float* eps, const float* cond, const float* z,
+                    uint64_t seed, int64_t row0, int t, int T, int B, int L, void* stream);
+
+/* replaces: SDDM.infer (model/model.py:50-124, non-continuous branch): x_T init + T x (eps_hat, update).
+ * noises: NULL (Philox) or injected [T, B, L] (noises[0] -> x_T, noises[k] -> step t = T + 1 - k).
+ * eps_trace: NULL or [T, B, L] receiving eps_hat of step t at index T - t (verification mode).
+ * x_trace:   NULL or [T, B, L] receiving x_{t-1} of step t at index T - t. */
+SDDM_API int sddm_sample(sddm_plan* plan, int variant, const float* cond, const float* noises, uint64_t seed, int64_t row0,
+                float* out, float* eps_trace, float* x_trace, int B, void* ws, size_t ws_bytes, void* stream);
+
+/* replaces: infer.py:72-77 (H2D copy, model.infer, D2H copy) for HOST buffers: cond/out are host
+ * [B,1,L] fp32 (pinned for full-speed copies).  The plan keeps an internal device arena; rows are
+ * processed in sub-batches of at most `max_rows_per_pass` (<=0: library default).  Blocks until done. */
+SDDM_API int sddm_enhance_host(sddm_plan* plan, int variant, const float* cond_host, float* out_host, int B,
+                      uint64_t seed, int64_t row0, int max_rows_per_pass);
+
+/* ---- framing helpers (standalone; the sampler uses fused versions) -------------------------------- */
+/* replaces: SignalToFrames.forward (UNetModified2.py:23-28): [B,1,n] -> [B,1,n_frames,F]. */
+SDDM_API int sddm_frames(const float* sig, float* frames, int B, int n_samples, int frame_len, int stride, void* stream);
+/* replaces: SignalToFrames.overlapAdd (UNetModified2.py:30-41): [B,1,n_frames,F] -> [B,1,n]. */
+SDDM_API int sddm_overlap_add(const float* frames, float* sig, int B, int n_samples, int frame_len, int stride, void* stream);
+
+/* ---- introspection / test hooks ------------------------------------------------------------------- */
+/* number of kernel launches one sddm_eps call enqueues for this plan. */
+SDDM_API int sddm_plan_launches_per_eps(const sddm_plan* plan);
+/* copies the NHWC activation of a named UNet node ("downs.3", "mid.0", "ups.7", ...) produced by the last
+ * sddm_eps call on this workspace into out (device, [B,H,W,C] fp32); returns C*H*W via *chw. */
+SDDM_API int sddm_debug_fetch(sddm_plan* plan, const char* node, void* ws, int B, float* out, int64_t* chw, void* stream);
+/* single-tile tcgen05 descriptor self-test: returns max |err| of a 128 x N x K bf16 MMA vs an fp32 reference
+ * computed on the device with CUDA cores, through *max_err. variant selects the descriptor convention. */
+SDDM_API int sddm_debug_umma_probe(int variant, int N, int K, float* max_err_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDDM_B200_H */

@@ -1,0 +1,918 @@
+// C ABI (include/sddm_b200.h): plan lifecycle, weight packing, the static op program of one UNetModified2
+// forward, and the reverse-diffusion driver.  Host-side only; kernels live in the other translation units.
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/sddm_b200.h"
+#include "kernels.cuh"
+
+namespace sddm {
+
+static thread_local char g_err[1024] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------------------------------
+// network description derived from the config (mirrors UNetModified2.__init__, UNetModified2.py:146-235)
+// ---------------------------------------------------------------------------------------------------
+struct NodeDesc {
+    enum Kind { STEM, RES, DOWN, UP } kind;
+    std::string key;   // "downs.3", "mid.0", "ups.7"
+    int cin, cout;     // RES: cin is the (concatenated) input channel count
+    bool cat;          // RES in `ups`: input = cat(current, skip)
+};
+
+struct TensorInfo {
+    std::string name;
+    int C, H, W, nparts;
+    size_t data_off, parts_off;   // float offsets PER SAMPLE (section base = off * B)
+};
+
+struct Op {
+    enum Kind { STEM, GN, CONV, FINAL } kind;
+    // GN
+    int gn_src[2] = {-1, -1};
+    int gn_nsrc = 0;
+    size_t gamma_off = 0, beta_off = 0;   // offsets into the packed fp32 arena
+    size_t ss_off = 0;                    // per-sample float offset of [scale(Ctot), shift(Ctot)]
+    int Ctot = 0;
+    // CONV / FINAL
+    int src[2] = {-1, -1};
+    int nsrc = 0;
+    bool in_gn = false;
+    size_t in_ss_off = 0;
+    int mode = CONV_S1;
+    int out = -1;
+    size_t w_off = 0, wtc_off = 0, bias_off = 0;
+    int temb_off = -1;
+    int res_kind = 0;   // 0 none, 1 identity, 2 1x1 conv
+    size_t resw_off = 0, reswtc_off = 0, resb_off = 0;
+    bool use_tc = false;
+};
+
+}  // namespace sddm
+
+using namespace sddm;
+
+struct sddm_plan {
+    sddm_config cfg{};
+    int H = 0, W = 0;   // frame grid: n_frames x segment_len
+    int E = 0;          // concatenated noise-embedding width
+    std::vector<NodeDesc> nodes;
+    std::map<std::string, std::vector<int64_t>> expect;   // weight name -> shape
+    std::map<std::string, std::vector<float>> host_w;
+    bool have_sched = false, finalized = false;
+    std::vector<float> sch[12];   // order of sddm_schedule fields
+    // device-resident packed parameters
+    float* d_f32 = nullptr;
+    __nv_bfloat16* d_bf16 = nullptr;
+    float* d_temb_table = nullptr;   // [T+1][E]
+    size_t off_freq = 0, off_w1 = 0, off_b1 = 0, off_w2 = 0, off_b2 = 0, off_wn = 0, off_bn = 0;
+    size_t off_stem_w = 0, off_stem_b = 0, off_final_w = 0;
+    float final_bias = 0.f;
+    // program
+    std::vector<TensorInfo> tensors;
+    std::vector<Op> ops;
+    size_t off_x = 0, off_frames = 0, off_temb_rows = 0, off_nl = 0;
+    size_t floats_per_sample = 0;
+    int launches_per_eps = 0;
+    // internal arena for sddm_enhance_host
+    cudaStream_t own_stream = nullptr;
+    float* d_cond = nullptr;
+    float* d_out = nullptr;
+    void* d_ws = nullptr;
+    int arena_rows = 0;
+};
+
+namespace sddm {
+
+static void add_expect(sddm_plan* p, const std::string& k, std::vector<int64_t> shape) { p->expect[k] = std::move(shape); }
+
+static void expect_res(sddm_plan* p, const std::string& key, int cin, int cout, int emb) {
+    add_expect(p, key + ".noise_func.noise_func.0.weight", {cout, emb});
+    add_expect(p, key + ".noise_func.noise_func.0.bias", {cout});
+    add_expect(p, key + ".block1.block.0.weight", {cin});
+    add_expect(p, key + ".block1.block.0.bias", {cin});
+    add_expect(p, key + ".block1.block.3.weight", {cout, cin, 3, 3});
+    add_expect(p, key + ".block1.block.3.bias", {cout});
+    add_expect(p, key + ".block2.block.0.weight", {cout});
+    add_expect(p, key + ".block2.block.0.bias", {cout});
+    add_expect(p, key + ".block2.block.3.weight", {cout, cout, 3, 3});
+    add_expect(p, key + ".block2.block.3.bias", {cout});
+    if (cin != cout) {
+        add_expect(p, key + ".res_conv.weight", {cout, cin, 1, 1});
+        add_expect(p, key + ".res_conv.bias", {cout});
+    }
+}
+
+static int build_nodes(sddm_plan* p) {
+    const sddm_config& c = p->cfg;
+    const int inner = c.inner_channel, rb = c.res_blocks;
+    add_expect(p, "noise_level_mlp.1.weight", {4 * inner, inner});
+    add_expect(p, "noise_level_mlp.1.bias", {4 * inner});
+    add_expect(p, "noise_level_mlp.3.weight", {inner, 4 * inner});
+    add_expect(p, "noise_level_mlp.3.bias", {inner});
+    add_expect(p, "downs.0.weight", {inner, c.in_channel, 3, 3});
+    add_expect(p, "downs.0.bias", {inner});
+    p->nodes.push_back({NodeDesc::STEM, "downs.0", c.in_channel, inner, false});
+    std::vector<int> feat{inner};
+    int cin = inner, idx = 1;
+    for (int l = 0; l < c.n_mults; ++l) {
+        const int cout = inner * c.channel_mults[l];
+        for (int r = 0; r < rb; ++r) {
+            const std::string key = "downs." + std::to_string(idx++);
+            p->nodes.push_back({NodeDesc::RES, key, cin, cout, false});
+            expect_res(p, key, cin, cout, inner);
+            feat.push_back(cout);
+            cin = cout;
+        }
+        const std::string key = "downs." + std::to_string(idx++);
+        p->nodes.push_back({NodeDesc::DOWN, key, cout, cout, false});
+        add_expect(p, key + ".conv.weight", {cout, cout, 3, 3});
+        add_expect(p, key + ".conv.bias", {cout});
+        feat.push_back(cout);
+    }
+    p->nodes.push_back({NodeDesc::RES, "mid.0", cin, cin, false});
+    expect_res(p, "mid.0", cin, cin, inner);
+    idx = 0;
+    int cout = cin;
+    for (int l = c.n_mults - 1; l >= 0; --l) {
+        cin = inner * c.channel_mults[l];
+        cout = cin;
+        {
+            const std::string key = "ups." + std::to_string(idx++);
+            const int ctot = cin + feat.back();
+            feat.pop_back();
+            p->nodes.push_back({NodeDesc::RES, key, ctot, cout, true});
+            expect_res(p, key, ctot, cout, inner);
+        }
+        {
+            const std::string key = "ups." + std::to_string(idx++);
+            p->nodes.push_back({NodeDesc::UP, key, cout, cout, false});
+            add_expect(p, key + ".conv.weight", {cout, cout, 3, 3});
+            add_expect(p, key + ".conv.bias", {cout});
+        }
+        cout = (l == 0) ? inner : inner * c.channel_mults[l - 1];
+        for (int r = 0; r < rb; ++r) {
+            const std::string key = "ups." + std::to_string(idx++);
+            const int ctot = cin + feat.back();
+            feat.pop_back();
+            p->nodes.push_back({NodeDesc::RES, key, ctot, cout, true});
+            expect_res(p, key, ctot, cout, inner);
+            cin = cout;
+        }
+    }
+    add_expect(p, "final_conv.block.0.weight", {cout});
+    add_expect(p, "final_conv.block.0.bias", {cout});
+    add_expect(p, "final_conv.block.3.weight", {c.out_channel, cout, 3, 3});
+    add_expect(p, "final_conv.block.3.bias", {c.out_channel});
+    return SDDM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// packing
+// ---------------------------------------------------------------------------------------------------
+struct Arena {
+    std::vector<float> f;
+    std::vector<__nv_bfloat16> h;
+    size_t put(const std::vector<float>& v) {
+        size_t o = align_up(f.size(), 32);
+        f.resize(o);
+        f.insert(f.end(), v.begin(), v.end());
+        return o;
+    }
+    size_t put_h(const std::vector<__nv_bfloat16>& v) {
+        size_t o = align_up(h.size(), 64);
+        h.resize(o);
+        h.insert(h.end(), v.begin(), v.end());
+        return o;
+    }
+};
+
+// [Cout][Cin][k][k] -> fp32 [Cin/8][k*k][8][Cout]
+static std::vector<float> pack_conv_f32(const std::vector<float>& w, int cout, int cin, int kk) {
+    std::vector<float> o((size_t)cin * kk * cout);
+    for (int ci = 0; ci < cin; ++ci)
+        for (int t = 0; t < kk; ++t)
+            for (int co = 0; co < cout; ++co)
+                o[((size_t)((ci / 8) * kk + t) * 8 + (ci % 8)) * cout + co] = w[((size_t)co * cin + ci) * kk + t];
+    return o;
+}
+
+// [Cout][Cin][k][k] -> bf16 [Cin/32][k*k][4][Cout][8]: per (chunk, tap) a K-major UMMA operand image made of
+// 8x8 core matrices (8 couts x 8 cin, 128 contiguous bytes); LBO (K step) = Cout*16 B, SBO (N step) = 128 B.
+static std::vector<__nv_bfloat16> pack_conv_tc(const std::vector<float>& w, int cout, int cin, int kk) {
+    std::vector<__nv_bfloat16> o((size_t)cin * kk * cout);
+    for (int ci = 0; ci < cin; ++ci)
+        for (int t = 0; t < kk; ++t)
+            for (int co = 0; co < cout; ++co) {
+                const int ch = ci / 32, j = (ci % 32) / 8, e = ci % 8;
+                o[((((size_t)ch * kk + t) * 4 + j) * cout + co) * 8 + e] = __float2bfloat16(w[((size_t)co * cin + ci) * kk + t]);
+            }
+    return o;
+}
+
+static int new_tensor(sddm_plan* p, const std::string& name, int C, int H, int W) {
+    TensorInfo t{name, C, H, W, 0, 0, 0};
+    p->tensors.push_back(t);
+    return (int)p->tensors.size() - 1;
+}
+
+static const std::vector<float>& W_(sddm_plan* p, const std::string& k) { return p->host_w.at(k); }
+
+static void fill_conv_op(sddm_plan* p, Arena& a, Op& op, const std::string& wkey, int cout, int cin, bool tc_ok) {
+    op.w_off = a.put(pack_conv_f32(W_(p, wkey + ".weight"), cout, cin, 9));
+    op.bias_off = a.put(W_(p, wkey + ".bias"));
+    if (tc_ok && cin % 32 == 0) op.wtc_off = a.put_h(pack_conv_tc(W_(p, wkey + ".weight"), cout, cin, 9));
+}
+
+static int emit_gn(sddm_plan* p, Arena& a, std::vector<int> srcs, const std::string& gkey, size_t* ss_off_cursor) {
+    Op op;
+    op.kind = Op::GN;
+    op.gn_nsrc = (int)srcs.size();
+    int ctot = 0;
+    for (size_t i = 0; i < srcs.size(); ++i) {
+        op.gn_src[i] = srcs[i];
+        ctot += p->tensors[srcs[i]].C;
+    }
+    op.Ctot = ctot;
+    op.gamma_off = a.put(W_(p, gkey + ".weight"));
+    op.beta_off = a.put(W_(p, gkey + ".bias"));
+    op.ss_off = *ss_off_cursor;
+    *ss_off_cursor += align_up((size_t)2 * ctot, 32);
+    p->ops.push_back(op);
+    return (int)p->ops.size() - 1;
+}
+
+static ConvP shape_probe(const sddm_plan* p, const Op& op) {
+    ConvP c{};
+    const TensorInfo& o = p->tensors[op.out];
+    c.Hout = o.H; c.Wout = o.W; c.Cout = o.C;
+    c.Hin = p->tensors[op.src[0]].H; c.Win = p->tensors[op.src[0]].W;
+    c.nsrc = op.nsrc; c.mode = op.mode;
+    c.Cin = 0;
+    for (int i = 0; i < op.nsrc; ++i) { c.src[i].C = p->tensors[op.src[i]].C; c.Cin += c.src[i].C; }
+    c.res_identity = op.res_kind == 1;
+    c.res_Cin = op.res_kind == 2 ? c.Cin : 0;
+    return c;
+}
+
+static int build_program(sddm_plan* p, Arena& a) {
+    const sddm_config& c = p->cfg;
+    const bool want_tc = c.precision == SDDM_PREC_BF16;
+    size_t ss_cursor = 0;   // relative; rebased after tensors are laid out
+    int temb_cursor = 0;
+    std::vector<int> feats;
+    int cur = -1, H = p->H, W = p->W;
+    auto set_tc = [&](Op& op) {
+        ConvP probe = shape_probe(p, op);
+        op.use_tc = want_tc && conv_tc_supported(probe);
+        p->tensors[op.out].nparts = op.use_tc ? conv_tc_nparts(probe.Hout, probe.Wout) : conv_fp32_nparts(probe.Hout, probe.Wout);
+    };
+    auto emit_res = [&](const NodeDesc& nd, std::vector<int> srcs) {
+        const int gn1 = emit_gn(p, a, srcs, nd.key + ".block1.block.0", &ss_cursor);
+        const int h = new_tensor(p, nd.key + ".h", nd.cout, H, W);
+        Op c1;
+        c1.kind = Op::CONV;
+        c1.nsrc = (int)srcs.size();
+        for (size_t i = 0; i < srcs.size(); ++i) c1.src[i] = srcs[i];
+        c1.in_gn = true;
+        c1.in_ss_off = p->ops[gn1].ss_off;
+        c1.out = h;
+        fill_conv_op(p, a, c1, nd.key + ".block1.block.3", nd.cout, nd.cin, want_tc);
+        c1.temb_off = temb_cursor;
+        temb_cursor += nd.cout;
+        set_tc(c1);
+        p->ops.push_back(c1);
+        const int gn2 = emit_gn(p, a, {h}, nd.key + ".block2.block.0", &ss_cursor);
+        const int out = new_tensor(p, nd.key, nd.cout, H, W);
+        Op c2;
+        c2.kind = Op::CONV;
+        c2.nsrc = 1;
+        c2.src[0] = h;
+        c2.in_gn = true;
+        c2.in_ss_off = p->ops[gn2].ss_off;
+        c2.out = out;
+        fill_conv_op(p, a, c2, nd.key + ".block2.block.3", nd.cout, nd.cout, want_tc);
+        if (nd.cin != nd.cout) {
+            c2.res_kind = 2;
+            c2.resw_off = a.put(pack_conv_f32(W_(p, nd.key + ".res_conv.weight"), nd.cout, nd.cin, 1));
+            c2.resb_off = a.put(W_(p, nd.key + ".res_conv.bias"));
+            if (want_tc && nd.cin % 32 == 0) c2.reswtc_off = a.put_h(pack_conv_tc(W_(p, nd.key + ".res_conv.weight"), nd.cout, nd.cin, 1));
+            // the residual reads the raw block input; record its sources in gn_src (unused by CONV otherwise)
+            c2.gn_nsrc = (int)srcs.size();
+            for (size_t i = 0; i < srcs.size(); ++i) c2.gn_src[i] = srcs[i];
+        } else {
+            c2.res_kind = 1;
+            c2.gn_nsrc = 1;
+            c2.gn_src[0] = srcs[0];
+        }
+        set_tc(c2);
+        p->ops.push_back(c2);
+        return out;
+    };
+    auto emit_plain = [&](const NodeDesc& nd, int src, int mode, int Ho, int Wo) {
+        const int out = new_tensor(p, nd.key, nd.cout, Ho, Wo);
+        Op cv;
+        cv.kind = Op::CONV;
+        cv.nsrc = 1;
+        cv.src[0] = src;
+        cv.mode = mode;
+        cv.out = out;
+        fill_conv_op(p, a, cv, nd.key + ".conv", nd.cout, nd.cin, want_tc);
+        set_tc(cv);
+        p->ops.push_back(cv);
+        return out;
+    };
+
+    // weights of the embedding MLP and the concatenated per-block Linear layers
+    {
+        const int inner = c.inner_channel;
+        std::vector<float> freq;
+        auto it = p->host_w.find("noise_level_mlp.0.embedding_vector");
+        if (it != p->host_w.end()) {
+            freq = it->second;
+        } else {   // UNetModified2.py:55: 1e4 * 10^(-4k/half)
+            for (int k = 0; k < inner / 2; ++k) freq.push_back((float)(1e4 * std::pow(10.0, -(double)k * 4.0 / (inner / 2))));
+        }
+        p->off_freq = a.put(freq);
+        p->off_w1 = a.put(W_(p, "noise_level_mlp.1.weight"));
+        p->off_b1 = a.put(W_(p, "noise_level_mlp.1.bias"));
+        p->off_w2 = a.put(W_(p, "noise_level_mlp.3.weight"));
+        p->off_b2 = a.put(W_(p, "noise_level_mlp.3.bias"));
+        std::vector<float> wn, bn;
+        for (const NodeDesc& nd : p->nodes)
+            if (nd.kind == NodeDesc::RES) {
+                const auto& w = W_(p, nd.key + ".noise_func.noise_func.0.weight");
+                const auto& b = W_(p, nd.key + ".noise_func.noise_func.0.bias");
+                wn.insert(wn.end(), w.begin(), w.end());
+                bn.insert(bn.end(), b.begin(), b.end());
+            }
+        p->E = (int)bn.size();
+        p->off_wn = a.put(wn);
+        p->off_bn = a.put(bn);
+    }
+
+    for (const NodeDesc& nd : p->nodes) {
+        switch (nd.kind) {
+            case NodeDesc::STEM: {
+                const auto& w = W_(p, "downs.0.weight");   // [CO][2][3][3] -> [2][9][CO]
+                std::vector<float> pk((size_t)18 * nd.cout);
+                for (int co = 0; co < nd.cout; ++co)
+                    for (int ci = 0; ci < 2; ++ci)
+                        for (int t = 0; t < 9; ++t) pk[((size_t)ci * 9 + t) * nd.cout + co] = w[((size_t)co * 2 + ci) * 9 + t];
+                p->off_stem_w = a.put(pk);
+                p->off_stem_b = a.put(W_(p, "downs.0.bias"));
+                cur = new_tensor(p, nd.key, nd.cout, H, W);
+                p->tensors[cur].nparts = stem_nparts(H, W);
+                Op op;
+                op.kind = Op::STEM;
+                op.out = cur;
+                p->ops.push_back(op);
+                feats.push_back(cur);
+                break;
+            }
+            case NodeDesc::RES: {
+                std::vector<int> srcs{cur};
+                if (nd.cat) {
+                    srcs.push_back(feats.back());
+                    feats.pop_back();
+                }
+                cur = emit_res(nd, srcs);
+                if (nd.key.rfind("downs.", 0) == 0) feats.push_back(cur);
+                break;
+            }
+            case NodeDesc::DOWN:
+                if (H % 2 || W % 2) { set_error("Downsample of odd size %dx%d", H, W); return SDDM_E_INVALID; }
+                H /= 2; W /= 2;
+                cur = emit_plain(nd, cur, CONV_S2, H, W);
+                feats.push_back(cur);
+                break;
+            case NodeDesc::UP:
+                H *= 2; W *= 2;
+                cur = emit_plain(nd, cur, CONV_UP, H, W);
+                break;
+        }
+    }
+    // final Block
+    {
+        const int gnf = emit_gn(p, a, {cur}, "final_conv.block.0", &ss_cursor);
+        const auto& w = W_(p, "final_conv.block.3.weight");   // [1][C][3][3] -> [9][C]
+        const int C = p->tensors[cur].C;
+        std::vector<float> pk((size_t)9 * C);
+        for (int ci = 0; ci < C; ++ci)
+            for (int t = 0; t < 9; ++t) pk[(size_t)t * C + ci] = w[(size_t)ci * 9 + t];
+        p->off_final_w = a.put(pk);
+        p->final_bias = W_(p, "final_conv.block.3.bias")[0];
+        Op op;
+        op.kind = Op::FINAL;
+        op.nsrc = 1;
+        op.src[0] = cur;
+        op.in_gn = true;
+        op.in_ss_off = p->ops[gnf].ss_off;
+        p->ops.push_back(op);
+    }
+    if (temb_cursor != p->E) { set_error("internal: embedding width mismatch"); return SDDM_E_INVALID; }
+
+    // workspace layout (per-sample float offsets)
+    size_t off = 0;
+    auto take = [&](size_t n) { size_t o = off; off += align_up(n, 32); return o; };
+    p->off_x = take((size_t)c.num_samples);
+    p->off_frames = take((size_t)p->H * p->W);
+    p->off_temb_rows = take((size_t)p->E);
+    p->off_nl = take(32);
+    for (TensorInfo& t : p->tensors) {
+        t.data_off = take((size_t)t.C * t.H * t.W);
+        t.parts_off = take((size_t)t.nparts * t.C * 2);
+    }
+    const size_t ss_base = take(ss_cursor);
+    for (Op& op : p->ops) {
+        if (op.kind == Op::GN) op.ss_off += ss_base;
+        if (op.in_gn) op.in_ss_off += ss_base;
+    }
+    p->floats_per_sample = off;
+    p->launches_per_eps = (int)p->ops.size() + 1;   // + the overlap-add / posterior kernel
+    return SDDM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// execution
+// ---------------------------------------------------------------------------------------------------
+static inline float* sect(const sddm_plan*, void* ws, size_t off, int B) { return reinterpret_cast<float*>(ws) + off * (size_t)B; }
+
+// one UNetModified2 forward up to the final conv frames (ws.frames); temb: device pointer, row stride
+static int run_unet(sddm_plan* p, const float* cond, const float* x_t, const float* temb, int temb_stride, int B, void* ws,
+                    cudaStream_t st) {
+    const sddm_config& c = p->cfg;
+    for (const Op& op : p->ops) {
+        int rc = SDDM_OK;
+        switch (op.kind) {
+            case Op::STEM: {
+                const TensorInfo& o = p->tensors[op.out];
+                StemP sp{cond, x_t, p->d_f32 + p->off_stem_w, p->d_f32 + p->off_stem_b, sect(p, ws, o.data_off, B),
+                         sect(p, ws, o.parts_off, B), B, c.num_samples, o.H, o.W, c.segment_stride, o.C, o.nparts};
+                rc = launch_stem(sp, st);
+                break;
+            }
+            case Op::GN: {
+                GnP g{};
+                g.nsrc = op.gn_nsrc;
+                for (int i = 0; i < op.gn_nsrc; ++i) {
+                    const TensorInfo& t = p->tensors[op.gn_src[i]];
+                    g.parts[i] = sect(p, ws, t.parts_off, B);
+                    g.C[i] = t.C;
+                    g.nparts[i] = t.nparts;
+                }
+                const TensorInfo& t0 = p->tensors[op.gn_src[0]];
+                g.gamma = p->d_f32 + op.gamma_off;
+                g.beta = p->d_f32 + op.beta_off;
+                g.scale = sect(p, ws, op.ss_off, B);
+                g.shift = g.scale + (size_t)op.Ctot * B;
+                g.B = B; g.Ctot = op.Ctot; g.groups = c.norm_groups; g.HW = t0.H * t0.W; g.eps = 1e-5f;
+                rc = launch_gn_finalize(g, st);
+                break;
+            }
+            case Op::CONV: {
+                ConvP cp{};
+                const TensorInfo& o = p->tensors[op.out];
+                cp.nsrc = op.nsrc;
+                cp.Cin = 0;
+                for (int i = 0; i < op.nsrc; ++i) cp.Cin += p->tensors[op.src[i]].C;
+                for (int i = 0; i < op.nsrc; ++i) {
+                    const TensorInfo& t = p->tensors[op.src[i]];
+                    cp.src[i].x = sect(p, ws, t.data_off, B);
+                    cp.src[i].C = t.C;
+                    if (op.in_gn) {
+                        cp.src[i].scale = sect(p, ws, op.in_ss_off, B);
+                        cp.src[i].shift = cp.src[i].scale + (size_t)cp.Cin * B;
+                    }
+                }
+                cp.Hin = p->tensors[op.src[0]].H; cp.Win = p->tensors[op.src[0]].W;
+                cp.Hout = o.H; cp.Wout = o.W; cp.Cout = o.C; cp.mode = op.mode;
+                cp.w = p->d_f32 + op.w_off;
+                cp.w_tc = p->d_bf16 ? p->d_bf16 + op.wtc_off : nullptr;
+                cp.bias = p->d_f32 + op.bias_off;
+                if (op.temb_off >= 0) { cp.temb = temb + op.temb_off; cp.temb_stride = temb_stride; }
+                if (op.res_kind) {
+                    cp.res_nsrc = op.gn_nsrc;
+                    cp.res_Cin = 0;
+                    for (int i = 0; i < op.gn_nsrc; ++i) {
+                        const TensorInfo& t = p->tensors[op.gn_src[i]];
+                        cp.res_src[i].x = sect(p, ws, t.data_off, B);
+                        cp.res_src[i].C = t.C;
+                        cp.res_Cin += t.C;
+                    }
+                    if (op.res_kind == 1) {
+                        cp.res_identity = 1;
+                    } else {
+                        cp.res_w = p->d_f32 + op.resw_off;
+                        cp.res_w_tc = p->d_bf16 ? p->d_bf16 + op.reswtc_off : nullptr;
+                        cp.res_bias = p->d_f32 + op.resb_off;
+                    }
+                }
+                cp.out = sect(p, ws, o.data_off, B);
+                cp.parts = sect(p, ws, o.parts_off, B);
+                cp.nparts = o.nparts;
+                cp.B = B;
+                rc = op.use_tc ? launch_conv_tc(cp, st) : launch_conv_fp32(cp, st);
+                break;
+            }
+            case Op::FINAL: {
+                const TensorInfo& t = p->tensors[op.src[0]];
+                FinalP f{};
+                f.x = sect(p, ws, t.data_off, B);
+                f.scale = sect(p, ws, op.in_ss_off, B);
+                f.shift = f.scale + (size_t)t.C * B;
+                f.w = p->d_f32 + p->off_final_w;
+                f.bias = p->final_bias;
+                f.frames = sect(p, ws, p->off_frames, B);
+                f.B = B; f.H = t.H; f.W = t.W; f.C = t.C;
+                rc = launch_final_conv(f, st);
+                break;
+            }
+        }
+        if (rc != SDDM_OK) return rc;
+    }
+    return SDDM_OK;
+}
+
+static void step_coefs(const sddm_plan* p, int variant, int t, float* k8) {
+    enum { BETAS, ALPHAS, SAB, PNC, SIGMA, SGAM, SSIG, SQD, CXT, CYT, CEPS, SDE };
+    volatile float gam = p->sch[SGAM][t];
+    volatile float omg = 1.0f - gam;
+    float sig;
+    switch (variant) {
+        case SDDM_VAR_SR3: sig = sqrtf(p->sch[BETAS][t]); break;
+        case SDDM_VAR_SUPPORTIVE: sig = fmaxf(0.0f, p->sch[SSIG][t]); break;
+        case SDDM_VAR_CONDITIONAL: sig = p->sch[SDE][t]; break;
+        default: sig = p->sch[SIGMA][t];
+    }
+    k8[0] = p->sch[PNC][t];
+    k8[1] = sqrtf(p->sch[ALPHAS][t]);   // alphas[t] ** 0.5 (correctly rounded, as torch's pow(.,0.5) -> sqrt)
+    k8[2] = sig;
+    k8[3] = gam;
+    k8[4] = omg;
+    k8[5] = p->sch[CXT][t];
+    k8[6] = p->sch[CYT][t];
+    k8[7] = p->sch[CEPS][t];
+}
+
+static int check_ready(const sddm_plan* p) {
+    if (!p) { set_error("null plan"); return SDDM_E_INVALID; }
+    if (!p->finalized) { set_error("plan not finalised (load weights, set schedule, call sddm_plan_finalize)"); return SDDM_E_STATE; }
+    return SDDM_OK;
+}
+
+static int check_variant(int v) {
+    if (v < SDDM_VAR_ORIGINAL || v > SDDM_VAR_CONDITIONAL) { set_error("unknown p_transition variant %d", v); return SDDM_E_INVALID; }
+    return SDDM_OK;
+}
+
+}  // namespace sddm
+
+// ===================================================================================================
+// C ABI
+// ===================================================================================================
+extern "C" {
+
+const char* sddm_last_error(void) { return g_err; }
+int sddm_version(void) { return 100; }
+uint64_t sddm_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int sddm_plan_create(const sddm_config* cfg, sddm_plan** out) {
+    if (!cfg || !out) { set_error("null argument"); return SDDM_E_INVALID; }
+    const sddm_config& c = *cfg;
+    if (c.in_channel != 2 || c.out_channel != 1) { set_error("in_channel must be 2 and out_channel 1 (got %d, %d)", c.in_channel, c.out_channel); return SDDM_E_INVALID; }
+    if (c.n_mults < 1 || c.n_mults > 8 || c.res_blocks < 1 || c.n_timestep < 1) { set_error("bad n_mults / res_blocks / n_timestep"); return SDDM_E_INVALID; }
+    if (c.segment_len <= 0 || c.segment_stride <= 0 || c.num_samples < c.segment_len ||
+        (c.num_samples - c.segment_len) % c.segment_stride != 0) {   // UNetModified2.py:13
+        set_error("(num_samples - segment_len) %% segment_stride must be 0");
+        return SDDM_E_INVALID;
+    }
+    if (c.num_samples % 4 || c.segment_len % 4 || c.segment_stride % 4) { set_error("num_samples, segment_len, segment_stride must be multiples of 4"); return SDDM_E_INVALID; }
+    if (c.inner_channel != 32 && c.inner_channel != 64) { set_error("inner_channel must be 32 or 64"); return SDDM_E_INVALID; }
+    if (c.norm_groups < 1 || c.inner_channel % c.norm_groups) { set_error("inner_channel must be divisible by norm_groups"); return SDDM_E_INVALID; }
+    if (c.precision != SDDM_PREC_FP32 && c.precision != SDDM_PREC_BF16) { set_error("unknown precision %d", c.precision); return SDDM_E_INVALID; }
+    const int H = (c.num_samples - c.segment_len) / c.segment_stride + 1, W = c.segment_len;
+    // every level must tile: the deepest (H/2^n x W/2^n) by 8x4, all others by 16x8
+    if (H % (1 << c.n_mults) || W % (1 << c.n_mults) || (H >> c.n_mults) % 8 || (W >> c.n_mults) % 4) {
+        set_error("frame grid %dx%d does not tile through %d levels", H, W, c.n_mults);
+        return SDDM_E_INVALID;
+    }
+    for (int i = 0; i < c.n_mults; ++i)
+        if (c.channel_mults[i] < 1) { set_error("channel_mults must be positive"); return SDDM_E_INVALID; }
+    sddm_plan* p = new sddm_plan();
+    p->cfg = c;
+    p->H = H;
+    p->W = W;
+    build_nodes(p);
+    *out = p;
+    return SDDM_OK;
+}
+
+void sddm_plan_destroy(sddm_plan* p) {
+    if (!p) return;
+    cudaFree(p->d_f32);
+    cudaFree(p->d_bf16);
+    cudaFree(p->d_temb_table);
+    cudaFree(p->d_cond);
+    cudaFree(p->d_out);
+    cudaFree(p->d_ws);
+    if (p->own_stream) cudaStreamDestroy(p->own_stream);
+    delete p;
+}
+
+int sddm_plan_load_weight(sddm_plan* p, const char* name, const void* data, const int64_t* shape, int ndim) {
+    if (!p || !name || !data || (!shape && ndim > 0)) { set_error("null argument"); return SDDM_E_INVALID; }
+    if (p->finalized) { set_error("plan already finalised"); return SDDM_E_STATE; }
+    const std::string key(name);
+    size_t numel = 1;
+    for (int i = 0; i < ndim; ++i) numel *= (size_t)shape[i];
+    if (key == "noise_level_mlp.0.embedding_vector") {
+        if (numel != (size_t)p->cfg.inner_channel / 2) { set_error("embedding_vector must have inner_channel/2 entries"); return SDDM_E_INVALID; }
+    } else {
+        auto it = p->expect.find(key);
+        if (it == p->expect.end()) { set_error("unexpected weight '%s'", name); return SDDM_E_INVALID; }
+        const std::vector<int64_t>& e = it->second;
+        bool ok = (int)e.size() == ndim;
+        for (int i = 0; ok && i < ndim; ++i) ok = e[i] == shape[i];
+        if (!ok) { set_error("weight '%s': shape mismatch", name); return SDDM_E_INVALID; }
+    }
+    std::vector<float> v(numel);
+    cudaPointerAttributes attr{};
+    const cudaError_t qe = cudaPointerGetAttributes(&attr, data);
+    if (qe == cudaSuccess && (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged)) {
+        SDDM_CUDA_TRY(cudaMemcpy(v.data(), data, numel * sizeof(float), cudaMemcpyDeviceToHost));
+    } else {   // plain host memory (also the only possibility when no device is present)
+        if (qe != cudaSuccess) cudaGetLastError();
+        std::memcpy(v.data(), data, numel * sizeof(float));
+    }
+    p->host_w[key] = std::move(v);
+    return SDDM_OK;
+}
+
+int sddm_plan_set_schedule(sddm_plan* p, const sddm_schedule* s, int n) {
+    if (!p || !s) { set_error("null argument"); return SDDM_E_INVALID; }
+    if (n != p->cfg.n_timestep + 1) { set_error("schedule length %d != n_timestep + 1 = %d", n, p->cfg.n_timestep + 1); return SDDM_E_INVALID; }
+    const float* ptrs[12] = {s->betas, s->alphas, s->sqrt_alpha_bar, s->predicted_noise_coeff, s->sigma, s->supportive_gamma,
+                             s->supportive_sigma_hat, s->sqrt_delta, s->c_xt, s->c_yt, s->c_epst, s->sqrt_delta_estimated};
+    for (int i = 0; i < 12; ++i) {
+        if (!ptrs[i]) { set_error("schedule table %d is null", i); return SDDM_E_INVALID; }
+        p->sch[i].assign(ptrs[i], ptrs[i] + n);
+    }
+    p->have_sched = true;
+    return SDDM_OK;
+}
+
+int sddm_plan_finalize(sddm_plan* p) {
+    if (!p) { set_error("null plan"); return SDDM_E_INVALID; }
+    if (p->finalized) return SDDM_OK;
+    if (!p->have_sched) { set_error("schedule not set"); return SDDM_E_STATE; }
+    for (const auto& kv : p->expect)
+        if (!p->host_w.count(kv.first)) { set_error("missing weight '%s'", kv.first.c_str()); return SDDM_E_STATE; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device: this library has no CPU fallback");
+        return SDDM_E_CUDA;
+    }
+    Arena a;
+    int rc = build_program(p, a);
+    if (rc != SDDM_OK) return rc;
+    SDDM_CUDA_TRY(cudaMalloc(&p->d_f32, a.f.size() * sizeof(float)));
+    SDDM_CUDA_TRY(cudaMemcpy(p->d_f32, a.f.data(), a.f.size() * sizeof(float), cudaMemcpyHostToDevice));
+    if (!a.h.empty()) {
+        SDDM_CUDA_TRY(cudaMalloc(&p->d_bf16, a.h.size() * sizeof(__nv_bfloat16)));
+        SDDM_CUDA_TRY(cudaMemcpy(p->d_bf16, a.h.data(), a.h.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+    }
+    // per-timestep embedding table: row t = E(noise level sqrt_alpha_bar[t])
+    const int T1 = p->cfg.n_timestep + 1;
+    float* d_nl = nullptr;
+    SDDM_CUDA_TRY(cudaMalloc(&p->d_temb_table, (size_t)T1 * p->E * sizeof(float)));
+    SDDM_CUDA_TRY(cudaMalloc(&d_nl, T1 * sizeof(float)));
+    SDDM_CUDA_TRY(cudaMemcpy(d_nl, p->sch[2].data(), T1 * sizeof(float), cudaMemcpyHostToDevice));
+    TembP tp{d_nl, p->d_f32 + p->off_freq, p->d_f32 + p->off_w1, p->d_f32 + p->off_b1, p->d_f32 + p->off_w2, p->d_f32 + p->off_b2,
+             p->d_f32 + p->off_wn, p->d_f32 + p->off_bn, p->d_temb_table, T1, p->cfg.inner_channel, p->E};
+    rc = launch_temb(tp, nullptr);
+    if (rc != SDDM_OK) { cudaFree(d_nl); return rc; }
+    SDDM_CUDA_TRY(cudaDeviceSynchronize());
+    cudaFree(d_nl);
+    p->host_w.clear();
+    p->finalized = true;
+    return SDDM_OK;
+}
+
+size_t sddm_workspace_bytes(const sddm_plan* p, int B) {
+    if (!p || !p->finalized || B <= 0) return 0;
+    return p->floats_per_sample * (size_t)B * sizeof(float) + 256;
+}
+
+int sddm_plan_launches_per_eps(const sddm_plan* p) { return (p && p->finalized) ? p->launches_per_eps : 0; }
+
+static int check_ws(const sddm_plan* p, int B, const void* ws, size_t ws_bytes) {
+    if (B <= 0) { set_error("batch must be positive"); return SDDM_E_INVALID; }
+    if (!ws || ws_bytes < sddm_workspace_bytes(p, B)) { set_error("workspace too small: %zu < %zu", ws_bytes, sddm_workspace_bytes(p, B)); return SDDM_E_WORKSPACE; }
+    if ((uintptr_t)ws % 256) { set_error("workspace must be 256-byte aligned"); return SDDM_E_INVALID; }
+    return SDDM_OK;
+}
+
+int sddm_eps(sddm_plan* p, const float* cond, const float* x_t, const float* noise_level, int t, float* eps_out, int B, void* ws,
+             size_t ws_bytes, void* stream) {
+    int rc = check_ready(p);
+    if (rc) return rc;
+    if ((rc = check_ws(p, B, ws, ws_bytes))) return rc;
+    if (!cond || !x_t || !eps_out) { set_error("null buffer"); return SDDM_E_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const float* temb;
+    int stride;
+    if (noise_level) {
+        float* rows = sect(p, ws, p->off_temb_rows, B);
+        TembP tp{noise_level, p->d_f32 + p->off_freq, p->d_f32 + p->off_w1, p->d_f32 + p->off_b1, p->d_f32 + p->off_w2,
+                 p->d_f32 + p->off_b2, p->d_f32 + p->off_wn, p->d_f32 + p->off_bn, rows, B, p->cfg.inner_channel, p->E};
+        if ((rc = launch_temb(tp, st))) return rc;
+        temb = rows;
+        stride = p->E;
+    } else {
+        if (t < 0 || t > p->cfg.n_timestep) { set_error("t=%d out of range", t); return SDDM_E_INVALID; }
+        temb = p->d_temb_table + (size_t)t * p->E;
+        stride = 0;
+    }
+    if ((rc = run_unet(p, cond, x_t, temb, stride, B, ws, st))) return rc;
+    PostP pp{};
+    pp.frames = sect(p, ws, p->off_frames, B);
+    pp.eps_out = eps_out;
+    pp.do_update = 0;
+    pp.B = B; pp.L = p->cfg.num_samples; pp.F = p->cfg.segment_len; pp.hop = p->cfg.segment_stride; pp.n_frames = p->H;
+    pp.t = 1; pp.T = p->cfg.n_timestep;
+    float k8[8] = {0};
+    return launch_post_coef(pp, k8, st);
+}
+
+int sddm_x_T(sddm_plan* p, int variant, const float* cond, const float* z, uint64_t seed, int64_t row0, float* x_out, int B,
+             void* stream) {
+    int rc = check_ready(p);
+    if (rc) return rc;
+    if ((rc = check_variant(variant))) return rc;
+    if (!x_out || B <= 0 || (!cond && variant != SDDM_VAR_ORIGINAL && variant != SDDM_VAR_SR3)) { set_error("null buffer / bad batch"); return SDDM_E_INVALID; }
+    const int T = p->cfg.n_timestep;
+    volatile float a = p->sch[2][T];
+    volatile float sq = a * a;
+    volatile float om = 1.0f - sq;
+    float b = sqrtf(om);                              // diffusion.py:297
+    if (variant == SDDM_VAR_CONDITIONAL) b = p->sch[7][T];   // sqrt_delta[T], diffusion.py:317
+    return launch_x_T_coef(variant, a, b, cond, z, seed, row0, x_out, B, p->cfg.num_samples, (cudaStream_t)stream);
+}
+
+int sddm_p_step(sddm_plan* p, int variant, float* x_t, const float* eps, const float* cond, const float* z, uint64_t seed,
+                int64_t row0, int t, int B, void* stream) {
+    int rc = check_ready(p);
+    if (rc) return rc;
+    if ((rc = check_variant(variant))) return rc;
+    if (!x_t || !eps || B <= 0) { set_error("null buffer / bad batch"); return SDDM_E_INVALID; }
+    if (t < 1 || t > p->cfg.n_timestep) { set_error("t=%d out of range [1, %d]", t, p->cfg.n_timestep); return SDDM_E_INVALID; }
+    if ((variant == SDDM_VAR_SUPPORTIVE || variant == SDDM_VAR_CONDITIONAL) && !cond) { set_error("variant needs the condition"); return SDDM_E_INVALID; }
+    PostP pp{};
+    pp.eps_in = eps;
+    pp.x_in = x_t; pp.x_out = x_t;
+    pp.cond = cond; pp.z = z; pp.seed = seed; pp.row0 = row0;
+    pp.variant = variant; pp.t = t; pp.T = p->cfg.n_timestep; pp.do_update = 1;
+    pp.B = B; pp.L = p->cfg.num_samples; pp.F = p->cfg.segment_len; pp.hop = p->cfg.segment_stride; pp.n_frames = p->H;
+    float k8[8];
+    step_coefs(p, variant, t, k8);
+    return launch_post_coef(pp, k8, (cudaStream_t)stream);
+}
+
+int sddm_x_T_raw(int variant, float a, float b, const float* cond, const float* z, uint64_t seed, int64_t row0, float* x_out,
+                 int B, int L, void* stream) {
+    int rc = check_variant(variant);
+    if (rc) return rc;
+    if (!x_out || B <= 0 || L <= 0 || L % 4) { set_error("bad buffer / batch / length (L must be a multiple of 4)"); return SDDM_E_INVALID; }
+    if (!cond && variant != SDDM_VAR_ORIGINAL && variant != SDDM_VAR_SR3) { set_error("variant needs the condition"); return SDDM_E_INVALID; }
+    return launch_x_T_coef(variant, a, b, cond, z, seed, row0, x_out, B, L, (cudaStream_t)stream);
+}
+
+int sddm_p_step_raw(int variant, const float* k8, float* x_t, const float* eps, const float* cond, const float* z, uint64_t seed,
+                    int64_t row0, int t, int T, int B, int L, void* stream) {
+    int rc = check_variant(variant);
+    if (rc) return rc;
+    if (!k8 || !x_t || !eps || B <= 0 || L <= 0 || L % 4) { set_error("bad buffer / batch / length (L must be a multiple of 4)"); return SDDM_E_INVALID; }
+    if (t < 1 || t > T) { set_error("t=%d out of range [1, %d]", t, T); return SDDM_E_INVALID; }
+    if ((variant == SDDM_VAR_SUPPORTIVE || variant == SDDM_VAR_CONDITIONAL) && !cond) { set_error("variant needs the condition"); return SDDM_E_INVALID; }
+    PostP pp{};
+    pp.eps_in = eps;
+    pp.x_in = x_t; pp.x_out = x_t;
+    pp.cond = cond; pp.z = z; pp.seed = seed; pp.row0 = row0;
+    pp.variant = variant; pp.t = t; pp.T = T; pp.do_update = 1;
+    pp.B = B; pp.L = L; pp.F = 4; pp.hop = 4; pp.n_frames = 0;
+    return launch_post_coef(pp, k8, (cudaStream_t)stream);
+}
+
+int sddm_sample(sddm_plan* p, int variant, const float* cond, const float* noises, uint64_t seed, int64_t row0, float* out,
+                float* eps_trace, float* x_trace, int B, void* ws, size_t ws_bytes, void* stream) {
+    int rc = check_ready(p);
+    if (rc) return rc;
+    if ((rc = check_variant(variant))) return rc;
+    if ((rc = check_ws(p, B, ws, ws_bytes))) return rc;
+    if (!cond || !out) { set_error("null buffer"); return SDDM_E_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int T = p->cfg.n_timestep, L = p->cfg.num_samples;
+    const size_t BL = (size_t)B * L;
+    float* x = sect(p, ws, p->off_x, B);
+    if ((rc = sddm_x_T(p, variant, cond, noises, seed, row0, x, B, stream))) return rc;
+    for (int t = T; t >= 1; --t) {
+        if ((rc = run_unet(p, cond, x, p->d_temb_table + (size_t)t * p->E, 0, B, ws, st))) return rc;
+        PostP pp{};
+        pp.frames = sect(p, ws, p->off_frames, B);
+        pp.eps_out = eps_trace ? eps_trace + (size_t)(T - t) * BL : nullptr;
+        pp.x_in = x;
+        pp.x_out = (t == 1) ? out : x;
+        pp.x_trace = x_trace ? x_trace + (size_t)(T - t) * BL : nullptr;
+        pp.cond = cond;
+        pp.z = (noises && t > 1) ? noises + (size_t)(T + 1 - t) * BL : nullptr;
+        pp.seed = seed; pp.row0 = row0;
+        pp.variant = variant; pp.t = t; pp.T = T; pp.do_update = 1;
+        pp.B = B; pp.L = L; pp.F = p->cfg.segment_len; pp.hop = p->cfg.segment_stride; pp.n_frames = p->H;
+        float k8[8];
+        step_coefs(p, variant, t, k8);
+        if ((rc = launch_post_coef(pp, k8, st))) return rc;
+    }
+    return SDDM_OK;
+}
+
+int sddm_enhance_host(sddm_plan* p, int variant, const float* cond_host, float* out_host, int B, uint64_t seed, int64_t row0,
+                      int max_rows) {
+    int rc = check_ready(p);
+    if (rc) return rc;
+    if (!cond_host || !out_host || B <= 0) { set_error("null buffer / bad batch"); return SDDM_E_INVALID; }
+    if (max_rows <= 0) max_rows = 64;
+    const int R = B < max_rows ? B : max_rows;
+    const size_t L = (size_t)p->cfg.num_samples;
+    if (!p->own_stream) SDDM_CUDA_TRY(cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking));
+    if (p->arena_rows < R) {
+        cudaFree(p->d_cond); cudaFree(p->d_out); cudaFree(p->d_ws);
+        p->d_cond = p->d_out = nullptr; p->d_ws = nullptr; p->arena_rows = 0;
+        SDDM_CUDA_TRY(cudaMalloc(&p->d_cond, R * L * sizeof(float)));
+        SDDM_CUDA_TRY(cudaMalloc(&p->d_out, R * L * sizeof(float)));
+        SDDM_CUDA_TRY(cudaMalloc(&p->d_ws, sddm_workspace_bytes(p, R)));
+        p->arena_rows = R;
+    }
+    for (int r0 = 0; r0 < B; r0 += R) {
+        const int nb = (B - r0) < R ? (B - r0) : R;
+        SDDM_CUDA_TRY(cudaMemcpyAsync(p->d_cond, cond_host + (size_t)r0 * L, nb * L * sizeof(float), cudaMemcpyHostToDevice, p->own_stream));
+        rc = sddm_sample(p, variant, p->d_cond, nullptr, seed, row0 + r0, p->d_out, nullptr, nullptr, nb, p->d_ws,
+                         sddm_workspace_bytes(p, p->arena_rows), p->own_stream);
+        if (rc) return rc;
+        SDDM_CUDA_TRY(cudaMemcpyAsync(out_host + (size_t)r0 * L, p->d_out, nb * L * sizeof(float), cudaMemcpyDeviceToHost, p->own_stream));
+    }
+    SDDM_CUDA_TRY(cudaStreamSynchronize(p->own_stream));
+    return SDDM_OK;
+}
+
+int sddm_frames(const float* sig, float* frames, int B, int n, int F, int hop, void* stream) {
+    if (!sig || !frames || B <= 0 || F <= 0 || hop <= 0 || n < F) { set_error("bad argument"); return SDDM_E_INVALID; }
+    if ((n - F) % hop) { set_error("(n_samples - F) %% stride must be 0"); return SDDM_E_INVALID; }
+    return launch_frames(sig, frames, B, n, F, hop, (cudaStream_t)stream);
+}
+
+int sddm_overlap_add(const float* frames, float* sig, int B, int n, int F, int hop, void* stream) {
+    if (!sig || !frames || B <= 0 || F <= 0 || hop <= 0 || n < F) { set_error("bad argument"); return SDDM_E_INVALID; }
+    if ((n - F) % hop) { set_error("(n_samples - F) %% stride must be 0"); return SDDM_E_INVALID; }
+    return launch_overlap_add(frames, sig, B, n, F, hop, (cudaStream_t)stream);
+}
+
+int sddm_debug_fetch(sddm_plan* p, const char* node, void* ws, int B, float* out, int64_t* chw, void* stream) {
+    int rc = check_ready(p);
+    if (rc) return rc;
+    if (!node || !ws || B <= 0) { set_error("bad argument"); return SDDM_E_INVALID; }
+    for (const TensorInfo& t : p->tensors)
+        if (t.name == node) {
+            const size_t n = (size_t)t.C * t.H * t.W;
+            if (chw) { chw[0] = t.C; chw[1] = t.H; chw[2] = t.W; }
+            if (out) SDDM_CUDA_TRY(cudaMemcpyAsync(out, sect(p, ws, t.data_off, B), n * B * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+            return SDDM_OK;
+        }
+    if (std::string(node) == "frames") {
+        if (chw) { chw[0] = 1; chw[1] = p->H; chw[2] = p->W; }
+        if (out) SDDM_CUDA_TRY(cudaMemcpyAsync(out, sect(p, ws, p->off_frames, B), (size_t)p->H * p->W * B * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+        return SDDM_OK;
+    }
+    set_error("unknown node '%s'", node);
+    return SDDM_E_INVALID;
+}
+
+}  // extern "C"

@@ -1,0 +1,138 @@
+// Shared declarations for the sddm_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stddef.h>
+
+namespace sddm {
+
+// ---------------------------------------------------------------------------------------------------
+// error plumbing (thread-local message, see sddm_last_error in api.cu)
+// ---------------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define SDDM_CUDA_TRY(expr)                                                                          \
+    do {                                                                                             \
+        cudaError_t _e = (expr);                                                                     \
+        if (_e != cudaSuccess) {                                                                     \
+            ::sddm::set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__, \
+                              cudaGetErrorString(_e));                                               \
+            return SDDM_E_CUDA;                                                                      \
+        }                                                                                            \
+    } while (0)
+
+#define SDDM_LAUNCH_CHECK()                                                                          \
+    do {                                                                                             \
+        ::sddm::count_launch();                                                                      \
+        cudaError_t _e = cudaPeekAtLastError();                                                      \
+        if (_e != cudaSuccess) {                                                                     \
+            ::sddm::set_error("kernel launch failed %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, \
+                              __LINE__, cudaGetErrorString(_e));                                     \
+            return SDDM_E_CUDA;                                                                      \
+        }                                                                                            \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------
+// convolution op descriptor, shared by the CUDA-core fp32 kernel and the tcgen05 bf16 kernel.
+// Activations are NHWC fp32 ("raw", i.e. pre-GroupNorm); a source with scale != nullptr is consumed as
+// swish(x * scale[n][c] + shift[n][c]) (GroupNorm-apply + Swish fused into the operand staging); the
+// zero padding of the convolution is applied AFTER that transform (UNetModified2.py:116-121).
+// ---------------------------------------------------------------------------------------------------
+struct ConvSrc {
+    const float* x;      // [B][Hin][Win][C]
+    const float* scale;  // [B][Cin_total] (indexed with the concatenated channel index) or nullptr = raw
+    const float* shift;
+    int C;
+};
+
+enum ConvMode { CONV_S1 = 0, CONV_S2 = 1, CONV_UP = 2 };  // 3x3 pad 1: stride 1 | stride 2 | nearest x2 then stride 1
+
+struct ConvP {
+    ConvSrc src[2];  // channel concatenation [src0, src1] (torch.cat(dim=1), UNetModified2.py:263)
+    int nsrc;
+    int Cin;         // total input channels
+    int Hin, Win;    // source spatial size
+    int Hout, Wout;
+    int Cout;
+    int mode;
+    const float* w;             // fp32 pack  [Cin/8][9][8][Cout]
+    const __nv_bfloat16* w_tc;  // bf16 pack  [Cin/32][9][4][Cout][8]  (UMMA K-major core-matrix image)
+    const float* bias;          // [Cout]
+    const float* temb;          // nullable; + temb[n * temb_stride + co]  (FeatureWiseAffine, additive)
+    int temb_stride;
+    // residual: out += res_conv(x) with x = raw concat of res_src (1x1 conv), or += x when res_identity
+    ConvSrc res_src[2];
+    int res_nsrc;
+    int res_Cin;
+    int res_identity;
+    const float* res_w;             // fp32 pack [Cin/8][8][Cout]
+    const __nv_bfloat16* res_w_tc;  // bf16 pack [Cin/32][4][Cout][8]
+    const float* res_bias;
+    float* out;    // [B][Hout][Wout][Cout]
+    float* parts;  // GroupNorm partial statistics of `out`: [B][nparts][Cout][2] (sum, sum of squares)
+    int nparts;
+    int B;
+};
+
+int launch_conv_fp32(const ConvP& p, cudaStream_t st);
+int launch_conv_tc(const ConvP& p, cudaStream_t st);   // tcgen05 path; requires Hout%16==0, Wout%8==0, C%32==0
+bool conv_tc_supported(const ConvP& p);
+int conv_fp32_nparts(int Hout, int Wout);
+int conv_tc_nparts(int Hout, int Wout);
+
+// ---------------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float swish_accurate(float v) { return v / (1.0f + expf(-v)); }
+__device__ __forceinline__ float swish_fast(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+
+// Philox4x32-10 (Salmon et al. 2011), counter-based: results depend only on (key, counter).
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+        uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += W0;
+        key.y += W1;
+    }
+    return ctr;
+}
+
+// four N(0,1) samples from one Philox block (Box-Muller on (0,1] uniforms)
+__device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint32_t elem4, uint64_t row, uint32_t draw) {
+    uint4 r = philox4x32_10(make_uint4(elem4, (uint32_t)row, draw, (uint32_t)(row >> 32)),
+                            make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const float k = 2.3283064365386963e-10f;  // 2^-32
+    float u0 = ((float)r.x + 1.0f) * k, u1 = (float)r.y * k;
+    float u2 = ((float)r.z + 1.0f) * k, u3 = (float)r.w * k;
+    u0 = fminf(u0, 1.0f);
+    u2 = fminf(u2, 1.0f);
+    float m0 = sqrtf(-2.0f * logf(u0)), m1 = sqrtf(-2.0f * logf(u2));
+    float s0, c0, s1, c1;
+    sincospif(2.0f * u1, &s0, &c0);
+    sincospif(2.0f * u3, &s1, &c1);
+    return make_float4(m0 * c0, m0 * s0, m1 * c1, m1 * s1);
+}
+
+// Warp-wide column sums of 32 per-lane values with 31 shuffles (recursive halving):
+// on return, lane l holds in v[0] the sum over all 32 lanes of the value with index l.
+__device__ __forceinline__ float warp_transpose_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int step = 0; step < 5; ++step) {
+        const int width = 16 >> step;
+        const bool upper = (lane & width) != 0;
+#pragma unroll
+        for (int i = 0; i < width; ++i) {
+            float send = upper ? v[i] : v[i + width];
+            float keep = upper ? v[i + width] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, width);
+        }
+    }
+    return v[0];
+}
+
+}  // namespace sddm

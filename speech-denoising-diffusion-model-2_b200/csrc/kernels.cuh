@@ -1,0 +1,80 @@
+// Host-callable launchers of the non-convolution kernels (kernels_misc.cu).
+#pragma once
+#include "common.cuh"
+
+namespace sddm {
+
+// x_T = a * cond + b * z                       (diffusion.py:281-320); a, b are the step-T scalars
+int launch_x_T_coef(int variant, float a, float b, const float* cond, const float* z, uint64_t seed, int64_t row0,
+                    float* x_out, int B, int L, cudaStream_t st);
+
+// posterior update incl. clamp, optionally fused with the overlap-add of the final conv frames.
+//   frames != nullptr : eps[s] = frames[a][j] + frames[a-1][j+hop]   (UNetModified2.py:30-41)
+//   frames == nullptr : eps read from eps_in
+//   do_update == 0    : only eps_out is written (sddm_eps)
+struct PostP {
+    const float* frames;   // [B][n_frames][F] or nullptr
+    const float* eps_in;   // [B][L] or nullptr
+    float* eps_out;        // [B][L] or nullptr
+    const float* x_in;     // [B][L]
+    float* x_out;          // [B][L]
+    float* x_trace;        // [B][L] or nullptr
+    const float* cond;     // [B][L] (supportive / conditional)
+    const float* z;        // [B][L] injected noise or nullptr (Philox)
+    uint64_t seed;
+    int64_t row0;
+    int variant, t, T, do_update;
+    int B, L, F, hop, n_frames;
+};
+// k8 = {c2, sqrt(alpha_t), noise std, gamma, 1-gamma, c_xt, c_yt, c_epst} of step t (host scalars)
+int launch_post_coef(const PostP& p, const float* k8, cudaStream_t st);
+
+int launch_frames(const float* sig, float* frames, int B, int n, int F, int hop, cudaStream_t st);
+int launch_overlap_add(const float* frames, float* sig, int B, int n, int F, int hop, cudaStream_t st);
+
+// noise-level embedding: PE -> Linear -> Swish -> Linear -> Swish -> all per-block Linear(inner -> Cout)
+// out[row][E]                                   (UNetModified2.py:49-89,168-174)
+struct TembP {
+    const float* nl;       // [rows] noise levels
+    const float* freq;     // [inner/2] PE frequencies
+    const float* w1; const float* b1;   // [4*inner][inner]
+    const float* w2; const float* b2;   // [inner][4*inner]
+    const float* wn; const float* bn;   // [E][inner], [E]
+    float* out;            // [rows][E]
+    int rows, inner, E;
+};
+int launch_temb(const TembP& p, cudaStream_t st);
+
+// stem: framing + channel concat + conv3x3(2 -> CO), NHWC output + GroupNorm partial statistics
+struct StemP {
+    const float* cond; const float* x_t;   // [B][L]
+    const float* w;      // [2][9][CO] fp32 pack
+    const float* bias;   // [CO]
+    float* out;          // [B][H][W][CO]
+    float* parts;        // [B][nparts][CO][2]
+    int B, L, H, W, hop, CO, nparts;
+};
+int launch_stem(const StemP& p, cudaStream_t st);
+int stem_nparts(int H, int W);
+
+// GroupNorm finalize: partial sums -> per-(sample, channel) scale / shift
+struct GnP {
+    const float* parts[2]; int C[2]; int nparts[2]; int nsrc;
+    const float* gamma; const float* beta;   // [Ctot]
+    float* scale; float* shift;              // [B][Ctot]
+    int B, Ctot, groups, HW;
+    float eps;
+};
+int launch_gn_finalize(const GnP& p, cudaStream_t st);
+
+// final Block: GN-apply + Swish + conv3x3(C -> 1); output frames [B][H][W]
+struct FinalP {
+    const float* x; const float* scale; const float* shift;   // [B][H][W][C], [B][C]
+    const float* w;     // [9][C]
+    float bias;
+    float* frames;      // [B][H][W]
+    int B, H, W, C;
+};
+int launch_final_conv(const FinalP& p, cudaStream_t st);
+
+}  // namespace sddm

@@ -1,0 +1,85 @@
+"""Batch-shape contract of the inference path (reference data_loader/data_loaders.py:101-164).
+
+The reference ``InferDataset`` zero-pads every utterance to a multiple of T = num_samples and views it as
+``[n_chunk, 1, T]``; ``infer_data_collate`` concatenates the chunks of several utterances along dim 0 and carries an
+index tensor (utterance id per chunk); infer.py:81-120 regroups rows by that index.  Audio file decoding is out of
+scope here (torchaudio.load needs torchcodec, absent): datasets are built from in-memory waveforms or ``.npy`` files.
+"""
+from __future__ import annotations
+
+from math import ceil
+from pathlib import Path
+from typing import List, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+
+def chunk_waveform(wave: torch.Tensor, T: int) -> torch.Tensor:
+    """[1, n] or [n] -> [ceil(n/T), 1, T], zero padded at the end (reference :112-118)."""
+    wave = wave.reshape(1, -1)
+    n = wave.shape[-1]
+    n_chunk = max(1, ceil(n / T))
+    return F.pad(wave, (0, n_chunk * T - n), "constant", 0).view(n_chunk, 1, T)
+
+
+class InferDataset(torch.utils.data.Dataset):
+    """(clean, noisy) utterance pairs -> (clean_chunks, noisy_chunks, index) exactly as the reference yields them.
+
+    ``items`` is a sequence of (clean, noisy) waveforms (tensors / arrays / paths to .npy); ``clean`` may be None
+    (then the noisy waveform stands in: enhancement needs no target)."""
+
+    def __init__(self, items: Sequence, sample_rate: int = 16000, T: int = 16448, names: Sequence[str] = None):
+        self.items, self.sample_rate, self.T = list(items), sample_rate, T
+        self.names = list(names) if names is not None else ["utt%05d" % i for i in range(len(self.items))]
+
+    @staticmethod
+    def _load(x):
+        if isinstance(x, (str, Path)):
+            x = np.load(x)
+        return torch.as_tensor(x, dtype=torch.float32).reshape(1, -1)
+
+    def __len__(self):
+        return len(self.items)
+
+    def getName(self, idx):
+        return self.names[idx]
+
+    def __getitem__(self, index):
+        clean, noisy = self.items[index]
+        noisy = self._load(noisy)
+        clean = noisy if clean is None else self._load(clean)
+        assert clean.shape[-1] == noisy.shape[-1]
+        noisy_c = chunk_waveform(noisy, self.T)
+        clean_c = chunk_waveform(clean, self.T)
+        return clean_c, noisy_c, index * torch.ones(noisy_c.shape[0], dtype=torch.long)
+
+
+def infer_data_collate(batch) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Concatenate the chunk stacks of several utterances (reference :143-155)."""
+    clean = torch.cat([b[0] for b in batch], dim=0)
+    noisy = torch.cat([b[1] for b in batch], dim=0)
+    index = torch.cat([b[2] for b in batch], dim=0)
+    return clean, noisy, index
+
+
+class InferDataLoader(torch.utils.data.DataLoader):
+    def __init__(self, dataset, batch_size, num_workers=0):
+        super().__init__(dataset, batch_size=batch_size, shuffle=False, num_workers=num_workers, collate_fn=infer_data_collate)
+
+
+def regroup(rows: torch.Tensor, index: torch.Tensor, lengths: Sequence[int] = None) -> List[torch.Tensor]:
+    """Inverse of the collate: rows [N,1,T] + utterance id per row -> list of [1, n_i] waveforms
+    (reference infer.py:81-120; optionally trimmed back to the un-padded lengths)."""
+    out = []
+    ids = index.tolist()
+    start = 0
+    for k in range(1, len(ids) + 1):
+        if k == len(ids) or ids[k] != ids[start]:
+            wav = rows[start:k].reshape(1, -1)
+            if lengths is not None:
+                wav = wav[:, :lengths[len(out)]]
+            out.append(wav)
+            start = k
+    return out

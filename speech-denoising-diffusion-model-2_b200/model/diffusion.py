@@ -1,0 +1,195 @@
+"""``GaussianDiffusion`` — host mirror of reference model/diffusion.py:49-326.
+
+Same constructor kwargs, the same 14 registered buffers (so reference checkpoints load), the same method names.
+The schedule tables are built once on the CPU in fp32 with the reference's op order (bit-identical to the
+reference built with ``device='cpu'``) and then moved to ``device``; every per-element update runs in the
+hand-written CUDA kernels behind ``sddm_x_T_raw`` / ``sddm_p_step_raw`` (csrc/kernels_misc.cu).  CPU tensors are
+rejected: there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+from torch import nn
+
+from .. import _lib
+
+_BUFFERS = ("betas", "alphas", "alpha_bar", "sqrt_alpha_bar", "predicted_noise_coeff", "sigma", "supportive_gamma",
+            "supportive_sigma_hat", "m", "sqrt_delta", "c_xt", "c_yt", "c_epst", "sqrt_delta_estimated")
+
+
+def build_schedule(schedule: str, n_timestep: int, linear_start: float, linear_end: float):
+    """fp32 CPU tables of length T+1 (reference diffusion.py:65-161)."""
+    T, f32 = n_timestep, torch.float32
+    betas = torch.zeros(T + 1, dtype=f32)
+    if schedule == "linear":
+        betas[1:] = torch.linspace(linear_start, linear_end, T, dtype=f32)
+        alphas = 1 - betas
+        alpha_bar = torch.cumprod(alphas, dim=0)
+    elif schedule == "quad":
+        betas[1:] = torch.linspace(linear_start ** 0.5, linear_end ** 0.5, T, dtype=f32) ** 2
+        alphas = 1 - betas
+        alpha_bar = torch.cumprod(alphas, dim=0)
+    elif schedule == "cosine":
+        s = 0.008
+        grid = torch.arange(T + 1, dtype=f32) / T + s
+        f = torch.cos(grid / (1 + s) * (torch.pi / 2)).pow(2)
+        alpha_bar = f / f[0]
+        betas[1:] = 1 - alpha_bar[1:] / alpha_bar[:-1]
+        betas = betas.clamp(max=0.999)
+        alphas = 1 - betas
+    else:
+        raise NotImplementedError
+    tab = dict(betas=betas, alphas=alphas, alpha_bar=alpha_bar, sqrt_alpha_bar=torch.sqrt(alpha_bar))
+    one_m_ab = 1.0 - alpha_bar
+    sigma = torch.zeros_like(betas)
+    sigma[1:] = (one_m_ab[:-1] / one_m_ab[1:] * betas[1:]) ** 0.5
+    coeff = torch.zeros_like(betas)
+    coeff[1:] = betas[1:] / torch.sqrt(1 - alpha_bar[1:])
+    gamma = torch.zeros_like(betas)
+    gamma[1] = 0.2
+    gamma[2:] = sigma[2:]
+    sigma_hat = torch.zeros_like(betas)
+    sigma_hat[1:] = sigma[1:] - gamma[1:] / torch.sqrt(alphas[1:])
+    tab.update(predicted_noise_coeff=coeff, sigma=sigma, supportive_gamma=gamma, supportive_sigma_hat=sigma_hat)
+    # conditional diffusion (Lu et al.) coefficients
+    sab = tab["sqrt_alpha_bar"]
+    m = torch.sqrt((1 - alpha_bar) / sab)
+    delta = (1 - alpha_bar) - m ** 2 * alpha_bar
+    r = (1 - m[1:]) / (1 - m[:-1])
+    ad = alphas[1:] * delta[:-1]
+    d_step = delta[1:] - r ** 2 * ad
+    root_a = torch.sqrt(alphas[1:])
+    c_xt, c_yt, c_epst, d_est = (torch.zeros_like(betas) for _ in range(4))
+    c_xt[1:] = r * delta[:-1] / delta[1:] * root_a + (1 - m[:-1]) * (d_step / delta[1:]) * (1 / root_a)
+    c_yt[1:] = (m[:-1] * delta[1:] - m[1:] * r * ad) * sab[:-1] / delta[1:]
+    c_epst[1:] = (1 - m[:-1]) * d_step / delta[1:] * torch.sqrt(1 - alpha_bar[1:]) / root_a
+    d_est[1:] = d_step * delta[:-1] / delta[1:]
+    tab.update(m=m, sqrt_delta=torch.sqrt(delta), c_xt=c_xt, c_yt=c_yt, c_epst=c_epst,
+               sqrt_delta_estimated=torch.sqrt(d_est))
+    return tab
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("sddm_b200 runs on CUDA tensors only (no CPU fallback); got a %s tensor" % t.device)
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _prep(t, like=None):
+    if t is None:
+        return None
+    t = t.detach()
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+class GaussianDiffusion(nn.Module):
+    def __init__(self, schedule="linear", n_timestep=1000, linear_start=1e-4, linear_end=2e-2, device="cuda"):
+        super().__init__()
+        self.num_timesteps = n_timestep
+        self.device = device
+        self.schedule = schedule
+        tab = build_schedule(schedule, n_timestep, linear_start, linear_end)
+        for k in _BUFFERS:
+            self.register_buffer(k, tab[k].to(device))
+        self._host = None
+
+    # -- host-side scalar access (no device sync inside the loop) -------------------------------------
+    def host_tables(self):
+        if self._host is None:
+            self._host = {k: getattr(self, k).detach().cpu().numpy().astype(np.float32) for k in _BUFFERS}
+        return self._host
+
+    def _load_from_state_dict(self, *a, **k):
+        self._host = None
+        return super()._load_from_state_dict(*a, **k)
+
+    def step_scalars(self, t: int, variant: str):
+        """k8 of sddm_p_step_raw for step t, each scalar rounded exactly as the reference's eager ops do."""
+        h, f = self.host_tables(), np.float32
+        if variant == "sr3":
+            std = np.sqrt(h["betas"][t])
+        elif variant == "supportive":
+            std = max(f(0), h["supportive_sigma_hat"][t])
+        elif variant == "conditional":
+            std = h["sqrt_delta_estimated"][t]
+        else:
+            std = h["sigma"][t]
+        g = h["supportive_gamma"][t]
+        vals = [h["predicted_noise_coeff"][t], np.sqrt(h["alphas"][t]), std, g, f(1) - g, h["c_xt"][t], h["c_yt"][t],
+                h["c_epst"][t]]
+        return (C.c_float * 8)(*[float(v) for v in vals])
+
+    # -- reference API ---------------------------------------------------------------------------------
+    def get_noise_level(self, t):
+        return self.sqrt_alpha_bar[t]
+
+    def _x_T(self, variant, condition, noise, seed):
+        _need_cuda(condition, noise)
+        cond = _prep(condition)
+        z = _prep(noise)
+        h, T = self.host_tables(), self.num_timesteps
+        a = h["sqrt_alpha_bar"][T]
+        b = h["sqrt_delta"][T] if variant == "conditional" else np.sqrt(np.float32(1) - a * a)
+        out = torch.empty_like(cond)
+        B, L = cond.shape[0], cond.numel() // cond.shape[0]
+        with torch.cuda.device(cond.device):
+            st = torch.cuda.current_stream().cuda_stream
+            _lib.check(_lib.lib().sddm_x_T_raw(_lib.VARIANTS[variant], float(a), float(b), _ptr(cond), _ptr(z),
+                                              _seed(seed), 0, _ptr(out), B, L, C.c_void_p(st)))
+        return out
+
+    def get_x_T(self, condition, noise=None, seed=None):
+        """x_T = sqrt_ab[T]*y + sqrt(1-sqrt_ab[T]^2)*z; z injected or Philox in-kernel (reference :281-300)."""
+        return self._x_T("condition_in", condition, noise, seed)
+
+    def get_x_T_conditional(self, condition, noise=None, seed=None):
+        return self._x_T("conditional", condition, noise, seed)
+
+    def _step(self, variant, x_t, t, predicted, condition=None, noise=None, seed=None):
+        _need_cuda(x_t, predicted, condition, noise)
+        x = _prep(x_t).clone()
+        eps, cond, z = _prep(predicted), _prep(condition), _prep(noise)
+        B, L = x.shape[0], x.numel() // x.shape[0]
+        with torch.cuda.device(x.device):
+            st = torch.cuda.current_stream().cuda_stream
+            _lib.check(_lib.lib().sddm_p_step_raw(_lib.VARIANTS[variant], self.step_scalars(int(t), variant), _ptr(x),
+                                                 _ptr(eps), _ptr(cond), _ptr(z), _seed(seed), 0, int(t),
+                                                 self.num_timesteps, B, L, C.c_void_p(st)))
+        return x
+
+    @torch.no_grad()
+    def p_transition(self, x_t, t, predicted, noise=None, seed=None):
+        return self._step("original", x_t, t, predicted, None, noise, seed)
+
+    @torch.no_grad()
+    def p_transition_sr3(self, x_t, t, predicted, noise=None, seed=None):
+        return self._step("sr3", x_t, t, predicted, None, noise, seed)
+
+    @torch.no_grad()
+    def p_transition_supportive(self, x_t, t, predicted_noise, condition, noise=None, seed=None):
+        return self._step("supportive", x_t, t, predicted_noise, condition, noise, seed)
+
+    @torch.no_grad()
+    def p_transition_conditional(self, x_t, t, predicted_noise, condition, noise=None, seed=None):
+        return self._step("conditional", x_t, t, predicted_noise, condition, noise, seed)
+
+    def q_stochastic(self, x_0, noise, t_is_integer=False):
+        raise NotImplementedError("q_stochastic belongs to the training step (SURVEY.md §8f row 1), not built yet")
+
+    def q_stochastic_conditional(self, x_0, y, noise):
+        raise NotImplementedError("q_stochastic_conditional belongs to the training step (SURVEY.md §8f), not built yet")
+
+
+def _seed(seed):
+    if seed is None:   # draw from torch's CPU generator so torch.manual_seed governs reproducibility
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    return C.c_uint64(int(seed) & (2 ** 64 - 1))

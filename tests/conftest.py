@@ -1,0 +1,71 @@
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+UNET_CFG = dict(num_samples=16448, in_channel=2, out_channel=1, inner_channel=32, norm_groups=32,
+                channel_mults=(1, 2, 3, 4, 5), res_blocks=1, dropout=0, segment_len=128, segment_stride=64)
+L = 16448
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def pytest_collection_modifyitems(config, items):
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def meta():
+    with open(os.path.join(GOLDEN, "meta.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
+def golden():
+    def load(name):
+        return {k: torch.from_numpy(v) for k, v in np.load(os.path.join(GOLDEN, name)).items()}
+    return load
+
+
+@pytest.fixture(scope="session")
+def built_lib():
+    """Builds (if stale) and loads the extension; CPU-only hosts can still load it and call non-compute entry points."""
+    import __graft_entry__ as ge
+    ge.build()
+    from sddm_b200 import _lib
+    return _lib.lib()
+
+
+def seed0_state_dict():
+    """Reference-identical default init under torch.manual_seed(0), produced by the host mirror classes."""
+    from sddm_b200.model.network import UNetModified2
+    torch.manual_seed(0)
+    net = UNetModified2(**UNET_CFG)
+    sd = {"noise_estimate_model." + k: v.detach().clone() for k, v in net.state_dict().items()}
+    return sd, net
+
+
+def cfg1_condition():
+    """SURVEY.md §8d cfg 1: one 32000-sample clip, seed 1, zero padded to 2 chunks."""
+    clip = 0.05 * torch.randn(1, 32000, generator=torch.Generator().manual_seed(1))
+    return torch.nn.functional.pad(clip, (0, 2 * L - 32000)).view(2, 1, L)
+
+
+def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
+    """max|a-b| / max|b| — the per-tensor error metric of BASELINE.md §3."""
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))

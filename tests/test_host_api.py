@@ -1,0 +1,138 @@
+"""Host-side mirror of the reference's config / registry / model API (no GPU needed)."""
+import argparse
+import collections
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import L, ROOT, UNET_CFG
+
+
+def sha(t):
+    return hashlib.sha256(t.detach().contiguous().numpy().tobytes()).hexdigest()
+
+
+def test_config_parser_builds_the_reference_objects(tmp_path, monkeypatch):
+    from sddm_b200.model import diffusion as module_diffusion, model as module_arch, network as module_network
+    from sddm_b200.parse_config import ConfigParser, read_json
+    cfg = read_json(os.path.join(ROOT, "configs", "config_unet.json"))
+    cfg["trainer"]["save_dir"] = str(tmp_path)
+    config = ConfigParser(cfg, run_id="t0")
+    assert (tmp_path / "SDDM2_UNet" / "t0" / "config.json").exists()           # run dir + config copy
+    assert config["num_samples"] == 16448 and config.save_dir == config.log_dir
+    diffusion = config.init_obj("diffusion", module_diffusion, device="cpu")
+    network = config.init_obj("network", module_network, num_samples=config["num_samples"])
+    model = config.init_obj("arch", module_arch, diffusion, network)
+    assert type(model).__name__ == "SDDM" and model.num_timesteps == 100 and model.p_transition == "condition_in"
+    with pytest.raises(AssertionError, match="Overwriting kwargs"):
+        config.init_obj("diffusion", module_diffusion, n_timestep=5)
+    ftn = config.init_ftn("diffusion", module_diffusion, device="cpu")
+    assert ftn().num_timesteps == 100
+    assert config.get_logger("x", 1).level == 20
+    with pytest.raises(AssertionError):
+        config.get_logger("x", 5)
+    assert "Trainable parameters: 5229793" in str(model)
+
+
+def test_config_parser_from_args_and_overrides(tmp_path):
+    from sddm_b200.parse_config import ConfigParser, read_json
+    cfg = read_json(os.path.join(ROOT, "configs", "config_unet.json"))
+    cfg["trainer"]["save_dir"] = str(tmp_path)
+    path = tmp_path / "c.json"
+    path.write_text(json.dumps(cfg))
+    Opt = collections.namedtuple("CustomArgs", "flags type target")
+    args = argparse.ArgumentParser()
+    args.add_argument("-c", "--config", default=None, type=str)
+    args.add_argument("-r", "--resume", default=None, type=str)
+    args.add_argument("-d", "--device", default=None, type=str)
+    options = [Opt(["--bs", "--batch_size"], int, "infer_data_loader;args;batch_size")]
+    for o in options:
+        args.add_argument(*o.flags, default=None, type=o.type)
+    ns = args.parse_args(["-c", str(path), "--bs", "8"])
+    config = ConfigParser.from_args(ns, options=[])
+    assert config.resume is None
+    config2 = ConfigParser(read_json(path), modification={"infer_data_loader;args;batch_size": 8}, run_id="m")
+    assert config2["infer_data_loader"]["args"]["batch_size"] == 8
+    with pytest.raises(AssertionError, match="Configuration file"):
+        ConfigParser.from_args(args.parse_args([]))
+
+
+def test_state_dict_layout_and_init_match_reference(meta):
+    from sddm_b200.model.diffusion import GaussianDiffusion
+    from sddm_b200.model.model import SDDM
+    from sddm_b200.model.network import UNetModified2
+    torch.manual_seed(0)
+    d = GaussianDiffusion("linear", 100, 1e-6, 1e-3, device="cpu")
+    net = UNetModified2(**UNET_CFG)
+    sd = SDDM(d, net, p_transition="condition_in").state_dict()
+    ref = meta["weights_seed0"]
+    assert list(sd) == list(ref)                                 # same keys in the same order (232 tensors)
+    for k, v in sd.items():
+        assert list(v.shape) == ref[k]["shape"] and sha(v) == ref[k]["sha256"], k
+    assert sha(net.noise_level_mlp[0].embedding_vector) == meta["pe_vector_sha256"]
+    # a reference checkpoint's state_dict loads (incl. DataParallel 'module.' prefixes handled by build_model)
+    m2 = SDDM(GaussianDiffusion("linear", 100, 1e-6, 1e-3, device="cpu"), UNetModified2(**UNET_CFG))
+    m2.load_state_dict(sd)
+
+
+@pytest.mark.parametrize("tag,args", [("linear100", ("linear", 100, 1e-6, 1e-3)), ("quad50", ("quad", 50, 1e-4, 2e-2)),
+                                      ("cosine20", ("cosine", 20, 1e-4, 2e-2))])
+def test_diffusion_buffers_bit_exact(golden, tag, args):
+    from sddm_b200.model.diffusion import GaussianDiffusion
+    g = golden("schedules.npz")
+    d = GaussianDiffusion(*args, device="cpu")
+    for name in ("betas", "alphas", "alpha_bar", "sqrt_alpha_bar", "predicted_noise_coeff", "sigma", "supportive_gamma",
+                 "supportive_sigma_hat", "m", "sqrt_delta", "c_xt", "c_yt", "c_epst", "sqrt_delta_estimated"):
+        a, b = getattr(d, name), g[f"{tag}.{name}"]
+        assert torch.equal(torch.nan_to_num(a), torch.nan_to_num(b)), name
+    k8 = d.step_scalars(args[1], "original")
+    assert k8[1] == float(np.sqrt(np.float32(d.alphas[args[1]].item())))
+
+
+def test_reference_error_behaviour():
+    from sddm_b200.model.diffusion import GaussianDiffusion
+    from sddm_b200.model.model import SDDM
+    from sddm_b200.model.network import UNetModified2
+    with pytest.raises(NotImplementedError):
+        GaussianDiffusion("warmup10", 10, device="cpu")              # diffusion.py:83-84
+    d = GaussianDiffusion("linear", 10, device="cpu")
+    net = UNetModified2(**UNET_CFG)
+    for kw in (dict(noise_condition="foo"), dict(p_transition="foo"), dict(q_transition="foo")):
+        with pytest.raises(NotImplementedError):                     # model.py:17-26
+            SDDM(d, net, **kw)
+    with pytest.raises(AssertionError):
+        UNetModified2(num_samples=16449)                             # UNetModified2.py:13
+    with pytest.raises(NotImplementedError):
+        SDDM(d, net).forward(torch.zeros(1, 1, L), torch.zeros(1, 1, L))
+
+
+def test_chunking_collate_regroup_roundtrip():
+    from sddm_b200.data_loader.data_loaders import InferDataset, chunk_waveform, infer_data_collate, regroup
+    g = torch.Generator().manual_seed(0)
+    waves = [torch.randn(n, generator=g) for n in (32000, 16448, 5, 16449)]
+    ds = InferDataset([(None, w) for w in waves], T=L)
+    assert [ds[i][1].shape[0] for i in range(4)] == [2, 1, 1, 2]       # ceil(n / 16448) chunks each
+    assert chunk_waveform(waves[0], L)[1, 0, 32000 - L:].abs().sum() == 0    # zero padded tail
+    clean, noisy, index = infer_data_collate([ds[i] for i in range(4)])
+    assert noisy.shape == (6, 1, L) and index.tolist() == [0, 0, 1, 2, 3, 3]
+    back = regroup(noisy, index, [w.numel() for w in waves])
+    for w, b in zip(waves, back):
+        assert torch.equal(w.reshape(1, -1), b)
+    assert ds.getName(2) == "utt00002"
+
+
+def test_shard_bounds_cover_rows_exactly():
+    from sddm_b200.sharding import all_bounds, shard_bounds
+    for n in (0, 1, 7, 64, 2301):
+        for world in (1, 2, 3, 8):
+            b = all_bounds(n, world)
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in b]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_bounds(4, 2, 2)
