@@ -158,6 +158,12 @@ SDDM_API int sddm_overlap_add(const float* frames, float* sig, int B, int n_samp
 /* ---- introspection / test hooks ------------------------------------------------------------------- */
 /* number of kernel launches one sddm_eps call enqueues for this plan. */
 SDDM_API int sddm_plan_launches_per_eps(const sddm_plan* plan);
+/* per-launch CUDA-event timing of the op program (bench.py's live roofline measurement; off by default).
+ * ops 0..num_ops-2 are the UNet program in launch order, the last index is the overlap-add + posterior kernel. */
+SDDM_API int sddm_plan_num_ops(const sddm_plan* plan);
+SDDM_API int sddm_profile_enable(sddm_plan* plan, int on);   /* also resets the accumulated totals */
+SDDM_API int sddm_profile_read(sddm_plan* plan, int op, double* total_ms, int64_t* launches, double* flops_per_row,
+                      double* bytes_per_row, int* uses_tensor_cores, char* label, int label_cap);
 /* copies the NHWC activation of a named UNet node ("downs.3", "mid.0", "ups.7", ...) produced by the last
  * sddm_eps call on this workspace into out (device, [B,H,W,C] fp32); returns C*H*W via *chw. */
 SDDM_API int sddm_debug_fetch(sddm_plan* plan, const char* node, void* ws, int B, float* out, int64_t* chw, void* stream);

@@ -63,6 +63,10 @@ SIGNATURES = {
     "sddm_frames": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "sddm_overlap_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "sddm_plan_launches_per_eps": (C.c_int, [C.c_void_p]),
+    "sddm_plan_num_ops": (C.c_int, [C.c_void_p]),
+    "sddm_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
+    "sddm_profile_read": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double),
+                                    C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_char_p, C.c_int]),
     "sddm_debug_fetch": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]),
     "sddm_debug_umma_probe": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
 }

@@ -63,6 +63,18 @@ struct Op {
     int res_kind = 0;   // 0 none, 1 identity, 2 1x1 conv
     size_t resw_off = 0, reswtc_off = 0, resb_off = 0;
     bool use_tc = false;
+    // introspection (bench roofline): algorithmic work per batch row
+    std::string label;
+    double flops = 0.0, bytes = 0.0;
+};
+
+struct Prof {   // CUDA-event timing of every launch of the op program (bench.py roofline; off by default)
+    bool on = false;
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> op_of;
+    size_t used = 0;
+    std::vector<double> ms;
+    std::vector<long long> cnt;
 };
 
 }  // namespace sddm
@@ -97,6 +109,7 @@ struct sddm_plan {
     float* d_out = nullptr;
     void* d_ws = nullptr;
     int arena_rows = 0;
+    Prof prof;
 };
 
 namespace sddm {
@@ -255,6 +268,9 @@ static int emit_gn(sddm_plan* p, Arena& a, std::vector<int> srcs, const std::str
     op.beta_off = a.put(W_(p, gkey + ".bias"));
     op.ss_off = *ss_off_cursor;
     *ss_off_cursor += align_up((size_t)2 * ctot, 32);
+    op.label = "gn:" + gkey;
+    for (size_t i = 0; i < srcs.size(); ++i) op.bytes += 8.0 * p->tensors[srcs[i]].nparts * p->tensors[srcs[i]].C;
+    op.bytes += 8.0 * ctot;
     p->ops.push_back(op);
     return (int)p->ops.size() - 1;
 }
@@ -279,8 +295,12 @@ static int build_program(sddm_plan* p, Arena& a) {
     int temb_cursor = 0;
     std::vector<int> feats;
     int cur = -1, H = p->H, W = p->W;
-    auto set_tc = [&](Op& op) {
+    auto set_tc = [&](Op& op, const std::string& label) {
         ConvP probe = shape_probe(p, op);
+        op.label = "conv:" + label;
+        op.flops = 2.0 * 9.0 * probe.Cin * probe.Cout * probe.Hout * probe.Wout + 2.0 * probe.res_Cin * probe.Cout * probe.Hout * probe.Wout;
+        op.bytes = 4.0 * ((double)probe.Cin * probe.Hin * probe.Win + (double)probe.Cout * probe.Hout * probe.Wout +
+                          (probe.res_identity ? (double)probe.Cout * probe.Hout * probe.Wout : 0.0));
         op.use_tc = want_tc && conv_tc_supported(probe);
         p->tensors[op.out].nparts = op.use_tc ? conv_tc_nparts(probe.Hout, probe.Wout) : conv_fp32_nparts(probe.Hout, probe.Wout);
     };
@@ -297,7 +317,7 @@ static int build_program(sddm_plan* p, Arena& a) {
         fill_conv_op(p, a, c1, nd.key + ".block1.block.3", nd.cout, nd.cin, want_tc);
         c1.temb_off = temb_cursor;
         temb_cursor += nd.cout;
-        set_tc(c1);
+        set_tc(c1, nd.key + ".block1");
         p->ops.push_back(c1);
         const int gn2 = emit_gn(p, a, {h}, nd.key + ".block2.block.0", &ss_cursor);
         const int out = new_tensor(p, nd.key, nd.cout, H, W);
@@ -322,7 +342,7 @@ static int build_program(sddm_plan* p, Arena& a) {
             c2.gn_nsrc = 1;
             c2.gn_src[0] = srcs[0];
         }
-        set_tc(c2);
+        set_tc(c2, nd.key + ".block2");
         p->ops.push_back(c2);
         return out;
     };
@@ -335,7 +355,7 @@ static int build_program(sddm_plan* p, Arena& a) {
         cv.mode = mode;
         cv.out = out;
         fill_conv_op(p, a, cv, nd.key + ".conv", nd.cout, nd.cin, want_tc);
-        set_tc(cv);
+        set_tc(cv, nd.key + ".conv");
         p->ops.push_back(cv);
         return out;
     };
@@ -383,6 +403,9 @@ static int build_program(sddm_plan* p, Arena& a) {
                 Op op;
                 op.kind = Op::STEM;
                 op.out = cur;
+                op.label = "stem:downs.0";
+                op.flops = 2.0 * 18.0 * nd.cout * H * W;
+                op.bytes = 4.0 * (2.0 * c.num_samples + (double)nd.cout * H * W);
                 p->ops.push_back(op);
                 feats.push_back(cur);
                 break;
@@ -425,6 +448,9 @@ static int build_program(sddm_plan* p, Arena& a) {
         op.src[0] = cur;
         op.in_gn = true;
         op.in_ss_off = p->ops[gnf].ss_off;
+        op.label = "final_conv";
+        op.flops = 2.0 * 9.0 * C * p->H * p->W;
+        op.bytes = 4.0 * ((double)C * p->H * p->W + (double)p->H * p->W);
         p->ops.push_back(op);
     }
     if (temb_cursor != p->E) { set_error("internal: embedding width mismatch"); return SDDM_E_INVALID; }
@@ -455,12 +481,54 @@ static int build_program(sddm_plan* p, Arena& a) {
 // ---------------------------------------------------------------------------------------------------
 static inline float* sect(const sddm_plan*, void* ws, size_t off, int B) { return reinterpret_cast<float*>(ws) + off * (size_t)B; }
 
+static int prof_flush(sddm_plan* p) {
+    Prof& pr = p->prof;
+    if (pr.used == 0) return SDDM_OK;
+    SDDM_CUDA_TRY(cudaEventSynchronize(pr.ev[2 * pr.used - 1]));
+    for (size_t k = 0; k < pr.used; ++k) {
+        float ms = 0.f;
+        SDDM_CUDA_TRY(cudaEventElapsedTime(&ms, pr.ev[2 * k], pr.ev[2 * k + 1]));
+        pr.ms[pr.op_of[k]] += ms;
+        pr.cnt[pr.op_of[k]] += 1;
+    }
+    pr.used = 0;
+    return SDDM_OK;
+}
+
+static int prof_mark(sddm_plan* p, int op, bool begin, cudaStream_t st) {
+    Prof& pr = p->prof;
+    if (!pr.on) return SDDM_OK;
+    if (begin) {
+        if (2 * pr.used + 2 > pr.ev.size()) {
+            if (pr.ev.size() >= 65536) {
+                int rc = prof_flush(p);
+                if (rc) return rc;
+            } else {
+                for (int i = 0; i < 1024; ++i) {
+                    cudaEvent_t e;
+                    SDDM_CUDA_TRY(cudaEventCreate(&e));
+                    pr.ev.push_back(e);
+                }
+                pr.op_of.resize(pr.ev.size() / 2);
+            }
+        }
+        pr.op_of[pr.used] = op;
+        SDDM_CUDA_TRY(cudaEventRecord(pr.ev[2 * pr.used], st));
+    } else {
+        SDDM_CUDA_TRY(cudaEventRecord(pr.ev[2 * pr.used + 1], st));
+        pr.used += 1;
+    }
+    return SDDM_OK;
+}
+
 // one UNetModified2 forward up to the final conv frames (ws.frames); temb: device pointer, row stride
 static int run_unet(sddm_plan* p, const float* cond, const float* x_t, const float* temb, int temb_stride, int B, void* ws,
                     cudaStream_t st) {
     const sddm_config& c = p->cfg;
-    for (const Op& op : p->ops) {
-        int rc = SDDM_OK;
+    for (size_t oi = 0; oi < p->ops.size(); ++oi) {
+        const Op& op = p->ops[oi];
+        int rc = prof_mark(p, (int)oi, true, st);
+        if (rc != SDDM_OK) return rc;
         switch (op.kind) {
             case Op::STEM: {
                 const TensorInfo& o = p->tensors[op.out];
@@ -547,6 +615,7 @@ static int run_unet(sddm_plan* p, const float* cond, const float* x_t, const flo
             }
         }
         if (rc != SDDM_OK) return rc;
+        if ((rc = prof_mark(p, (int)oi, false, st))) return rc;
     }
     return SDDM_OK;
 }
@@ -634,6 +703,7 @@ void sddm_plan_destroy(sddm_plan* p) {
     cudaFree(p->d_out);
     cudaFree(p->d_ws);
     if (p->own_stream) cudaStreamDestroy(p->own_stream);
+    for (cudaEvent_t e : p->prof.ev) cudaEventDestroy(e);
     delete p;
 }
 
@@ -849,7 +919,9 @@ int sddm_sample(sddm_plan* p, int variant, const float* cond, const float* noise
         pp.B = B; pp.L = L; pp.F = p->cfg.segment_len; pp.hop = p->cfg.segment_stride; pp.n_frames = p->H;
         float k8[8];
         step_coefs(p, variant, t, k8);
+        if ((rc = prof_mark(p, (int)p->ops.size(), true, st))) return rc;
         if ((rc = launch_post_coef(pp, k8, st))) return rc;
+        if ((rc = prof_mark(p, (int)p->ops.size(), false, st))) return rc;
     }
     return SDDM_OK;
 }
@@ -893,6 +965,36 @@ int sddm_overlap_add(const float* frames, float* sig, int B, int n, int F, int h
     if (!sig || !frames || B <= 0 || F <= 0 || hop <= 0 || n < F) { set_error("bad argument"); return SDDM_E_INVALID; }
     if ((n - F) % hop) { set_error("(n_samples - F) %% stride must be 0"); return SDDM_E_INVALID; }
     return launch_overlap_add(frames, sig, B, n, F, hop, (cudaStream_t)stream);
+}
+
+int sddm_plan_num_ops(const sddm_plan* p) { return (p && p->finalized) ? (int)p->ops.size() + 1 : 0; }
+
+int sddm_profile_enable(sddm_plan* p, int on) {
+    int rc = check_ready(p);
+    if (rc) return rc;
+    if ((rc = prof_flush(p))) return rc;
+    p->prof.on = on != 0;
+    p->prof.ms.assign(p->ops.size() + 1, 0.0);
+    p->prof.cnt.assign(p->ops.size() + 1, 0);
+    return SDDM_OK;
+}
+
+int sddm_profile_read(sddm_plan* p, int op, double* total_ms, int64_t* launches, double* flops_per_row, double* bytes_per_row,
+                      int* uses_tensor_cores, char* label, int label_cap) {
+    int rc = check_ready(p);
+    if (rc) return rc;
+    if (op < 0 || op > (int)p->ops.size()) { set_error("op index %d out of range", op); return SDDM_E_INVALID; }
+    if ((rc = prof_flush(p))) return rc;
+    const bool is_post = op == (int)p->ops.size();
+    const double L = p->cfg.num_samples;
+    if (total_ms) *total_ms = p->prof.ms.empty() ? 0.0 : p->prof.ms[op];
+    if (launches) *launches = p->prof.cnt.empty() ? 0 : (int64_t)p->prof.cnt[op];
+    if (flops_per_row) *flops_per_row = is_post ? 8.0 * L : p->ops[op].flops;
+    // ola + posterior with in-kernel Philox: read frames (2 per sample) + x_t, write x_{t-1}
+    if (bytes_per_row) *bytes_per_row = is_post ? 4.0 * (2.0 * L + 2.0 * L) : p->ops[op].bytes;
+    if (uses_tensor_cores) *uses_tensor_cores = is_post ? 0 : (p->ops[op].use_tc ? 1 : 0);
+    if (label && label_cap > 0) snprintf(label, (size_t)label_cap, "%s", is_post ? "ola_posterior" : p->ops[op].label.c_str());
+    return SDDM_OK;
 }
 
 int sddm_debug_fetch(sddm_plan* p, const char* node, void* ws, int B, float* out, int64_t* chw, void* stream) {

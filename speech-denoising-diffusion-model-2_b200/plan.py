@@ -166,6 +166,24 @@ class Plan:
                                                     C.c_uint64(seed & (2 ** 64 - 1)), int(row0), int(max_rows)))
         return out
 
+    def profile(self, on: bool) -> None:
+        """Enable / reset per-launch CUDA-event timing inside the library (bench.py roofline)."""
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().sddm_profile_enable(self._h, int(on)))
+
+    def profile_report(self):
+        """[{label, ms, launches, flops_per_row, bytes_per_row, tensor_cores}] for every op of the program."""
+        lib, out = _lib.lib(), []
+        with torch.cuda.device(self.device):
+            for i in range(int(lib.sddm_plan_num_ops(self._h))):
+                ms, n, fl, by, tc = C.c_double(), C.c_int64(), C.c_double(), C.c_double(), C.c_int()
+                label = C.create_string_buffer(128)
+                _lib.check(lib.sddm_profile_read(self._h, i, C.byref(ms), C.byref(n), C.byref(fl), C.byref(by), C.byref(tc),
+                                                 label, 128))
+                out.append(dict(label=label.value.decode(), ms=ms.value, launches=n.value, flops_per_row=fl.value,
+                                bytes_per_row=by.value, tensor_cores=bool(tc.value)))
+        return out
+
     def fetch(self, node: str, B: int) -> torch.Tensor:
         """Debug: NHWC activation of a UNet node from the last eps/sample call with batch B -> [B,C,H,W]."""
         chw = (C.c_int64 * 3)()
