@@ -227,15 +227,16 @@ static std::vector<float> pack_conv_f32(const std::vector<float>& w, int cout, i
     return o;
 }
 
-// [Cout][Cin][k][k] -> bf16 [Cin/32][k*k][4][Cout][8]: per (chunk, tap) a K-major UMMA operand image made of
-// 8x8 core matrices (8 couts x 8 cin, 128 contiguous bytes); LBO (K step) = Cout*16 B, SBO (N step) = 128 B.
+// [Cout][Cin][k][k] -> bf16 [Cin/16][k*k][2][Cout][8]: per (16-channel chunk, tap) a K-major UMMA operand image made of
+// 8x8 core matrices (8 couts x 8 cin = 128 contiguous bytes); LBO (K step) = Cout*16 B, SBO (N step) = 128 B.  One chunk
+// (all taps) is one contiguous block of 288*Cout bytes (k=3) / 32*Cout bytes (k=1): a single bulk copy in conv_tc.cu.
 static std::vector<__nv_bfloat16> pack_conv_tc(const std::vector<float>& w, int cout, int cin, int kk) {
     std::vector<__nv_bfloat16> o((size_t)cin * kk * cout);
     for (int ci = 0; ci < cin; ++ci)
         for (int t = 0; t < kk; ++t)
             for (int co = 0; co < cout; ++co) {
-                const int ch = ci / 32, j = (ci % 32) / 8, e = ci % 8;
-                o[((((size_t)ch * kk + t) * 4 + j) * cout + co) * 8 + e] = __float2bfloat16(w[((size_t)co * cin + ci) * kk + t]);
+                const int ch = ci / 16, j = (ci % 16) / 8, e = ci % 8;
+                o[((((size_t)ch * kk + t) * 2 + j) * cout + co) * 8 + e] = __float2bfloat16(w[((size_t)co * cin + ci) * kk + t]);
             }
     return o;
 }

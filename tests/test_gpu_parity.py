@@ -112,6 +112,22 @@ def test_philox_noise(dev):
 
 
 # ----------------------------------------------------------------------------------------------------
+# tcgen05 descriptor self-test: one 128 x N x K bf16 MMA tile through smem descriptors / TMEM, vs a host fp64 reference
+# ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("variant", [0, 1, 2])
+def test_umma_probe(dev, built_lib, variant):
+    """variant 0: canonical K-major no-swizzle operand; 1: the stride-1 halo-window geometry of conv_tc.cu (SBO 160 B,
+    LBO 181*16 B, start address offset by the centre tap); 2: the stride-2 (parity-split) geometry."""
+    import ctypes as C
+    from sddm_b200 import _lib
+    for N, K in ((32, 16), (96, 64), (160, 32), (256, 64)):
+        err = C.c_float(-1.0)
+        _lib.check(built_lib.sddm_debug_umma_probe(variant, N, K, C.byref(err)))
+        report(f"umma probe variant={variant} N={N} K={K}: max abs err {err.value:.3e}")
+        assert 0.0 <= err.value < 1e-3, (variant, N, K, err.value)
+
+
+# ----------------------------------------------------------------------------------------------------
 # the denoiser, node by node
 # ----------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])

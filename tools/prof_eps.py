@@ -1,0 +1,46 @@
+#!/usr/bin/env python
+"""Profiling driver: N denoiser forwards (sddm_eps) + posterior steps of a B-row batch, nothing else.
+Used under ncu (see profiles/README.md); also prints CUDA-event ms per forward when run plain."""
+import argparse
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--iters", type=int, default=2)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    args = ap.parse_args()
+    import torch
+    import __graft_entry__ as ge
+    ge.build()
+    from sddm_b200 import PREC_BF16, PREC_FP32
+    from sddm_b200.model.diffusion import GaussianDiffusion
+    from sddm_b200.model.model import SDDM
+    from sddm_b200.model.network import UNetModified2
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    net = UNetModified2(num_samples=16448, res_blocks=1)
+    net.precision = PREC_FP32 if args.precision == "fp32" else PREC_BF16
+    model = SDDM(GaussianDiffusion("linear", 100, 1e-6, 1e-3, device=dev), net, p_transition="condition_in").to(dev).eval()
+    plan = net.get_plan(model.diffusion)
+    cond = (0.1 * torch.randn(args.batch, 1, 16448, generator=torch.Generator().manual_seed(1))).clamp(-1, 1).to(dev)
+    x = cond.clone()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for it in range(args.iters):
+        e0.record()
+        eps = plan.eps(cond, x, t=100 - it)
+        e1.record()
+        torch.cuda.synchronize()
+        print("forward %d: %.3f ms (B=%d, %s)" % (it, e0.elapsed_time(e1), args.batch, args.precision))
+        x = model.diffusion.p_transition(x, 100 - it, eps)
+    torch.cuda.synchronize()
+    print("ok", float(x.abs().max()))
+
+
+if __name__ == "__main__":
+    main()
