@@ -24,6 +24,9 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-DSDDM_BUILD",
 ]
+# per-file extras: the tensor-core kernel computes Swish with ex2.approx / rcp.approx and flushes denormals (its operands
+# are rounded to bf16 anyway); every other translation unit keeps IEEE arithmetic (bit-exact posterior update, fp32 parity mode)
+EXTRA_FLAGS = {"conv_tc.cu": ["-use_fast_math"]}
 
 
 def _nvcc() -> str:
@@ -39,6 +42,7 @@ def _stamp(paths) -> str:
         with open(p, "rb") as f:
             h.update(p.encode() + b"\0" + f.read())
     h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(repr(sorted(EXTRA_FLAGS.items())).encode())
     return h.hexdigest()
 
 
@@ -59,7 +63,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         stamp = _stamp([src] + headers)
         if not force and os.path.exists(obj) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
             return obj, False
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + EXTRA_FLAGS.get(os.path.basename(src), []) + ["-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))

@@ -1,24 +1,31 @@
 // tcgen05 / TMEM implicit-GEMM 3x3 convolution of the UNetModified2 denoiser (sm_100a).
 //
 //   GEMM view : M = 128 output pixels (a 16 x 8 window of one sample), N = Cout (32..160), K = 9 * Cin (+ res_Cin)
-//   operands  : bf16, fp32 accumulation in tensor memory (two accumulator stages: MMA of tile i+1 overlaps the
+//   operands  : bf16, fp32 accumulation in tensor memory (two accumulator stages: the MMAs of tile i+1 overlap the
 //               epilogue of tile i)
-//   A operand : the zero-padded, post-activation halo window is staged ONCE per 32-channel K slab in shared memory
-//               in the no-swizzle K-major core-matrix layout  [k8 plane][halo pixel][8 channels = 16 B];  the 9 taps
-//               are 9 shared-memory descriptors with shifted start addresses over the same slab (im2col-free).
-//               Producer warps fuse GroupNorm-apply + Swish + concat / nearest-x2 / stride-2 addressing + bf16
-//               conversion into the staging pass (zero padding is applied AFTER the activation, UNetModified2.py:116-121).
-//   B operand : weights pre-packed on the host as [Cin/16][tap][2][Cout][8] bf16, streamed per 16-channel chunk with
-//               cp.async.bulk (or kept resident in shared memory for the whole persistent CTA when they fit).
+//   raw load  : one TMA tensor load (cp.async.bulk.tensor.4d) per K slab brings the fp32 NHWC halo window of the source
+//               (zero filled outside the image) into a shared-memory ring; stride-2 and nearest-x2 convolutions only
+//               change the box (33x17 / 10x6 input pixels) - concat is a choice of tensor map.
+//   A operand : transform warps turn a raw slab into the zero-padded, post-activation bf16 operand ONCE per slab, in the
+//               no-swizzle K-major core-matrix layout [k8 plane][halo pixel][8 channels = 16 B]; the 9 taps are 9
+//               shared-memory descriptors with shifted start addresses over the same slab (im2col-free).  The transform
+//               fuses GroupNorm-apply + Swish + padding mask + nearest-x2 replication + stride-2 parity split + bf16
+//               conversion (zero padding is applied AFTER the activation, UNetModified2.py:116-121).
+//   B operand : weights pre-packed on the host as [Cin/16][tap][2][Cout][8] bf16, moved per chunk with cp.async.bulk and
+//               kept resident in shared memory for the whole persistent CTA when they fit (else streamed through a ring).
 //   extra K   : the ResnetBlock 1x1 res_conv over the raw block input accumulates into the same TMEM tile.
-//   epilogue  : tcgen05.ld -> + bias (+ noise-level embedding, + res bias) (+ identity residual) -> NHWC fp32 store
-//               + GroupNorm partial statistics (sum, sum of squares per channel per warp) for the next layer.
+//   epilogue  : tcgen05.ld -> + bias (+ noise-level embedding, + res bias) (+ identity residual, prefetched by TMA) ->
+//               128B-swizzled shared-memory tile -> TMA tensor store (NHWC fp32) + GroupNorm partial statistics
+//               (column sums of the staged tile: sum, sum of squares per channel per 32-pixel quarter).
 //
-// Warp roles (448 threads, persistent CTA, static tile schedule):
+// Warp roles (512 threads, persistent CTA, static tile schedule):
 //   warps 0-3 epilogue (TMEM lane quarter = warp id) | warp 4 MMA issuer + TMEM owner | warp 5 weight loader
-//   warps 6-13 A-operand producers
+//   warp 6 raw-slab TMA issuer | warp 7 idle | warps 8-15 transform
 //
 // reference: Block / ResnetBlock / Downsample / Upsample, model/UNetModified2.py:93-142
+#include <cuda.h>
+
+#include <cstring>
 #include <vector>
 
 #include "common.cuh"
@@ -28,28 +35,39 @@ namespace sddm {
 namespace {
 
 constexpr int TH = 16, TW = 8;            // output window of one tile
-constexpr int kEpiWarps = 4;
-constexpr int kProdWarp0 = 6, kProdWarps = 8;
-constexpr int kProdThreads = kProdWarps * 32;
-constexpr int kThreads = (kProdWarp0 + kProdWarps) * 32;   // 448
-constexpr int kMaxA = 4, kMaxW = 16;
-constexpr int kItems = 3;                 // halo items (pixel x 8 channels) per producer thread per batch
+constexpr int kEpiThreads = 128;
+constexpr int kXfWarp0 = 8, kXfThreads = 256;
+constexpr int kThreads = kXfWarp0 * 32 + kXfThreads;   // 512
+constexpr int kMaxRing = 4, kMaxW = 16;
+constexpr uint32_t kOutTileBytes = 128 * 32 * 4;       // one 128-pixel x 32-channel fp32 staging tile
 
-// halo geometry per mode ------------------------------------------------------------------------------
+// geometry per mode ---------------------------------------------------------------------------------------
+//   SLAB          input channels per A slab (one raw TMA box, SLAB/16 MMA K steps per tap)
+//   RAW_H x RAW_W raw box in INPUT pixels;  PH x PW  operand halo grid;  PLANE  slots (16 B) between k8 planes
+//   SBO           byte distance between consecutive 8-pixel groups of the M dimension (one output row)
 template <int MODE> struct Geo;
-template <> struct Geo<CONV_S1> { static constexpr int PH = 18, PW = 10, PLANE = 181, SBO = 10 * 16; };
-template <> struct Geo<CONV_UP> { static constexpr int PH = 18, PW = 10, PLANE = 181, SBO = 10 * 16; };
-template <> struct Geo<CONV_S2> { static constexpr int PH = 33, PW = 17, PLANE = 565, SBO = 2 * 17 * 16; };
-// PLANE (slots of 16 B between the k8 planes) is = 5 (mod 8): the four planes of one pixel then fall into disjoint banks.
+template <> struct Geo<CONV_S1> { static constexpr int SLAB = 32, RAW_H = 18, RAW_W = 10, PH = 18, PW = 10, PLANE = 181, SBO = 10 * 16; };
+template <> struct Geo<CONV_UP> { static constexpr int SLAB = 32, RAW_H = 10, RAW_W = 6, PH = 18, PW = 10, PLANE = 181, SBO = 10 * 16; };
+template <> struct Geo<CONV_S2> { static constexpr int SLAB = 16, RAW_H = 33, RAW_W = 17, PH = 33, PW = 17, PLANE = 565, SBO = 2 * 17 * 16; };
+// PLANE = 5 (mod 8): the k8 planes of one pixel fall into disjoint shared-memory banks.
+
+struct alignas(64) TcMaps {
+    CUtensorMap src[4];   // main source 0 / 1, res_conv source 0 / 1
+    CUtensorMap out;      // output store, box 32 ch x 8 x 16, 128B swizzle
+    CUtensorMap res;      // identity residual load, same geometry
+};
 
 struct TcArgs {
     ConvP p;
     int tiles_x, tiles_y, ntiles;   // per-sample tile grid, total tiles (B * tiles_x * tiles_y)
-    int nA_main, nA_res;            // 32-channel A slabs of the main conv / the 1x1 res_conv
-    int NA, NW;                     // ring depths
+    int n_main, n_res;              // A slabs of the main conv (SLAB channels) / the 1x1 res_conv (32 channels)
+    int n_main_chunks, n_res_chunks;   // weight chunks: 16 channels x 9 taps / up to 128 channels x 1 tap
+    int NR, NA, NW, NRES, NOUT;     // ring depths: raw slabs, operand slabs, weight chunks, residual tiles, out staging tiles
     int resident;                   // all weight chunks stay in shared memory
     int acc_stride, tmem_cols;
-    uint32_t a_stage_bytes, w_stage_bytes;
+    int temb_per_row;
+    uint32_t off_out, off_res, off_raw, off_a, off_w;   // byte offsets from the 1024-aligned shared-memory base
+    uint32_t raw_stage, a_stage, w_stage;
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------
@@ -94,6 +112,21 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+                 "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
@@ -149,45 +182,69 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
 }
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ float lds32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
 
-// shared-memory carve-up (dynamic smem, 128-byte aligned base)
+// shared-memory header (at the 1024-aligned base)
 struct SmemHdr {
-    uint64_t full_a[kMaxA], empty_a[kMaxA];
+    uint64_t raw_full[kMaxRing], raw_empty[kMaxRing];
+    uint64_t full_a[kMaxRing], empty_a[kMaxRing];
     uint64_t full_w[kMaxW], empty_w[kMaxW];
     uint64_t tmem_full[2], tmem_empty[2];
+    uint64_t res_full[kMaxRing];
     uint32_t tmem_base;
-    uint32_t pad[31];
+    uint32_t pad[15];
     float addv[256];
 };
-constexpr int kHdrBytes = 2048;
+constexpr uint32_t kHdrBytes = 2048;
 static_assert(sizeof(SmemHdr) <= kHdrBytes, "header too large");
 
-struct PBatch {   // one producer batch in flight: raw values + the per-channel affine of the slab
-    float4 v[kItems][2];
-    float4 sc[2], sh[2];
-    int slot[kItems];      // halo slot to write (-1: no item)
-    uint32_t okmask;       // bit r: item r reads real data (else zero padding)
-    int has_affine;
-};
+struct TileCoord { int n, oy0, ox0, trem; };
+__device__ __forceinline__ TileCoord decode_tile(const TcArgs& a, int tile) {
+    TileCoord t;
+    const int per = a.tiles_x * a.tiles_y;
+    t.n = tile / per;
+    t.trem = tile - t.n * per;
+    const int ty = t.trem / a.tiles_x;
+    t.oy0 = ty * TH;
+    t.ox0 = (t.trem - ty * a.tiles_x) * TW;
+    return t;
+}
+template <int MODE> __device__ __forceinline__ int org_of(int o0) {   // first input row / column of the raw box
+    return MODE == CONV_S2 ? 2 * o0 - 1 : (MODE == CONV_UP ? (o0 >> 1) - 1 : o0 - 1);
+}
 
 // =====================================================================================================
 template <int MODE>
-__global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a) {
+__global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a, const __grid_constant__ TcMaps maps) {
     using G = Geo<MODE>;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    SmemHdr* hdr = reinterpret_cast<SmemHdr*>(smem_raw);
-    const uint32_t smem_base = smem_u32(smem_raw);
-    const uint32_t a_base = smem_base + kHdrBytes;
-    const uint32_t w_base = a_base + (uint32_t)a.NA * a.a_stage_bytes;
+    extern __shared__ unsigned char smem_dyn[];
+    const uint32_t dyn_u32 = smem_u32(smem_dyn);
+    const uint32_t base_u32 = (dyn_u32 + 1023u) & ~1023u;
+    SmemHdr* hdr = reinterpret_cast<SmemHdr*>(smem_dyn + (base_u32 - dyn_u32));
     const ConvP& p = a.p;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int nA = a.nA_main + a.nA_res;
-    const int tiles_per_img = a.tiles_x * a.tiles_y;
+    const int nA = a.n_main + a.n_res;
 
     if (tid == 0) {
-        for (int i = 0; i < kMaxA; ++i) { mbar_init(smem_u32(&hdr->full_a[i]), kProdThreads); mbar_init(smem_u32(&hdr->empty_a[i]), 1); }
+        for (int i = 0; i < kMaxRing; ++i) {
+            mbar_init(smem_u32(&hdr->raw_full[i]), 1); mbar_init(smem_u32(&hdr->raw_empty[i]), kXfThreads);
+            mbar_init(smem_u32(&hdr->full_a[i]), kXfThreads); mbar_init(smem_u32(&hdr->empty_a[i]), 1);
+            mbar_init(smem_u32(&hdr->res_full[i]), 1);
+        }
         for (int i = 0; i < kMaxW; ++i) { mbar_init(smem_u32(&hdr->full_w[i]), 1); mbar_init(smem_u32(&hdr->empty_w[i]), 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&hdr->tmem_full[i]), 1); mbar_init(smem_u32(&hdr->tmem_empty[i]), kEpiWarps * 32); }
+        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&hdr->tmem_full[i]), 1); mbar_init(smem_u32(&hdr->tmem_empty[i]), kEpiThreads); }
         fence_barrier_init();
     }
     if (warp == 4) tmem_alloc(smem_u32(&hdr->tmem_base), (uint32_t)a.tmem_cols);
@@ -196,80 +253,123 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a)
     tc_fence_after();
     const uint32_t tmem_base = hdr->tmem_base;
 
-    if (warp < kEpiWarps) {
+    if (warp < 4) {
         // ============================== epilogue ==========================================================
         const int m = tid, py = m >> 3, px = m & 7;
         const int nblk = p.Cout >> 5;
+        const bool has_res = p.res_identity != 0;
+        const uint32_t obuf0 = base_u32 + a.off_out, rbuf0 = base_u32 + a.off_res;
+        const uint32_t addv_u32 = smem_u32(hdr->addv);
+        int my_tiles = 0;
+        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) ++my_tiles;
+        const int total_blocks = my_tiles * nblk;
+        auto issue_res = [&](int g) {   // thread 0: prefetch the identity-residual tile of block g
+            const int it = g / nblk, cb = g - it * nblk;
+            const TileCoord t = decode_tile(a, blockIdx.x + it * gridDim.x);
+            const int buf = g % a.NRES;
+            const uint32_t bar = smem_u32(&hdr->res_full[buf]);
+            mbar_expect_tx(bar, kOutTileBytes);
+            tma_load_4d(rbuf0 + (uint32_t)buf * kOutTileBytes, &maps.res, cb * 32, t.ox0, t.oy0, t.n, bar);
+        };
+        if (!a.temb_per_row) {
+            for (int c = tid; c < p.Cout; c += kEpiThreads) {
+                float v = __ldg(p.bias + c);
+                if (p.temb) v += __ldg(p.temb + c);
+                if (a.n_res) v += __ldg(p.res_bias + c);
+                hdr->addv[c] = v;
+            }
+        }
+        if (has_res && tid == 0)
+            for (int g = 0; g < a.NRES - 1 && g < total_blocks; ++g) issue_res(g);
+        epi_bar();
+        int g = 0;
         for (int it = 0, tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
             const int as = it & 1;
             const uint32_t aph = (uint32_t)(it >> 1) & 1u;
-            const int n = tile / tiles_per_img, trem = tile - n * tiles_per_img;
-            const int oy = (trem / a.tiles_x) * TH + py, ox = (trem % a.tiles_x) * TW + px;
-            const bool valid = oy < p.Hout && ox < p.Wout;
-            epi_bar();   // previous tile's readers of addv are done
-            for (int c = tid; c < p.Cout; c += kEpiWarps * 32) {
-                float v = __ldg(p.bias + c);
-                if (p.temb) v += __ldg(p.temb + (int64_t)n * p.temb_stride + c);
-                if (p.res_w_tc) v += __ldg(p.res_bias + c);
-                hdr->addv[c] = v;
-            }
-            epi_bar();
-            const int64_t obase = (((int64_t)n * p.Hout + oy) * p.Wout + ox) * p.Cout;
-            const float* rptr = (p.res_identity && valid) ? p.res_src[0].x + obase : nullptr;
-            float4 rn[8];
-            if (rptr) {
-#pragma unroll
-                for (int q = 0; q < 8; ++q) rn[q] = __ldg(reinterpret_cast<const float4*>(rptr) + q);
+            const TileCoord t = decode_tile(a, tile);
+            const bool valid = (t.oy0 + py) < p.Hout && (t.ox0 + px) < p.Wout;
+            if (a.temb_per_row) {   // explicit per-row noise levels (sddm_eps with a noise_level vector)
+                epi_bar();
+                for (int c = tid; c < p.Cout; c += kEpiThreads) {
+                    float v = __ldg(p.bias + c) + __ldg(p.temb + (int64_t)t.n * p.temb_stride + c);
+                    if (a.n_res) v += __ldg(p.res_bias + c);
+                    hdr->addv[c] = v;
+                }
+                epi_bar();
             }
             mbar_wait(smem_u32(&hdr->tmem_full[as]), aph);
             tc_fence_after();
             const uint32_t tacc = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * a.acc_stride);
-            for (int cb = 0; cb < nblk; ++cb) {
-                float v[32], q2[32];
-                tmem_ld32(tacc + (uint32_t)(cb * 32), v);
-                float4 rc[8];
-                if (rptr) {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) rc[q] = rn[q];
-                    if (cb + 1 < nblk) {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) rn[q] = __ldg(reinterpret_cast<const float4*>(rptr + (cb + 1) * 32) + q);
-                    }
+            for (int cb = 0; cb < nblk; ++cb, ++g) {
+                const uint32_t obuf = obuf0 + (uint32_t)(a.NOUT == 2 ? (g & 1) : 0) * kOutTileBytes;
+                if (tid == 0) {   // the TMA store that last read this staging buffer is done with it
+                    if (a.NOUT == 2) bulk_wait_read_1(); else bulk_wait_read_0();
                 }
+                epi_bar();
+                if (has_res && tid == 0 && g + a.NRES - 1 < total_blocks) issue_res(g + a.NRES - 1);
+                float v[32];
+                tmem_ld32(tacc + (uint32_t)(cb * 32), v);
 #pragma unroll
-                for (int k = 0; k < 32; ++k) v[k] += hdr->addv[cb * 32 + k];
-                if (rptr) {
+                for (int q = 0; q < 8; ++q) {
+                    const uint4 u = lds128(addv_u32 + (uint32_t)(cb * 32 + q * 4) * 4u);
+                    v[4 * q + 0] += __uint_as_float(u.x); v[4 * q + 1] += __uint_as_float(u.y);
+                    v[4 * q + 2] += __uint_as_float(u.z); v[4 * q + 3] += __uint_as_float(u.w);
+                }
+                if (has_res) {
+                    const int buf = g % a.NRES;
+                    mbar_wait(smem_u32(&hdr->res_full[buf]), (uint32_t)(g / a.NRES) & 1u);
+                    const uint32_t rrow = rbuf0 + (uint32_t)buf * kOutTileBytes + (uint32_t)m * 128u;
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
-                        v[4 * q + 0] += rc[q].x; v[4 * q + 1] += rc[q].y; v[4 * q + 2] += rc[q].z; v[4 * q + 3] += rc[q].w;
+                        const uint4 u = lds128(rrow + (uint32_t)((q ^ (m & 7)) << 4));
+                        v[4 * q + 0] += __uint_as_float(u.x); v[4 * q + 1] += __uint_as_float(u.y);
+                        v[4 * q + 2] += __uint_as_float(u.z); v[4 * q + 3] += __uint_as_float(u.w);
                     }
                 }
-                if (valid) {
-                    float4* o = reinterpret_cast<float4*>(p.out + obase + cb * 32);
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                } else {
+                if (!valid) {
 #pragma unroll
                     for (int k = 0; k < 32; ++k) v[k] = 0.f;
                 }
-                if (p.parts) {
+                const uint32_t orow = obuf + (uint32_t)m * 128u;
 #pragma unroll
-                    for (int k = 0; k < 32; ++k) q2[k] = v[k] * v[k];
-                    const float s1 = warp_transpose_reduce32(v, lane);
-                    const float s2 = warp_transpose_reduce32(q2, lane);
-                    float2* dst = reinterpret_cast<float2*>(p.parts) + ((int64_t)n * p.nparts + trem * 4 + warp) * p.Cout + cb * 32 + lane;
+                for (int q = 0; q < 8; ++q) {
+                    uint4 u;
+                    u.x = __float_as_uint(v[4 * q + 0]); u.y = __float_as_uint(v[4 * q + 1]);
+                    u.z = __float_as_uint(v[4 * q + 2]); u.w = __float_as_uint(v[4 * q + 3]);
+                    sts128(orow + (uint32_t)((q ^ (m & 7)) << 4), u);
+                }
+                fence_async_smem();
+                epi_bar();
+                if (tid == 0) {
+                    tma_store_4d(&maps.out, obuf, cb * 32, t.ox0, t.oy0, t.n);
+                    bulk_commit();
+                }
+                if (p.parts) {   // column sums of the staged tile: channel = lane, pixel quarter = warp
+                    float s1 = 0.f, s2 = 0.f;
+                    const uint32_t col = obuf + (uint32_t)(lane & 3) * 4u;
+#pragma unroll 8
+                    for (int r = 0; r < 32; ++r) {
+                        const int row = warp * 32 + r;
+                        const float x = lds32(col + (uint32_t)row * 128u + (uint32_t)(((lane >> 2) ^ (row & 7)) << 4));
+                        s1 += x;
+                        s2 = fmaf(x, x, s2);
+                    }
+                    float2* dst = reinterpret_cast<float2*>(p.parts) + ((int64_t)t.n * p.nparts + t.trem * 4 + warp) * p.Cout + cb * 32 + lane;
                     *dst = make_float2(s1, s2);
                 }
             }
             tc_fence_before();
             mbar_arrive(smem_u32(&hdr->tmem_empty[as]));
         }
+        if (tid == 0) bulk_wait_all();
     } else if (warp == 4) {
         // ============================== MMA issuer (one thread) ===========================================
         if (lane == 0) {
+            constexpr int KS = G::SLAB / 16;
             const uint32_t idesc = make_idesc(p.Cout);
             const uint32_t b_lbo = (uint32_t)p.Cout * 16u, b_sbo = 128u;
             const uint32_t a_lbo = (uint32_t)G::PLANE * 16u, a_sbo = (uint32_t)G::SBO;
+            const uint32_t a_ring = base_u32 + a.off_a, w_ring = base_u32 + a.off_w;
             int sa = 0, sw = 0;
             uint32_t pa = 0, pw = 0;
             for (int it = 0, tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
@@ -279,32 +379,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a)
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * a.acc_stride);
                 uint32_t acc = 0;
-                for (int ai = 0; ai < nA; ++ai) {
-                    const bool is_res = ai >= a.nA_main;
+                for (int ai = 0; ai < a.n_main; ++ai) {
                     mbar_wait(smem_u32(&hdr->full_a[sa]), pa);
-                    const uint32_t a_stage = a_base + (uint32_t)sa * a.a_stage_bytes;
-                    for (int h = 0; h < 2; ++h) {
-                        const int c = 2 * ai + h;
+                    const uint32_t a_stage = a_ring + (uint32_t)sa * a.a_stage;
+#pragma unroll
+                    for (int h = 0; h < KS; ++h) {
+                        const int c = ai * KS + h;
                         int wslot;
                         if (a.resident) { wslot = c; mbar_wait(smem_u32(&hdr->full_w[c]), 0u); }
                         else { wslot = sw; mbar_wait(smem_u32(&hdr->full_w[sw]), pw); }
                         tc_fence_after();
-                        const uint32_t w_stage = w_base + (uint32_t)wslot * a.w_stage_bytes;
+                        const uint32_t w_stage = w_ring + (uint32_t)wslot * a.w_stage;
                         const uint32_t a_half = a_stage + (uint32_t)h * 2u * a_lbo;
-                        if (!is_res) {
 #pragma unroll
-                            for (int tap = 0; tap < 9; ++tap) {
-                                const int ky = tap / 3, kx = tap - 3 * ky;
-                                uint32_t aoff;
-                                if (MODE == CONV_S2) aoff = (uint32_t)(ky * G::PW + (kx == 1 ? 9 : (kx >> 1))) * 16u;
-                                else aoff = (uint32_t)(ky * G::PW + kx) * 16u;
-                                umma(d_tmem, make_desc(a_half + aoff, a_lbo, a_sbo),
-                                     make_desc(w_stage + (uint32_t)tap * 2u * b_lbo, b_lbo, b_sbo), idesc, acc);
-                                acc = 1;
-                            }
-                        } else {   // 1x1 res_conv: centre tap of the raw (stride-1) halo
-                            umma(d_tmem, make_desc(a_half + (uint32_t)(G::PW + 1) * 16u, a_lbo, a_sbo),
-                                 make_desc(w_stage, b_lbo, b_sbo), idesc, acc);
+                        for (int tap = 0; tap < 9; ++tap) {
+                            const int ky = tap / 3, kx = tap - 3 * ky;
+                            uint32_t aoff;
+                            if (MODE == CONV_S2) aoff = (uint32_t)(ky * G::PW + (kx == 1 ? 9 : (kx >> 1))) * 16u;
+                            else aoff = (uint32_t)(ky * G::PW + kx) * 16u;
+                            umma(d_tmem, make_desc(a_half + aoff, a_lbo, a_sbo),
+                                 make_desc(w_stage + (uint32_t)tap * 2u * b_lbo, b_lbo, b_sbo), idesc, acc);
                             acc = 1;
                         }
                         if (!a.resident) {
@@ -315,142 +409,206 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a)
                     umma_commit(smem_u32(&hdr->empty_a[sa]));
                     if (++sa == a.NA) { sa = 0; pa ^= 1u; }
                 }
+                // 1x1 res_conv over the raw block input: centre tap of a stride-1 halo slab (32 channels per slab,
+                // up to 128 channels = 4 slabs per weight chunk)
+                int wslot = 0;
+                for (int ar = 0; ar < a.n_res; ++ar) {
+                    mbar_wait(smem_u32(&hdr->full_a[sa]), pa);
+                    const uint32_t a_stage = a_ring + (uint32_t)sa * a.a_stage;
+                    const int sub = ar & 3;
+                    if (sub == 0) {
+                        const int c = a.n_main_chunks + (ar >> 2);
+                        if (a.resident) { wslot = c; mbar_wait(smem_u32(&hdr->full_w[c]), 0u); }
+                        else { wslot = sw; mbar_wait(smem_u32(&hdr->full_w[sw]), pw); }
+                    }
+                    tc_fence_after();
+                    const uint32_t w_stage = w_ring + (uint32_t)wslot * a.w_stage;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        umma(d_tmem, make_desc(a_stage + (uint32_t)h * 2u * a_lbo + (uint32_t)(G::PW + 1) * 16u, a_lbo, a_sbo),
+                             make_desc(w_stage + (uint32_t)(sub * 2 + h) * 2u * b_lbo, b_lbo, b_sbo), idesc, acc);
+                        acc = 1;
+                    }
+                    if (!a.resident && (sub == 3 || ar == a.n_res - 1)) {
+                        umma_commit(smem_u32(&hdr->empty_w[sw]));
+                        if (++sw == a.NW) { sw = 0; pw ^= 1u; }
+                    }
+                    umma_commit(smem_u32(&hdr->empty_a[sa]));
+                    if (++sa == a.NA) { sa = 0; pa ^= 1u; }
+                }
                 umma_commit(smem_u32(&hdr->tmem_full[as]));
             }
         }
     } else if (warp == 5) {
         // ============================== weight loader (one thread) ========================================
         if (lane == 0) {
-            const int nchunks = 2 * nA, nmain = 2 * a.nA_main;
-            const uint32_t main_bytes = 288u * (uint32_t)p.Cout, res_bytes = 32u * (uint32_t)p.Cout;
+            const int nchunks = a.n_main_chunks + a.n_res_chunks;
+            const uint32_t w_ring = base_u32 + a.off_w;
             int sw = 0;
             uint32_t pw = 0;
             for (int it = 0, tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
                 if (a.resident && it > 0) break;
                 for (int c = 0; c < nchunks; ++c) {
-                    const bool is_res = c >= nmain;
+                    const bool is_res = c >= a.n_main_chunks;
                     const int wslot = a.resident ? c : sw;
                     if (!a.resident) mbar_wait(smem_u32(&hdr->empty_w[sw]), pw ^ 1u);
-                    const uint32_t bytes = is_res ? res_bytes : main_bytes;
-                    const void* src = is_res ? (const void*)(p.res_w_tc + (size_t)(c - nmain) * 16 * p.Cout)
-                                             : (const void*)(p.w_tc + (size_t)c * 144 * p.Cout);
+                    uint32_t bytes;
+                    const void* src;
+                    if (!is_res) {
+                        bytes = 288u * (uint32_t)p.Cout;
+                        src = p.w_tc + (size_t)c * 144 * p.Cout;
+                    } else {
+                        const int c0 = (c - a.n_main_chunks) * 128;
+                        const int nch = (p.res_Cin - c0) < 128 ? (p.res_Cin - c0) : 128;
+                        bytes = (uint32_t)nch * 2u * (uint32_t)p.Cout;
+                        src = p.res_w_tc + (size_t)c0 * p.Cout;
+                    }
                     const uint32_t bar = smem_u32(&hdr->full_w[wslot]);
                     mbar_expect_tx(bar, bytes);
-                    bulk_g2s(w_base + (uint32_t)wslot * a.w_stage_bytes, src, bytes, bar);
+                    bulk_g2s(w_ring + (uint32_t)wslot * a.w_stage, src, bytes, bar);
                     if (!a.resident && ++sw == a.NW) { sw = 0; pw ^= 1u; }
                 }
             }
         }
-    } else {
-        // ============================== A-operand producers ===============================================
-        constexpr int NPIX = G::PH * G::PW;
-        constexpr int RPS = (NPIX * 4 + kProdThreads * kItems - 1) / (kProdThreads * kItems);   // batches per slab
-        const int ptid = tid - kProdWarp0 * 32;
-        const int j = ptid & 3;          // k8 plane of this thread (channels j*8 .. j*8+7 of the slab)
-        const int pix0 = ptid >> 2;      // first halo pixel
-        unsigned char* a_gen = smem_raw + kHdrBytes;
+    } else if (warp == 6) {
+        // ============================== raw-slab TMA issuer (one thread) ==================================
+        if (lane == 0) {
+            constexpr uint32_t RAW_BYTES = (uint32_t)G::RAW_H * G::RAW_W * G::SLAB * 4u;
+            const uint32_t raw_ring = base_u32 + a.off_raw;
+            int rs = 0;
+            uint32_t pr = 0;
+            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+                const TileCoord t = decode_tile(a, tile);
+                const int yo = org_of<MODE>(t.oy0), xo = org_of<MODE>(t.ox0);
+                for (int ai = 0; ai < nA; ++ai) {
+                    const bool is_res = ai >= a.n_main;
+                    const int cbase = is_res ? (ai - a.n_main) * 32 : ai * G::SLAB;
+                    const ConvSrc* srcs = is_res ? p.res_src : p.src;
+                    const int s = (cbase < srcs[0].C) ? 0 : 1;
+                    const int coff = cbase - (s ? srcs[0].C : 0);
+                    const uint32_t bar = smem_u32(&hdr->raw_full[rs]);
+                    mbar_wait(smem_u32(&hdr->raw_empty[rs]), pr ^ 1u);
+                    mbar_expect_tx(bar, is_res ? 18u * 10u * 32u * 4u : RAW_BYTES);
+                    tma_load_4d(raw_ring + (uint32_t)rs * a.raw_stage, &maps.src[(is_res ? 2 : 0) + s], coff,
+                                is_res ? t.ox0 - 1 : xo, is_res ? t.oy0 - 1 : yo, t.n, bar);
+                    if (++rs == a.NR) { rs = 0; pr ^= 1u; }
+                }
+            }
+        }
+    } else if (warp >= kXfWarp0) {
+        // ============================== transform: raw fp32 slab -> bf16 operand slab ====================
+        constexpr int NPL = G::SLAB / 8;                       // k8 planes per slab
+        constexpr int PSTEP = kXfThreads / NPL;                // pixels covered per round
+        constexpr int PIXB = G::SLAB * 4;                      // raw bytes per pixel
+        const int ptid = tid - kXfWarp0 * 32;
+        const int j = ptid % NPL;
+        const int pix0 = ptid / NPL;
+        const uint32_t raw_ring = base_u32 + a.off_raw, a_ring = base_u32 + a.off_a;
+        int rs = 0, sa = 0;
+        uint32_t pr = 0, pa = 0;
+        const float kNegLog2e = -1.4426950408889634f;
 
-        // flattened batch iterator: (tile, slab, round)
-        int b_tile = blockIdx.x, b_ai = 0, b_round = 0;
-        auto issue = [&](PBatch& B) {
-            const int tile = b_tile, ai = b_ai, round = b_round;
-            const int n = tile / tiles_per_img, trem = tile - n * tiles_per_img;
-            const int oy0 = (trem / a.tiles_x) * TH, ox0 = (trem % a.tiles_x) * TW;
-            const bool is_res = ai >= a.nA_main;
-            const int cbase = (is_res ? ai - a.nA_main : ai) * 32;
-            const ConvSrc* srcs = is_res ? p.res_src : p.src;
-            const int s = (cbase < srcs[0].C) ? 0 : 1;
-            const float* x = srcs[s].x;
-            const int C = srcs[s].C;
-            const int coff = cbase - (s ? srcs[0].C : 0) + j * 8;
-            const float* scale = srcs[s].scale;
-            B.has_affine = (!is_res && scale != nullptr) ? 1 : 0;
-            if (B.has_affine) {
-                const int ctot = p.Cin;
-                const float4* sp = reinterpret_cast<const float4*>(scale + (int64_t)n * ctot + cbase + j * 8);
-                const float4* hp = reinterpret_cast<const float4*>(srcs[s].shift + (int64_t)n * ctot + cbase + j * 8);
-                B.sc[0] = __ldg(sp); B.sc[1] = __ldg(sp + 1);
-                B.sh[0] = __ldg(hp); B.sh[1] = __ldg(hp + 1);
-            }
-            B.okmask = 0;
+        // one 8-channel item: raw fp32 -> (affine, swish) -> masked -> packed bf16
+        auto convert = [&](uint32_t raw_addr, bool swap, bool ok, bool affine, const float (&sc)[8], const float (&sh)[8],
+                           const float (&sc2)[8], const float (&sh2)[8]) -> uint4 {
+            const uint4 lo = lds128(raw_addr + (swap ? 16u : 0u)), hi = lds128(raw_addr + (swap ? 0u : 16u));
+            const uint4 u0 = swap ? hi : lo, u1 = swap ? lo : hi;
+            float f[8] = {__uint_as_float(u0.x), __uint_as_float(u0.y), __uint_as_float(u0.z), __uint_as_float(u0.w),
+                          __uint_as_float(u1.x), __uint_as_float(u1.y), __uint_as_float(u1.z), __uint_as_float(u1.w)};
+            if (affine) {
 #pragma unroll
-            for (int r = 0; r < kItems; ++r) {
-                const int pix = pix0 + (kProdThreads / 4) * (round * kItems + r);
-                B.slot[r] = -1;
-                if (pix >= NPIX) continue;
-                const int hy = pix / G::PW, hx = pix - hy * G::PW;
-                int iy, ix, slot;
-                bool ok;
-                if (MODE == CONV_UP && !is_res) {
-                    const int uy = oy0 + hy - 1, ux = ox0 + hx - 1;
-                    ok = uy >= 0 && uy < p.Hout && ux >= 0 && ux < p.Wout;
-                    iy = uy >> 1; ix = ux >> 1;
-                    slot = pix;
-                } else if (MODE == CONV_S2) {
-                    iy = 2 * oy0 + hy - 1; ix = 2 * ox0 + hx - 1;
-                    ok = iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win;
-                    slot = hy * G::PW + ((hx & 1) ? 9 + (hx >> 1) : (hx >> 1));
-                } else {
-                    iy = oy0 + hy - 1; ix = ox0 + hx - 1;
-                    ok = iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win;
-                    slot = pix;
-                }
-                B.slot[r] = slot;
-                if (ok) {
-                    B.okmask |= 1u << r;
-                    const float4* g = reinterpret_cast<const float4*>(x + (((int64_t)n * p.Hin + iy) * p.Win + ix) * C + coff);
-                    B.v[r][0] = __ldg(g);
-                    B.v[r][1] = __ldg(g + 1);
+                for (int k = 0; k < 8; ++k) {
+                    const float y = fmaf(f[k], sc[k], sh[k]);
+                    const float e = exp2f(fmaf(f[k], sc2[k], sh2[k]));     // exp(-y)
+                    f[k] = __fdividef(y, 1.0f + e);                        // y * sigmoid(y)
                 }
             }
-            // advance the iterator
-            if (++b_round == RPS) {
-                b_round = 0;
-                if (++b_ai == nA) { b_ai = 0; b_tile += gridDim.x; }
-            }
+            uint4 o = make_uint4(0u, 0u, 0u, 0u);
+            if (ok) { o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]); o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]); }
+            return o;
         };
 
-        int sa = 0;
-        uint32_t pa = 0;
-        int c_round = 0;
-        auto finish = [&](const PBatch& B) {
-            if (c_round == 0) mbar_wait(smem_u32(&hdr->empty_a[sa]), pa ^ 1u);
-            unsigned char* stage = a_gen + (size_t)sa * a.a_stage_bytes + (size_t)j * G::PLANE * 16;
+        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+            const TileCoord t = decode_tile(a, tile);
+            for (int ai = 0; ai < nA; ++ai) {
+                const bool is_res = ai >= a.n_main;
+                const int cbase = is_res ? (ai - a.n_main) * 32 : ai * G::SLAB;
+                const ConvSrc* srcs = is_res ? p.res_src : p.src;
+                const int s = (cbase < srcs[0].C) ? 0 : 1;
+                const bool affine = !is_res && srcs[s].scale != nullptr;
+                float sc[8], sh[8], sc2[8], sh2[8];
+                if (affine) {
+                    const float4* sp = reinterpret_cast<const float4*>(srcs[s].scale + (int64_t)t.n * p.Cin + cbase + j * 8);
+                    const float4* hp = reinterpret_cast<const float4*>(srcs[s].shift + (int64_t)t.n * p.Cin + cbase + j * 8);
+                    const float4 s0 = __ldg(sp), s1 = __ldg(sp + 1), h0 = __ldg(hp), h1 = __ldg(hp + 1);
+                    sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
+                    sh[0] = h0.x; sh[1] = h0.y; sh[2] = h0.z; sh[3] = h0.w; sh[4] = h1.x; sh[5] = h1.y; sh[6] = h1.z; sh[7] = h1.w;
 #pragma unroll
-            for (int r = 0; r < kItems; ++r) {
-                if (B.slot[r] < 0) continue;
-                float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                if (B.okmask & (1u << r)) {
-                    f[0] = B.v[r][0].x; f[1] = B.v[r][0].y; f[2] = B.v[r][0].z; f[3] = B.v[r][0].w;
-                    f[4] = B.v[r][1].x; f[5] = B.v[r][1].y; f[6] = B.v[r][1].z; f[7] = B.v[r][1].w;
-                    if (B.has_affine) {
-                        const float scv[8] = {B.sc[0].x, B.sc[0].y, B.sc[0].z, B.sc[0].w, B.sc[1].x, B.sc[1].y, B.sc[1].z, B.sc[1].w};
-                        const float shv[8] = {B.sh[0].x, B.sh[0].y, B.sh[0].z, B.sh[0].w, B.sh[1].x, B.sh[1].y, B.sh[1].z, B.sh[1].w};
+                    for (int k = 0; k < 8; ++k) { sc2[k] = sc[k] * kNegLog2e; sh2[k] = sh[k] * kNegLog2e; }
+                }
+                // valid window of the raw box (in box coordinates): everything else is zero padding
+                int yo, xo, rh, rw;
+                if (is_res || MODE == CONV_S1) { yo = t.oy0 - 1; xo = t.ox0 - 1; rh = 18; rw = 10; }
+                else { yo = org_of<MODE>(t.oy0); xo = org_of<MODE>(t.ox0); rh = G::RAW_H; rw = G::RAW_W; }
+                const int ylo = yo < 0 ? -yo : 0, xlo = xo < 0 ? -xo : 0;
+                const int yhi = (p.Hin - yo) < rh ? (p.Hin - yo) : rh, xhi = (p.Win - xo) < rw ? (p.Win - xo) : rw;
+
+                mbar_wait(smem_u32(&hdr->raw_full[rs]), pr);
+                mbar_wait(smem_u32(&hdr->empty_a[sa]), pa ^ 1u);
+                const uint32_t raw = raw_ring + (uint32_t)rs * a.raw_stage;
+                const uint32_t opd = a_ring + (uint32_t)sa * a.a_stage + (uint32_t)j * (uint32_t)G::PLANE * 16u;
+                if (MODE == CONV_UP && !is_res) {
+                    if (pix0 < G::RAW_H * G::RAW_W) {
+                        const int ry = pix0 / G::RAW_W, rx = pix0 - ry * G::RAW_W;
+                        const bool ok = ry >= ylo && ry < yhi && rx >= xlo && rx < xhi;
+                        const uint32_t ra = raw + (uint32_t)pix0 * PIXB + (uint32_t)j * 32u;
+                        const uint4 o = convert(ra, ((pix0 * PIXB) >> 7) & 1, ok, affine, sc, sh, sc2, sh2);
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) f[k] = swish_fast(fmaf(f[k], scv[k], shv[k]));
+                        for (int dy = 0; dy < 2; ++dy) {
+                            const int hy = 2 * ry - 1 + dy;
+                            if (hy < 0 || hy >= G::PH) continue;
+#pragma unroll
+                            for (int dx = 0; dx < 2; ++dx) {
+                                const int hx = 2 * rx - 1 + dx;
+                                if (hx < 0 || hx >= G::PW) continue;
+                                sts128(opd + (uint32_t)(hy * G::PW + hx) * 16u, o);
+                            }
+                        }
+                    }
+                } else if (MODE == CONV_S2) {
+                    constexpr int NPIX = G::RAW_H * G::RAW_W, ROUNDS = (NPIX + PSTEP - 1) / PSTEP;
+#pragma unroll
+                    for (int r = 0; r < ROUNDS; ++r) {
+                        const int pix = pix0 + r * PSTEP;
+                        if (pix >= NPIX) break;
+                        const int hy = pix / G::RAW_W, hx = pix - hy * G::RAW_W;
+                        const bool ok = hy >= ylo && hy < yhi && hx >= xlo && hx < xhi;
+                        const uint32_t ra = raw + (uint32_t)pix * PIXB + (uint32_t)j * 32u;
+                        const uint4 o = convert(ra, ((pix * PIXB) >> 7) & 1, ok, affine, sc, sh, sc2, sh2);
+                        const int slot = hy * G::PW + ((hx & 1) ? 9 + (hx >> 1) : (hx >> 1));
+                        sts128(opd + (uint32_t)slot * 16u, o);
+                    }
+                } else {   // stride-1 halo (main conv of CONV_S1, res_conv slabs)
+                    constexpr int NPIX = 18 * 10, PST = kXfThreads / 4, ROUNDS = (NPIX + PST - 1) / PST;
+                    const int jj = ptid & 3, pp = ptid >> 2;   // res slabs always have 4 planes of 32 raw channels
+                    const uint32_t opd4 = a_ring + (uint32_t)sa * a.a_stage + (uint32_t)jj * (uint32_t)G::PLANE * 16u;
+#pragma unroll
+                    for (int r = 0; r < ROUNDS; ++r) {
+                        const int pix = pp + r * PST;
+                        if (pix >= NPIX) break;
+                        const int hy = pix / 10, hx = pix - hy * 10;
+                        const bool ok = hy >= ylo && hy < yhi && hx >= xlo && hx < xhi;
+                        const uint32_t ra = raw + (uint32_t)pix * 128u + (uint32_t)jj * 32u;
+                        const uint4 o = convert(ra, pix & 1, ok, affine, sc, sh, sc2, sh2);
+                        sts128(opd4 + (uint32_t)pix * 16u, o);
                     }
                 }
-                uint4 o;
-                o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]); o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
-                *reinterpret_cast<uint4*>(stage + (size_t)B.slot[r] * 16) = o;
-            }
-            if (++c_round == RPS) {
-                c_round = 0;
                 fence_async_smem();
                 mbar_arrive(smem_u32(&hdr->full_a[sa]));
+                mbar_arrive(smem_u32(&hdr->raw_empty[rs]));
+                if (++rs == a.NR) { rs = 0; pr ^= 1u; }
                 if (++sa == a.NA) { sa = 0; pa ^= 1u; }
             }
-        };
-
-        int my_tiles = 0;
-        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) ++my_tiles;
-        const int total = my_tiles * nA * RPS;
-        PBatch cur, nxt;
-        if (total > 0) issue(cur);
-        for (int b = 0; b < total; ++b) {
-            if (b + 1 < total) issue(nxt);
-            finish(cur);
-            cur = nxt;
         }
     }
 
@@ -525,28 +683,100 @@ int num_sms() {
 
 constexpr size_t kSmemMax = 232448;   // 227 KB opt-in limit per CTA on sm_100
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !f) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        fn = reinterpret_cast<EncodeTiledFn>(f);
+    }
+    return fn;
+}
+
+// fp32 NHWC tensor [B][H][W][C] as a 4-D tensor map (C innermost) with box (bc, bw, bh, 1)
+int encode_nhwc(CUtensorMap* m, const float* base, int B, int H, int W, int C, int bc, int bw, int bh, bool swizzle128) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { set_error("conv tc: cuTensorMapEncodeTiled is unavailable"); return SDDM_E_CUDA; }
+    const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    const cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+    const cuuint32_t box[4] = {(cuuint32_t)bc, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("conv tc: cuTensorMapEncodeTiled failed (%d) for [%d,%d,%d,%d] box %dx%dx%d", (int)r, B, H, W, C, bc, bw, bh); return SDDM_E_CUDA; }
+    return SDDM_OK;
+}
+
+inline size_t align_up_sz(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
 template <int MODE>
 int launch_mode(TcArgs& a, cudaStream_t st) {
     using G = Geo<MODE>;
     const ConvP& p = a.p;
-    a.a_stage_bytes = 4u * G::PLANE * 16u;
-    a.w_stage_bytes = 288u * (uint32_t)p.Cout;
-    a.NA = (MODE == CONV_S2) ? 2 : 4;
-    const int nchunks = 2 * (a.nA_main + a.nA_res);
-    const size_t budget = kSmemMax - kHdrBytes - (size_t)a.NA * a.a_stage_bytes;
-    int nw = (int)(budget / a.w_stage_bytes);
-    if (nw > kMaxW) nw = kMaxW;
-    if (nw < 2) { set_error("conv tc: Cout=%d leaves no room for a weight ring", p.Cout); return SDDM_E_INVALID; }
-    a.resident = nchunks <= nw;
-    a.NW = a.resident ? nchunks : nw;
-    const size_t smem = kHdrBytes + (size_t)a.NA * a.a_stage_bytes + (size_t)a.NW * a.w_stage_bytes;
+    a.n_main = p.Cin / G::SLAB;
+    a.n_main_chunks = p.Cin / 16;
+    a.raw_stage = (uint32_t)align_up_sz((size_t)G::RAW_H * G::RAW_W * G::SLAB * 4, 1024);
+    if (a.n_res && a.raw_stage < 18u * 10u * 32u * 4u) a.raw_stage = (uint32_t)align_up_sz(18 * 10 * 32 * 4, 1024);
+    a.a_stage = (uint32_t)align_up_sz((size_t)(G::SLAB / 8) * G::PLANE * 16, 128);
+    if (a.n_res && a.a_stage < 4u * 181u * 16u) a.a_stage = (uint32_t)align_up_sz(4 * 181 * 16, 128);
+    a.w_stage = 288u * (uint32_t)p.Cout;
+    const int nchunks = a.n_main_chunks + a.n_res_chunks;
+    // shared-memory plan: header | out staging (2 tiles) | residual ring | raw ring | operand ring | weights
+    const size_t cap = kSmemMax - 1024;   // slack for the 1024-byte alignment of the base
+    a.NR = 2; a.NA = 2;
+    auto fixed = [&]() { return (size_t)kHdrBytes + (size_t)a.NOUT * kOutTileBytes + (size_t)a.NRES * kOutTileBytes + (size_t)a.NR * a.raw_stage + (size_t)a.NA * a.a_stage; };
+    const int try_out[4] = {2, 2, 1, 1}, try_res[4] = {3, 2, 2, 1};
+    bool fits = false;
+    for (int k = 0; k < 4 && !fits; ++k) {   // shrink the epilogue staging before giving up
+        a.NOUT = try_out[k];
+        a.NRES = p.res_identity ? try_res[k] : 0;
+        a.resident = nchunks <= kMaxW && fixed() + (size_t)nchunks * a.w_stage <= cap;
+        a.NW = a.resident ? nchunks : (nchunks < 3 ? nchunks : 3);
+        if (!a.resident && fixed() + (size_t)a.NW * a.w_stage > cap) a.NW = 2;
+        fits = fixed() + (size_t)a.NW * a.w_stage <= cap;
+    }
+    if (!fits) { set_error("conv tc: Cout=%d does not fit the shared-memory plan", p.Cout); return SDDM_E_INVALID; }
+    auto total = [&]() { return fixed() + (size_t)a.NW * a.w_stage; };
+    for (bool grew = true; grew;) {   // spend what is left on deeper rings: raw slabs first (they hide the HBM latency)
+        grew = false;
+        if (a.NR < kMaxRing) { ++a.NR; if (total() <= cap) grew = true; else --a.NR; }
+        if (a.NA < kMaxRing && a.NA < a.NR) { ++a.NA; if (total() <= cap) grew = true; else --a.NA; }
+        if (!a.resident && a.NW < 8 && a.NW < nchunks) { ++a.NW; if (total() <= cap) grew = true; else --a.NW; }
+    }
+    a.off_out = kHdrBytes;
+    a.off_res = a.off_out + (uint32_t)a.NOUT * kOutTileBytes;
+    a.off_raw = a.off_res + (uint32_t)a.NRES * kOutTileBytes;
+    a.off_a = a.off_raw + (uint32_t)a.NR * a.raw_stage;
+    a.off_w = a.off_a + (uint32_t)a.NA * a.a_stage;
+    const size_t smem = total() + 1024;
+
+    TcMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    int rc;
+    for (int i = 0; i < p.nsrc; ++i)
+        if ((rc = encode_nhwc(&maps.src[i], p.src[i].x, p.B, p.Hin, p.Win, p.src[i].C, G::SLAB, G::RAW_W, G::RAW_H, false))) return rc;
+    if (a.n_res)
+        for (int i = 0; i < p.res_nsrc; ++i)
+            if ((rc = encode_nhwc(&maps.src[2 + i], p.res_src[i].x, p.B, p.Hin, p.Win, p.res_src[i].C, 32, 10, 18, false))) return rc;
+    if ((rc = encode_nhwc(&maps.out, p.out, p.B, p.Hout, p.Wout, p.Cout, 32, TW, TH, true))) return rc;
+    if (p.res_identity && (rc = encode_nhwc(&maps.res, p.res_src[0].x, p.B, p.Hout, p.Wout, p.Cout, 32, TW, TH, true))) return rc;
+
     static bool attr_set = false;
     if (!attr_set) {
         SDDM_CUDA_TRY(cudaFuncSetAttribute(conv3x3_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
         attr_set = true;
     }
     const int grid = a.ntiles < num_sms() ? a.ntiles : num_sms();
-    conv3x3_tc_kernel<MODE><<<grid, kThreads, smem, st>>>(a);
+    conv3x3_tc_kernel<MODE><<<grid, kThreads, smem, st>>>(a, maps);
     SDDM_LAUNCH_CHECK();
     return SDDM_OK;
 }
@@ -568,17 +798,20 @@ int launch_conv_tc(const ConvP& p, cudaStream_t st) {
     const int ein_h = p.mode == CONV_S2 ? p.Hout * 2 : (p.mode == CONV_UP ? p.Hout / 2 : p.Hout);
     const int ein_w = p.mode == CONV_S2 ? p.Wout * 2 : (p.mode == CONV_UP ? p.Wout / 2 : p.Wout);
     if (ein_h != p.Hin || ein_w != p.Win) { set_error("conv tc: inconsistent spatial sizes"); return SDDM_E_INVALID; }
-    if (p.res_Cin && !p.res_identity && (!p.res_w_tc || p.mode != CONV_S1)) { set_error("conv tc: res_conv needs packed weights and stride 1"); return SDDM_E_INVALID; }
+    const bool has_res_conv = p.res_Cin && !p.res_identity;
+    if (has_res_conv && (!p.res_w_tc || p.mode != CONV_S1)) { set_error("conv tc: res_conv needs packed weights and stride 1"); return SDDM_E_INVALID; }
+    if (p.mode == CONV_UP && ((p.Hout % TH) || (p.Wout % TW))) { set_error("conv tc: upsampled output must tile by 16x8"); return SDDM_E_INVALID; }
     TcArgs a{};
     a.p = p;
     a.tiles_x = (p.Wout + TW - 1) / TW;
     a.tiles_y = (p.Hout + TH - 1) / TH;
     a.ntiles = p.B * a.tiles_x * a.tiles_y;
     if (p.parts && p.nparts != a.tiles_x * a.tiles_y * 4) { set_error("conv tc: nparts mismatch"); return SDDM_E_INVALID; }
-    a.nA_main = p.Cin / 32;
-    a.nA_res = (p.res_w_tc && !p.res_identity) ? p.res_Cin / 32 : 0;
+    a.n_res = has_res_conv ? p.res_Cin / 32 : 0;
+    a.n_res_chunks = has_res_conv ? (p.res_Cin + 127) / 128 : 0;
     a.acc_stride = p.Cout <= 32 ? 32 : (p.Cout <= 64 ? 64 : (p.Cout <= 128 ? 128 : 256));
     a.tmem_cols = 2 * a.acc_stride;
+    a.temb_per_row = (p.temb && p.temb_stride != 0) ? 1 : 0;
     switch (p.mode) {
         case CONV_S1: return launch_mode<CONV_S1>(a, st);
         case CONV_S2: return launch_mode<CONV_S2>(a, st);
