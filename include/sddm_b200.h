@@ -170,6 +170,9 @@ SDDM_API int sddm_debug_fetch(sddm_plan* plan, const char* node, void* ws, int B
 /* single-tile tcgen05 descriptor self-test: returns max |err| of a 128 x N x K bf16 MMA vs an fp32 reference
  * computed on the device with CUDA cores, through *max_err. variant selects the descriptor convention. */
 SDDM_API int sddm_debug_umma_probe(int variant, int N, int K, float* max_err_host);
+/* pipeline trace of the tcgen05 conv kernel: enable != 0 starts recording (next 64 conv launches, CTA 0 of each: cycles per
+ * role spent waiting on each barrier); enable == 0 copies the [64][48] int64 counters to host_out and stops. */
+SDDM_API int sddm_debug_tc_trace(int enable, long long* host_out);
 
 #ifdef __cplusplus
 }

@@ -18,9 +18,10 @@
 //               128B-swizzled shared-memory tile -> TMA tensor store (NHWC fp32) + GroupNorm partial statistics
 //               (column sums of the staged tile: sum, sum of squares per channel per 32-pixel quarter).
 //
-// Warp roles (512 threads, persistent CTA, static tile schedule):
-//   warps 0-3 epilogue (TMEM lane quarter = warp id) | warp 4 MMA issuer + TMEM owner | warp 5 weight loader
-//   warp 6 raw-slab TMA issuer | warp 7 idle | warps 8-15 transform
+// Warp roles (640 threads, persistent CTA, static tile schedule):
+//   warps 0-3 / 4-7 epilogue groups 0 / 1 (group e drains accumulator stage e; TMEM lane quarter = warp id % 4)
+//   warp 8 MMA issuer + TMEM owner | warp 9 weight loader | warp 10 raw-slab TMA issuer | warp 11 idle
+//   warps 12-15 / 16-19 transform groups 0 / 1 (alternate slabs, so two slabs are converted concurrently)
 //
 // reference: Block / ResnetBlock / Downsample / Upsample, model/UNetModified2.py:93-142
 #include <cuda.h>
@@ -35,10 +36,11 @@ namespace sddm {
 namespace {
 
 constexpr int TH = 16, TW = 8;            // output window of one tile
-constexpr int kEpiThreads = 128;
-constexpr int kXfWarp0 = 8, kXfThreads = 256;
-constexpr int kThreads = kXfWarp0 * 32 + kXfThreads;   // 512
-constexpr int kMaxRing = 4, kMaxW = 16;
+constexpr int kEpiGroups = 2, kEpiGroupThreads = 128;         // epilogue group e owns accumulator stage e
+constexpr int kMmaWarp = 8, kWldWarp = 9, kTmaWarp = 10;
+constexpr int kXfWarp0 = 12, kXfGroups = 2, kXfGroupThreads = 128;
+constexpr int kThreads = kXfWarp0 * 32 + kXfGroups * kXfGroupThreads;   // 640
+constexpr int kMaxRing = 6, kMaxW = 32;
 constexpr uint32_t kOutTileBytes = 128 * 32 * 4;       // one 128-pixel x 32-channel fp32 staging tile
 
 // geometry per mode ---------------------------------------------------------------------------------------
@@ -52,7 +54,7 @@ template <> struct Geo<CONV_S2> { static constexpr int SLAB = 16, RAW_H = 33, RA
 // PLANE = 5 (mod 8): the k8 planes of one pixel fall into disjoint shared-memory banks.
 
 struct alignas(64) TcMaps {
-    CUtensorMap src[4];   // main source 0 / 1, res_conv source 0 / 1
+    CUtensorMap src[4];   // main source 0 / 1, res_conv source 0 / 1 (32-channel boxes: 128B swizzle)
     CUtensorMap out;      // output store, box 32 ch x 8 x 16, 128B swizzle
     CUtensorMap res;      // identity residual load, same geometry
 };
@@ -60,14 +62,17 @@ struct alignas(64) TcMaps {
 struct TcArgs {
     ConvP p;
     int tiles_x, tiles_y, ntiles;   // per-sample tile grid, total tiles (B * tiles_x * tiles_y)
+    unsigned long long magic_per, magic_tx;   // ceil(2^32 / d) for d = tiles per sample, tiles_x
     int n_main, n_res;              // A slabs of the main conv (SLAB channels) / the 1x1 res_conv (32 channels)
-    int n_main_chunks, n_res_chunks;   // weight chunks: 16 channels x 9 taps / up to 128 channels x 1 tap
-    int NR, NA, NW, NRES, NOUT;     // ring depths: raw slabs, operand slabs, weight chunks, residual tiles, out staging tiles
+    int n_main_chunks, n_res_chunks;   // weight chunks: 16 channels x 3 taps (one filter row) / 32 channels x 1 tap
+    int NR, NA, NW;                 // ring depths: raw slabs, operand slabs, weight chunks
+    int NRES, NOUT;                 // per epilogue group: residual tiles, out staging tiles
     int resident;                   // all weight chunks stay in shared memory
     int acc_stride, tmem_cols;
     int temb_per_row;
     uint32_t off_out, off_res, off_raw, off_a, off_w;   // byte offsets from the 1024-aligned shared-memory base
     uint32_t raw_stage, a_stage, w_stage;
+    long long* trace;               // debug: per-role wait / busy cycle counters of CTA 0 (nullptr = off)
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------
@@ -95,12 +100,17 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
 }
 // Bounded wait: a pipeline bug must surface as a trap (CUDA error), never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    if (mbar_try(bar, parity)) return;
-    const long long t0 = clock64();
     uint32_t spins = 0;
     while (!mbar_try(bar, parity)) {
-        if ((++spins & 1023u) == 0 && clock64() - t0 > 4000000000LL) __trap();
+        if (++spins > 40000000u) __trap();
     }
+}
+// wait + (when tracing) accumulate the cycles spent into acc
+__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, bool trace, long long& acc) {
+    if (!trace) { mbar_wait(bar, parity); return; }
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    acc += clock64() - t0;
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -176,7 +186,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// one lane of the (converged) warp; the same lane every time, so commits track the MMAs issued under earlier elections
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void group_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -195,6 +215,11 @@ __device__ __forceinline__ float lds32(uint32_t addr) {
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ float tanh_approx(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 // shared-memory header (at the 1024-aligned base)
 struct SmemHdr {
@@ -202,21 +227,20 @@ struct SmemHdr {
     uint64_t full_a[kMaxRing], empty_a[kMaxRing];
     uint64_t full_w[kMaxW], empty_w[kMaxW];
     uint64_t tmem_full[2], tmem_empty[2];
-    uint64_t res_full[kMaxRing];
+    uint64_t res_full[kEpiGroups][4];
     uint32_t tmem_base;
     uint32_t pad[15];
-    float addv[256];
+    float addv[kEpiGroups][256];
 };
-constexpr uint32_t kHdrBytes = 2048;
+constexpr uint32_t kHdrBytes = 3072;
 static_assert(sizeof(SmemHdr) <= kHdrBytes, "header too large");
 
 struct TileCoord { int n, oy0, ox0, trem; };
 __device__ __forceinline__ TileCoord decode_tile(const TcArgs& a, int tile) {
     TileCoord t;
-    const int per = a.tiles_x * a.tiles_y;
-    t.n = tile / per;
-    t.trem = tile - t.n * per;
-    const int ty = t.trem / a.tiles_x;
+    t.n = (int)(((unsigned long long)(unsigned)tile * a.magic_per) >> 32);
+    t.trem = tile - t.n * (a.tiles_x * a.tiles_y);
+    const int ty = (int)(((unsigned long long)(unsigned)t.trem * a.magic_tx) >> 32);
     t.oy0 = ty * TH;
     t.ox0 = (t.trem - ty * a.tiles_x) * TW;
     return t;
@@ -226,7 +250,7 @@ template <int MODE> __device__ __forceinline__ int org_of(int o0) {   // first i
 }
 
 // =====================================================================================================
-template <int MODE>
+template <int MODE, int TPC>
 __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a, const __grid_constant__ TcMaps maps) {
     using G = Geo<MODE>;
     extern __shared__ unsigned char smem_dyn[];
@@ -239,76 +263,97 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
 
     if (tid == 0) {
         for (int i = 0; i < kMaxRing; ++i) {
-            mbar_init(smem_u32(&hdr->raw_full[i]), 1); mbar_init(smem_u32(&hdr->raw_empty[i]), kXfThreads);
-            mbar_init(smem_u32(&hdr->full_a[i]), kXfThreads); mbar_init(smem_u32(&hdr->empty_a[i]), 1);
-            mbar_init(smem_u32(&hdr->res_full[i]), 1);
+            mbar_init(smem_u32(&hdr->raw_full[i]), 1); mbar_init(smem_u32(&hdr->raw_empty[i]), kXfGroupThreads);
+            mbar_init(smem_u32(&hdr->full_a[i]), kXfGroupThreads); mbar_init(smem_u32(&hdr->empty_a[i]), 1);
         }
         for (int i = 0; i < kMaxW; ++i) { mbar_init(smem_u32(&hdr->full_w[i]), 1); mbar_init(smem_u32(&hdr->empty_w[i]), 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&hdr->tmem_full[i]), 1); mbar_init(smem_u32(&hdr->tmem_empty[i]), kEpiThreads); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(smem_u32(&hdr->tmem_full[i]), 1); mbar_init(smem_u32(&hdr->tmem_empty[i]), kEpiGroupThreads);
+            for (int k = 0; k < 4; ++k) mbar_init(smem_u32(&hdr->res_full[i][k]), 1);
+        }
         fence_barrier_init();
     }
-    if (warp == 4) tmem_alloc(smem_u32(&hdr->tmem_base), (uint32_t)a.tmem_cols);
+    if (warp == kMmaWarp) tmem_alloc(smem_u32(&hdr->tmem_base), (uint32_t)a.tmem_cols);
+    if (warp < 8 && !a.temb_per_row) {   // per-channel additive term of the epilogue (same for every row of the batch)
+        for (int c = tid & 127; c < p.Cout; c += 128) {
+            float v = __ldg(p.bias + c);
+            if (p.temb) v += __ldg(p.temb + c);
+            if (a.n_res) v += __ldg(p.res_bias + c);
+            hdr->addv[warp >> 2][c] = v;
+        }
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = hdr->tmem_base;
+    const bool tr = a.trace != nullptr && blockIdx.x == 0;   // trace: cycles CTA 0 spends in each kind of wait
+    long long tw[6] = {0, 0, 0, 0, 0, 0};
+    const long long t_begin = tr ? clock64() : 0;
 
-    if (warp < 4) {
-        // ============================== epilogue ==========================================================
-        const int m = tid, py = m >> 3, px = m & 7;
+    if (warp < 8) {
+        // ============================== epilogue (group e = accumulator stage e) ==========================
+        const int e = warp >> 2, w4 = warp & 3;
+        const int m = tid & 127;
+        const int py = m >> 3, px = m & 7;
+        const int bar_id = 1 + e;
+        const bool leader = m == 0;
         const int nblk = p.Cout >> 5;
         const bool has_res = p.res_identity != 0;
-        const uint32_t obuf0 = base_u32 + a.off_out, rbuf0 = base_u32 + a.off_res;
-        const uint32_t addv_u32 = smem_u32(hdr->addv);
+        const uint32_t obuf0 = base_u32 + a.off_out + (uint32_t)(e * a.NOUT) * kOutTileBytes;
+        const uint32_t rbuf0 = base_u32 + a.off_res + (uint32_t)(e * a.NRES) * kOutTileBytes;
+        const uint32_t addv_u32 = smem_u32(hdr->addv[e]);
+        // tiles of this group: it = e, e + 2, ...
         int my_tiles = 0;
-        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) ++my_tiles;
+        for (int it = e, tile = blockIdx.x + e * gridDim.x; tile < a.ntiles; tile += 2 * gridDim.x, it += 2) ++my_tiles;
         const int total_blocks = my_tiles * nblk;
-        auto issue_res = [&](int g) {   // thread 0: prefetch the identity-residual tile of block g
-            const int it = g / nblk, cb = g - it * nblk;
-            const TileCoord t = decode_tile(a, blockIdx.x + it * gridDim.x);
+        auto issue_res = [&](int g) {   // leader: prefetch the identity-residual tile of this group's block g
+            const int k = g / nblk, cb = g - k * nblk;
+            const TileCoord t = decode_tile(a, blockIdx.x + (e + 2 * k) * gridDim.x);
             const int buf = g % a.NRES;
-            const uint32_t bar = smem_u32(&hdr->res_full[buf]);
+            const uint32_t bar = smem_u32(&hdr->res_full[e][buf]);
             mbar_expect_tx(bar, kOutTileBytes);
             tma_load_4d(rbuf0 + (uint32_t)buf * kOutTileBytes, &maps.res, cb * 32, t.ox0, t.oy0, t.n, bar);
         };
-        if (!a.temb_per_row) {
-            for (int c = tid; c < p.Cout; c += kEpiThreads) {
-                float v = __ldg(p.bias + c);
-                if (p.temb) v += __ldg(p.temb + c);
-                if (a.n_res) v += __ldg(p.res_bias + c);
-                hdr->addv[c] = v;
-            }
-        }
-        if (has_res && tid == 0)
+        if (has_res && leader)
             for (int g = 0; g < a.NRES - 1 && g < total_blocks; ++g) issue_res(g);
-        epi_bar();
+        // swizzled column offsets for the statistics pass: row r of the staged tile keeps channel c at
+        // r * 128 + (((c >> 2) ^ (r & 7)) << 4) + (c & 3) * 4
+        uint32_t coloff[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) coloff[k] = (uint32_t)((((lane >> 2) ^ k) << 4) + (lane & 3) * 4);
         int g = 0;
-        for (int it = 0, tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
-            const int as = it & 1;
-            const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+        uint32_t aph = 0;
+        for (int tile = blockIdx.x + e * gridDim.x; tile < a.ntiles; tile += 2 * gridDim.x, aph ^= 1u) {
             const TileCoord t = decode_tile(a, tile);
             const bool valid = (t.oy0 + py) < p.Hout && (t.ox0 + px) < p.Wout;
             if (a.temb_per_row) {   // explicit per-row noise levels (sddm_eps with a noise_level vector)
-                epi_bar();
-                for (int c = tid; c < p.Cout; c += kEpiThreads) {
+                group_bar(bar_id);
+                for (int c = m; c < p.Cout; c += 128) {
                     float v = __ldg(p.bias + c) + __ldg(p.temb + (int64_t)t.n * p.temb_stride + c);
                     if (a.n_res) v += __ldg(p.res_bias + c);
-                    hdr->addv[c] = v;
+                    hdr->addv[e][c] = v;
                 }
-                epi_bar();
+                group_bar(bar_id);
             }
-            mbar_wait(smem_u32(&hdr->tmem_full[as]), aph);
+            mbar_wait_t(smem_u32(&hdr->tmem_full[e]), aph, tr, tw[0]);
             tc_fence_after();
-            const uint32_t tacc = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * a.acc_stride);
+            const uint32_t tacc = tmem_base + ((uint32_t)(w4 * 32) << 16) + (uint32_t)(e * a.acc_stride);
             for (int cb = 0; cb < nblk; ++cb, ++g) {
                 const uint32_t obuf = obuf0 + (uint32_t)(a.NOUT == 2 ? (g & 1) : 0) * kOutTileBytes;
-                if (tid == 0) {   // the TMA store that last read this staging buffer is done with it
+                const long long tb0 = tr ? clock64() : 0;
+                if (leader) {   // the TMA store that last read this staging buffer is done with it
                     if (a.NOUT == 2) bulk_wait_read_1(); else bulk_wait_read_0();
                 }
-                epi_bar();
-                if (has_res && tid == 0 && g + a.NRES - 1 < total_blocks) issue_res(g + a.NRES - 1);
+                if (tr) tw[2] += clock64() - tb0;
+                group_bar(bar_id);
+                if (tr) tw[3] += clock64() - tb0;
+                if (has_res && leader && g + a.NRES - 1 < total_blocks) issue_res(g + a.NRES - 1);
                 float v[32];
                 tmem_ld32(tacc + (uint32_t)(cb * 32), v);
+                if (cb == nblk - 1) {   // accumulator fully drained: hand the TMEM stage back to the MMA warp early
+                    tc_fence_before();
+                    mbar_arrive(smem_u32(&hdr->tmem_empty[e]));
+                }
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     const uint4 u = lds128(addv_u32 + (uint32_t)(cb * 32 + q * 4) * 4u);
@@ -317,7 +362,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
                 }
                 if (has_res) {
                     const int buf = g % a.NRES;
-                    mbar_wait(smem_u32(&hdr->res_full[buf]), (uint32_t)(g / a.NRES) & 1u);
+                    mbar_wait_t(smem_u32(&hdr->res_full[e][buf]), (uint32_t)(g / a.NRES) & 1u, tr, tw[1]);
                     const uint32_t rrow = rbuf0 + (uint32_t)buf * kOutTileBytes + (uint32_t)m * 128u;
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
@@ -339,107 +384,122 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
                     sts128(orow + (uint32_t)((q ^ (m & 7)) << 4), u);
                 }
                 fence_async_smem();
-                epi_bar();
-                if (tid == 0) {
+                group_bar(bar_id);
+                if (leader) {
                     tma_store_4d(&maps.out, obuf, cb * 32, t.ox0, t.oy0, t.n);
                     bulk_commit();
                 }
                 if (p.parts) {   // column sums of the staged tile: channel = lane, pixel quarter = warp
                     float s1 = 0.f, s2 = 0.f;
-                    const uint32_t col = obuf + (uint32_t)(lane & 3) * 4u;
-#pragma unroll 8
+                    const uint32_t qbase = obuf + (uint32_t)(w4 * 32) * 128u;
+#pragma unroll
                     for (int r = 0; r < 32; ++r) {
-                        const int row = warp * 32 + r;
-                        const float x = lds32(col + (uint32_t)row * 128u + (uint32_t)(((lane >> 2) ^ (row & 7)) << 4));
+                        const float x = lds32(qbase + (uint32_t)r * 128u + coloff[r & 7]);
                         s1 += x;
                         s2 = fmaf(x, x, s2);
                     }
-                    float2* dst = reinterpret_cast<float2*>(p.parts) + ((int64_t)t.n * p.nparts + t.trem * 4 + warp) * p.Cout + cb * 32 + lane;
+                    float2* dst = reinterpret_cast<float2*>(p.parts) + ((int64_t)t.n * p.nparts + t.trem * 4 + w4) * p.Cout + cb * 32 + lane;
                     *dst = make_float2(s1, s2);
                 }
             }
-            tc_fence_before();
-            mbar_arrive(smem_u32(&hdr->tmem_empty[as]));
         }
-        if (tid == 0) bulk_wait_all();
-    } else if (warp == 4) {
-        // ============================== MMA issuer (one thread) ===========================================
-        if (lane == 0) {
-            constexpr int KS = G::SLAB / 16;
-            const uint32_t idesc = make_idesc(p.Cout);
-            const uint32_t b_lbo = (uint32_t)p.Cout * 16u, b_sbo = 128u;
-            const uint32_t a_lbo = (uint32_t)G::PLANE * 16u, a_sbo = (uint32_t)G::SBO;
-            const uint32_t a_ring = base_u32 + a.off_a, w_ring = base_u32 + a.off_w;
-            int sa = 0, sw = 0;
-            uint32_t pa = 0, pw = 0;
-            for (int it = 0, tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
-                const int as = it & 1;
-                const uint32_t aph = (uint32_t)(it >> 1) & 1u;
-                mbar_wait(smem_u32(&hdr->tmem_empty[as]), aph ^ 1u);
+        if (leader) bulk_wait_all();
+        if (tr && leader) {
+            long long* o = a.trace + (e == 0 ? 0 : 8);
+            o[0] = clock64() - t_begin; o[1] = tw[0]; o[2] = tw[1]; o[3] = tw[2]; o[4] = tw[3]; o[5] = my_tiles;
+        }
+    } else if (warp == kMmaWarp) {
+        // ============================== MMA issuer ========================================================
+        // The whole warp runs the (warp-uniform) control flow so that descriptors live in uniform registers; one elected
+        // lane issues the tcgen05.mma / tcgen05.commit instructions.
+        constexpr int KS = G::SLAB / 16;
+        constexpr int CPK = 9 / TPC;                         // weight chunks per 16-channel K step
+        const uint32_t idesc = make_idesc(p.Cout);
+        const uint32_t b_lbo = (uint32_t)p.Cout * 16u, b_sbo = 128u;
+        const uint32_t a_lbo = (uint32_t)G::PLANE * 16u, a_sbo = (uint32_t)G::SBO;
+        const uint64_t a_desc0 = make_desc(base_u32 + a.off_a, a_lbo, a_sbo);
+        const uint64_t w_desc0 = make_desc(base_u32 + a.off_w, b_lbo, b_sbo);
+        const uint32_t a_step = a.a_stage >> 4, w_step = a.w_stage >> 4, tap_step = 2u * (uint32_t)p.Cout;   // in 16-byte units
+        int sa = 0, sw = 0;
+        uint32_t pa = 0, pw = 0;
+        bool w_ready = false;   // resident weights: all chunks have landed (after the first tile)
+        for (int it = 0, tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
+            const int as = it & 1;
+            const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+            mbar_wait_t(smem_u32(&hdr->tmem_empty[as]), aph ^ 1u, tr, tw[0]);
+            const uint32_t d_tmem = tmem_base + (uint32_t)(as * a.acc_stride);
+            uint32_t acc = 0;
+            for (int ai = 0; ai < a.n_main; ++ai) {
+                mbar_wait_t(smem_u32(&hdr->full_a[sa]), pa, tr, tw[1]);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(as * a.acc_stride);
-                uint32_t acc = 0;
-                for (int ai = 0; ai < a.n_main; ++ai) {
-                    mbar_wait(smem_u32(&hdr->full_a[sa]), pa);
-                    const uint32_t a_stage = a_ring + (uint32_t)sa * a.a_stage;
+                const uint64_t adesc = a_desc0 + (uint64_t)((uint32_t)sa * a_step);
 #pragma unroll
-                    for (int h = 0; h < KS; ++h) {
-                        const int c = ai * KS + h;
+                for (int h = 0; h < KS; ++h) {
+#pragma unroll
+                    for (int q = 0; q < CPK; ++q) {
+                        const int c = (ai * KS + h) * CPK + q;
                         int wslot;
-                        if (a.resident) { wslot = c; mbar_wait(smem_u32(&hdr->full_w[c]), 0u); }
-                        else { wslot = sw; mbar_wait(smem_u32(&hdr->full_w[sw]), pw); }
-                        tc_fence_after();
-                        const uint32_t w_stage = w_ring + (uint32_t)wslot * a.w_stage;
-                        const uint32_t a_half = a_stage + (uint32_t)h * 2u * a_lbo;
+                        if (a.resident) {
+                            wslot = c;
+                            if (!w_ready) { mbar_wait_t(smem_u32(&hdr->full_w[c]), 0u, tr, tw[2]); tc_fence_after(); }
+                        } else {
+                            wslot = sw;
+                            mbar_wait_t(smem_u32(&hdr->full_w[sw]), pw, tr, tw[2]);
+                            tc_fence_after();
+                        }
+                        const uint64_t wdesc = w_desc0 + (uint64_t)((uint32_t)wslot * w_step);
+                        if (elect_one()) {
 #pragma unroll
-                        for (int tap = 0; tap < 9; ++tap) {
-                            const int ky = tap / 3, kx = tap - 3 * ky;
-                            uint32_t aoff;
-                            if (MODE == CONV_S2) aoff = (uint32_t)(ky * G::PW + (kx == 1 ? 9 : (kx >> 1))) * 16u;
-                            else aoff = (uint32_t)(ky * G::PW + kx) * 16u;
-                            umma(d_tmem, make_desc(a_half + aoff, a_lbo, a_sbo),
-                                 make_desc(w_stage + (uint32_t)tap * 2u * b_lbo, b_lbo, b_sbo), idesc, acc);
-                            acc = 1;
+                            for (int tt = 0; tt < TPC; ++tt) {
+                                const int tap = q * TPC + tt, ky = tap / 3, kx = tap - 3 * ky;
+                                const int aslot = (MODE == CONV_S2) ? ky * G::PW + (kx == 1 ? 9 : (kx >> 1)) : ky * G::PW + kx;
+                                umma(d_tmem, adesc + (uint64_t)(uint32_t)(h * 2 * G::PLANE + aslot), wdesc + (uint64_t)((uint32_t)tt * tap_step),
+                                     idesc, acc);
+                                acc = 1;
+                            }
+                            if (!a.resident) umma_commit(smem_u32(&hdr->empty_w[sw]));
                         }
-                        if (!a.resident) {
-                            umma_commit(smem_u32(&hdr->empty_w[sw]));
-                            if (++sw == a.NW) { sw = 0; pw ^= 1u; }
-                        }
+                        acc = 1;
+                        if (!a.resident && ++sw == a.NW) { sw = 0; pw ^= 1u; }
                     }
-                    umma_commit(smem_u32(&hdr->empty_a[sa]));
-                    if (++sa == a.NA) { sa = 0; pa ^= 1u; }
                 }
-                // 1x1 res_conv over the raw block input: centre tap of a stride-1 halo slab (32 channels per slab,
-                // up to 128 channels = 4 slabs per weight chunk)
-                int wslot = 0;
-                for (int ar = 0; ar < a.n_res; ++ar) {
-                    mbar_wait(smem_u32(&hdr->full_a[sa]), pa);
-                    const uint32_t a_stage = a_ring + (uint32_t)sa * a.a_stage;
-                    const int sub = ar & 3;
-                    if (sub == 0) {
-                        const int c = a.n_main_chunks + (ar >> 2);
-                        if (a.resident) { wslot = c; mbar_wait(smem_u32(&hdr->full_w[c]), 0u); }
-                        else { wslot = sw; mbar_wait(smem_u32(&hdr->full_w[sw]), pw); }
-                    }
+                if (elect_one()) umma_commit(smem_u32(&hdr->empty_a[sa]));
+                if (++sa == a.NA) { sa = 0; pa ^= 1u; }
+            }
+            // 1x1 res_conv over the raw block input: centre tap of a stride-1 halo slab, one weight chunk per 32-channel slab
+            for (int ar = 0; ar < a.n_res; ++ar) {
+                mbar_wait_t(smem_u32(&hdr->full_a[sa]), pa, tr, tw[1]);
+                tc_fence_after();
+                const uint64_t adesc = a_desc0 + (uint64_t)((uint32_t)sa * a_step + (uint32_t)(G::PW + 1));
+                const int c = a.n_main_chunks + ar;
+                int wslot;
+                if (a.resident) {
+                    wslot = c;
+                    if (!w_ready) { mbar_wait_t(smem_u32(&hdr->full_w[c]), 0u, tr, tw[2]); tc_fence_after(); }
+                } else {
+                    wslot = sw;
+                    mbar_wait_t(smem_u32(&hdr->full_w[sw]), pw, tr, tw[2]);
                     tc_fence_after();
-                    const uint32_t w_stage = w_ring + (uint32_t)wslot * a.w_stage;
+                }
+                const uint64_t wdesc = w_desc0 + (uint64_t)((uint32_t)wslot * w_step);
+                if (elect_one()) {
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        umma(d_tmem, make_desc(a_stage + (uint32_t)h * 2u * a_lbo + (uint32_t)(G::PW + 1) * 16u, a_lbo, a_sbo),
-                             make_desc(w_stage + (uint32_t)(sub * 2 + h) * 2u * b_lbo, b_lbo, b_sbo), idesc, acc);
+                        umma(d_tmem, adesc + (uint64_t)(uint32_t)(h * 2 * G::PLANE), wdesc + (uint64_t)((uint32_t)h * tap_step), idesc, acc);
                         acc = 1;
                     }
-                    if (!a.resident && (sub == 3 || ar == a.n_res - 1)) {
-                        umma_commit(smem_u32(&hdr->empty_w[sw]));
-                        if (++sw == a.NW) { sw = 0; pw ^= 1u; }
-                    }
+                    if (!a.resident) umma_commit(smem_u32(&hdr->empty_w[sw]));
                     umma_commit(smem_u32(&hdr->empty_a[sa]));
-                    if (++sa == a.NA) { sa = 0; pa ^= 1u; }
                 }
-                umma_commit(smem_u32(&hdr->tmem_full[as]));
+                acc = 1;
+                if (!a.resident && ++sw == a.NW) { sw = 0; pw ^= 1u; }
+                if (++sa == a.NA) { sa = 0; pa ^= 1u; }
             }
+            if (elect_one()) umma_commit(smem_u32(&hdr->tmem_full[as]));
+            w_ready = true;
         }
-    } else if (warp == 5) {
+        if (tr && lane == 0) { long long* o = a.trace + 16; o[0] = clock64() - t_begin; o[1] = tw[0]; o[2] = tw[1]; o[3] = tw[2]; }
+    } else if (warp == kWldWarp) {
         // ============================== weight loader (one thread) ========================================
         if (lane == 0) {
             const int nchunks = a.n_main_chunks + a.n_res_chunks;
@@ -454,14 +514,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
                     if (!a.resident) mbar_wait(smem_u32(&hdr->empty_w[sw]), pw ^ 1u);
                     uint32_t bytes;
                     const void* src;
-                    if (!is_res) {
-                        bytes = 288u * (uint32_t)p.Cout;
-                        src = p.w_tc + (size_t)c * 144 * p.Cout;
+                    if (!is_res) {   // packed [Cin/16][tap][2][Cout][8]: filter row ky of chunk c16 is contiguous: TPC taps = 32*TPC*Cout bytes
+                        bytes = 32u * TPC * (uint32_t)p.Cout;
+                        src = p.w_tc + (size_t)c * 16 * TPC * p.Cout;
                     } else {
-                        const int c0 = (c - a.n_main_chunks) * 128;
-                        const int nch = (p.res_Cin - c0) < 128 ? (p.res_Cin - c0) : 128;
-                        bytes = (uint32_t)nch * 2u * (uint32_t)p.Cout;
-                        src = p.res_w_tc + (size_t)c0 * p.Cout;
+                        bytes = 64u * (uint32_t)p.Cout;
+                        src = p.res_w_tc + (size_t)(c - a.n_main_chunks) * 32 * p.Cout;
                     }
                     const uint32_t bar = smem_u32(&hdr->full_w[wslot]);
                     mbar_expect_tx(bar, bytes);
@@ -470,7 +528,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
                 }
             }
         }
-    } else if (warp == 6) {
+    } else if (warp == kTmaWarp) {
         // ============================== raw-slab TMA issuer (one thread) ==================================
         if (lane == 0) {
             constexpr uint32_t RAW_BYTES = (uint32_t)G::RAW_H * G::RAW_W * G::SLAB * 4u;
@@ -487,40 +545,34 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
                     const int s = (cbase < srcs[0].C) ? 0 : 1;
                     const int coff = cbase - (s ? srcs[0].C : 0);
                     const uint32_t bar = smem_u32(&hdr->raw_full[rs]);
-                    mbar_wait(smem_u32(&hdr->raw_empty[rs]), pr ^ 1u);
+                    mbar_wait_t(smem_u32(&hdr->raw_empty[rs]), pr ^ 1u, tr, tw[0]);
                     mbar_expect_tx(bar, is_res ? 18u * 10u * 32u * 4u : RAW_BYTES);
                     tma_load_4d(raw_ring + (uint32_t)rs * a.raw_stage, &maps.src[(is_res ? 2 : 0) + s], coff,
                                 is_res ? t.ox0 - 1 : xo, is_res ? t.oy0 - 1 : yo, t.n, bar);
                     if (++rs == a.NR) { rs = 0; pr ^= 1u; }
                 }
             }
+            if (tr) { long long* o = a.trace + 24; o[0] = clock64() - t_begin; o[1] = tw[0]; }
         }
     } else if (warp >= kXfWarp0) {
         // ============================== transform: raw fp32 slab -> bf16 operand slab ====================
+        // group gi handles the slabs gi, gi + kXfGroups, ... of the CTA's (tile, slab) sequence, so kXfGroups slabs are
+        // in flight at once.  32-channel raw slabs are 128B-swizzled by the TMA (16-byte chunk c of pixel p sits at
+        // chunk c ^ (p & 7)): reading chunks 2j and 2j+1 of consecutive pixels is bank-conflict free.
         constexpr int NPL = G::SLAB / 8;                       // k8 planes per slab
-        constexpr int PSTEP = kXfThreads / NPL;                // pixels covered per round
-        constexpr int PIXB = G::SLAB * 4;                      // raw bytes per pixel
-        const int ptid = tid - kXfWarp0 * 32;
-        const int j = ptid % NPL;
-        const int pix0 = ptid / NPL;
+        const int gi = (warp - kXfWarp0) >> 2;
+        const int gt = tid - (kXfWarp0 * 32 + gi * kXfGroupThreads);   // thread within the group
         const uint32_t raw_ring = base_u32 + a.off_raw, a_ring = base_u32 + a.off_a;
-        int rs = 0, sa = 0;
-        uint32_t pr = 0, pa = 0;
-        const float kNegLog2e = -1.4426950408889634f;
 
-        // one 8-channel item: raw fp32 -> (affine, swish) -> masked -> packed bf16
-        auto convert = [&](uint32_t raw_addr, bool swap, bool ok, bool affine, const float (&sc)[8], const float (&sh)[8],
-                           const float (&sc2)[8], const float (&sh2)[8]) -> uint4 {
-            const uint4 lo = lds128(raw_addr + (swap ? 16u : 0u)), hi = lds128(raw_addr + (swap ? 0u : 16u));
-            const uint4 u0 = swap ? hi : lo, u1 = swap ? lo : hi;
+        // one 8-channel item: raw fp32 -> (affine, swish) -> masked -> packed bf16.   swish(y) = h + h * tanh(h), h = y / 2
+        auto convert = [&](const uint4 u0, const uint4 u1, bool ok, bool affine, const float (&sch)[8], const float (&shh)[8]) -> uint4 {
             float f[8] = {__uint_as_float(u0.x), __uint_as_float(u0.y), __uint_as_float(u0.z), __uint_as_float(u0.w),
                           __uint_as_float(u1.x), __uint_as_float(u1.y), __uint_as_float(u1.z), __uint_as_float(u1.w)};
             if (affine) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                    const float y = fmaf(f[k], sc[k], sh[k]);
-                    const float e = exp2f(fmaf(f[k], sc2[k], sh2[k]));     // exp(-y)
-                    f[k] = __fdividef(y, 1.0f + e);                        // y * sigmoid(y)
+                    const float h = fmaf(f[k], sch[k], shh[k]);
+                    f[k] = fmaf(h, tanh_approx(h), h);
                 }
             }
             uint4 o = make_uint4(0u, 0u, 0u, 0u);
@@ -528,41 +580,54 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
             return o;
         };
 
+        int k_slab = 0;   // CTA-wide slab counter
         for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-            const TileCoord t = decode_tile(a, tile);
-            for (int ai = 0; ai < nA; ++ai) {
+            TileCoord t;
+            bool have_t = false;
+            for (int ai = 0; ai < nA; ++ai, ++k_slab) {
+                if ((k_slab % kXfGroups) != gi) continue;
+                if (!have_t) { t = decode_tile(a, tile); have_t = true; }
+                const int rs = k_slab % a.NR, sa = k_slab % a.NA;
+                const uint32_t pr = (uint32_t)(k_slab / a.NR) & 1u, pa = (uint32_t)(k_slab / a.NA) & 1u;
                 const bool is_res = ai >= a.n_main;
+                const bool s1_like = is_res || MODE == CONV_S1;
+                const int npl = s1_like ? 4 : NPL;
+                const int j = gt % npl, pix0 = gt / npl, pstep = kXfGroupThreads / npl;
                 const int cbase = is_res ? (ai - a.n_main) * 32 : ai * G::SLAB;
                 const ConvSrc* srcs = is_res ? p.res_src : p.src;
                 const int s = (cbase < srcs[0].C) ? 0 : 1;
                 const bool affine = !is_res && srcs[s].scale != nullptr;
-                float sc[8], sh[8], sc2[8], sh2[8];
+                float sch[8], shh[8];
                 if (affine) {
                     const float4* sp = reinterpret_cast<const float4*>(srcs[s].scale + (int64_t)t.n * p.Cin + cbase + j * 8);
                     const float4* hp = reinterpret_cast<const float4*>(srcs[s].shift + (int64_t)t.n * p.Cin + cbase + j * 8);
                     const float4 s0 = __ldg(sp), s1 = __ldg(sp + 1), h0 = __ldg(hp), h1 = __ldg(hp + 1);
-                    sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
-                    sh[0] = h0.x; sh[1] = h0.y; sh[2] = h0.z; sh[3] = h0.w; sh[4] = h1.x; sh[5] = h1.y; sh[6] = h1.z; sh[7] = h1.w;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) { sc2[k] = sc[k] * kNegLog2e; sh2[k] = sh[k] * kNegLog2e; }
+                    sch[0] = 0.5f * s0.x; sch[1] = 0.5f * s0.y; sch[2] = 0.5f * s0.z; sch[3] = 0.5f * s0.w;
+                    sch[4] = 0.5f * s1.x; sch[5] = 0.5f * s1.y; sch[6] = 0.5f * s1.z; sch[7] = 0.5f * s1.w;
+                    shh[0] = 0.5f * h0.x; shh[1] = 0.5f * h0.y; shh[2] = 0.5f * h0.z; shh[3] = 0.5f * h0.w;
+                    shh[4] = 0.5f * h1.x; shh[5] = 0.5f * h1.y; shh[6] = 0.5f * h1.z; shh[7] = 0.5f * h1.w;
                 }
                 // valid window of the raw box (in box coordinates): everything else is zero padding
                 int yo, xo, rh, rw;
-                if (is_res || MODE == CONV_S1) { yo = t.oy0 - 1; xo = t.ox0 - 1; rh = 18; rw = 10; }
+                if (s1_like) { yo = t.oy0 - 1; xo = t.ox0 - 1; rh = 18; rw = 10; }
                 else { yo = org_of<MODE>(t.oy0); xo = org_of<MODE>(t.ox0); rh = G::RAW_H; rw = G::RAW_W; }
                 const int ylo = yo < 0 ? -yo : 0, xlo = xo < 0 ? -xo : 0;
                 const int yhi = (p.Hin - yo) < rh ? (p.Hin - yo) : rh, xhi = (p.Win - xo) < rw ? (p.Win - xo) : rw;
 
-                mbar_wait(smem_u32(&hdr->raw_full[rs]), pr);
-                mbar_wait(smem_u32(&hdr->empty_a[sa]), pa ^ 1u);
+                mbar_wait_t(smem_u32(&hdr->raw_full[rs]), pr, tr, tw[0]);
+                mbar_wait_t(smem_u32(&hdr->empty_a[sa]), pa ^ 1u, tr, tw[1]);
                 const uint32_t raw = raw_ring + (uint32_t)rs * a.raw_stage;
                 const uint32_t opd = a_ring + (uint32_t)sa * a.a_stage + (uint32_t)j * (uint32_t)G::PLANE * 16u;
                 if (MODE == CONV_UP && !is_res) {
-                    if (pix0 < G::RAW_H * G::RAW_W) {
-                        const int ry = pix0 / G::RAW_W, rx = pix0 - ry * G::RAW_W;
+                    constexpr int NPIX = G::RAW_H * G::RAW_W;
+#pragma unroll
+                    for (int r = 0; r < (NPIX + 31) / 32; ++r) {
+                        const int pix = pix0 + r * pstep;
+                        if (pix >= NPIX) break;
+                        const int ry = pix / G::RAW_W, rx = pix - ry * G::RAW_W;
                         const bool ok = ry >= ylo && ry < yhi && rx >= xlo && rx < xhi;
-                        const uint32_t ra = raw + (uint32_t)pix0 * PIXB + (uint32_t)j * 32u;
-                        const uint4 o = convert(ra, ((pix0 * PIXB) >> 7) & 1, ok, affine, sc, sh, sc2, sh2);
+                        const uint32_t ra = raw + (uint32_t)pix * 128u + (uint32_t)(((2 * j) ^ (pix & 7)) << 4);
+                        const uint4 o = convert(lds128(ra), lds128(ra ^ 16u), ok, affine, sch, shh);
 #pragma unroll
                         for (int dy = 0; dy < 2; ++dy) {
                             const int hy = 2 * ry - 1 + dy;
@@ -576,45 +641,44 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
                         }
                     }
                 } else if (MODE == CONV_S2) {
-                    constexpr int NPIX = G::RAW_H * G::RAW_W, ROUNDS = (NPIX + PSTEP - 1) / PSTEP;
+                    constexpr int NPIX = G::RAW_H * G::RAW_W, PST = kXfGroupThreads / NPL, ROUNDS = (NPIX + PST - 1) / PST;
 #pragma unroll
                     for (int r = 0; r < ROUNDS; ++r) {
-                        const int pix = pix0 + r * PSTEP;
+                        const int pix = pix0 + r * PST;
                         if (pix >= NPIX) break;
                         const int hy = pix / G::RAW_W, hx = pix - hy * G::RAW_W;
                         const bool ok = hy >= ylo && hy < yhi && hx >= xlo && hx < xhi;
-                        const uint32_t ra = raw + (uint32_t)pix * PIXB + (uint32_t)j * 32u;
-                        const uint4 o = convert(ra, ((pix * PIXB) >> 7) & 1, ok, affine, sc, sh, sc2, sh2);
+                        const uint32_t ra = raw + (uint32_t)pix * 64u + (uint32_t)j * 32u;   // unswizzled 64-byte pixels
+                        const bool swap = (pix >> 1) & 1;
+                        const uint4 lo = lds128(ra + (swap ? 16u : 0u)), hi = lds128(ra + (swap ? 0u : 16u));
+                        const uint4 o = convert(swap ? hi : lo, swap ? lo : hi, ok, affine, sch, shh);
                         const int slot = hy * G::PW + ((hx & 1) ? 9 + (hx >> 1) : (hx >> 1));
                         sts128(opd + (uint32_t)slot * 16u, o);
                     }
                 } else {   // stride-1 halo (main conv of CONV_S1, res_conv slabs)
-                    constexpr int NPIX = 18 * 10, PST = kXfThreads / 4, ROUNDS = (NPIX + PST - 1) / PST;
-                    const int jj = ptid & 3, pp = ptid >> 2;   // res slabs always have 4 planes of 32 raw channels
-                    const uint32_t opd4 = a_ring + (uint32_t)sa * a.a_stage + (uint32_t)jj * (uint32_t)G::PLANE * 16u;
+                    constexpr int NPIX = 18 * 10, PST = kXfGroupThreads / 4, ROUNDS = (NPIX + PST - 1) / PST;
 #pragma unroll
                     for (int r = 0; r < ROUNDS; ++r) {
-                        const int pix = pp + r * PST;
+                        const int pix = pix0 + r * PST;
                         if (pix >= NPIX) break;
                         const int hy = pix / 10, hx = pix - hy * 10;
                         const bool ok = hy >= ylo && hy < yhi && hx >= xlo && hx < xhi;
-                        const uint32_t ra = raw + (uint32_t)pix * 128u + (uint32_t)jj * 32u;
-                        const uint4 o = convert(ra, pix & 1, ok, affine, sc, sh, sc2, sh2);
-                        sts128(opd4 + (uint32_t)pix * 16u, o);
+                        const uint32_t ra = raw + (uint32_t)pix * 128u + (uint32_t)(((2 * j) ^ (pix & 7)) << 4);
+                        const uint4 o = convert(lds128(ra), lds128(ra ^ 16u), ok, affine, sch, shh);
+                        sts128(opd + (uint32_t)pix * 16u, o);
                     }
                 }
                 fence_async_smem();
                 mbar_arrive(smem_u32(&hdr->full_a[sa]));
                 mbar_arrive(smem_u32(&hdr->raw_empty[rs]));
-                if (++rs == a.NR) { rs = 0; pr ^= 1u; }
-                if (++sa == a.NA) { sa = 0; pa ^= 1u; }
             }
         }
+        if (tr && gt == 0) { long long* o = a.trace + 32 + 8 * gi; o[0] = clock64() - t_begin; o[1] = tw[0]; o[2] = tw[1]; }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == kMmaWarp) {
         __syncwarp();
         tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
     }
@@ -681,6 +745,9 @@ int num_sms() {
     return n;
 }
 
+long long* g_trace = nullptr;   // device buffer [64 launches][48 counters], set by sddm_debug_tc_trace
+int g_trace_launch = 0;
+
 constexpr size_t kSmemMax = 232448;   // 227 KB opt-in limit per CTA on sm_100
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
@@ -718,43 +785,49 @@ int encode_nhwc(CUtensorMap* m, const float* base, int B, int H, int W, int C, i
 
 inline size_t align_up_sz(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-template <int MODE>
-int launch_mode(TcArgs& a, cudaStream_t st) {
+// returns 1 when the shared-memory plan does not fit with TPC taps per weight chunk (the caller retries with smaller chunks)
+template <int MODE, int TPC>
+int launch_mode(TcArgs a, cudaStream_t st) {
     using G = Geo<MODE>;
     const ConvP& p = a.p;
     a.n_main = p.Cin / G::SLAB;
-    a.n_main_chunks = p.Cin / 16;
+    a.n_main_chunks = (9 / TPC) * (p.Cin / 16);
     a.raw_stage = (uint32_t)align_up_sz((size_t)G::RAW_H * G::RAW_W * G::SLAB * 4, 1024);
     if (a.n_res && a.raw_stage < 18u * 10u * 32u * 4u) a.raw_stage = (uint32_t)align_up_sz(18 * 10 * 32 * 4, 1024);
     a.a_stage = (uint32_t)align_up_sz((size_t)(G::SLAB / 8) * G::PLANE * 16, 128);
     if (a.n_res && a.a_stage < 4u * 181u * 16u) a.a_stage = (uint32_t)align_up_sz(4 * 181 * 16, 128);
-    a.w_stage = 288u * (uint32_t)p.Cout;
+    a.w_stage = 32u * TPC * (uint32_t)p.Cout;
     const int nchunks = a.n_main_chunks + a.n_res_chunks;
-    // shared-memory plan: header | out staging (2 tiles) | residual ring | raw ring | operand ring | weights
+    const int nblk = p.Cout / 32;
+    // shared-memory plan: header | out staging (per epilogue group) | residual ring (per group) | raw ring | operand ring |
+    // weights.  Ring depth is worth more than epilogue double buffering: try the staging variants and keep the deepest rings.
     const size_t cap = kSmemMax - 1024;   // slack for the 1024-byte alignment of the base
-    a.NR = 2; a.NA = 2;
-    auto fixed = [&]() { return (size_t)kHdrBytes + (size_t)a.NOUT * kOutTileBytes + (size_t)a.NRES * kOutTileBytes + (size_t)a.NR * a.raw_stage + (size_t)a.NA * a.a_stage; };
-    const int try_out[4] = {2, 2, 1, 1}, try_res[4] = {3, 2, 2, 1};
-    bool fits = false;
-    for (int k = 0; k < 4 && !fits; ++k) {   // shrink the epilogue staging before giving up
-        a.NOUT = try_out[k];
-        a.NRES = p.res_identity ? try_res[k] : 0;
-        a.resident = nchunks <= kMaxW && fixed() + (size_t)nchunks * a.w_stage <= cap;
-        a.NW = a.resident ? nchunks : (nchunks < 3 ? nchunks : 3);
-        if (!a.resident && fixed() + (size_t)a.NW * a.w_stage > cap) a.NW = 2;
-        fits = fixed() + (size_t)a.NW * a.w_stage <= cap;
-    }
-    if (!fits) { set_error("conv tc: Cout=%d does not fit the shared-memory plan", p.Cout); return SDDM_E_INVALID; }
+    auto fixed = [&]() { return (size_t)kHdrBytes + (size_t)kEpiGroups * (a.NOUT + a.NRES) * kOutTileBytes + (size_t)a.NR * a.raw_stage + (size_t)a.NA * a.a_stage; };
     auto total = [&]() { return fixed() + (size_t)a.NW * a.w_stage; };
-    for (bool grew = true; grew;) {   // spend what is left on deeper rings: raw slabs first (they hide the HBM latency)
-        grew = false;
-        if (a.NR < kMaxRing) { ++a.NR; if (total() <= cap) grew = true; else --a.NR; }
-        if (a.NA < kMaxRing && a.NA < a.NR) { ++a.NA; if (total() <= cap) grew = true; else --a.NA; }
-        if (!a.resident && a.NW < 8 && a.NW < nchunks) { ++a.NW; if (total() <= cap) grew = true; else --a.NW; }
+    const int want_out = nblk > 1 ? 2 : 1, want_res = p.res_identity ? 2 : 0;
+    const int try_out[3] = {want_out, 1, 1}, try_res[3] = {want_res, want_res, want_res ? 1 : 0};
+    int best_score = -1;
+    TcArgs best = a;
+    for (int k = 0; k < 3; ++k) {
+        a.NOUT = try_out[k]; a.NRES = try_res[k];
+        a.NR = 2; a.NA = 2;
+        a.resident = nchunks <= kMaxW && fixed() + (size_t)nchunks * a.w_stage <= cap;
+        a.NW = a.resident ? nchunks : (TPC == 9 ? 2 : 4);
+        if (total() > cap) continue;
+        for (bool grew = true; grew;) {   // spend what is left on deeper rings
+            grew = false;
+            if (a.NR < kMaxRing) { ++a.NR; if (total() <= cap) grew = true; else --a.NR; }
+            if (a.NA < kMaxRing && a.NA < a.NR) { ++a.NA; if (total() <= cap) grew = true; else --a.NA; }
+            if (!a.resident && a.NW < 12 && a.NW < nchunks) { ++a.NW; if (total() <= cap) grew = true; else --a.NW; }
+        }
+        const int score = (a.NR < 4 ? a.NR : 4) * 100 + (a.NA < 4 ? a.NA : 4) * 10 + (2 - k);
+        if (score > best_score) { best_score = score; best = a; }
     }
+    if (best_score < 0) return 1;
+    a = best;
     a.off_out = kHdrBytes;
-    a.off_res = a.off_out + (uint32_t)a.NOUT * kOutTileBytes;
-    a.off_raw = a.off_res + (uint32_t)a.NRES * kOutTileBytes;
+    a.off_res = a.off_out + (uint32_t)(kEpiGroups * a.NOUT) * kOutTileBytes;
+    a.off_raw = a.off_res + (uint32_t)(kEpiGroups * a.NRES) * kOutTileBytes;
     a.off_a = a.off_raw + (uint32_t)a.NR * a.raw_stage;
     a.off_w = a.off_a + (uint32_t)a.NA * a.a_stage;
     const size_t smem = total() + 1024;
@@ -762,21 +835,23 @@ int launch_mode(TcArgs& a, cudaStream_t st) {
     TcMaps maps;
     memset(&maps, 0, sizeof(maps));
     int rc;
+    const bool swz = G::SLAB == 32;   // 128-byte pixels: let the TMA swizzle the raw slab
     for (int i = 0; i < p.nsrc; ++i)
-        if ((rc = encode_nhwc(&maps.src[i], p.src[i].x, p.B, p.Hin, p.Win, p.src[i].C, G::SLAB, G::RAW_W, G::RAW_H, false))) return rc;
+        if ((rc = encode_nhwc(&maps.src[i], p.src[i].x, p.B, p.Hin, p.Win, p.src[i].C, G::SLAB, G::RAW_W, G::RAW_H, swz))) return rc;
     if (a.n_res)
         for (int i = 0; i < p.res_nsrc; ++i)
-            if ((rc = encode_nhwc(&maps.src[2 + i], p.res_src[i].x, p.B, p.Hin, p.Win, p.res_src[i].C, 32, 10, 18, false))) return rc;
+            if ((rc = encode_nhwc(&maps.src[2 + i], p.res_src[i].x, p.B, p.Hin, p.Win, p.res_src[i].C, 32, 10, 18, true))) return rc;
     if ((rc = encode_nhwc(&maps.out, p.out, p.B, p.Hout, p.Wout, p.Cout, 32, TW, TH, true))) return rc;
     if (p.res_identity && (rc = encode_nhwc(&maps.res, p.res_src[0].x, p.B, p.Hout, p.Wout, p.Cout, 32, TW, TH, true))) return rc;
 
     static bool attr_set = false;
     if (!attr_set) {
-        SDDM_CUDA_TRY(cudaFuncSetAttribute(conv3x3_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+        SDDM_CUDA_TRY(cudaFuncSetAttribute(conv3x3_tc_kernel<MODE, TPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
         attr_set = true;
     }
+    a.trace = g_trace ? g_trace + (size_t)(g_trace_launch++ % 64) * 48 : nullptr;
     const int grid = a.ntiles < num_sms() ? a.ntiles : num_sms();
-    conv3x3_tc_kernel<MODE><<<grid, kThreads, smem, st>>>(a, maps);
+    conv3x3_tc_kernel<MODE, TPC><<<grid, kThreads, smem, st>>>(a, maps);
     SDDM_LAUNCH_CHECK();
     return SDDM_OK;
 }
@@ -806,17 +881,22 @@ int launch_conv_tc(const ConvP& p, cudaStream_t st) {
     a.tiles_x = (p.Wout + TW - 1) / TW;
     a.tiles_y = (p.Hout + TH - 1) / TH;
     a.ntiles = p.B * a.tiles_x * a.tiles_y;
+    a.magic_per = (0x100000000ull + (unsigned long long)(a.tiles_x * a.tiles_y) - 1) / (unsigned long long)(a.tiles_x * a.tiles_y);
+    a.magic_tx = (0x100000000ull + (unsigned long long)a.tiles_x - 1) / (unsigned long long)a.tiles_x;
     if (p.parts && p.nparts != a.tiles_x * a.tiles_y * 4) { set_error("conv tc: nparts mismatch"); return SDDM_E_INVALID; }
     a.n_res = has_res_conv ? p.res_Cin / 32 : 0;
-    a.n_res_chunks = has_res_conv ? (p.res_Cin + 127) / 128 : 0;
+    a.n_res_chunks = has_res_conv ? p.res_Cin / 32 : 0;
     a.acc_stride = p.Cout <= 32 ? 32 : (p.Cout <= 64 ? 64 : (p.Cout <= 128 ? 128 : 256));
     a.tmem_cols = 2 * a.acc_stride;
     a.temb_per_row = (p.temb && p.temb_stride != 0) ? 1 : 0;
+    int rc;
     switch (p.mode) {
-        case CONV_S1: return launch_mode<CONV_S1>(a, st);
-        case CONV_S2: return launch_mode<CONV_S2>(a, st);
-        default: return launch_mode<CONV_UP>(a, st);
+        case CONV_S1: rc = launch_mode<CONV_S1, 9>(a, st); if (rc == 1) rc = launch_mode<CONV_S1, 3>(a, st); break;
+        case CONV_S2: rc = launch_mode<CONV_S2, 9>(a, st); if (rc == 1) rc = launch_mode<CONV_S2, 3>(a, st); break;
+        default: rc = launch_mode<CONV_UP, 9>(a, st); if (rc == 1) rc = launch_mode<CONV_UP, 3>(a, st); break;
     }
+    if (rc == 1) { set_error("conv tc: Cout=%d does not fit the shared-memory plan", p.Cout); return SDDM_E_INVALID; }
+    return rc;
 }
 
 }  // namespace sddm
@@ -867,5 +947,23 @@ extern "C" SDDM_API int sddm_debug_umma_probe(int variant, int N, int K, float* 
             if (err > worst) worst = err;
         }
     *max_err_host = worst;
+    return SDDM_OK;
+}
+
+// debug: enable != 0 -> (re)start tracing: the next 64 conv_tc launches record per-role wait cycles of CTA 0;
+// enable == 0 -> copy the [64][48] counters to host_out (may be null) and stop tracing.
+extern "C" SDDM_API int sddm_debug_tc_trace(int enable, long long* host_out) {
+    using namespace sddm;
+    if (enable) {
+        if (!g_trace) SDDM_CUDA_TRY(cudaMalloc(&g_trace, 64 * 48 * sizeof(long long)));
+        SDDM_CUDA_TRY(cudaMemset(g_trace, 0, 64 * 48 * sizeof(long long)));
+        g_trace_launch = 0;
+        return SDDM_OK;
+    }
+    if (!g_trace) { set_error("tracing was not enabled"); return SDDM_E_STATE; }
+    SDDM_CUDA_TRY(cudaDeviceSynchronize());
+    if (host_out) SDDM_CUDA_TRY(cudaMemcpy(host_out, g_trace, 64 * 48 * sizeof(long long), cudaMemcpyDeviceToHost));
+    cudaFree(g_trace);
+    g_trace = nullptr;
     return SDDM_OK;
 }

@@ -14,6 +14,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--iters", type=int, default=2)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--trace", action="store_true", help="per-role wait-cycle trace of every tcgen05 conv launch of the last forward")
     args = ap.parse_args()
     import torch
     import __graft_entry__ as ge
@@ -39,6 +40,24 @@ def main():
         print("forward %d: %.3f ms (B=%d, %s)" % (it, e0.elapsed_time(e1), args.batch, args.precision))
         x = model.diffusion.p_transition(x, 100 - it, eps)
     torch.cuda.synchronize()
+    if args.trace:
+        import ctypes as C
+        import numpy as np
+        from sddm_b200 import _lib
+        lib = _lib.lib()
+        _lib.check(lib.sddm_debug_tc_trace(1, None))
+        plan.eps(cond, x, t=50)
+        buf = np.zeros((64, 48), dtype=np.int64)
+        _lib.check(lib.sddm_debug_tc_trace(0, C.c_void_p(buf.ctypes.data)))
+        print("conv#  role: total_cycles | waits...   (epilogue: tmem_full, res_full, store_read, store_read+bar, tiles; mma: tmem_empty, full_a, full_w; tma: raw_empty; xform: raw_full, empty_a)")
+        for i in range(64):
+            r = buf[i]
+            if r[16] == 0:
+                continue
+            f = lambda v: "%7.1fk" % (v / 1e3)
+            print("%2d epi0 %s | %s %s %s %s tiles=%d || mma %s | %s %s %s || tma %s | %s || xf0 %s | %s %s || xf1 %s | %s %s" % (
+                i, f(r[0]), f(r[1]), f(r[2]), f(r[3]), f(r[4]), r[5], f(r[16]), f(r[17]), f(r[18]), f(r[19]), f(r[24]), f(r[25]),
+                f(r[32]), f(r[33]), f(r[34]), f(r[40]), f(r[41]), f(r[42])))
     print("ok", float(x.abs().max()))
 
 
