@@ -611,6 +611,7 @@ static int run_unet(sddm_plan* p, const float* cond, const float* x_t, const flo
                 f.bias = p->final_bias;
                 f.frames = sect(p, ws, p->off_frames, B);
                 f.B = B; f.H = t.H; f.W = t.W; f.C = t.C;
+                f.fast_math = c.precision == SDDM_PREC_BF16;
                 rc = launch_final_conv(f, st);
                 break;
             }

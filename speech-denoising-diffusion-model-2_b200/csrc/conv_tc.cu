@@ -48,10 +48,12 @@ constexpr uint32_t kOutTileBytes = 128 * 32 * 4;       // one 128-pixel x 32-cha
 //   RAW_H x RAW_W raw box in INPUT pixels;  PH x PW  operand halo grid;  PLANE  slots (16 B) between k8 planes
 //   SBO           byte distance between consecutive 8-pixel groups of the M dimension (one output row)
 template <int MODE> struct Geo;
-template <> struct Geo<CONV_S1> { static constexpr int SLAB = 32, RAW_H = 18, RAW_W = 10, PH = 18, PW = 10, PLANE = 181, SBO = 10 * 16; };
-template <> struct Geo<CONV_UP> { static constexpr int SLAB = 32, RAW_H = 10, RAW_W = 6, PH = 18, PW = 10, PLANE = 181, SBO = 10 * 16; };
-template <> struct Geo<CONV_S2> { static constexpr int SLAB = 16, RAW_H = 33, RAW_W = 17, PH = 33, PW = 17, PLANE = 565, SBO = 2 * 17 * 16; };
-// PLANE = 5 (mod 8): the k8 planes of one pixel fall into disjoint shared-memory banks.
+//   EVEN_OFF      (stride 2 only) slot of the first even input column within an operand row (odd columns start at 0)
+template <> struct Geo<CONV_S1> { static constexpr int SLAB = 32, RAW_H = 18, RAW_W = 10, PH = 18, PW = 10, PLANE = 182, SBO = 10 * 16, EVEN_OFF = 0; };
+template <> struct Geo<CONV_UP> { static constexpr int SLAB = 32, RAW_H = 10, RAW_W = 6, PH = 18, PW = 10, PLANE = 182, SBO = 10 * 16, EVEN_OFF = 0; };
+template <> struct Geo<CONV_S2> { static constexpr int SLAB = 16, RAW_H = 33, RAW_W = 17, PH = 33, PW = 20, PLANE = 662, SBO = 2 * 20 * 16, EVEN_OFF = 12; };
+// PLANE = 6 (mod 8) slots: a quarter warp storing 2 consecutive pixels x 4 planes (or, stride 2, 4 pixels x 2 planes with the
+// even columns 12 slots after the odd ones) hits 8 distinct 16-byte bank groups.
 
 struct alignas(64) TcMaps {
     CUtensorMap src[4];   // main source 0 / 1, res_conv source 0 / 1 (32-channel boxes: 128B swizzle)
@@ -348,8 +350,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
                 group_bar(bar_id);
                 if (tr) tw[3] += clock64() - tb0;
                 if (has_res && leader && g + a.NRES - 1 < total_blocks) issue_res(g + a.NRES - 1);
+                const long long te0 = tr ? clock64() : 0;
                 float v[32];
                 tmem_ld32(tacc + (uint32_t)(cb * 32), v);
+                if (tr) tw[4] += clock64() - te0;
                 if (cb == nblk - 1) {   // accumulator fully drained: hand the TMEM stage back to the MMA warp early
                     tc_fence_before();
                     mbar_arrive(smem_u32(&hdr->tmem_empty[e]));
@@ -385,6 +389,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
                 }
                 fence_async_smem();
                 group_bar(bar_id);
+                if (tr) tw[5] += clock64() - te0;
                 if (leader) {
                     tma_store_4d(&maps.out, obuf, cb * 32, t.ox0, t.oy0, t.n);
                     bulk_commit();
@@ -406,7 +411,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
         if (leader) bulk_wait_all();
         if (tr && leader) {
             long long* o = a.trace + (e == 0 ? 0 : 8);
-            o[0] = clock64() - t_begin; o[1] = tw[0]; o[2] = tw[1]; o[3] = tw[2]; o[4] = tw[3]; o[5] = my_tiles;
+            o[0] = clock64() - t_begin; o[1] = tw[0]; o[2] = tw[1]; o[3] = tw[2]; o[4] = tw[3]; o[5] = my_tiles; o[6] = tw[4]; o[7] = tw[5];
         }
     } else if (warp == kMmaWarp) {
         // ============================== MMA issuer ========================================================
@@ -452,7 +457,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
 #pragma unroll
                             for (int tt = 0; tt < TPC; ++tt) {
                                 const int tap = q * TPC + tt, ky = tap / 3, kx = tap - 3 * ky;
-                                const int aslot = (MODE == CONV_S2) ? ky * G::PW + (kx == 1 ? 9 : (kx >> 1)) : ky * G::PW + kx;
+                                const int aslot = (MODE == CONV_S2) ? ky * G::PW + (kx == 1 ? G::EVEN_OFF : (kx >> 1)) : ky * G::PW + kx;
                                 umma(d_tmem, adesc + (uint64_t)(uint32_t)(h * 2 * G::PLANE + aslot), wdesc + (uint64_t)((uint32_t)tt * tap_step),
                                      idesc, acc);
                                 acc = 1;
@@ -546,9 +551,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
                     const int coff = cbase - (s ? srcs[0].C : 0);
                     const uint32_t bar = smem_u32(&hdr->raw_full[rs]);
                     mbar_wait_t(smem_u32(&hdr->raw_empty[rs]), pr ^ 1u, tr, tw[0]);
-                    mbar_expect_tx(bar, is_res ? 18u * 10u * 32u * 4u : RAW_BYTES);
-                    tma_load_4d(raw_ring + (uint32_t)rs * a.raw_stage, &maps.src[(is_res ? 2 : 0) + s], coff,
-                                is_res ? t.ox0 - 1 : xo, is_res ? t.oy0 - 1 : yo, t.n, bar);
+                    const bool affine = !is_res && srcs[s].scale != nullptr;
+                    const uint32_t nch = is_res ? 32u : (uint32_t)G::SLAB;
+                    mbar_expect_tx(bar, (is_res ? 18u * 10u * 32u * 4u : RAW_BYTES) + (affine ? 8u * nch : 0u));
+                    const uint32_t dst = raw_ring + (uint32_t)rs * a.raw_stage;
+                    tma_load_4d(dst, &maps.src[(is_res ? 2 : 0) + s], coff, is_res ? t.ox0 - 1 : xo, is_res ? t.oy0 - 1 : yo, t.n, bar);
+                    if (affine) {   // GroupNorm scale / shift of the slab's channels travel with the slab
+                        bulk_g2s(dst + a.raw_stage - 256u, srcs[s].scale + (int64_t)t.n * p.Cin + cbase, 4u * nch, bar);
+                        bulk_g2s(dst + a.raw_stage - 128u, srcs[s].shift + (int64_t)t.n * p.Cin + cbase, 4u * nch, bar);
+                    }
                     if (++rs == a.NR) { rs = 0; pr ^= 1u; }
                 }
             }
@@ -580,100 +591,141 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
             return o;
         };
 
-        int k_slab = 0;   // CTA-wide slab counter
-        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-            TileCoord t;
-            bool have_t = false;
-            for (int ai = 0; ai < nA; ++ai, ++k_slab) {
-                if ((k_slab % kXfGroups) != gi) continue;
-                if (!have_t) { t = decode_tile(a, tile); have_t = true; }
-                const int rs = k_slab % a.NR, sa = k_slab % a.NA;
-                const uint32_t pr = (uint32_t)(k_slab / a.NR) & 1u, pa = (uint32_t)(k_slab / a.NA) & 1u;
-                const bool is_res = ai >= a.n_main;
-                const bool s1_like = is_res || MODE == CONV_S1;
-                const int npl = s1_like ? 4 : NPL;
-                const int j = gt % npl, pix0 = gt / npl, pstep = kXfGroupThreads / npl;
-                const int cbase = is_res ? (ai - a.n_main) * 32 : ai * G::SLAB;
-                const ConvSrc* srcs = is_res ? p.res_src : p.src;
-                const int s = (cbase < srcs[0].C) ? 0 : 1;
-                const bool affine = !is_res && srcs[s].scale != nullptr;
-                float sch[8], shh[8];
-                if (affine) {
-                    const float4* sp = reinterpret_cast<const float4*>(srcs[s].scale + (int64_t)t.n * p.Cin + cbase + j * 8);
-                    const float4* hp = reinterpret_cast<const float4*>(srcs[s].shift + (int64_t)t.n * p.Cin + cbase + j * 8);
-                    const float4 s0 = __ldg(sp), s1 = __ldg(sp + 1), h0 = __ldg(hp), h1 = __ldg(hp + 1);
-                    sch[0] = 0.5f * s0.x; sch[1] = 0.5f * s0.y; sch[2] = 0.5f * s0.z; sch[3] = 0.5f * s0.w;
-                    sch[4] = 0.5f * s1.x; sch[5] = 0.5f * s1.y; sch[6] = 0.5f * s1.z; sch[7] = 0.5f * s1.w;
-                    shh[0] = 0.5f * h0.x; shh[1] = 0.5f * h0.y; shh[2] = 0.5f * h0.z; shh[3] = 0.5f * h0.w;
-                    shh[4] = 0.5f * h1.x; shh[5] = 0.5f * h1.y; shh[6] = 0.5f * h1.z; shh[7] = 0.5f * h1.w;
-                }
-                // valid window of the raw box (in box coordinates): everything else is zero padding
-                int yo, xo, rh, rw;
-                if (s1_like) { yo = t.oy0 - 1; xo = t.ox0 - 1; rh = 18; rw = 10; }
-                else { yo = org_of<MODE>(t.oy0); xo = org_of<MODE>(t.ox0); rh = G::RAW_H; rw = G::RAW_W; }
-                const int ylo = yo < 0 ? -yo : 0, xlo = xo < 0 ? -xo : 0;
-                const int yhi = (p.Hin - yo) < rh ? (p.Hin - yo) : rh, xhi = (p.Win - xo) < rw ? (p.Win - xo) : rw;
-
-                mbar_wait_t(smem_u32(&hdr->raw_full[rs]), pr, tr, tw[0]);
-                mbar_wait_t(smem_u32(&hdr->empty_a[sa]), pa ^ 1u, tr, tw[1]);
-                const uint32_t raw = raw_ring + (uint32_t)rs * a.raw_stage;
-                const uint32_t opd = a_ring + (uint32_t)sa * a.a_stage + (uint32_t)j * (uint32_t)G::PLANE * 16u;
-                if (MODE == CONV_UP && !is_res) {
-                    constexpr int NPIX = G::RAW_H * G::RAW_W;
+        // this group's position in the CTA-wide (tile, slab) sequence and in the rings; it advances kXfGroups slabs at a time
+        int tile = blockIdx.x, ai = gi;
+        while (ai >= nA) { ai -= nA; tile += gridDim.x; }
+        int rs = gi % a.NR, sa = gi % a.NA;
+        uint32_t pr = (uint32_t)(gi / a.NR) & 1u, pa = (uint32_t)(gi / a.NA) & 1u;
+        int cur_tile = -1;
+        TileCoord t{0, 0, 0, 0};
+        while (tile < a.ntiles) {
+            const long long ts0 = tr ? clock64() : 0;
+            if (tile != cur_tile) { t = decode_tile(a, tile); cur_tile = tile; }
+            const bool is_res = ai >= a.n_main;
+            const bool s1_like = is_res || MODE == CONV_S1;
+            const int npl = s1_like ? 4 : NPL;
+            const int j = gt % npl, pix0 = gt / npl;
+            const int cbase = is_res ? (ai - a.n_main) * 32 : ai * G::SLAB;
+            const ConvSrc* srcs = is_res ? p.res_src : p.src;
+            const int s = (cbase < srcs[0].C) ? 0 : 1;
+            const bool affine = !is_res && srcs[s].scale != nullptr;
+            // valid window of the raw box (in box coordinates): everything else is zero padding
+            int yo, xo, rh, rw;
+            if (s1_like) { yo = t.oy0 - 1; xo = t.ox0 - 1; rh = 18; rw = 10; }
+            else { yo = org_of<MODE>(t.oy0); xo = org_of<MODE>(t.ox0); rh = G::RAW_H; rw = G::RAW_W; }
+            const int ylo = yo < 0 ? -yo : 0, xlo = xo < 0 ? -xo : 0;
+            const int yhi = (p.Hin - yo) < rh ? (p.Hin - yo) : rh, xhi = (p.Win - xo) < rw ? (p.Win - xo) : rw;
+            const uint32_t raw = raw_ring + (uint32_t)rs * a.raw_stage;
+            const uint32_t opd = a_ring + (uint32_t)sa * a.a_stage + (uint32_t)j * (uint32_t)G::PLANE * 16u;
+            if (tr) tw[2] += clock64() - ts0;
+            mbar_wait_t(smem_u32(&hdr->raw_full[rs]), pr, tr, tw[0]);
+            mbar_wait_t(smem_u32(&hdr->empty_a[sa]), pa ^ 1u, tr, tw[1]);
+            const long long ts1 = tr ? clock64() : 0;
+            // per-channel affine of this thread's 8 channels, halved: swish(y) = h + h * tanh(h) with h = y / 2.
+            // (scale, shift) of the slab were bulk-copied behind the raw box by the TMA warp.
+            float sch[8], shh[8];
+            if (affine) {
+                const uint32_t ss = raw + a.raw_stage - 256u + (uint32_t)j * 32u;
+                const uint4 s0 = lds128(ss), s1 = lds128(ss + 16u), h0 = lds128(ss + 128u), h1 = lds128(ss + 144u);
+                sch[0] = 0.5f * __uint_as_float(s0.x); sch[1] = 0.5f * __uint_as_float(s0.y); sch[2] = 0.5f * __uint_as_float(s0.z); sch[3] = 0.5f * __uint_as_float(s0.w);
+                sch[4] = 0.5f * __uint_as_float(s1.x); sch[5] = 0.5f * __uint_as_float(s1.y); sch[6] = 0.5f * __uint_as_float(s1.z); sch[7] = 0.5f * __uint_as_float(s1.w);
+                shh[0] = 0.5f * __uint_as_float(h0.x); shh[1] = 0.5f * __uint_as_float(h0.y); shh[2] = 0.5f * __uint_as_float(h0.z); shh[3] = 0.5f * __uint_as_float(h0.w);
+                shh[4] = 0.5f * __uint_as_float(h1.x); shh[5] = 0.5f * __uint_as_float(h1.y); shh[6] = 0.5f * __uint_as_float(h1.z); shh[7] = 0.5f * __uint_as_float(h1.w);
+            }
+            if (MODE == CONV_UP && !is_res) {
+                constexpr int NPIX = G::RAW_H * G::RAW_W, PST = kXfGroupThreads / 4, ROUNDS = (NPIX + PST - 1) / PST;
+                uint4 rv[ROUNDS][2];
 #pragma unroll
-                    for (int r = 0; r < (NPIX + 31) / 32; ++r) {
-                        const int pix = pix0 + r * pstep;
-                        if (pix >= NPIX) break;
-                        const int ry = pix / G::RAW_W, rx = pix - ry * G::RAW_W;
-                        const bool ok = ry >= ylo && ry < yhi && rx >= xlo && rx < xhi;
+                for (int r = 0; r < ROUNDS; ++r) {   // all shared-memory loads first: their latency overlaps
+                    const int pix = pix0 + r * PST;
+                    if (pix < NPIX) {
                         const uint32_t ra = raw + (uint32_t)pix * 128u + (uint32_t)(((2 * j) ^ (pix & 7)) << 4);
-                        const uint4 o = convert(lds128(ra), lds128(ra ^ 16u), ok, affine, sch, shh);
+                        rv[r][0] = lds128(ra); rv[r][1] = lds128(ra ^ 16u);
+                    }
+                }
 #pragma unroll
-                        for (int dy = 0; dy < 2; ++dy) {
-                            const int hy = 2 * ry - 1 + dy;
-                            if (hy < 0 || hy >= G::PH) continue;
+                for (int r = 0; r < ROUNDS; ++r) {
+                    const int pix = pix0 + r * PST;
+                    if (pix >= NPIX) break;
+                    const int ry = pix / G::RAW_W, rx = pix - ry * G::RAW_W;
+                    const bool ok = ry >= ylo && ry < yhi && rx >= xlo && rx < xhi;
+                    const uint4 o = convert(rv[r][0], rv[r][1], ok, affine, sch, shh);
 #pragma unroll
-                            for (int dx = 0; dx < 2; ++dx) {
-                                const int hx = 2 * rx - 1 + dx;
-                                if (hx < 0 || hx >= G::PW) continue;
-                                sts128(opd + (uint32_t)(hy * G::PW + hx) * 16u, o);
-                            }
+                    for (int dy = 0; dy < 2; ++dy) {
+                        const int hy = 2 * ry - 1 + dy;
+                        if (hy < 0 || hy >= G::PH) continue;
+#pragma unroll
+                        for (int dx = 0; dx < 2; ++dx) {
+                            const int hx = 2 * rx - 1 + dx;
+                            if (hx < 0 || hx >= G::PW) continue;
+                            sts128(opd + (uint32_t)(hy * G::PW + hx) * 16u, o);
                         }
                     }
-                } else if (MODE == CONV_S2) {
-                    constexpr int NPIX = G::RAW_H * G::RAW_W, PST = kXfGroupThreads / NPL, ROUNDS = (NPIX + PST - 1) / PST;
+                }
+            } else if (MODE == CONV_S2) {
+                constexpr int NPIX = G::RAW_H * G::RAW_W, PST = kXfGroupThreads / NPL, ROUNDS = (NPIX + PST - 1) / PST, RB = 3;
+                static_assert(MODE != CONV_S2 || ROUNDS % RB == 0, "stride-2 rounds come in batches");
+#pragma unroll 1
+                for (int rb = 0; rb < ROUNDS / RB; ++rb) {
+                    uint4 rv[RB][2];
 #pragma unroll
-                    for (int r = 0; r < ROUNDS; ++r) {
-                        const int pix = pix0 + r * PST;
+                    for (int q = 0; q < RB; ++q) {
+                        const int pix = pix0 + (rb * RB + q) * PST;
+                        if (pix < NPIX) {
+                            const uint32_t ra = raw + (uint32_t)pix * 64u + (uint32_t)j * 32u;   // unswizzled 64-byte pixels
+                            const bool swap = (pix >> 1) & 1;
+                            const uint4 lo = lds128(ra + (swap ? 16u : 0u)), hi = lds128(ra + (swap ? 0u : 16u));
+                            rv[q][0] = swap ? hi : lo; rv[q][1] = swap ? lo : hi;
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < RB; ++q) {
+                        const int pix = pix0 + (rb * RB + q) * PST;
                         if (pix >= NPIX) break;
                         const int hy = pix / G::RAW_W, hx = pix - hy * G::RAW_W;
                         const bool ok = hy >= ylo && hy < yhi && hx >= xlo && hx < xhi;
-                        const uint32_t ra = raw + (uint32_t)pix * 64u + (uint32_t)j * 32u;   // unswizzled 64-byte pixels
-                        const bool swap = (pix >> 1) & 1;
-                        const uint4 lo = lds128(ra + (swap ? 16u : 0u)), hi = lds128(ra + (swap ? 0u : 16u));
-                        const uint4 o = convert(swap ? hi : lo, swap ? lo : hi, ok, affine, sch, shh);
-                        const int slot = hy * G::PW + ((hx & 1) ? 9 + (hx >> 1) : (hx >> 1));
+                        const uint4 o = convert(rv[q][0], rv[q][1], ok, affine, sch, shh);
+                        const int slot = hy * G::PW + ((hx & 1) ? G::EVEN_OFF + (hx >> 1) : (hx >> 1));
                         sts128(opd + (uint32_t)slot * 16u, o);
                     }
-                } else {   // stride-1 halo (main conv of CONV_S1, res_conv slabs)
-                    constexpr int NPIX = 18 * 10, PST = kXfGroupThreads / 4, ROUNDS = (NPIX + PST - 1) / PST;
+                }
+            } else {   // stride-1 halo (main conv of CONV_S1, res_conv slabs)
+                constexpr int NPIX = 18 * 10, PST = kXfGroupThreads / 4, ROUNDS = (NPIX + PST - 1) / PST, RB = 3;
+                static_assert(ROUNDS % RB == 0, "stride-1 rounds come in batches");
 #pragma unroll
-                    for (int r = 0; r < ROUNDS; ++r) {
-                        const int pix = pix0 + r * PST;
+                for (int rb = 0; rb < ROUNDS / RB; ++rb) {
+                    uint4 rv[RB][2];
+#pragma unroll
+                    for (int q = 0; q < RB; ++q) {   // a batch of shared-memory loads first: their latencies overlap
+                        const int pix = pix0 + (rb * RB + q) * PST;
+                        if (pix < NPIX) {
+                            const uint32_t ra = raw + (uint32_t)pix * 128u + (uint32_t)(((2 * j) ^ (pix & 7)) << 4);
+                            rv[q][0] = lds128(ra); rv[q][1] = lds128(ra ^ 16u);
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < RB; ++q) {
+                        const int pix = pix0 + (rb * RB + q) * PST;
                         if (pix >= NPIX) break;
                         const int hy = pix / 10, hx = pix - hy * 10;
                         const bool ok = hy >= ylo && hy < yhi && hx >= xlo && hx < xhi;
-                        const uint32_t ra = raw + (uint32_t)pix * 128u + (uint32_t)(((2 * j) ^ (pix & 7)) << 4);
-                        const uint4 o = convert(lds128(ra), lds128(ra ^ 16u), ok, affine, sch, shh);
+                        const uint4 o = convert(rv[q][0], rv[q][1], ok, affine, sch, shh);
                         sts128(opd + (uint32_t)pix * 16u, o);
                     }
                 }
-                fence_async_smem();
-                mbar_arrive(smem_u32(&hdr->full_a[sa]));
-                mbar_arrive(smem_u32(&hdr->raw_empty[rs]));
             }
+            const long long ts2 = tr ? clock64() : 0;
+            fence_async_smem();
+            mbar_arrive(smem_u32(&hdr->full_a[sa]));
+            mbar_arrive(smem_u32(&hdr->raw_empty[rs]));
+            if (tr) { tw[3] += ts2 - ts1; tw[4] += clock64() - ts2; }
+            // advance by kXfGroups slabs
+            ai += kXfGroups;
+            while (ai >= nA) { ai -= nA; tile += gridDim.x; }
+            rs += kXfGroups; if (rs >= a.NR) { rs -= a.NR; pr ^= 1u; }
+            sa += kXfGroups; if (sa >= a.NA) { sa -= a.NA; pa ^= 1u; }
         }
-        if (tr && gt == 0) { long long* o = a.trace + 32 + 8 * gi; o[0] = clock64() - t_begin; o[1] = tw[0]; o[2] = tw[1]; }
+        if (tr && gt == 0) { long long* o = a.trace + 32 + 8 * gi; o[0] = clock64() - t_begin; o[1] = tw[0]; o[2] = tw[1]; o[3] = tw[2]; o[4] = tw[3]; o[5] = tw[4]; }
     }
 
     tc_fence_before();
@@ -792,10 +844,10 @@ int launch_mode(TcArgs a, cudaStream_t st) {
     const ConvP& p = a.p;
     a.n_main = p.Cin / G::SLAB;
     a.n_main_chunks = (9 / TPC) * (p.Cin / 16);
-    a.raw_stage = (uint32_t)align_up_sz((size_t)G::RAW_H * G::RAW_W * G::SLAB * 4, 1024);
-    if (a.n_res && a.raw_stage < 18u * 10u * 32u * 4u) a.raw_stage = (uint32_t)align_up_sz(18 * 10 * 32 * 4, 1024);
+    a.raw_stage = (uint32_t)align_up_sz((size_t)G::RAW_H * G::RAW_W * G::SLAB * 4 + 256, 1024);   // + scale / shift tail
+    if (a.n_res && a.raw_stage < 18u * 10u * 32u * 4u + 256u) a.raw_stage = (uint32_t)align_up_sz(18 * 10 * 32 * 4 + 256, 1024);
     a.a_stage = (uint32_t)align_up_sz((size_t)(G::SLAB / 8) * G::PLANE * 16, 128);
-    if (a.n_res && a.a_stage < 4u * 181u * 16u) a.a_stage = (uint32_t)align_up_sz(4 * 181 * 16, 128);
+    if (a.n_res && a.a_stage < 4u * 182u * 16u) a.a_stage = (uint32_t)align_up_sz(4 * 182 * 16, 128);
     a.w_stage = 32u * TPC * (uint32_t)p.Cout;
     const int nchunks = a.n_main_chunks + a.n_res_chunks;
     const int nblk = p.Cout / 32;
@@ -911,8 +963,8 @@ extern "C" SDDM_API int sddm_debug_umma_probe(int variant, int N, int K, float* 
     if (!max_err_host || N % 32 || N < 32 || N > 256 || K % 16 || K < 16 || K > 64) { set_error("probe: N in 32..256 step 32, K in 16..64 step 16"); return SDDM_E_INVALID; }
     const int geo = variant % 10, swap = variant / 10;
     uint32_t a_off = 0, a_lbo = 2048, a_sbo = 128;
-    if (geo == 1) { a_off = 11 * 16; a_lbo = 181 * 16; a_sbo = 160; }
-    if (geo == 2) { a_off = (17 + 9) * 16; a_lbo = 565 * 16; a_sbo = 544; }
+    if (geo == 1) { a_off = 11 * 16; a_lbo = 182 * 16; a_sbo = 160; }
+    if (geo == 2) { a_off = (20 + 12) * 16; a_lbo = 662 * 16; a_sbo = 640; }
     std::vector<__nv_bfloat16> hA((size_t)128 * K), hB((size_t)N * K);
     std::vector<float> fA(hA.size()), fB(hB.size());
     uint32_t s = 12345u;

@@ -51,7 +51,7 @@ struct StemP {
     const float* w;      // [2][9][CO] fp32 pack
     const float* bias;   // [CO]
     float* out;          // [B][H][W][CO]
-    float* parts;        // [B][nparts][CO][2]
+    float* parts;        // [B][nparts][CO][2], nparts = tiles per sample (16 x 8 pixels each)
     int B, L, H, W, hop, CO, nparts;
 };
 int launch_stem(const StemP& p, cudaStream_t st);
@@ -74,6 +74,7 @@ struct FinalP {
     float bias;
     float* frames;      // [B][H][W]
     int B, H, W, C;
+    int fast_math;      // approximate exp / divide in the Swish (bf16 mode); exact-ish expf / IEEE divide otherwise
 };
 int launch_final_conv(const FinalP& p, cudaStream_t st);
 

@@ -206,73 +206,97 @@ int launch_temb(const TembP& p, cudaStream_t st) {
 
 // ===================================================================================================
 // stem: SignalToFrames x2 + cat + conv3x3(2 -> CO)      reference: UNetModified2.py:23-28,244-247,177-178
-// tile = 16 frames x 8 positions, one pixel per thread, all CO outputs in registers.
+// HBM-write bound (2 x 64 KB in, CO x 128 KB out per chunk).  Tile = 16 frames x 8 positions; a thread owns 4 output
+// channels of one pixel per pass, so the CO/4 threads of a pixel write its CO*4 contiguous bytes and a warp writes whole
+// 128-byte lines.  The 18 x 10 x 2 input window is staged in shared memory; weights stay in registers across the
+// persistent CTA's tiles.  GroupNorm partial statistics: one (sum, sumsq) per channel per tile, fixed summation order.
 // ===================================================================================================
-int stem_nparts(int H, int W) { return (H / 16) * (W / 8) * 4; }
+int stem_nparts(int H, int W) { return (H / 16) * (W / 8); }
 
 template <int CO>
-__global__ void __launch_bounds__(128) stem_kernel(StemP p) {
-    __shared__ __align__(16) float sw[18 * CO];
-    __shared__ float sb[CO];
+__global__ void __launch_bounds__(256) stem_kernel(StemP p) {
+    constexpr int CG = CO / 4;            // channel groups (threads) per pixel
+    constexpr int PPP = 256 / CG;         // pixels per pass
+    constexpr int PASSES = 128 / PPP;
+    __shared__ float sin_[2][18][10];
+    __shared__ float red[8][CO][2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < 18 * CO; i += 128) sw[i] = p.w[i];
-    for (int i = tid; i < CO; i += 128) sb[i] = p.bias[i];
-    __syncthreads();
-    const int tiles_x = p.W / 8, tiles_y = p.H / 16;
-    const int tile = blockIdx.x % (tiles_x * tiles_y), n = blockIdx.x / (tiles_x * tiles_y);
-    const int y = (tile / tiles_x) * 16 + (tid >> 3), x = (tile % tiles_x) * 8 + (tid & 7);
-    float in[2][9];
+    const int cg = tid % CG, pl = tid / CG;
+    float4 w[18];
 #pragma unroll
-    for (int ci = 0; ci < 2; ++ci) {
+    for (int k = 0; k < 18; ++k) w[k] = __ldg(reinterpret_cast<const float4*>(p.w + (size_t)k * CO) + cg);
+    const float4 bias = __ldg(reinterpret_cast<const float4*>(p.bias) + cg);
+    const int tiles_x = p.W / 8, tiles_y = p.H / 16, per = tiles_x * tiles_y, ntiles = p.B * per;
+    // input window element(s) of this thread: i = tid and tid + 256 of the 2 x 18 x 10 window; the NEXT tile's values are
+    // fetched into registers while the current tile is computed (hides the global latency of the persistent loop)
+    auto fetch = [&](int tl, int i) -> float {
+        if (tl >= ntiles || i >= 360) return 0.f;
+        const int n = tl / per, tile = tl - n * per;
+        const int y0 = (tile / tiles_x) * 16, x0 = (tile % tiles_x) * 8;
+        const int ci = i / 180, r = i - ci * 180, hy = r / 10, hx = r - hy * 10;
+        const int iy = y0 + hy - 1, ix = x0 + hx - 1;
         const float* sig = (ci == 0 ? p.cond : p.x_t) + (int64_t)n * p.L;
+        return (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) ? __ldg(sig + (int64_t)iy * p.hop + ix) : 0.f;
+    };
+    float nx0 = fetch(blockIdx.x, tid), nx1 = fetch(blockIdx.x, tid + 256);
+    for (int tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
+        const int n = tl / per, tile = tl - n * per;
+        const int y0 = (tile / tiles_x) * 16, x0 = (tile % tiles_x) * 8;
+        __syncthreads();   // previous tile's readers of sin_ / red are done
+        (&sin_[0][0][0])[tid] = nx0;
+        if (tid + 256 < 360) (&sin_[0][0][0])[tid + 256] = nx1;
+        __syncthreads();
+        nx0 = fetch(tl + gridDim.x, tid);
+        nx1 = fetch(tl + gridDim.x, tid + 256);
+        float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
+        for (int ps = 0; ps < PASSES; ++ps) {
+            const int pix = ps * PPP + pl, py = pix >> 3, px = pix & 7;
+            float4 acc = bias;
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const int iy = y + ky - 1, ix = x + kx - 1;
-                in[ci][ky * 3 + kx] = (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) ? __ldg(sig + (int64_t)iy * p.hop + ix) : 0.f;
+            for (int ci = 0; ci < 2; ++ci)
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const float v = sin_[ci][py + ky][px + kx];
+                        const float4 ww = w[ci * 9 + ky * 3 + kx];
+                        acc.x = fmaf(v, ww.x, acc.x); acc.y = fmaf(v, ww.y, acc.y);
+                        acc.z = fmaf(v, ww.z, acc.z); acc.w = fmaf(v, ww.w, acc.w);
+                    }
+            *reinterpret_cast<float4*>(p.out + (((int64_t)n * p.H + y0 + py) * p.W + x0 + px) * CO + cg * 4) = acc;
+            s1[0] += acc.x; s1[1] += acc.y; s1[2] += acc.z; s1[3] += acc.w;
+            s2[0] = fmaf(acc.x, acc.x, s2[0]); s2[1] = fmaf(acc.y, acc.y, s2[1]);
+            s2[2] = fmaf(acc.z, acc.z, s2[2]); s2[3] = fmaf(acc.w, acc.w, s2[3]);
+        }
+#pragma unroll
+        for (int o = CG; o < 32; o <<= 1)   // lanes with the same channel group: fixed butterfly order
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], o);
+                s2[k] += __shfl_xor_sync(0xffffffffu, s2[k], o);
             }
-    }
-    float* op = p.out + (((int64_t)n * p.H + y) * p.W + x) * CO;
+        if (lane < CG) {
 #pragma unroll
-    for (int c0 = 0; c0 < CO; c0 += 32) {
-        float acc[32];
+            for (int k = 0; k < 4; ++k) { red[warp][lane * 4 + k][0] = s1[k]; red[warp][lane * 4 + k][1] = s2[k]; }
+        }
+        __syncthreads();
+        if (tid < CO) {
+            float a = 0.f, b = 0.f;
 #pragma unroll
-        for (int c = 0; c < 32; ++c) acc[c] = sb[c0 + c];
-#pragma unroll
-        for (int ci = 0; ci < 2; ++ci)
-#pragma unroll
-            for (int tp = 0; tp < 9; ++tp) {
-                const float v = in[ci][tp];
-                const float4* w4 = reinterpret_cast<const float4*>(sw + (ci * 9 + tp) * CO + c0);
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const float4 w = w4[q];
-                    acc[4 * q + 0] = fmaf(v, w.x, acc[4 * q + 0]);
-                    acc[4 * q + 1] = fmaf(v, w.y, acc[4 * q + 1]);
-                    acc[4 * q + 2] = fmaf(v, w.z, acc[4 * q + 2]);
-                    acc[4 * q + 3] = fmaf(v, w.w, acc[4 * q + 3]);
-                }
-            }
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-            reinterpret_cast<float4*>(op + c0)[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
-        float sq[32];
-#pragma unroll
-        for (int c = 0; c < 32; ++c) sq[c] = acc[c] * acc[c];
-        const float s1 = warp_transpose_reduce32(acc, lane);
-        const float s2 = warp_transpose_reduce32(sq, lane);
-        float* pp = p.parts + (((int64_t)n * p.nparts + tile * 4 + warp) * CO + c0 + lane) * 2;
-        pp[0] = s1;
-        pp[1] = s2;
+            for (int wq = 0; wq < 8; ++wq) { a += red[wq][tid][0]; b += red[wq][tid][1]; }
+            *reinterpret_cast<float2*>(p.parts + (((int64_t)n * p.nparts + tile) * CO + tid) * 2) = make_float2(a, b);
+        }
     }
 }
 
 int launch_stem(const StemP& p, cudaStream_t st) {
     if (p.H % 16 || p.W % 8) { set_error("stem: frame grid %dx%d must be a multiple of 16x8", p.H, p.W); return SDDM_E_INVALID; }
-    const int grid = p.B * (p.H / 16) * (p.W / 8);
-    if (p.CO == 32) stem_kernel<32><<<grid, 128, 0, st>>>(p);
-    else if (p.CO == 64) stem_kernel<64><<<grid, 128, 0, st>>>(p);
+    if (p.nparts != stem_nparts(p.H, p.W)) { set_error("stem: nparts mismatch"); return SDDM_E_INVALID; }
+    const int ntiles = p.B * (p.H / 16) * (p.W / 8);
+    const int grid = ntiles < 148 * 8 ? ntiles : 148 * 8;
+    if (p.CO == 32) stem_kernel<32><<<grid, 256, 0, st>>>(p);
+    else if (p.CO == 64) stem_kernel<64><<<grid, 256, 0, st>>>(p);
     else { set_error("stem: inner_channel %d unsupported (32 or 64)", p.CO); return SDDM_E_INVALID; }
     SDDM_LAUNCH_CHECK();
     return SDDM_OK;
@@ -330,64 +354,106 @@ int launch_gn_finalize(const GnP& p, cudaStream_t st) {
 
 // ===================================================================================================
 // final Block: GN-apply + Swish + conv3x3(C -> 1)       reference: UNetModified2.py:235,267 (Block, :113-124)
-// tile = 16 x 8 pixels, one pixel per thread; halo tile staged in smem post-activation (zero padded).
+// HBM-read bound.  Tile = 16 x 16 pixels; the post-activation, zero-padded 18 x 18 halo is staged in shared memory with
+// coalesced 128-bit loads (the C/4 threads of a pixel read its C*4 contiguous bytes).  A thread owns one pixel column and
+// 4 channels: it walks the 18 halo rows once (3 x LDS.128 per row) and feeds 16 row accumulators, so every staged value is
+// read 3 times instead of 9; the C/4 partial dot products of a pixel are combined with a shuffle butterfly.
 // ===================================================================================================
-__global__ void __launch_bounds__(128) final_conv_kernel(FinalP p) {
-    extern __shared__ __align__(16) float smem[];
-    const int C = p.C, CP = C + 4;
-    float* sa = smem;                 // [18*10][CP]
-    float* sw = smem + 180 * CP;      // [9][C]
-    const int tid = threadIdx.x;
-    const int tiles_x = p.W / 8, tiles_y = p.H / 16;
-    const int tile = blockIdx.x % (tiles_x * tiles_y), n = blockIdx.x / (tiles_x * tiles_y);
-    const int y0 = (tile / tiles_x) * 16, x0 = (tile % tiles_x) * 8;
-    for (int i = tid; i < 9 * C; i += 128) sw[i] = p.w[i];
-    const int c4n = C / 4;
-    const float4* sc4 = reinterpret_cast<const float4*>(p.scale + (int64_t)n * C);
-    const float4* sh4 = reinterpret_cast<const float4*>(p.shift + (int64_t)n * C);
-    for (int i = tid; i < 180 * c4n; i += 128) {
-        const int pix = i / c4n, c4 = i - pix * c4n;
-        const int hy = pix / 10, hx = pix - hy * 10;
-        const int iy = y0 + hy - 1, ix = x0 + hx - 1;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
-            const float4 r = __ldg(reinterpret_cast<const float4*>(p.x + (((int64_t)n * p.H + iy) * p.W + ix) * C) + c4);
-            const float4 a = __ldg(sc4 + c4), b = __ldg(sh4 + c4);
-            v.x = swish_accurate(fmaf(r.x, a.x, b.x));
-            v.y = swish_accurate(fmaf(r.y, a.y, b.y));
-            v.z = swish_accurate(fmaf(r.z, a.z, b.z));
-            v.w = swish_accurate(fmaf(r.w, a.w, b.w));
-        }
-        *reinterpret_cast<float4*>(sa + pix * CP + c4 * 4) = v;
-    }
-    __syncthreads();
-    const int ty = tid >> 3, tx = tid & 7;
-    float acc = p.bias;
+template <int C, bool FAST>
+__global__ void __launch_bounds__(4 * C) final_conv_kernel(FinalP p) {
+    constexpr int CG = C / 4, NT = 16 * CG;
+    extern __shared__ __align__(16) float smem[];   // [18*18][C]
+    const int tid = threadIdx.x, cg = tid % CG, col = tid / CG;
+    float4 w[9];
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky)
+    for (int k = 0; k < 9; ++k) w[k] = __ldg(reinterpret_cast<const float4*>(p.w + (size_t)k * C) + cg);
+    const int tiles_x = p.W / 16, tiles_y = p.H / 16, per = tiles_x * tiles_y, ntiles = p.B * per;
+    for (int tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
+        const int n = tl / per, tile = tl - n * per;
+        const int y0 = (tile / tiles_x) * 16, x0 = (tile % tiles_x) * 16;
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + (int64_t)n * C) + cg);
+        const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + (int64_t)n * C) + cg);
+        __syncthreads();   // previous tile's readers are done
+        constexpr int U = 7;   // 128-bit loads in flight per thread
+#pragma unroll 1
+        for (int base = col; base < 18 * 18; base += 16 * U) {
+            float4 rv[U];
+            bool okv[U];
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-            const float4* a4 = reinterpret_cast<const float4*>(sa + ((ty + ky) * 10 + tx + kx) * CP);
-            const float4* w4 = reinterpret_cast<const float4*>(sw + (ky * 3 + kx) * C);
-            for (int c4 = 0; c4 < c4n; ++c4) {
-                const float4 a = a4[c4], w = w4[c4];
-                acc = fmaf(a.x, w.x, acc);
-                acc = fmaf(a.y, w.y, acc);
-                acc = fmaf(a.z, w.z, acc);
-                acc = fmaf(a.w, w.w, acc);
+            for (int u = 0; u < U; ++u) {
+                const int pix = base + 16 * u;
+                const int hy = pix / 18, hx = pix - hy * 18;
+                const int iy = y0 + hy - 1, ix = x0 + hx - 1;
+                okv[u] = pix < 18 * 18 && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+                if (okv[u]) rv[u] = __ldg(reinterpret_cast<const float4*>(p.x + (((int64_t)n * p.H + iy) * p.W + ix) * C) + cg);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int pix = base + 16 * u;
+                if (pix >= 18 * 18) break;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (okv[u]) {
+                    const float4 r = rv[u];
+                    if (FAST) {
+                        v.x = swish_fast(fmaf(r.x, sc.x, sh.x)); v.y = swish_fast(fmaf(r.y, sc.y, sh.y));
+                        v.z = swish_fast(fmaf(r.z, sc.z, sh.z)); v.w = swish_fast(fmaf(r.w, sc.w, sh.w));
+                    } else {
+                        v.x = swish_accurate(fmaf(r.x, sc.x, sh.x)); v.y = swish_accurate(fmaf(r.y, sc.y, sh.y));
+                        v.z = swish_accurate(fmaf(r.z, sc.z, sh.z)); v.w = swish_accurate(fmaf(r.w, sc.w, sh.w));
+                    }
+                }
+                *reinterpret_cast<float4*>(smem + (size_t)pix * C + cg * 4) = v;
             }
         }
-    p.frames[((int64_t)n * p.H + y0 + ty) * p.W + x0 + tx] = acc;
+        __syncthreads();
+        float acc[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) acc[r] = 0.f;
+#pragma unroll
+        for (int hr = 0; hr < 18; ++hr) {
+            float4 a[3];
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) a[kx] = *reinterpret_cast<const float4*>(smem + (size_t)(hr * 18 + col + kx) * C + cg * 4);
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                const int r = hr - ky;
+                if (r < 0 || r >= 16) continue;
+                float t = acc[r];
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const float4 ww = w[ky * 3 + kx];
+                    t = fmaf(a[kx].x, ww.x, t); t = fmaf(a[kx].y, ww.y, t); t = fmaf(a[kx].z, ww.z, t); t = fmaf(a[kx].w, ww.w, t);
+                }
+                acc[r] = t;
+            }
+        }
+#pragma unroll
+        for (int o = 1; o < CG; o <<= 1)
+#pragma unroll
+            for (int r = 0; r < 16; ++r) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
+#pragma unroll
+        for (int r = 0; r < 16; ++r)
+            if ((r % CG) == cg) p.frames[((int64_t)n * p.H + y0 + r) * p.W + x0 + col] = acc[r] + p.bias;
+    }
 }
 
 int launch_final_conv(const FinalP& p, cudaStream_t st) {
-    if (p.H % 16 || p.W % 8 || p.C % 4) { set_error("final conv: unsupported shape"); return SDDM_E_INVALID; }
-    const size_t smem = (size_t)(180 * (p.C + 4) + 9 * p.C) * sizeof(float);
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(final_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) { set_error("final conv: smem %zu too large", smem); return SDDM_E_CUDA; }
-    }
-    final_conv_kernel<<<p.B * (p.H / 16) * (p.W / 8), 128, smem, st>>>(p);
+    if (p.H % 16 || p.W % 16 || (p.C != 32 && p.C != 64)) { set_error("final conv: unsupported shape %dx%dx%d", p.H, p.W, p.C); return SDDM_E_INVALID; }
+    const size_t smem = (size_t)18 * 18 * p.C * sizeof(float);
+    const int ntiles = p.B * (p.H / 16) * (p.W / 16);
+    const int grid = ntiles < 148 * 4 ? ntiles : 148 * 4;
+#define SDDM_FINAL_LAUNCH(CC, FF)                                                                                          \
+    do {                                                                                                                  \
+        static bool attr = false;                                                                                         \
+        if (!attr) {                                                                                                      \
+            SDDM_CUDA_TRY(cudaFuncSetAttribute(final_conv_kernel<CC, FF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 18 * 18 * CC * 4)); \
+            attr = true;                                                                                                  \
+        }                                                                                                                 \
+        final_conv_kernel<CC, FF><<<grid, 4 * CC, smem, st>>>(p);                                                         \
+    } while (0)
+    if (p.C == 32) { if (p.fast_math) SDDM_FINAL_LAUNCH(32, true); else SDDM_FINAL_LAUNCH(32, false); }
+    else { if (p.fast_math) SDDM_FINAL_LAUNCH(64, true); else SDDM_FINAL_LAUNCH(64, false); }
+#undef SDDM_FINAL_LAUNCH
     SDDM_LAUNCH_CHECK();
     return SDDM_OK;
 }
