@@ -173,6 +173,8 @@ SDDM_API int sddm_debug_umma_probe(int variant, int N, int K, float* max_err_hos
 /* pipeline trace of the tcgen05 conv kernel: enable != 0 starts recording (next 64 conv launches, CTA 0 of each: cycles per
  * role spent waiting on each barrier); enable == 0 copies the [64][48] int64 counters to host_out and stops. */
 SDDM_API int sddm_debug_tc_trace(int enable, long long* host_out);
+/* issue-rate microbenchmark: average cycles per back-to-back tcgen05.mma (M 128, K 16, bf16, shared-memory operands) */
+SDDM_API int sddm_debug_umma_rate(int N, int reps, int nA, float* cycles_per_mma);
 
 #ifdef __cplusplus
 }

@@ -785,6 +785,39 @@ __global__ void __launch_bounds__(128) umma_probe_kernel(const __nv_bfloat16* __
     if (warp == 0) { __syncwarp(); tmem_dealloc(tmem, 256); }
 }
 
+// issue-rate microbenchmark: `reps` back-to-back 128 x N x 16 MMAs over `nA` distinct A tiles (canonical layout), one CTA.
+__global__ void __launch_bounds__(128) umma_rate_kernel(int N, int reps, int nA, long long* cycles) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tbase;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t sA = smem_u32(smem_raw);
+    const uint32_t a_bytes = 128u * 32u, b_off = (uint32_t)nA * a_bytes;
+    for (uint32_t i = tid; i < (b_off + (uint32_t)N * 32u) / 4u; i += 128) reinterpret_cast<uint32_t*>(smem_raw)[i] = 0x3c003c00u;
+    if (tid == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
+    if (warp == 0) tmem_alloc(smem_u32(&tbase), 256);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tbase;
+    if (warp == 0) {
+        const uint32_t idesc = make_idesc(N);
+        const uint64_t da0 = make_desc(sA, 2048, 128), db = make_desc(sA + b_off, (uint32_t)N * 16u, 128);
+        long long t0 = 0;
+        if (elect_one()) {
+            t0 = clock64();
+            for (int r = 0; r < reps; ++r) umma(tmem, da0 + (uint64_t)((uint32_t)(r % nA) * (a_bytes >> 4)), db, idesc, r > 0 ? 1u : 0u);
+            umma_commit(smem_u32(&bar));
+        }
+        mbar_wait(smem_u32(&bar), 0);
+        if (tid == 0) cycles[0] = clock64() - t0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) { __syncwarp(); tmem_dealloc(tmem, 256); }
+}
+
 int num_sms() {
     static int n = 0;
     if (n == 0) {
@@ -1017,5 +1050,24 @@ extern "C" SDDM_API int sddm_debug_tc_trace(int enable, long long* host_out) {
     if (host_out) SDDM_CUDA_TRY(cudaMemcpy(host_out, g_trace, 64 * 48 * sizeof(long long), cudaMemcpyDeviceToHost));
     cudaFree(g_trace);
     g_trace = nullptr;
+    return SDDM_OK;
+}
+
+// debug: average cycles per back-to-back tcgen05.mma (M 128, K 16, bf16) for a given N, cycling over nA distinct A tiles
+extern "C" SDDM_API int sddm_debug_umma_rate(int N, int reps, int nA, float* cycles_per_mma) {
+    using namespace sddm;
+    if (!cycles_per_mma || N % 16 || N < 16 || N > 256 || reps < 1 || nA < 1 || nA > 16) { set_error("umma_rate: bad arguments"); return SDDM_E_INVALID; }
+    long long* d = nullptr;
+    SDDM_CUDA_TRY(cudaMalloc(&d, sizeof(long long)));
+    const size_t smem = (size_t)nA * 4096 + (size_t)N * 32 + 256;
+    SDDM_CUDA_TRY(cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    umma_rate_kernel<<<1, 128, smem>>>(N, reps, nA, d);
+    count_launch();
+    long long h = 0;
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) { set_error("umma_rate: CUDA error %s", cudaGetErrorName(e)); return SDDM_E_CUDA; }
+    *cycles_per_mma = (float)h / (float)reps;
     return SDDM_OK;
 }

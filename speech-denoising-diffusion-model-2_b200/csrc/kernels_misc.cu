@@ -314,10 +314,14 @@ __global__ void __launch_bounds__(64) gn_finalize_kernel(GnP p) {
     const int cl = c_lo - (s ? p.C[0] : 0);
     const int C = p.C[s], np = p.nparts[s];
     const float* base = p.parts[s] + (int64_t)n * np * C * 2;
+    // affine parameters first: their latency overlaps the partial-sum loads instead of following the reduction
+    float gam = 0.f, bet = 0.f;
+    if (tid < cpg) { gam = __ldg(p.gamma + c_lo + tid); bet = __ldg(p.beta + c_lo + tid); }
     double sum = 0.0, sq = 0.0;
+#pragma unroll 4
     for (int i = tid; i < np * cpg; i += 64) {
         const int part = i / cpg, j = i - part * cpg;
-        const float2 v = *reinterpret_cast<const float2*>(base + ((int64_t)part * C + cl + j) * 2);
+        const float2 v = __ldg(reinterpret_cast<const float2*>(base + ((int64_t)part * C + cl + j) * 2));
         sum += (double)v.x;
         sq += (double)v.y;
     }
@@ -336,17 +340,18 @@ __global__ void __launch_bounds__(64) gn_finalize_kernel(GnP p) {
     double var = sq / cnt - mean * mean;
     if (var < 0.0) var = 0.0;
     const double rstd = 1.0 / sqrt(var + (double)p.eps);
-    for (int j = tid; j < cpg; j += 64) {
-        const int c = c_lo + j;
-        const double sc = (double)p.gamma[c] * rstd;
+    if (tid < cpg) {
+        const int c = c_lo + tid;
+        const double sc = (double)gam * rstd;
         p.scale[(int64_t)n * p.Ctot + c] = (float)sc;
-        p.shift[(int64_t)n * p.Ctot + c] = (float)((double)p.beta[c] - mean * sc);
+        p.shift[(int64_t)n * p.Ctot + c] = (float)((double)bet - mean * sc);
     }
 }
 
 int launch_gn_finalize(const GnP& p, cudaStream_t st) {
     const int cpg = p.Ctot / p.groups;
     if (p.Ctot % p.groups || (p.nsrc == 2 && p.C[0] % cpg)) { set_error("GroupNorm: groups straddle the concat boundary"); return SDDM_E_INVALID; }
+    if (cpg > 64) { set_error("GroupNorm: more than 64 channels per group"); return SDDM_E_INVALID; }
     gn_finalize_kernel<<<dim3(p.groups, p.B), 64, 0, st>>>(p);
     SDDM_LAUNCH_CHECK();
     return SDDM_OK;
