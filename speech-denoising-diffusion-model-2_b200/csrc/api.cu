@@ -301,7 +301,8 @@ static int build_program(sddm_plan* p, Arena& a) {
         op.label = "conv:" + label;
         op.flops = 2.0 * 9.0 * probe.Cin * probe.Cout * probe.Hout * probe.Wout + 2.0 * probe.res_Cin * probe.Cout * probe.Hout * probe.Wout;
         op.bytes = 4.0 * ((double)probe.Cin * probe.Hin * probe.Win + (double)probe.Cout * probe.Hout * probe.Wout +
-                          (probe.res_identity ? (double)probe.Cout * probe.Hout * probe.Wout : 0.0));
+                          (probe.res_identity ? (double)probe.Cout * probe.Hout * probe.Wout : 0.0) +
+                          (double)probe.res_Cin * probe.Hin * probe.Win);   // the 1x1 res_conv re-reads the raw block input
         op.use_tc = want_tc && conv_tc_supported(probe);
         p->tensors[op.out].nparts = op.use_tc ? conv_tc_nparts(probe.Hout, probe.Wout) : conv_fp32_nparts(probe.Hout, probe.Wout);
     };
