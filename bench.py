@@ -157,7 +157,7 @@ def run_ours(args):
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         dist.barrier()
-    from sddm_b200 import PREC_BF16, PREC_FP32, _lib
+    from sddm_b200 import PREC_BF16, PREC_BF16_ACT, PREC_FP32, _lib
     from sddm_b200.infer import enhance_batch
     from sddm_b200.model.diffusion import GaussianDiffusion
     from sddm_b200.model.model import SDDM
@@ -166,7 +166,7 @@ def run_ours(args):
     torch.cuda.set_device(dev)
     torch.manual_seed(0)
     net = UNetModified2(**UNET)
-    net.precision = PREC_FP32 if args.precision == "fp32" else PREC_BF16
+    net.precision = {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16act": PREC_BF16_ACT}[args.precision]
     model = SDDM(GaussianDiffusion("linear", T_STEPS, 1e-6, 1e-3, device=dev), net, p_transition="condition_in").to(dev).eval()
     B = args.batch
     cond_host = synth_batch(B, 1000 + rank).pin_memory()
@@ -229,7 +229,7 @@ def run_ours(args):
     pk = peaks()
     line = {"metric": "utterances_per_sec", "value": value, "unit": "utt/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "fp32", "data": "synthetic",
+            "vs_baseline": None, "dtype": "fp32" if args.precision == "fp32" else "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "reverse_steps": T_STEPS, "noise": "in-kernel Philox4x32-10",
                        "weights": "config-shaped random init (torch.manual_seed(0))", "precision": args.precision,
                        "l2": "per-step working set (~40 MB of activations per chunk, x64 chunks) >> 126 MB L2; no flush needed",
@@ -289,7 +289,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64)
-    ap.add_argument("--precision", default=os.environ.get("SDDM_B200_PRECISION", "bf16"), choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default=os.environ.get("SDDM_B200_PRECISION", "bf16"), choices=["bf16", "fp32", "bf16act"])
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -39,7 +39,8 @@ extern "C" {
 
 /* precision modes for the denoiser convolutions */
 #define SDDM_PREC_FP32 0        /* CUDA-core fp32 FMA (parity mode: eps_hat error ~1e-6) */
-#define SDDM_PREC_BF16 1        /* tcgen05 / TMEM implicit GEMM, bf16 operands, fp32 accumulate */
+#define SDDM_PREC_BF16 1        /* tcgen05 / TMEM implicit GEMM, bf16 operands, fp32 accumulate, fp32 activations in HBM */
+#define SDDM_PREC_BF16_ACT 2    /* same, and the UNet's intermediate activations are stored as bf16 in HBM */
 
 /* posterior-update variants: SDDM.p_transition argument, model/model.py:17-26 */
 #define SDDM_VAR_ORIGINAL 0     /* diffusion.py:177-190, x_T = pure noise               */
@@ -174,7 +175,7 @@ SDDM_API int sddm_debug_umma_probe(int variant, int N, int K, float* max_err_hos
  * role spent waiting on each barrier); enable == 0 copies the [64][48] int64 counters to host_out and stops. */
 SDDM_API int sddm_debug_tc_trace(int enable, long long* host_out);
 /* issue-rate microbenchmark: average cycles per back-to-back tcgen05.mma (M 128, K 16, bf16, shared-memory operands) */
-SDDM_API int sddm_debug_umma_rate(int N, int reps, int nA, float* cycles_per_mma);
+SDDM_API int sddm_debug_umma_rate(int N, int reps, int nA, int geo, float* cycles_per_mma);
 
 #ifdef __cplusplus
 }

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 from typing import Optional
 
-PREC_FP32, PREC_BF16 = 0, 1
+PREC_FP32, PREC_BF16, PREC_BF16_ACT = 0, 1, 2
 VARIANTS = {"original": 0, "condition_in": 1, "sr3": 2, "supportive": 3, "conditional": 4}
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -70,7 +70,7 @@ SIGNATURES = {
     "sddm_debug_fetch": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]),
     "sddm_debug_umma_probe": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "sddm_debug_tc_trace": (C.c_int, [C.c_int, C.c_void_p]),
-    "sddm_debug_umma_rate": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "sddm_debug_umma_rate": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
 }
 
 

@@ -291,7 +291,10 @@ static ConvP shape_probe(const sddm_plan* p, const Op& op) {
 
 static int build_program(sddm_plan* p, Arena& a) {
     const sddm_config& c = p->cfg;
-    const bool want_tc = c.precision == SDDM_PREC_BF16;
+    const bool want_tc = c.precision != SDDM_PREC_FP32;
+    const bool act16 = c.precision == SDDM_PREC_BF16_ACT;
+    const double esz = act16 ? 2.0 : 4.0;
+    bool act16_ok = true;
     size_t ss_cursor = 0;   // relative; rebased after tensors are laid out
     int temb_cursor = 0;
     std::vector<int> feats;
@@ -300,10 +303,11 @@ static int build_program(sddm_plan* p, Arena& a) {
         ConvP probe = shape_probe(p, op);
         op.label = "conv:" + label;
         op.flops = 2.0 * 9.0 * probe.Cin * probe.Cout * probe.Hout * probe.Wout + 2.0 * probe.res_Cin * probe.Cout * probe.Hout * probe.Wout;
-        op.bytes = 4.0 * ((double)probe.Cin * probe.Hin * probe.Win + (double)probe.Cout * probe.Hout * probe.Wout +
+        op.bytes = esz * ((double)probe.Cin * probe.Hin * probe.Win + (double)probe.Cout * probe.Hout * probe.Wout +
                           (probe.res_identity ? (double)probe.Cout * probe.Hout * probe.Wout : 0.0) +
                           (double)probe.res_Cin * probe.Hin * probe.Win);   // the 1x1 res_conv re-reads the raw block input
         op.use_tc = want_tc && conv_tc_supported(probe);
+        if (act16 && !op.use_tc) act16_ok = false;
         p->tensors[op.out].nparts = op.use_tc ? conv_tc_nparts(probe.Hout, probe.Wout) : conv_fp32_nparts(probe.Hout, probe.Wout);
     };
     auto emit_res = [&](const NodeDesc& nd, std::vector<int> srcs) {
@@ -407,7 +411,7 @@ static int build_program(sddm_plan* p, Arena& a) {
                 op.out = cur;
                 op.label = "stem:downs.0";
                 op.flops = 2.0 * 18.0 * nd.cout * H * W;
-                op.bytes = 4.0 * (2.0 * c.num_samples + (double)nd.cout * H * W);
+                op.bytes = 8.0 * c.num_samples + esz * (double)nd.cout * H * W;
                 p->ops.push_back(op);
                 feats.push_back(cur);
                 break;
@@ -452,10 +456,11 @@ static int build_program(sddm_plan* p, Arena& a) {
         op.in_ss_off = p->ops[gnf].ss_off;
         op.label = "final_conv";
         op.flops = 2.0 * 9.0 * C * p->H * p->W;
-        op.bytes = 4.0 * ((double)C * p->H * p->W + (double)p->H * p->W);
+        op.bytes = esz * (double)C * p->H * p->W + 4.0 * (double)p->H * p->W;
         p->ops.push_back(op);
     }
     if (temb_cursor != p->E) { set_error("internal: embedding width mismatch"); return SDDM_E_INVALID; }
+    if (!act16_ok) { set_error("bf16 activation storage needs every convolution on the tcgen05 path (channel counts multiples of 32)"); return SDDM_E_INVALID; }
 
     // workspace layout (per-sample float offsets)
     size_t off = 0;
@@ -465,7 +470,7 @@ static int build_program(sddm_plan* p, Arena& a) {
     p->off_temb_rows = take((size_t)p->E);
     p->off_nl = take(32);
     for (TensorInfo& t : p->tensors) {
-        t.data_off = take((size_t)t.C * t.H * t.W);
+        t.data_off = take(act16 ? ((size_t)t.C * t.H * t.W + 1) / 2 : (size_t)t.C * t.H * t.W);
         t.parts_off = take((size_t)t.nparts * t.C * 2);
     }
     const size_t ss_base = take(ss_cursor);
@@ -536,6 +541,7 @@ static int run_unet(sddm_plan* p, const float* cond, const float* x_t, const flo
                 const TensorInfo& o = p->tensors[op.out];
                 StemP sp{cond, x_t, p->d_f32 + p->off_stem_w, p->d_f32 + p->off_stem_b, sect(p, ws, o.data_off, B),
                          sect(p, ws, o.parts_off, B), B, c.num_samples, o.H, o.W, c.segment_stride, o.C, o.nparts};
+                sp.act16 = c.precision == SDDM_PREC_BF16_ACT;
                 rc = launch_stem(sp, st);
                 break;
             }
@@ -599,6 +605,7 @@ static int run_unet(sddm_plan* p, const float* cond, const float* x_t, const flo
                 cp.parts = sect(p, ws, o.parts_off, B);
                 cp.nparts = o.nparts;
                 cp.B = B;
+                cp.act16 = c.precision == SDDM_PREC_BF16_ACT;
                 rc = op.use_tc ? launch_conv_tc(cp, st) : launch_conv_fp32(cp, st);
                 break;
             }
@@ -612,7 +619,8 @@ static int run_unet(sddm_plan* p, const float* cond, const float* x_t, const flo
                 f.bias = p->final_bias;
                 f.frames = sect(p, ws, p->off_frames, B);
                 f.B = B; f.H = t.H; f.W = t.W; f.C = t.C;
-                f.fast_math = c.precision == SDDM_PREC_BF16;
+                f.fast_math = c.precision != SDDM_PREC_FP32;
+                f.act16 = c.precision == SDDM_PREC_BF16_ACT;
                 rc = launch_final_conv(f, st);
                 break;
             }
@@ -679,7 +687,7 @@ int sddm_plan_create(const sddm_config* cfg, sddm_plan** out) {
     if (c.num_samples % 4 || c.segment_len % 4 || c.segment_stride % 4) { set_error("num_samples, segment_len, segment_stride must be multiples of 4"); return SDDM_E_INVALID; }
     if (c.inner_channel != 32 && c.inner_channel != 64) { set_error("inner_channel must be 32 or 64"); return SDDM_E_INVALID; }
     if (c.norm_groups < 1 || c.inner_channel % c.norm_groups) { set_error("inner_channel must be divisible by norm_groups"); return SDDM_E_INVALID; }
-    if (c.precision != SDDM_PREC_FP32 && c.precision != SDDM_PREC_BF16) { set_error("unknown precision %d", c.precision); return SDDM_E_INVALID; }
+    if (c.precision != SDDM_PREC_FP32 && c.precision != SDDM_PREC_BF16 && c.precision != SDDM_PREC_BF16_ACT) { set_error("unknown precision %d", c.precision); return SDDM_E_INVALID; }
     const int H = (c.num_samples - c.segment_len) / c.segment_stride + 1, W = c.segment_len;
     // every level must tile: the deepest (H/2^n x W/2^n) by 8x4, all others by 16x8
     if (H % (1 << c.n_mults) || W % (1 << c.n_mults) || (H >> c.n_mults) % 8 || (W >> c.n_mults) % 4) {
@@ -1008,6 +1016,7 @@ int sddm_debug_fetch(sddm_plan* p, const char* node, void* ws, int B, float* out
         if (t.name == node) {
             const size_t n = (size_t)t.C * t.H * t.W;
             if (chw) { chw[0] = t.C; chw[1] = t.H; chw[2] = t.W; }
+            if (out && p->cfg.precision == SDDM_PREC_BF16_ACT) return launch_bf16_to_f32(sect(p, ws, t.data_off, B), out, n * B, (cudaStream_t)stream);
             if (out) SDDM_CUDA_TRY(cudaMemcpyAsync(out, sect(p, ws, t.data_off, B), n * B * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
             return SDDM_OK;
         }

@@ -36,7 +36,7 @@ void count_launch(int n = 1);
 
 // ---------------------------------------------------------------------------------------------------
 // convolution op descriptor, shared by the CUDA-core fp32 kernel and the tcgen05 bf16 kernel.
-// Activations are NHWC fp32 ("raw", i.e. pre-GroupNorm); a source with scale != nullptr is consumed as
+// Activations are NHWC fp32 (or bf16 when act16; the pointers below are then reinterpreted) ("raw", i.e. pre-GroupNorm); a source with scale != nullptr is consumed as
 // swish(x * scale[n][c] + shift[n][c]) (GroupNorm-apply + Swish fused into the operand staging); the
 // zero padding of the convolution is applied AFTER that transform (UNetModified2.py:116-121).
 // ---------------------------------------------------------------------------------------------------
@@ -74,6 +74,7 @@ struct ConvP {
     float* parts;  // GroupNorm partial statistics of `out`: [B][nparts][Cout][2] (sum, sum of squares)
     int nparts;
     int B;
+    int act16;     // activations (every src / res_src / out tensor) are bf16 in HBM instead of fp32 (tcgen05 path only)
 };
 
 int launch_conv_fp32(const ConvP& p, cudaStream_t st);

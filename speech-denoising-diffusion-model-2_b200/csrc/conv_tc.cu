@@ -41,7 +41,7 @@ constexpr int kMmaWarp = 8, kWldWarp = 9, kTmaWarp = 10;
 constexpr int kXfWarp0 = 12, kXfGroups = 2, kXfGroupThreads = 128;
 constexpr int kThreads = kXfWarp0 * 32 + kXfGroups * kXfGroupThreads;   // 640
 constexpr int kMaxRing = 6, kMaxW = 32;
-constexpr uint32_t kOutTileBytes = 128 * 32 * 4;       // one 128-pixel x 32-channel fp32 staging tile
+template <bool A16> struct OutTile { static constexpr uint32_t kBytes = 128u * 32u * (A16 ? 2u : 4u); };   // 128 pixels x 32 channels staging tile
 
 // geometry per mode ---------------------------------------------------------------------------------------
 //   SLAB          input channels per A slab (one raw TMA box, SLAB/16 MMA K steps per tap)
@@ -252,9 +252,11 @@ template <int MODE> __device__ __forceinline__ int org_of(int o0) {   // first i
 }
 
 // =====================================================================================================
-template <int MODE, int TPC>
+template <int MODE, int TPC, bool A16>
 __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a, const __grid_constant__ TcMaps maps) {
     using G = Geo<MODE>;
+    constexpr uint32_t kOutTileBytes = OutTile<A16>::kBytes;
+    constexpr uint32_t ESZ = A16 ? 2u : 4u;   // bytes per stored activation
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t dyn_u32 = smem_u32(smem_dyn);
     const uint32_t base_u32 = (dyn_u32 + 1023u) & ~1023u;
@@ -323,6 +325,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
         uint32_t coloff[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) coloff[k] = (uint32_t)((((lane >> 2) ^ k) << 4) + (lane & 3) * 4);
+        // bf16 staging tile: 64-byte rows, 64B swizzle (16-byte chunk q of row r sits at chunk q ^ ((r >> 1) & 3)); in the
+        // statistics pass a lane owns one 32-bit word (2 channels) and the two half-warps take even / odd rows
+        const int c2 = lane & 15, hrow = lane >> 4;
         int g = 0;
         uint32_t aph = 0;
         for (int tile = blockIdx.x + e * gridDim.x; tile < a.ntiles; tile += 2 * gridDim.x, aph ^= 1u) {
@@ -367,25 +372,50 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
                 if (has_res) {
                     const int buf = g % a.NRES;
                     mbar_wait_t(smem_u32(&hdr->res_full[e][buf]), (uint32_t)(g / a.NRES) & 1u, tr, tw[1]);
-                    const uint32_t rrow = rbuf0 + (uint32_t)buf * kOutTileBytes + (uint32_t)m * 128u;
+                    if (A16) {
+                        const uint32_t rrow = rbuf0 + (uint32_t)buf * kOutTileBytes + (uint32_t)m * 64u;
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const uint4 u = lds128(rrow + (uint32_t)((q ^ (m & 7)) << 4));
-                        v[4 * q + 0] += __uint_as_float(u.x); v[4 * q + 1] += __uint_as_float(u.y);
-                        v[4 * q + 2] += __uint_as_float(u.z); v[4 * q + 3] += __uint_as_float(u.w);
+                        for (int q = 0; q < 4; ++q) {
+                            const uint4 u = lds128(rrow + (uint32_t)((q ^ ((m >> 1) & 3)) << 4));
+                            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[k]));
+                                v[8 * q + 2 * k] += f.x; v[8 * q + 2 * k + 1] += f.y;
+                            }
+                        }
+                    } else {
+                        const uint32_t rrow = rbuf0 + (uint32_t)buf * kOutTileBytes + (uint32_t)m * 128u;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const uint4 u = lds128(rrow + (uint32_t)((q ^ (m & 7)) << 4));
+                            v[4 * q + 0] += __uint_as_float(u.x); v[4 * q + 1] += __uint_as_float(u.y);
+                            v[4 * q + 2] += __uint_as_float(u.z); v[4 * q + 3] += __uint_as_float(u.w);
+                        }
                     }
                 }
                 if (!valid) {
 #pragma unroll
                     for (int k = 0; k < 32; ++k) v[k] = 0.f;
                 }
-                const uint32_t orow = obuf + (uint32_t)m * 128u;
+                if (A16) {
+                    const uint32_t orow = obuf + (uint32_t)m * 64u;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    uint4 u;
-                    u.x = __float_as_uint(v[4 * q + 0]); u.y = __float_as_uint(v[4 * q + 1]);
-                    u.z = __float_as_uint(v[4 * q + 2]); u.w = __float_as_uint(v[4 * q + 3]);
-                    sts128(orow + (uint32_t)((q ^ (m & 7)) << 4), u);
+                    for (int q = 0; q < 4; ++q) {
+                        uint4 u;
+                        u.x = pack_bf16(v[8 * q + 0], v[8 * q + 1]); u.y = pack_bf16(v[8 * q + 2], v[8 * q + 3]);
+                        u.z = pack_bf16(v[8 * q + 4], v[8 * q + 5]); u.w = pack_bf16(v[8 * q + 6], v[8 * q + 7]);
+                        sts128(orow + (uint32_t)((q ^ ((m >> 1) & 3)) << 4), u);
+                    }
+                } else {
+                    const uint32_t orow = obuf + (uint32_t)m * 128u;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        uint4 u;
+                        u.x = __float_as_uint(v[4 * q + 0]); u.y = __float_as_uint(v[4 * q + 1]);
+                        u.z = __float_as_uint(v[4 * q + 2]); u.w = __float_as_uint(v[4 * q + 3]);
+                        sts128(orow + (uint32_t)((q ^ (m & 7)) << 4), u);
+                    }
                 }
                 fence_async_smem();
                 group_bar(bar_id);
@@ -394,7 +424,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
                     tma_store_4d(&maps.out, obuf, cb * 32, t.ox0, t.oy0, t.n);
                     bulk_commit();
                 }
-                if (p.parts) {   // column sums of the staged tile: channel = lane, pixel quarter = warp
+                if (p.parts && A16) {   // column sums of the staged (rounded) tile: 2 channels per lane, even / odd rows per half-warp
+                    float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+                    const uint32_t qbase = obuf + (uint32_t)(w4 * 32 + hrow) * 64u + (uint32_t)(c2 & 3) * 4u;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {   // row = w4 * 32 + 2 i + hrow; (row >> 1) & 3 = i & 3
+                        uint32_t wv;
+                        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(wv) : "r"(qbase + (uint32_t)i * 128u + (uint32_t)(((c2 >> 2) ^ (i & 3)) << 4)));
+                        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wv));
+                        s1a += f.x; s1b += f.y;
+                        s2a = fmaf(f.x, f.x, s2a); s2b = fmaf(f.y, f.y, s2b);
+                    }
+                    s1a += __shfl_xor_sync(0xffffffffu, s1a, 16); s1b += __shfl_xor_sync(0xffffffffu, s1b, 16);
+                    s2a += __shfl_xor_sync(0xffffffffu, s2a, 16); s2b += __shfl_xor_sync(0xffffffffu, s2b, 16);
+                    if (hrow == 0) {
+                        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float2*>(p.parts) + ((int64_t)t.n * p.nparts + t.trem * 4 + w4) * p.Cout + cb * 32 + 2 * c2);
+                        *dst = make_float4(s1a, s2a, s1b, s2b);
+                    }
+                } else if (p.parts) {   // column sums of the staged tile: channel = lane, pixel quarter = warp
                     float s1 = 0.f, s2 = 0.f;
                     const uint32_t qbase = obuf + (uint32_t)(w4 * 32) * 128u;
 #pragma unroll
@@ -536,7 +583,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
     } else if (warp == kTmaWarp) {
         // ============================== raw-slab TMA issuer (one thread) ==================================
         if (lane == 0) {
-            constexpr uint32_t RAW_BYTES = (uint32_t)G::RAW_H * G::RAW_W * G::SLAB * 4u;
+            constexpr uint32_t RAW_BYTES = (uint32_t)G::RAW_H * G::RAW_W * G::SLAB * ESZ;
             const uint32_t raw_ring = base_u32 + a.off_raw;
             int rs = 0;
             uint32_t pr = 0;
@@ -553,7 +600,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
                     mbar_wait_t(smem_u32(&hdr->raw_empty[rs]), pr ^ 1u, tr, tw[0]);
                     const bool affine = !is_res && srcs[s].scale != nullptr;
                     const uint32_t nch = is_res ? 32u : (uint32_t)G::SLAB;
-                    mbar_expect_tx(bar, (is_res ? 18u * 10u * 32u * 4u : RAW_BYTES) + (affine ? 8u * nch : 0u));
+                    mbar_expect_tx(bar, (is_res ? 18u * 10u * 32u * ESZ : RAW_BYTES) + (affine ? 8u * nch : 0u));
                     const uint32_t dst = raw_ring + (uint32_t)rs * a.raw_stage;
                     tma_load_4d(dst, &maps.src[(is_res ? 2 : 0) + s], coff, is_res ? t.ox0 - 1 : xo, is_res ? t.oy0 - 1 : yo, t.n, bar);
                     if (affine) {   // GroupNorm scale / shift of the slab's channels travel with the slab
@@ -576,9 +623,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
         const uint32_t raw_ring = base_u32 + a.off_raw, a_ring = base_u32 + a.off_a;
 
         // one 8-channel item: raw fp32 -> (affine, swish) -> masked -> packed bf16.   swish(y) = h + h * tanh(h), h = y / 2
+        // raw loads: fp32 storage = two 16-byte chunks per item (u0, u1); bf16 storage = one chunk (u0) holding all 8 channels
         auto convert = [&](const uint4 u0, const uint4 u1, bool ok, bool affine, const float (&sch)[8], const float (&shh)[8]) -> uint4 {
-            float f[8] = {__uint_as_float(u0.x), __uint_as_float(u0.y), __uint_as_float(u0.z), __uint_as_float(u0.w),
-                          __uint_as_float(u1.x), __uint_as_float(u1.y), __uint_as_float(u1.z), __uint_as_float(u1.w)};
+            float f[8];
+            if (A16) {
+                const uint32_t w[4] = {u0.x, u0.y, u0.z, u0.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float2 t2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[k]));
+                    f[2 * k] = t2.x; f[2 * k + 1] = t2.y;
+                }
+            } else {
+                f[0] = __uint_as_float(u0.x); f[1] = __uint_as_float(u0.y); f[2] = __uint_as_float(u0.z); f[3] = __uint_as_float(u0.w);
+                f[4] = __uint_as_float(u1.x); f[5] = __uint_as_float(u1.y); f[6] = __uint_as_float(u1.z); f[7] = __uint_as_float(u1.w);
+            }
             if (affine) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
@@ -639,8 +697,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
                 for (int r = 0; r < ROUNDS; ++r) {   // all shared-memory loads first: their latency overlaps
                     const int pix = pix0 + r * PST;
                     if (pix < NPIX) {
-                        const uint32_t ra = raw + (uint32_t)pix * 128u + (uint32_t)(((2 * j) ^ (pix & 7)) << 4);
-                        rv[r][0] = lds128(ra); rv[r][1] = lds128(ra ^ 16u);
+                        if (A16) {
+                            rv[r][0] = lds128(raw + (uint32_t)pix * 64u + (uint32_t)j * 16u); rv[r][1] = make_uint4(0u, 0u, 0u, 0u);
+                        } else {
+                            const uint32_t ra = raw + (uint32_t)pix * 128u + (uint32_t)(((2 * j) ^ (pix & 7)) << 4);
+                            rv[r][0] = lds128(ra); rv[r][1] = lds128(ra ^ 16u);
+                        }
                     }
                 }
 #pragma unroll
@@ -672,10 +734,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
                     for (int q = 0; q < RB; ++q) {
                         const int pix = pix0 + (rb * RB + q) * PST;
                         if (pix < NPIX) {
-                            const uint32_t ra = raw + (uint32_t)pix * 64u + (uint32_t)j * 32u;   // unswizzled 64-byte pixels
-                            const bool swap = (pix >> 1) & 1;
-                            const uint4 lo = lds128(ra + (swap ? 16u : 0u)), hi = lds128(ra + (swap ? 0u : 16u));
-                            rv[q][0] = swap ? hi : lo; rv[q][1] = swap ? lo : hi;
+                            if (A16) {
+                                rv[q][0] = lds128(raw + (uint32_t)pix * 32u + (uint32_t)j * 16u); rv[q][1] = make_uint4(0u, 0u, 0u, 0u);
+                            } else {
+                                const uint32_t ra = raw + (uint32_t)pix * 64u + (uint32_t)j * 32u;   // unswizzled 64-byte pixels
+                                const bool swap = (pix >> 1) & 1;
+                                const uint4 lo = lds128(ra + (swap ? 16u : 0u)), hi = lds128(ra + (swap ? 0u : 16u));
+                                rv[q][0] = swap ? hi : lo; rv[q][1] = swap ? lo : hi;
+                            }
                         }
                     }
 #pragma unroll
@@ -699,8 +765,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
                     for (int q = 0; q < RB; ++q) {   // a batch of shared-memory loads first: their latencies overlap
                         const int pix = pix0 + (rb * RB + q) * PST;
                         if (pix < NPIX) {
-                            const uint32_t ra = raw + (uint32_t)pix * 128u + (uint32_t)(((2 * j) ^ (pix & 7)) << 4);
-                            rv[q][0] = lds128(ra); rv[q][1] = lds128(ra ^ 16u);
+                            if (A16) {
+                                rv[q][0] = lds128(raw + (uint32_t)pix * 64u + (uint32_t)j * 16u); rv[q][1] = make_uint4(0u, 0u, 0u, 0u);
+                            } else {
+                                const uint32_t ra = raw + (uint32_t)pix * 128u + (uint32_t)(((2 * j) ^ (pix & 7)) << 4);
+                                rv[q][0] = lds128(ra); rv[q][1] = lds128(ra ^ 16u);
+                            }
                         }
                     }
 #pragma unroll
@@ -785,15 +855,17 @@ __global__ void __launch_bounds__(128) umma_probe_kernel(const __nv_bfloat16* __
     if (warp == 0) { __syncwarp(); tmem_dealloc(tmem, 256); }
 }
 
-// issue-rate microbenchmark: `reps` back-to-back 128 x N x 16 MMAs over `nA` distinct A tiles (canonical layout), one CTA.
-__global__ void __launch_bounds__(128) umma_rate_kernel(int N, int reps, int nA, long long* cycles) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+// issue-rate microbenchmark: `reps` back-to-back 128 x N x 16 MMAs, one CTA.  geo 0: canonical A tiles (SBO 128 B, 128-byte
+// aligned core matrices), cycling over nA tiles; geo 1: the stride-1 halo geometry of the conv kernel (SBO 160 B, LBO 182*16 B),
+// cycling over the 9 tap start offsets; geo 2: x-shifted dense copies (SBO 128 B, aligned), cycling over 9 (copy, row) offsets.
+__global__ void __launch_bounds__(128) umma_rate_kernel(int N, int reps, int nA, int geo, long long* cycles) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tbase;
     const int tid = threadIdx.x, warp = tid >> 5;
-    const uint32_t sA = smem_u32(smem_raw);
-    const uint32_t a_bytes = 128u * 32u, b_off = (uint32_t)nA * a_bytes;
-    for (uint32_t i = tid; i < (b_off + (uint32_t)N * 32u) / 4u; i += 128) reinterpret_cast<uint32_t*>(smem_raw)[i] = 0x3c003c00u;
+    const uint32_t sA = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t a_region = 64u * 1024u, b_off = a_region;
+    for (uint32_t i = tid; i < (a_region + (uint32_t)N * 32u + 1024u) / 4u; i += 128) reinterpret_cast<uint32_t*>(smem_raw)[i] = 0x3c003c00u;
     if (tid == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
     if (warp == 0) tmem_alloc(smem_u32(&tbase), 256);
     fence_async_smem();
@@ -803,11 +875,21 @@ __global__ void __launch_bounds__(128) umma_rate_kernel(int N, int reps, int nA,
     const uint32_t tmem = tbase;
     if (warp == 0) {
         const uint32_t idesc = make_idesc(N);
-        const uint64_t da0 = make_desc(sA, 2048, 128), db = make_desc(sA + b_off, (uint32_t)N * 16u, 128);
+        const uint64_t db = make_desc(sA + b_off, (uint32_t)N * 16u, 128);
+        const uint64_t da0 = geo == 1 ? make_desc(sA, 182u * 16u, 160u) : (geo == 2 ? make_desc(sA, 2304u + 128u, 128u) : make_desc(sA, 2048, 128));
         long long t0 = 0;
         if (elect_one()) {
             t0 = clock64();
-            for (int r = 0; r < reps; ++r) umma(tmem, da0 + (uint64_t)((uint32_t)(r % nA) * (a_bytes >> 4)), db, idesc, r > 0 ? 1u : 0u);
+            // 9 MMAs per iteration with compile-time start offsets (16-byte units): the issue loop itself must not be the limiter
+            uint32_t acc = 0;
+            for (int r = 0; r < reps / 9; ++r) {
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+                    const uint32_t o1 = (uint32_t)((tap / 3) * 10 + tap % 3), o2 = (uint32_t)((tap % 3) * 640 + (tap / 3) * 8), o0 = (uint32_t)tap * 256u;
+                    umma(tmem, da0 + (uint64_t)(geo == 1 ? o1 : (geo == 2 ? o2 : (nA > 1 ? o0 : 0u))), db, idesc, acc);
+                    acc = 1;
+                }
+            }
             umma_commit(smem_u32(&bar));
         }
         mbar_wait(smem_u32(&bar), 0);
@@ -853,16 +935,19 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// fp32 NHWC tensor [B][H][W][C] as a 4-D tensor map (C innermost) with box (bc, bw, bh, 1)
-int encode_nhwc(CUtensorMap* m, const float* base, int B, int H, int W, int C, int bc, int bw, int bh, bool swizzle128) {
+// NHWC tensor [B][H][W][C] (fp32, or bf16 when a16) as a 4-D tensor map (C innermost) with box (bc, bw, bh, 1);
+// swz: 0 none, 64 / 128 = CU_TENSOR_MAP_SWIZZLE_64B / 128B
+int encode_nhwc(CUtensorMap* m, const float* base, int B, int H, int W, int C, int bc, int bw, int bh, int swz, bool a16) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) { set_error("conv tc: cuTensorMapEncodeTiled is unavailable"); return SDDM_E_CUDA; }
     const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-    const cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+    const cuuint64_t es = a16 ? 2 : 4;
+    const cuuint64_t strides[3] = {(cuuint64_t)C * es, (cuuint64_t)W * C * es, (cuuint64_t)H * W * C * es};
     const cuuint32_t box[4] = {(cuuint32_t)bc, (cuuint32_t)bw, (cuuint32_t)bh, 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
-    const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+    const CUresult r = fn(m, a16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          swz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (swz == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE),
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("conv tc: cuTensorMapEncodeTiled failed (%d) for [%d,%d,%d,%d] box %dx%dx%d", (int)r, B, H, W, C, bc, bw, bh); return SDDM_E_CUDA; }
     return SDDM_OK;
@@ -871,14 +956,16 @@ int encode_nhwc(CUtensorMap* m, const float* base, int B, int H, int W, int C, i
 inline size_t align_up_sz(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // returns 1 when the shared-memory plan does not fit with TPC taps per weight chunk (the caller retries with smaller chunks)
-template <int MODE, int TPC>
+template <int MODE, int TPC, bool A16>
 int launch_mode(TcArgs a, cudaStream_t st) {
     using G = Geo<MODE>;
+    constexpr uint32_t kOutTileBytes = OutTile<A16>::kBytes;
+    constexpr size_t ESZ = A16 ? 2 : 4;
     const ConvP& p = a.p;
     a.n_main = p.Cin / G::SLAB;
     a.n_main_chunks = (9 / TPC) * (p.Cin / 16);
-    a.raw_stage = (uint32_t)align_up_sz((size_t)G::RAW_H * G::RAW_W * G::SLAB * 4 + 256, 1024);   // + scale / shift tail
-    if (a.n_res && a.raw_stage < 18u * 10u * 32u * 4u + 256u) a.raw_stage = (uint32_t)align_up_sz(18 * 10 * 32 * 4 + 256, 1024);
+    a.raw_stage = (uint32_t)align_up_sz((size_t)G::RAW_H * G::RAW_W * G::SLAB * ESZ + 256, 1024);   // + scale / shift tail
+    if (a.n_res && a.raw_stage < 18u * 10u * 32u * ESZ + 256u) a.raw_stage = (uint32_t)align_up_sz(18 * 10 * 32 * ESZ + 256, 1024);
     a.a_stage = (uint32_t)align_up_sz((size_t)(G::SLAB / 8) * G::PLANE * 16, 128);
     if (a.n_res && a.a_stage < 4u * 182u * 16u) a.a_stage = (uint32_t)align_up_sz(4 * 182 * 16, 128);
     a.w_stage = 32u * TPC * (uint32_t)p.Cout;
@@ -920,23 +1007,24 @@ int launch_mode(TcArgs a, cudaStream_t st) {
     TcMaps maps;
     memset(&maps, 0, sizeof(maps));
     int rc;
-    const bool swz = G::SLAB == 32;   // 128-byte pixels: let the TMA swizzle the raw slab
+    // raw slabs: fp32 pixels of 32 channels are 128 bytes -> 128B swizzle; bf16 pixels (64 / 32 bytes) are read chunk-contiguously
+    const int swz_raw = (!A16 && G::SLAB == 32) ? 128 : 0, swz_raw_res = A16 ? 0 : 128, swz_tile = A16 ? 64 : 128;
     for (int i = 0; i < p.nsrc; ++i)
-        if ((rc = encode_nhwc(&maps.src[i], p.src[i].x, p.B, p.Hin, p.Win, p.src[i].C, G::SLAB, G::RAW_W, G::RAW_H, swz))) return rc;
+        if ((rc = encode_nhwc(&maps.src[i], p.src[i].x, p.B, p.Hin, p.Win, p.src[i].C, G::SLAB, G::RAW_W, G::RAW_H, swz_raw, A16))) return rc;
     if (a.n_res)
         for (int i = 0; i < p.res_nsrc; ++i)
-            if ((rc = encode_nhwc(&maps.src[2 + i], p.res_src[i].x, p.B, p.Hin, p.Win, p.res_src[i].C, 32, 10, 18, true))) return rc;
-    if ((rc = encode_nhwc(&maps.out, p.out, p.B, p.Hout, p.Wout, p.Cout, 32, TW, TH, true))) return rc;
-    if (p.res_identity && (rc = encode_nhwc(&maps.res, p.res_src[0].x, p.B, p.Hout, p.Wout, p.Cout, 32, TW, TH, true))) return rc;
+            if ((rc = encode_nhwc(&maps.src[2 + i], p.res_src[i].x, p.B, p.Hin, p.Win, p.res_src[i].C, 32, 10, 18, swz_raw_res, A16))) return rc;
+    if ((rc = encode_nhwc(&maps.out, p.out, p.B, p.Hout, p.Wout, p.Cout, 32, TW, TH, swz_tile, A16))) return rc;
+    if (p.res_identity && (rc = encode_nhwc(&maps.res, p.res_src[0].x, p.B, p.Hout, p.Wout, p.Cout, 32, TW, TH, swz_tile, A16))) return rc;
 
     static bool attr_set = false;
     if (!attr_set) {
-        SDDM_CUDA_TRY(cudaFuncSetAttribute(conv3x3_tc_kernel<MODE, TPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+        SDDM_CUDA_TRY(cudaFuncSetAttribute(conv3x3_tc_kernel<MODE, TPC, A16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
         attr_set = true;
     }
     a.trace = g_trace ? g_trace + (size_t)(g_trace_launch++ % 64) * 48 : nullptr;
     const int grid = a.ntiles < num_sms() ? a.ntiles : num_sms();
-    conv3x3_tc_kernel<MODE, TPC><<<grid, kThreads, smem, st>>>(a, maps);
+    conv3x3_tc_kernel<MODE, TPC, A16><<<grid, kThreads, smem, st>>>(a, maps);
     SDDM_LAUNCH_CHECK();
     return SDDM_OK;
 }
@@ -975,11 +1063,17 @@ int launch_conv_tc(const ConvP& p, cudaStream_t st) {
     a.tmem_cols = 2 * a.acc_stride;
     a.temb_per_row = (p.temb && p.temb_stride != 0) ? 1 : 0;
     int rc;
+#define SDDM_TC_DISPATCH(M)                                                                                   \
+    do {                                                                                                     \
+        if (p.act16) { rc = launch_mode<M, 9, true>(a, st); if (rc == 1) rc = launch_mode<M, 3, true>(a, st); } \
+        else { rc = launch_mode<M, 9, false>(a, st); if (rc == 1) rc = launch_mode<M, 3, false>(a, st); }       \
+    } while (0)
     switch (p.mode) {
-        case CONV_S1: rc = launch_mode<CONV_S1, 9>(a, st); if (rc == 1) rc = launch_mode<CONV_S1, 3>(a, st); break;
-        case CONV_S2: rc = launch_mode<CONV_S2, 9>(a, st); if (rc == 1) rc = launch_mode<CONV_S2, 3>(a, st); break;
-        default: rc = launch_mode<CONV_UP, 9>(a, st); if (rc == 1) rc = launch_mode<CONV_UP, 3>(a, st); break;
+        case CONV_S1: SDDM_TC_DISPATCH(CONV_S1); break;
+        case CONV_S2: SDDM_TC_DISPATCH(CONV_S2); break;
+        default: SDDM_TC_DISPATCH(CONV_UP); break;
     }
+#undef SDDM_TC_DISPATCH
     if (rc == 1) { set_error("conv tc: Cout=%d does not fit the shared-memory plan", p.Cout); return SDDM_E_INVALID; }
     return rc;
 }
@@ -1053,21 +1147,21 @@ extern "C" SDDM_API int sddm_debug_tc_trace(int enable, long long* host_out) {
     return SDDM_OK;
 }
 
-// debug: average cycles per back-to-back tcgen05.mma (M 128, K 16, bf16) for a given N, cycling over nA distinct A tiles
-extern "C" SDDM_API int sddm_debug_umma_rate(int N, int reps, int nA, float* cycles_per_mma) {
+// debug: average cycles per back-to-back tcgen05.mma (M 128, K 16, bf16) for a given N and A-operand geometry (see umma_rate_kernel)
+extern "C" SDDM_API int sddm_debug_umma_rate(int N, int reps, int nA, int geo, float* cycles_per_mma) {
     using namespace sddm;
-    if (!cycles_per_mma || N % 16 || N < 16 || N > 256 || reps < 1 || nA < 1 || nA > 16) { set_error("umma_rate: bad arguments"); return SDDM_E_INVALID; }
+    if (!cycles_per_mma || N % 16 || N < 16 || N > 256 || reps < 1 || nA < 1 || nA > 16 || geo < 0 || geo > 2) { set_error("umma_rate: bad arguments"); return SDDM_E_INVALID; }
     long long* d = nullptr;
     SDDM_CUDA_TRY(cudaMalloc(&d, sizeof(long long)));
-    const size_t smem = (size_t)nA * 4096 + (size_t)N * 32 + 256;
+    const size_t smem = 64 * 1024 + (size_t)N * 32 + 2048;
     SDDM_CUDA_TRY(cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    umma_rate_kernel<<<1, 128, smem>>>(N, reps, nA, d);
+    umma_rate_kernel<<<1, 128, smem>>>(N, reps, nA, geo, d);
     count_launch();
     long long h = 0;
     cudaError_t e = cudaDeviceSynchronize();
     if (e == cudaSuccess) e = cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost);
     cudaFree(d);
     if (e != cudaSuccess) { set_error("umma_rate: CUDA error %s", cudaGetErrorName(e)); return SDDM_E_CUDA; }
-    *cycles_per_mma = (float)h / (float)reps;
+    *cycles_per_mma = (float)h / (float)((reps / 9) * 9);
     return SDDM_OK;
 }

@@ -53,6 +53,7 @@ struct StemP {
     float* out;          // [B][H][W][CO]
     float* parts;        // [B][nparts][CO][2], nparts = tiles per sample (16 x 8 pixels each)
     int B, L, H, W, hop, CO, nparts;
+    int act16;           // out is bf16 [B][H][W][CO]
 };
 int launch_stem(const StemP& p, cudaStream_t st);
 int stem_nparts(int H, int W);
@@ -74,8 +75,12 @@ struct FinalP {
     float bias;
     float* frames;      // [B][H][W]
     int B, H, W, C;
+    int act16;          // x is bf16
     int fast_math;      // approximate exp / divide in the Swish (bf16 mode); exact-ish expf / IEEE divide otherwise
 };
 int launch_final_conv(const FinalP& p, cudaStream_t st);
+
+// debug / tests: bf16 -> fp32 copy of an activation tensor
+int launch_bf16_to_f32(const void* src, float* dst, size_t n, cudaStream_t st);
 
 }  // namespace sddm

@@ -213,7 +213,7 @@ int launch_temb(const TembP& p, cudaStream_t st) {
 // ===================================================================================================
 int stem_nparts(int H, int W) { return (H / 16) * (W / 8); }
 
-template <int CO>
+template <int CO, bool A16>
 __global__ void __launch_bounds__(256) stem_kernel(StemP p) {
     constexpr int CG = CO / 4;            // channel groups (threads) per pixel
     constexpr int PPP = 256 / CG;         // pixels per pass
@@ -264,7 +264,20 @@ __global__ void __launch_bounds__(256) stem_kernel(StemP p) {
                         acc.x = fmaf(v, ww.x, acc.x); acc.y = fmaf(v, ww.y, acc.y);
                         acc.z = fmaf(v, ww.z, acc.z); acc.w = fmaf(v, ww.w, acc.w);
                     }
-            *reinterpret_cast<float4*>(p.out + (((int64_t)n * p.H + y0 + py) * p.W + x0 + px) * CO + cg * 4) = acc;
+            const int64_t oidx = (((int64_t)n * p.H + y0 + py) * p.W + x0 + px) * CO + cg * 4;
+            if (A16) {   // bf16 storage: the statistics are those of the stored (rounded) values
+                const __nv_bfloat162 lo = __floats2bfloat162_rn(acc.x, acc.y), hi = __floats2bfloat162_rn(acc.z, acc.w);
+                uint4 pk;   // neighbouring channel groups pair up: the even one writes 16 bytes (8 channels)
+                pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+                pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+                pk.z = __shfl_down_sync(0xffffffffu, pk.x, 1);
+                pk.w = __shfl_down_sync(0xffffffffu, pk.y, 1);
+                if ((cg & 1) == 0) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + oidx) = pk;
+                const float2 a = __bfloat1622float2(lo), b = __bfloat1622float2(hi);
+                acc = make_float4(a.x, a.y, b.x, b.y);
+            } else {
+                *reinterpret_cast<float4*>(p.out + oidx) = acc;
+            }
             s1[0] += acc.x; s1[1] += acc.y; s1[2] += acc.z; s1[3] += acc.w;
             s2[0] = fmaf(acc.x, acc.x, s2[0]); s2[1] = fmaf(acc.y, acc.y, s2[1]);
             s2[2] = fmaf(acc.z, acc.z, s2[2]); s2[3] = fmaf(acc.w, acc.w, s2[3]);
@@ -295,8 +308,8 @@ int launch_stem(const StemP& p, cudaStream_t st) {
     if (p.nparts != stem_nparts(p.H, p.W)) { set_error("stem: nparts mismatch"); return SDDM_E_INVALID; }
     const int ntiles = p.B * (p.H / 16) * (p.W / 8);
     const int grid = ntiles < 148 * 8 ? ntiles : 148 * 8;
-    if (p.CO == 32) stem_kernel<32><<<grid, 256, 0, st>>>(p);
-    else if (p.CO == 64) stem_kernel<64><<<grid, 256, 0, st>>>(p);
+    if (p.CO == 32) { if (p.act16) stem_kernel<32, true><<<grid, 256, 0, st>>>(p); else stem_kernel<32, false><<<grid, 256, 0, st>>>(p); }
+    else if (p.CO == 64) { if (p.act16) stem_kernel<64, true><<<grid, 256, 0, st>>>(p); else stem_kernel<64, false><<<grid, 256, 0, st>>>(p); }
     else { set_error("stem: inner_channel %d unsupported (32 or 64)", p.CO); return SDDM_E_INVALID; }
     SDDM_LAUNCH_CHECK();
     return SDDM_OK;
@@ -364,9 +377,9 @@ int launch_gn_finalize(const GnP& p, cudaStream_t st) {
 // 4 channels: it walks the 18 halo rows once (3 x LDS.128 per row) and feeds 16 row accumulators, so every staged value is
 // read 3 times instead of 9; the C/4 partial dot products of a pixel are combined with a shuffle butterfly.
 // ===================================================================================================
-template <int C, bool FAST>
+template <int C, bool FAST, bool A16>
 __global__ void __launch_bounds__(4 * C) final_conv_kernel(FinalP p) {
-    constexpr int CG = C / 4, NT = 16 * CG;
+    constexpr int CG = C / 4;
     extern __shared__ __align__(16) float smem[];   // [18*18][C]
     const int tid = threadIdx.x, cg = tid % CG, col = tid / CG;
     float4 w[9];
@@ -379,6 +392,42 @@ __global__ void __launch_bounds__(4 * C) final_conv_kernel(FinalP p) {
         const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + (int64_t)n * C) + cg);
         const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + (int64_t)n * C) + cg);
         __syncthreads();   // previous tile's readers are done
+        if (A16) {
+            // bf16 storage: a thread stages 8 channels of a pixel with one 16-byte load (C/8 threads per pixel)
+            constexpr int CH8 = C / 8, PPR = (4 * C) / CH8, U = 4;   // 8-channel chunks per pixel, pixels per round, loads in flight
+            const int ch = tid % CH8, pl = tid / CH8;
+            const float4 sc0 = __ldg(reinterpret_cast<const float4*>(p.scale + (int64_t)n * C) + 2 * ch), sc1 = __ldg(reinterpret_cast<const float4*>(p.scale + (int64_t)n * C) + 2 * ch + 1);
+            const float4 sh0 = __ldg(reinterpret_cast<const float4*>(p.shift + (int64_t)n * C) + 2 * ch), sh1 = __ldg(reinterpret_cast<const float4*>(p.shift + (int64_t)n * C) + 2 * ch + 1);
+#pragma unroll 1
+            for (int base = pl; base < 18 * 18; base += PPR * U) {
+                uint4 rv[U];
+                bool okv[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int pix = base + PPR * u;
+                    const int hy = pix / 18, hx = pix - hy * 18;
+                    const int iy = y0 + hy - 1, ix = x0 + hx - 1;
+                    okv[u] = pix < 18 * 18 && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+                    if (okv[u]) rv[u] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.x) + (((int64_t)n * p.H + iy) * p.W + ix) * C) + ch);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int pix = base + PPR * u;
+                    if (pix >= 18 * 18) break;
+                    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+                    if (okv[u]) {
+                        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rv[u].x)), b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rv[u].y));
+                        const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rv[u].z)), d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rv[u].w));
+                        v0.x = swish_fast(fmaf(a.x, sc0.x, sh0.x)); v0.y = swish_fast(fmaf(a.y, sc0.y, sh0.y));
+                        v0.z = swish_fast(fmaf(b.x, sc0.z, sh0.z)); v0.w = swish_fast(fmaf(b.y, sc0.w, sh0.w));
+                        v1.x = swish_fast(fmaf(c.x, sc1.x, sh1.x)); v1.y = swish_fast(fmaf(c.y, sc1.y, sh1.y));
+                        v1.z = swish_fast(fmaf(d.x, sc1.z, sh1.z)); v1.w = swish_fast(fmaf(d.y, sc1.w, sh1.w));
+                    }
+                    float4* dst = reinterpret_cast<float4*>(smem + (size_t)pix * C + ch * 8);
+                    dst[0] = v0; dst[1] = v1;
+                }
+            }
+        } else {
         constexpr int U = 7;   // 128-bit loads in flight per thread
 #pragma unroll 1
         for (int base = col; base < 18 * 18; base += 16 * U) {
@@ -390,7 +439,17 @@ __global__ void __launch_bounds__(4 * C) final_conv_kernel(FinalP p) {
                 const int hy = pix / 18, hx = pix - hy * 18;
                 const int iy = y0 + hy - 1, ix = x0 + hx - 1;
                 okv[u] = pix < 18 * 18 && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
-                if (okv[u]) rv[u] = __ldg(reinterpret_cast<const float4*>(p.x + (((int64_t)n * p.H + iy) * p.W + ix) * C) + cg);
+                if (okv[u]) {
+                    const int64_t idx = (((int64_t)n * p.H + iy) * p.W + ix) * C + cg * 4;
+                    if (A16) {
+                        const uint2 pk = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.x) + idx));
+                        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.x));
+                        const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.y));
+                        rv[u] = make_float4(a.x, a.y, b.x, b.y);
+                    } else {
+                        rv[u] = __ldg(reinterpret_cast<const float4*>(p.x + idx));
+                    }
+                }
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -409,6 +468,7 @@ __global__ void __launch_bounds__(4 * C) final_conv_kernel(FinalP p) {
                 }
                 *reinterpret_cast<float4*>(smem + (size_t)pix * C + cg * 4) = v;
             }
+        }
         }
         __syncthreads();
         float acc[16];
@@ -447,18 +507,29 @@ int launch_final_conv(const FinalP& p, cudaStream_t st) {
     const size_t smem = (size_t)18 * 18 * p.C * sizeof(float);
     const int ntiles = p.B * (p.H / 16) * (p.W / 16);
     const int grid = ntiles < 148 * 4 ? ntiles : 148 * 4;
-#define SDDM_FINAL_LAUNCH(CC, FF)                                                                                          \
+#define SDDM_FINAL_LAUNCH(CC, FF, AA)                                                                                      \
     do {                                                                                                                  \
         static bool attr = false;                                                                                         \
         if (!attr) {                                                                                                      \
-            SDDM_CUDA_TRY(cudaFuncSetAttribute(final_conv_kernel<CC, FF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 18 * 18 * CC * 4)); \
+            SDDM_CUDA_TRY(cudaFuncSetAttribute(final_conv_kernel<CC, FF, AA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 18 * 18 * CC * 4)); \
             attr = true;                                                                                                  \
         }                                                                                                                 \
-        final_conv_kernel<CC, FF><<<grid, 4 * CC, smem, st>>>(p);                                                         \
+        final_conv_kernel<CC, FF, AA><<<grid, 4 * CC, smem, st>>>(p);                                                     \
     } while (0)
-    if (p.C == 32) { if (p.fast_math) SDDM_FINAL_LAUNCH(32, true); else SDDM_FINAL_LAUNCH(32, false); }
-    else { if (p.fast_math) SDDM_FINAL_LAUNCH(64, true); else SDDM_FINAL_LAUNCH(64, false); }
+    if (p.act16 && !p.fast_math) { set_error("final conv: bf16 activations come with the tcgen05 path"); return SDDM_E_INVALID; }
+    if (p.C == 32) { if (p.act16) SDDM_FINAL_LAUNCH(32, true, true); else if (p.fast_math) SDDM_FINAL_LAUNCH(32, true, false); else SDDM_FINAL_LAUNCH(32, false, false); }
+    else { if (p.act16) SDDM_FINAL_LAUNCH(64, true, true); else if (p.fast_math) SDDM_FINAL_LAUNCH(64, true, false); else SDDM_FINAL_LAUNCH(64, false, false); }
 #undef SDDM_FINAL_LAUNCH
+    SDDM_LAUNCH_CHECK();
+    return SDDM_OK;
+}
+
+__global__ void __launch_bounds__(256) bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = __bfloat162float(src[i]);
+}
+
+int launch_bf16_to_f32(const void* src, float* dst, size_t n, cudaStream_t st) {
+    bf16_to_f32_kernel<<<grid_for((int64_t)n, 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(src), dst, n);
     SDDM_LAUNCH_CHECK();
     return SDDM_OK;
 }

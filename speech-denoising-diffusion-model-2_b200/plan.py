@@ -19,7 +19,9 @@ def default_precision() -> int:
         return _lib.PREC_FP32
     if v in ("bf16", "1"):
         return _lib.PREC_BF16
-    raise ValueError("SDDM_B200_PRECISION must be fp32 or bf16, got %r" % v)
+    if v in ("bf16act", "bf16_act", "2"):
+        return _lib.PREC_BF16_ACT
+    raise ValueError("SDDM_B200_PRECISION must be fp32, bf16 or bf16act, got %r" % v)
 
 
 def _ptr(t: Optional[torch.Tensor]):

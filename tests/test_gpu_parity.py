@@ -18,7 +18,7 @@ import sddm_oracle as O  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
-EPS_BAR = {"fp32": 1e-3, "bf16": 2e-2}
+EPS_BAR = {"fp32": 1e-3, "bf16": 2e-2, "bf16act": 2e-2}
 SNR_BAR = 40.0
 
 
@@ -35,8 +35,8 @@ def dev(built_lib):
 
 
 def prec_id(name):
-    from sddm_b200 import PREC_BF16, PREC_FP32
-    return {"fp32": PREC_FP32, "bf16": PREC_BF16}[name]
+    from sddm_b200 import PREC_BF16, PREC_BF16_ACT, PREC_FP32
+    return {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16act": PREC_BF16_ACT}[name]
 
 
 def make_model(dev, T=100, start=1e-6, end=1e-3, variant="condition_in", sd=None):
@@ -130,7 +130,7 @@ def test_umma_probe(dev, built_lib, variant):
 # ----------------------------------------------------------------------------------------------------
 # the denoiser, node by node
 # ----------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "bf16", "bf16act"])
 def test_unet_nodes_vs_oracle(dev, prec):
     """Random weights with non-trivial GroupNorm affine terms; every UNet node compared with the oracle."""
     cfg = dict(UNET_CFG)
@@ -158,7 +158,7 @@ def test_unet_nodes_vs_oracle(dev, prec):
     assert worst <= (1e-3 if prec == "fp32" else 6e-2)
 
 
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "bf16", "bf16act"])
 def test_unet_eps_vs_reference_golden(dev, golden, meta, prec):
     model, _ = make_model(dev)
     net = model.noise_estimate_model
@@ -182,7 +182,7 @@ def test_unet_eps_vs_reference_golden(dev, golden, meta, prec):
 # ----------------------------------------------------------------------------------------------------
 # the full loop
 # ----------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "bf16", "bf16act"])
 def test_sampling_cfg1_vs_reference_golden(dev, golden, prec):
     """config_unet.json, cfg-1 clip (2 chunks), full 100 steps, injected noise: per-step eps and final waveform."""
     model, _ = make_model(dev)
@@ -223,7 +223,7 @@ def test_batch_invariance_determinism_and_host_api(dev):
     net = model.noise_estimate_model
     g = torch.Generator().manual_seed(8)
     cond = (0.1 * torch.randn(7, 1, L, generator=g)).clamp(-1, 1)
-    for prec in ("fp32", "bf16"):
+    for prec in ("fp32", "bf16", "bf16act"):
         net.precision = prec_id(prec)
         full = model.infer(cond.to(dev), seed=77)
         again = model.infer(cond.to(dev), seed=77)
@@ -252,7 +252,7 @@ def test_full_size_cfg2(dev):
     cond = (0.1 * torch.randn(64, 1, L, generator=torch.Generator().manual_seed(0))).clamp(-1, 1).to(dev)
     noises = torch.randn(100, 64, 1, L, generator=torch.Generator().manual_seed(1234)).to(dev)
     outs = {}
-    for prec in ("fp32", "bf16"):
+    for prec in ("fp32", "bf16", "bf16act"):
         net.precision = prec_id(prec)
         torch.cuda.synchronize()
         t0 = time.time()
@@ -262,6 +262,7 @@ def test_full_size_cfg2(dev):
         two = model.infer(cond[:2], noises=noises[:, :2].contiguous())
         assert torch.equal(two, outs[prec][:2]), prec
         assert float(outs[prec].abs().max()) <= 1.0 and torch.isfinite(outs[prec]).all()
-    per_row = torch.stack([O.sisnr(outs["bf16"][i:i + 1].cpu(), outs["fp32"][i:i + 1].cpu()) for i in range(64)])
-    report(f"cfg2: bf16 vs fp32 SI-SNR per row: min {float(per_row.min()):.1f} dB, mean {float(per_row.mean()):.1f} dB")
-    assert float(per_row.min()) >= SNR_BAR
+    for prec in ("bf16", "bf16act"):
+        per_row = torch.stack([O.sisnr(outs[prec][i:i + 1].cpu(), outs["fp32"][i:i + 1].cpu()) for i in range(64)])
+        report(f"cfg2: {prec} vs fp32 SI-SNR per row: min {float(per_row.min()):.1f} dB, mean {float(per_row.mean()):.1f} dB")
+        assert float(per_row.min()) >= SNR_BAR
