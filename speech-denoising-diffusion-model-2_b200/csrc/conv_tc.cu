@@ -26,6 +26,7 @@
 // reference: Block / ResnetBlock / Downsample / Upsample, model/UNetModified2.py:93-142
 #include <cuda.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -37,9 +38,11 @@ namespace {
 
 constexpr int TH = 16, TW = 8;            // output window of one tile
 constexpr int kEpiGroups = 2, kEpiGroupThreads = 128;         // epilogue group e owns accumulator stage e
-constexpr int kMmaWarp = 8, kWldWarp = 9, kTmaWarp = 10;
-constexpr int kXfWarp0 = 12, kXfGroups = 2, kXfGroupThreads = 128;
-constexpr int kThreads = kXfWarp0 * 32 + kXfGroups * kXfGroupThreads;   // 640
+// The single-thread roles get the HIGHEST warp ids of their scheduler partition (warp id % 4): the issue arbiter favours
+// high warp ids, and a starved MMA issuer stalls the whole pipeline.
+constexpr int kXfWarp0 = 8, kXfGroups = 2, kXfGroupThreads = 128;
+constexpr int kMmaWarp = 16, kWldWarp = 17, kTmaWarp = 18, kMmaWarp2 = 19;
+constexpr int kThreads = 20 * 32;   // 640
 constexpr int kMaxRing = 6, kMaxW = 32;
 template <bool A16> struct OutTile { static constexpr uint32_t kBytes = 128u * 32u * (A16 ? 2u : 4u); };   // 128 pixels x 32 channels staging tile
 
@@ -74,6 +77,7 @@ struct TcArgs {
     int temb_per_row;
     uint32_t off_out, off_res, off_raw, off_a, off_w;   // byte offsets from the 1024-aligned shared-memory base
     uint32_t raw_stage, a_stage, w_stage;
+    int skip;                       // debug experiments: bit 0 no statistics pass, bit 1 no transform work, bit 2 no epilogue staging / store
     long long* trace;               // debug: per-role wait / busy cycle counters of CTA 0 (nullptr = off)
 };
 
@@ -100,11 +104,19 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+__device__ unsigned long long g_dead = 0ull;   // first watchdog victim: (blockIdx << 40) | (warp << 32) | (parity << 24) | barrier offset
 // Bounded wait: a pipeline bug must surface as a trap (CUDA error), never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try(bar, parity)) {
+#ifdef SDDM_TC_DEADLOCK_DEBUG
+        if (++spins > 2000000u) {
+            atomicCAS(&g_dead, 0ull, ((unsigned long long)blockIdx.x << 40) | ((unsigned long long)(threadIdx.x >> 5) << 32) | ((unsigned long long)parity << 24) | (unsigned long long)(bar & 0xFFFFFFu));
+            return;
+        }
+#else
         if (++spins > 40000000u) __trap();
+#endif
     }
 }
 // wait + (when tracing) accumulate the cycles spent into acc
@@ -398,7 +410,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
 #pragma unroll
                     for (int k = 0; k < 32; ++k) v[k] = 0.f;
                 }
-                if (A16) {
+                if (a.skip & 4) {
+                } else if (A16) {
                     const uint32_t orow = obuf + (uint32_t)m * 64u;
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
@@ -420,11 +433,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
                 fence_async_smem();
                 group_bar(bar_id);
                 if (tr) tw[5] += clock64() - te0;
-                if (leader) {
+                if (leader && !(a.skip & 4)) {
                     tma_store_4d(&maps.out, obuf, cb * 32, t.ox0, t.oy0, t.n);
                     bulk_commit();
                 }
-                if (p.parts && A16) {   // column sums of the staged (rounded) tile: 2 channels per lane, even / odd rows per half-warp
+                if (a.skip & 1) {
+                } else if (p.parts && A16) {   // column sums of the staged (rounded) tile: 2 channels per lane, even / odd rows per half-warp
                     float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
                     const uint32_t qbase = obuf + (uint32_t)(w4 * 32 + hrow) * 64u + (uint32_t)(c2 & 3) * 4u;
 #pragma unroll
@@ -460,8 +474,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
             long long* o = a.trace + (e == 0 ? 0 : 8);
             o[0] = clock64() - t_begin; o[1] = tw[0]; o[2] = tw[1]; o[3] = tw[2]; o[4] = tw[3]; o[5] = my_tiles; o[6] = tw[4]; o[7] = tw[5];
         }
-    } else if (warp == kMmaWarp) {
-        // ============================== MMA issuer ========================================================
+    } else if (warp == kMmaWarp || warp == kMmaWarp2) {
+        // ============================== MMA issuers =======================================================
+        // With resident weights two warps issue: warp mw owns the tiles it = mw, mw + 2, ... (= accumulator stage mw), so one
+        // warp's barrier round trips overlap the other's MMAs and the tensor pipe stays fed.  With streamed weights (one
+        // ordered chunk ring) only the first warp works.
         // The whole warp runs the (warp-uniform) control flow so that descriptors live in uniform registers; one elected
         // lane issues the tcgen05.mma / tcgen05.commit instructions.
         constexpr int KS = G::SLAB / 16;
@@ -472,10 +489,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
         const uint64_t a_desc0 = make_desc(base_u32 + a.off_a, a_lbo, a_sbo);
         const uint64_t w_desc0 = make_desc(base_u32 + a.off_w, b_lbo, b_sbo);
         const uint32_t a_step = a.a_stage >> 4, w_step = a.w_stage >> 4, tap_step = 2u * (uint32_t)p.Cout;   // in 16-byte units
+        // (mbarrier waits only see the phase PARITY: a warp that starts a tile may wait on operand stage s only if the
+        // previous use of s is known to be filled, which holds when the ring is deeper than one tile: NA >= nA + 1.)
+        const int mw = warp == kMmaWarp ? 0 : 1, nmma = (a.resident && a.NA >= nA + 1) ? 2 : 1;
         int sa = 0, sw = 0;
         uint32_t pa = 0, pw = 0;
-        bool w_ready = false;   // resident weights: all chunks have landed (after the first tile)
-        for (int it = 0, tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
+        auto skip_slabs = [&](int n) { sa += n; while (sa >= a.NA) { sa -= a.NA; pa ^= 1u; } };
+        bool w_ready = false;   // resident weights: all chunks have landed (after this warp's first tile)
+        if (mw < nmma) skip_slabs(mw * nA);
+        for (int it = mw, tile = blockIdx.x + mw * gridDim.x; mw < nmma && tile < a.ntiles; tile += nmma * gridDim.x, it += nmma) {
             const int as = it & 1;
             const uint32_t aph = (uint32_t)(it >> 1) & 1u;
             mbar_wait_t(smem_u32(&hdr->tmem_empty[as]), aph ^ 1u, tr, tw[0]);
@@ -500,6 +522,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
                             tc_fence_after();
                         }
                         const uint64_t wdesc = w_desc0 + (uint64_t)((uint32_t)wslot * w_step);
+                        const long long tm0 = tr ? clock64() : 0;
                         if (elect_one()) {
 #pragma unroll
                             for (int tt = 0; tt < TPC; ++tt) {
@@ -511,11 +534,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
                             }
                             if (!a.resident) umma_commit(smem_u32(&hdr->empty_w[sw]));
                         }
+                        if (tr) tw[3] += clock64() - tm0;
                         acc = 1;
                         if (!a.resident && ++sw == a.NW) { sw = 0; pw ^= 1u; }
                     }
                 }
+                const long long tc0 = tr ? clock64() : 0;
                 if (elect_one()) umma_commit(smem_u32(&hdr->empty_a[sa]));
+                if (tr) tw[4] += clock64() - tc0;
                 if (++sa == a.NA) { sa = 0; pa ^= 1u; }
             }
             // 1x1 res_conv over the raw block input: centre tap of a stride-1 halo slab, one weight chunk per 32-channel slab
@@ -549,8 +575,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
             }
             if (elect_one()) umma_commit(smem_u32(&hdr->tmem_full[as]));
             w_ready = true;
+            skip_slabs((nmma - 1) * nA);   // the other warp's tile
         }
-        if (tr && lane == 0) { long long* o = a.trace + 16; o[0] = clock64() - t_begin; o[1] = tw[0]; o[2] = tw[1]; o[3] = tw[2]; }
+        if (tr && lane == 0 && mw == 0) { long long* o = a.trace + 16; o[0] = clock64() - t_begin; o[1] = tw[0]; o[2] = tw[1]; o[3] = tw[2]; o[4] = tw[3]; o[5] = tw[4]; }
     } else if (warp == kWldWarp) {
         // ============================== weight loader (one thread) ========================================
         if (lane == 0) {
@@ -612,7 +639,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
             }
             if (tr) { long long* o = a.trace + 24; o[0] = clock64() - t_begin; o[1] = tw[0]; }
         }
-    } else if (warp >= kXfWarp0) {
+    } else if (warp >= kXfWarp0 && warp < kXfWarp0 + kXfGroups * 4) {
         // ============================== transform: raw fp32 slab -> bf16 operand slab ====================
         // group gi handles the slabs gi, gi + kXfGroups, ... of the CTA's (tile, slab) sequence, so kXfGroups slabs are
         // in flight at once.  32-channel raw slabs are 128B-swizzled by the TMA (16-byte chunk c of pixel p sits at
@@ -690,7 +717,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
                 shh[0] = 0.5f * __uint_as_float(h0.x); shh[1] = 0.5f * __uint_as_float(h0.y); shh[2] = 0.5f * __uint_as_float(h0.z); shh[3] = 0.5f * __uint_as_float(h0.w);
                 shh[4] = 0.5f * __uint_as_float(h1.x); shh[5] = 0.5f * __uint_as_float(h1.y); shh[6] = 0.5f * __uint_as_float(h1.z); shh[7] = 0.5f * __uint_as_float(h1.w);
             }
-            if (MODE == CONV_UP && !is_res) {
+            if (a.skip & 2) {
+            } else if (MODE == CONV_UP && !is_res) {
                 constexpr int NPIX = G::RAW_H * G::RAW_W, PST = kXfGroupThreads / 4, ROUNDS = (NPIX + PST - 1) / PST;
                 uint4 rv[ROUNDS][2];
 #pragma unroll
@@ -893,7 +921,7 @@ __global__ void __launch_bounds__(128) umma_rate_kernel(int N, int reps, int nA,
             umma_commit(smem_u32(&bar));
         }
         mbar_wait(smem_u32(&bar), 0);
-        if (tid == 0) cycles[0] = clock64() - t0;
+        if (tid == 0) cycles[blockIdx.x] = clock64() - t0;
     }
     tc_fence_before();
     __syncthreads();
@@ -1022,6 +1050,7 @@ int launch_mode(TcArgs a, cudaStream_t st) {
         SDDM_CUDA_TRY(cudaFuncSetAttribute(conv3x3_tc_kernel<MODE, TPC, A16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
         attr_set = true;
     }
+    { static int skip = -1; if (skip < 0) { const char* e = getenv("SDDM_TC_SKIP"); skip = e ? atoi(e) : 0; } a.skip = skip; }
     a.trace = g_trace ? g_trace + (size_t)(g_trace_launch++ % 64) * 48 : nullptr;
     const int grid = a.ntiles < num_sms() ? a.ntiles : num_sms();
     conv3x3_tc_kernel<MODE, TPC, A16><<<grid, kThreads, smem, st>>>(a, maps);
@@ -1151,17 +1180,28 @@ extern "C" SDDM_API int sddm_debug_tc_trace(int enable, long long* host_out) {
 extern "C" SDDM_API int sddm_debug_umma_rate(int N, int reps, int nA, int geo, float* cycles_per_mma) {
     using namespace sddm;
     if (!cycles_per_mma || N % 16 || N < 16 || N > 256 || reps < 1 || nA < 1 || nA > 16 || geo < 0 || geo > 2) { set_error("umma_rate: bad arguments"); return SDDM_E_INVALID; }
+    const int nblocks = nA > 9 ? 148 : 1;   // nA > 9: one CTA per SM, report the slowest
     long long* d = nullptr;
-    SDDM_CUDA_TRY(cudaMalloc(&d, sizeof(long long)));
+    SDDM_CUDA_TRY(cudaMalloc(&d, 148 * sizeof(long long)));
+    SDDM_CUDA_TRY(cudaMemset(d, 0, 148 * sizeof(long long)));
     const size_t smem = 64 * 1024 + (size_t)N * 32 + 2048;
     SDDM_CUDA_TRY(cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    umma_rate_kernel<<<1, 128, smem>>>(N, reps, nA, geo, d);
+    umma_rate_kernel<<<nblocks, 128, smem>>>(N, reps, nA, geo, d);
     count_launch();
-    long long h = 0;
+    long long hv[148], h = 0;
     cudaError_t e = cudaDeviceSynchronize();
-    if (e == cudaSuccess) e = cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(hv, d, sizeof(hv), cudaMemcpyDeviceToHost);
+    for (int i = 0; i < nblocks; ++i) h = hv[i] > h ? hv[i] : h;
     cudaFree(d);
     if (e != cudaSuccess) { set_error("umma_rate: CUDA error %s", cudaGetErrorName(e)); return SDDM_E_CUDA; }
     *cycles_per_mma = (float)h / (float)((reps / 9) * 9);
     return SDDM_OK;
 }
+
+#ifdef SDDM_TC_DEADLOCK_DEBUG
+extern "C" SDDM_API unsigned long long sddm_debug_dead(void) {
+    unsigned long long v = 0;
+    cudaMemcpyFromSymbol(&v, sddm::g_dead, sizeof(v));
+    return v;
+}
+#endif

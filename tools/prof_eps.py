@@ -55,8 +55,8 @@ def main():
             if r[16] == 0:
                 continue
             f = lambda v: "%7.1fk" % (v / 1e3)
-            print("%2d epi0 %s | %s %s %s %s tiles=%d tmem_ld %s ld..bar %s || mma %s | %s %s %s || tma %s | %s || xf0 %s | %s %s hdr %s rounds %s fence %s" % (
-                i, f(r[0]), f(r[1]), f(r[2]), f(r[3]), f(r[4]), r[5], f(r[6]), f(r[7]), f(r[16]), f(r[17]), f(r[18]), f(r[19]), f(r[24]), f(r[25]),
+            print("%2d epi0 %s | %s %s %s %s tiles=%d tmem_ld %s ld..bar %s || mma %s | %s %s %s issue %s commit %s || tma %s | %s || xf0 %s | %s %s hdr %s rounds %s fence %s" % (
+                i, f(r[0]), f(r[1]), f(r[2]), f(r[3]), f(r[4]), r[5], f(r[6]), f(r[7]), f(r[16]), f(r[17]), f(r[18]), f(r[19]), f(r[20]), f(r[21]), f(r[24]), f(r[25]),
                 f(r[32]), f(r[33]), f(r[34]), f(r[35]), f(r[36]), f(r[37])))
     print("ok", float(x.abs().max()))
 
