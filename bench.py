@@ -232,7 +232,8 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "fp32" if args.precision == "fp32" else "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "reverse_steps": T_STEPS, "noise": "in-kernel Philox4x32-10",
                        "weights": "config-shaped random init (torch.manual_seed(0))", "precision": args.precision,
-                       "l2": "per-step working set (~40 MB of activations per chunk, x64 chunks) >> 126 MB L2; no flush needed",
+                       "l2": "per-step working set (20-40 MB of activations per chunk, x64 chunks) >> 126 MB L2; no flush needed",
+                       "activations": {"fp32": "fp32", "bf16": "fp32 in HBM, bf16 tensor-core operands", "bf16act": "bf16 in HBM, bf16 tensor-core operands, fp32 accumulate"}[args.precision],
                        "utterance": "one 16448-sample chunk (1.028 s); a 2 s clip is 2 chunks"},
             "rtf": 1.0 / (value * L / SR), "chunks_per_sec": value,
             "e2e": {"value": e2e, "unit": "utt/s", "h2d_bytes_per_step": B * L * 4, "d2h_bytes_per_step": B * L * 4,
@@ -289,7 +290,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64)
-    ap.add_argument("--precision", default=os.environ.get("SDDM_B200_PRECISION", "bf16"), choices=["bf16", "fp32", "bf16act"])
+    ap.add_argument("--precision", default=os.environ.get("SDDM_B200_PRECISION", "bf16act"), choices=["bf16", "fp32", "bf16act"])
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

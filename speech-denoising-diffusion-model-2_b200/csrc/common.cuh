@@ -84,6 +84,29 @@ int conv_fp32_nparts(int Hout, int Wout);
 int conv_tc_nparts(int Hout, int Wout);
 
 // ---------------------------------------------------------------------------------------------------
+// programmatic dependent launch (PDL): a kernel launched with launch_pdl() may start while its predecessor in the stream
+// is still running; it must execute pdl_wait() before it touches anything the predecessor produced (and before it writes
+// global memory), and a predecessor calls pdl_launch_dependents() to let the successor's CTAs be scheduled early.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float swish_accurate(float v) { return v / (1.0f + expf(-v)); }

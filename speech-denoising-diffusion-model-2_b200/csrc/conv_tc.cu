@@ -276,6 +276,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
     const ConvP& p = a.p;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nA = a.n_main + a.n_res;
+    pdl_launch_dependents();   // PDL: the next kernel's CTAs may be scheduled as soon as SMs free up
 
     if (tid == 0) {
         for (int i = 0; i < kMaxRing; ++i) {
@@ -308,6 +309,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
 
     if (warp < 8) {
         // ============================== epilogue (group e = accumulator stage e) ==========================
+        pdl_wait();   // everything this role reads (residual) or writes (output, statistics) is ordered after the predecessor
         const int e = warp >> 2, w4 = warp & 3;
         const int m = tid & 127;
         const int py = m >> 3, px = m & 7;
@@ -610,6 +612,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
     } else if (warp == kTmaWarp) {
         // ============================== raw-slab TMA issuer (one thread) ==================================
         if (lane == 0) {
+            pdl_wait();   // activations and GroupNorm scale / shift come from the preceding kernels
             constexpr uint32_t RAW_BYTES = (uint32_t)G::RAW_H * G::RAW_W * G::SLAB * ESZ;
             const uint32_t raw_ring = base_u32 + a.off_raw;
             int rs = 0;
@@ -1053,7 +1056,7 @@ int launch_mode(TcArgs a, cudaStream_t st) {
     { static int skip = -1; if (skip < 0) { const char* e = getenv("SDDM_TC_SKIP"); skip = e ? atoi(e) : 0; } a.skip = skip; }
     a.trace = g_trace ? g_trace + (size_t)(g_trace_launch++ % 64) * 48 : nullptr;
     const int grid = a.ntiles < num_sms() ? a.ntiles : num_sms();
-    conv3x3_tc_kernel<MODE, TPC, A16><<<grid, kThreads, smem, st>>>(a, maps);
+    SDDM_CUDA_TRY(launch_pdl(conv3x3_tc_kernel<MODE, TPC, A16>, dim3(grid), dim3(kThreads), smem, st, a, maps));
     SDDM_LAUNCH_CHECK();
     return SDDM_OK;
 }

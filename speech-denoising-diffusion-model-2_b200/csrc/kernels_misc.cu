@@ -321,6 +321,8 @@ int launch_stem(const StemP& p, cudaStream_t st) {
 // (deterministic), emit scale = gamma * rstd, shift = beta - mean * scale per (sample, channel).
 // ===================================================================================================
 __global__ void __launch_bounds__(64) gn_finalize_kernel(GnP p) {
+    pdl_launch_dependents();   // the consumer convolution may set up (barriers, TMEM, weights) while this grid runs
+    pdl_wait();                // partial statistics come from the preceding kernel
     const int g = blockIdx.x, n = blockIdx.y, tid = threadIdx.x;
     const int cpg = p.Ctot / p.groups, c_lo = g * cpg;
     const int s = (c_lo < p.C[0]) ? 0 : 1;
@@ -365,7 +367,7 @@ int launch_gn_finalize(const GnP& p, cudaStream_t st) {
     const int cpg = p.Ctot / p.groups;
     if (p.Ctot % p.groups || (p.nsrc == 2 && p.C[0] % cpg)) { set_error("GroupNorm: groups straddle the concat boundary"); return SDDM_E_INVALID; }
     if (cpg > 64) { set_error("GroupNorm: more than 64 channels per group"); return SDDM_E_INVALID; }
-    gn_finalize_kernel<<<dim3(p.groups, p.B), 64, 0, st>>>(p);
+    SDDM_CUDA_TRY(launch_pdl(gn_finalize_kernel, dim3(p.groups, p.B), dim3(64), 0, st, p));
     SDDM_LAUNCH_CHECK();
     return SDDM_OK;
 }

@@ -14,7 +14,7 @@ from ._lib import Config, Schedule, SCHEDULE_FIELDS, VARIANTS
 
 
 def default_precision() -> int:
-    v = os.environ.get("SDDM_B200_PRECISION", "bf16").lower()
+    v = os.environ.get("SDDM_B200_PRECISION", "bf16act").lower()
     if v in ("fp32", "0"):
         return _lib.PREC_FP32
     if v in ("bf16", "1"):
