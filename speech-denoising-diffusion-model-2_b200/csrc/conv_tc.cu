@@ -28,6 +28,7 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -654,7 +655,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
 
         // one 8-channel item: raw fp32 -> (affine, swish) -> masked -> packed bf16.   swish(y) = h + h * tanh(h), h = y / 2
         // raw loads: fp32 storage = two 16-byte chunks per item (u0, u1); bf16 storage = one chunk (u0) holding all 8 channels
-        auto convert = [&](const uint4 u0, const uint4 u1, bool ok, bool affine, const float (&sch)[8], const float (&shh)[8]) -> uint4 {
+        auto convert = [&](auto aff_c, const uint4 u0, const uint4 u1, bool ok, const float (&sch)[8], const float (&shh)[8]) -> uint4 {
+            constexpr bool AFF = decltype(aff_c)::value;
             float f[8];
             if (A16) {
                 const uint32_t w[4] = {u0.x, u0.y, u0.z, u0.w};
@@ -667,15 +669,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
                 f[0] = __uint_as_float(u0.x); f[1] = __uint_as_float(u0.y); f[2] = __uint_as_float(u0.z); f[3] = __uint_as_float(u0.w);
                 f[4] = __uint_as_float(u1.x); f[5] = __uint_as_float(u1.y); f[6] = __uint_as_float(u1.z); f[7] = __uint_as_float(u1.w);
             }
-            if (affine) {
+            if (AFF) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const float h = fmaf(f[k], sch[k], shh[k]);
                     f[k] = fmaf(h, tanh_approx(h), h);
                 }
             }
-            uint4 o = make_uint4(0u, 0u, 0u, 0u);
-            if (ok) { o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]); o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]); }
+            uint4 o;
+            o.x = ok ? pack_bf16(f[0], f[1]) : 0u; o.y = ok ? pack_bf16(f[2], f[3]) : 0u;
+            o.z = ok ? pack_bf16(f[4], f[5]) : 0u; o.w = ok ? pack_bf16(f[6], f[7]) : 0u;
             return o;
         };
 
@@ -720,14 +723,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
                 shh[0] = 0.5f * __uint_as_float(h0.x); shh[1] = 0.5f * __uint_as_float(h0.y); shh[2] = 0.5f * __uint_as_float(h0.z); shh[3] = 0.5f * __uint_as_float(h0.w);
                 shh[4] = 0.5f * __uint_as_float(h1.x); shh[5] = 0.5f * __uint_as_float(h1.y); shh[6] = 0.5f * __uint_as_float(h1.z); shh[7] = 0.5f * __uint_as_float(h1.w);
             }
-            if (a.skip & 2) {
-            } else if (MODE == CONV_UP && !is_res) {
-                constexpr int NPIX = G::RAW_H * G::RAW_W, PST = kXfGroupThreads / 4, ROUNDS = (NPIX + PST - 1) / PST;
-                uint4 rv[ROUNDS][2];
+            // Branch-free batches: every thread handles a (clamped) pixel in every round - the surplus lanes of the last round
+            // redo the last pixel and store identical values - so the shared-memory loads of a batch issue back to back
+            // and the per-element chains of its items interleave.
+            auto run_slab = [&](auto aff_c) {
+                if (MODE == CONV_UP && !is_res) {
+                    constexpr int NPIX = G::RAW_H * G::RAW_W, PST = kXfGroupThreads / 4, ROUNDS = (NPIX + PST - 1) / PST;
+                    uint4 rv[ROUNDS][2];
+                    int pv[ROUNDS];
 #pragma unroll
-                for (int r = 0; r < ROUNDS; ++r) {   // all shared-memory loads first: their latency overlaps
-                    const int pix = pix0 + r * PST;
-                    if (pix < NPIX) {
+                    for (int r = 0; r < ROUNDS; ++r) {
+                        const int pix = min(pix0 + r * PST, NPIX - 1);
+                        pv[r] = pix;
                         if (A16) {
                             rv[r][0] = lds128(raw + (uint32_t)pix * 64u + (uint32_t)j * 16u); rv[r][1] = make_uint4(0u, 0u, 0u, 0u);
                         } else {
@@ -735,36 +742,35 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
                             rv[r][0] = lds128(ra); rv[r][1] = lds128(ra ^ 16u);
                         }
                     }
-                }
 #pragma unroll
-                for (int r = 0; r < ROUNDS; ++r) {
-                    const int pix = pix0 + r * PST;
-                    if (pix >= NPIX) break;
-                    const int ry = pix / G::RAW_W, rx = pix - ry * G::RAW_W;
-                    const bool ok = ry >= ylo && ry < yhi && rx >= xlo && rx < xhi;
-                    const uint4 o = convert(rv[r][0], rv[r][1], ok, affine, sch, shh);
+                    for (int r = 0; r < ROUNDS; ++r) {
+                        const int pix = pv[r];
+                        const int ry = pix / G::RAW_W, rx = pix - ry * G::RAW_W;
+                        const bool ok = ry >= ylo && ry < yhi && rx >= xlo && rx < xhi;
+                        const uint4 o = convert(aff_c, rv[r][0], rv[r][1], ok, sch, shh);
 #pragma unroll
-                    for (int dy = 0; dy < 2; ++dy) {
-                        const int hy = 2 * ry - 1 + dy;
-                        if (hy < 0 || hy >= G::PH) continue;
+                        for (int dy = 0; dy < 2; ++dy) {
+                            const int hy = 2 * ry - 1 + dy;
+                            if (hy < 0 || hy >= G::PH) continue;
 #pragma unroll
-                        for (int dx = 0; dx < 2; ++dx) {
-                            const int hx = 2 * rx - 1 + dx;
-                            if (hx < 0 || hx >= G::PW) continue;
-                            sts128(opd + (uint32_t)(hy * G::PW + hx) * 16u, o);
+                            for (int dx = 0; dx < 2; ++dx) {
+                                const int hx = 2 * rx - 1 + dx;
+                                if (hx < 0 || hx >= G::PW) continue;
+                                sts128(opd + (uint32_t)(hy * G::PW + hx) * 16u, o);
+                            }
                         }
                     }
-                }
-            } else if (MODE == CONV_S2) {
-                constexpr int NPIX = G::RAW_H * G::RAW_W, PST = kXfGroupThreads / NPL, ROUNDS = (NPIX + PST - 1) / PST, RB = 3;
-                static_assert(MODE != CONV_S2 || ROUNDS % RB == 0, "stride-2 rounds come in batches");
+                } else if (MODE == CONV_S2) {
+                    constexpr int NPIX = G::RAW_H * G::RAW_W, PST = kXfGroupThreads / NPL, ROUNDS = (NPIX + PST - 1) / PST, RB = 3;
+                    static_assert(MODE != CONV_S2 || ROUNDS % RB == 0, "stride-2 rounds come in batches");
 #pragma unroll 1
-                for (int rb = 0; rb < ROUNDS / RB; ++rb) {
-                    uint4 rv[RB][2];
+                    for (int rb = 0; rb < ROUNDS / RB; ++rb) {
+                        uint4 rv[RB][2];
+                        int pv[RB];
 #pragma unroll
-                    for (int q = 0; q < RB; ++q) {
-                        const int pix = pix0 + (rb * RB + q) * PST;
-                        if (pix < NPIX) {
+                        for (int q = 0; q < RB; ++q) {
+                            const int pix = min(pix0 + (rb * RB + q) * PST, NPIX - 1);
+                            pv[q] = pix;
                             if (A16) {
                                 rv[q][0] = lds128(raw + (uint32_t)pix * 32u + (uint32_t)j * 16u); rv[q][1] = make_uint4(0u, 0u, 0u, 0u);
                             } else {
@@ -774,28 +780,27 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
                                 rv[q][0] = swap ? hi : lo; rv[q][1] = swap ? lo : hi;
                             }
                         }
+#pragma unroll
+                        for (int q = 0; q < RB; ++q) {
+                            const int pix = pv[q];
+                            const int hy = pix / G::RAW_W, hx = pix - hy * G::RAW_W;
+                            const bool ok = hy >= ylo && hy < yhi && hx >= xlo && hx < xhi;
+                            const uint4 o = convert(aff_c, rv[q][0], rv[q][1], ok, sch, shh);
+                            const int slot = hy * G::PW + ((hx & 1) ? G::EVEN_OFF + (hx >> 1) : (hx >> 1));
+                            sts128(opd + (uint32_t)slot * 16u, o);
+                        }
                     }
+                } else {   // stride-1 halo (main conv of CONV_S1, res_conv slabs)
+                    constexpr int NPIX = 18 * 10, PST = kXfGroupThreads / 4, ROUNDS = (NPIX + PST - 1) / PST, RB = 3;
+                    static_assert(ROUNDS % RB == 0, "stride-1 rounds come in batches");
 #pragma unroll
-                    for (int q = 0; q < RB; ++q) {
-                        const int pix = pix0 + (rb * RB + q) * PST;
-                        if (pix >= NPIX) break;
-                        const int hy = pix / G::RAW_W, hx = pix - hy * G::RAW_W;
-                        const bool ok = hy >= ylo && hy < yhi && hx >= xlo && hx < xhi;
-                        const uint4 o = convert(rv[q][0], rv[q][1], ok, affine, sch, shh);
-                        const int slot = hy * G::PW + ((hx & 1) ? G::EVEN_OFF + (hx >> 1) : (hx >> 1));
-                        sts128(opd + (uint32_t)slot * 16u, o);
-                    }
-                }
-            } else {   // stride-1 halo (main conv of CONV_S1, res_conv slabs)
-                constexpr int NPIX = 18 * 10, PST = kXfGroupThreads / 4, ROUNDS = (NPIX + PST - 1) / PST, RB = 3;
-                static_assert(ROUNDS % RB == 0, "stride-1 rounds come in batches");
+                    for (int rb = 0; rb < ROUNDS / RB; ++rb) {
+                        uint4 rv[RB][2];
+                        int pv[RB];
 #pragma unroll
-                for (int rb = 0; rb < ROUNDS / RB; ++rb) {
-                    uint4 rv[RB][2];
-#pragma unroll
-                    for (int q = 0; q < RB; ++q) {   // a batch of shared-memory loads first: their latencies overlap
-                        const int pix = pix0 + (rb * RB + q) * PST;
-                        if (pix < NPIX) {
+                        for (int q = 0; q < RB; ++q) {
+                            const int pix = min(pix0 + (rb * RB + q) * PST, NPIX - 1);
+                            pv[q] = pix;
                             if (A16) {
                                 rv[q][0] = lds128(raw + (uint32_t)pix * 64u + (uint32_t)j * 16u); rv[q][1] = make_uint4(0u, 0u, 0u, 0u);
                             } else {
@@ -803,17 +808,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
                                 rv[q][0] = lds128(ra); rv[q][1] = lds128(ra ^ 16u);
                             }
                         }
-                    }
 #pragma unroll
-                    for (int q = 0; q < RB; ++q) {
-                        const int pix = pix0 + (rb * RB + q) * PST;
-                        if (pix >= NPIX) break;
-                        const int hy = pix / 10, hx = pix - hy * 10;
-                        const bool ok = hy >= ylo && hy < yhi && hx >= xlo && hx < xhi;
-                        const uint4 o = convert(rv[q][0], rv[q][1], ok, affine, sch, shh);
-                        sts128(opd + (uint32_t)pix * 16u, o);
+                        for (int q = 0; q < RB; ++q) {
+                            const int pix = pv[q];
+                            const int hy = pix / 10, hx = pix - hy * 10;
+                            const bool ok = hy >= ylo && hy < yhi && hx >= xlo && hx < xhi;
+                            const uint4 o = convert(aff_c, rv[q][0], rv[q][1], ok, sch, shh);
+                            sts128(opd + (uint32_t)pix * 16u, o);
+                        }
                     }
                 }
+            };
+            if (!(a.skip & 2)) {
+                if (affine) run_slab(std::true_type{}); else run_slab(std::false_type{});
             }
             const long long ts2 = tr ? clock64() : 0;
             fence_async_smem();
