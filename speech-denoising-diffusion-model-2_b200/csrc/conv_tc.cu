@@ -1023,6 +1023,7 @@ int launch_mode(TcArgs a, cudaStream_t st) {
         a.NR = 2; a.NA = 2;
         a.resident = nchunks <= kMaxW && fixed() + (size_t)nchunks * a.w_stage <= cap;
         a.NW = a.resident ? nchunks : (TPC == 9 ? 2 : 4);
+        if (!a.resident && total() > cap) a.NW = 2;   // last resort: a two-deep chunk ring
         if (total() > cap) continue;
         for (bool grew = true; grew;) {   // spend what is left on deeper rings
             grew = false;

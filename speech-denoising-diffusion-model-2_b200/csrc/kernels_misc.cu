@@ -325,20 +325,29 @@ __global__ void __launch_bounds__(64) gn_finalize_kernel(GnP p) {
     pdl_wait();                // partial statistics come from the preceding kernel
     const int g = blockIdx.x, n = blockIdx.y, tid = threadIdx.x;
     const int cpg = p.Ctot / p.groups, c_lo = g * cpg;
-    const int s = (c_lo < p.C[0]) ? 0 : 1;
-    const int cl = c_lo - (s ? p.C[0] : 0);
-    const int C = p.C[s], np = p.nparts[s];
-    const float* base = p.parts[s] + (int64_t)n * np * C * 2;
     // affine parameters first: their latency overlaps the partial-sum loads instead of following the reduction
     float gam = 0.f, bet = 0.f;
     if (tid < cpg) { gam = __ldg(p.gamma + c_lo + tid); bet = __ldg(p.beta + c_lo + tid); }
     double sum = 0.0, sq = 0.0;
+    // a group may straddle the concatenation boundary (e.g. cat(64, 32) channels in 32 groups of 3): take from every
+    // source the channels of [c_lo, c_lo + cpg) it holds
+    int off = 0;
+    for (int s = 0; s < p.nsrc; ++s) {
+        const int C = p.C[s], np = p.nparts[s];
+        const int lo = c_lo > off ? c_lo : off, hi = (c_lo + cpg) < (off + C) ? (c_lo + cpg) : (off + C);
+        const int w = hi - lo;   // channels of this group inside source s
+        if (w > 0) {
+            const float* base = p.parts[s] + (int64_t)n * np * C * 2;
+            const int cl = lo - off;
 #pragma unroll 4
-    for (int i = tid; i < np * cpg; i += 64) {
-        const int part = i / cpg, j = i - part * cpg;
-        const float2 v = __ldg(reinterpret_cast<const float2*>(base + ((int64_t)part * C + cl + j) * 2));
-        sum += (double)v.x;
-        sq += (double)v.y;
+            for (int i = tid; i < np * w; i += 64) {
+                const int part = i / w, j = i - part * w;
+                const float2 v = __ldg(reinterpret_cast<const float2*>(base + ((int64_t)part * C + cl + j) * 2));
+                sum += (double)v.x;
+                sq += (double)v.y;
+            }
+        }
+        off += C;
     }
     __shared__ double sh[2][2];
 #pragma unroll
@@ -365,7 +374,7 @@ __global__ void __launch_bounds__(64) gn_finalize_kernel(GnP p) {
 
 int launch_gn_finalize(const GnP& p, cudaStream_t st) {
     const int cpg = p.Ctot / p.groups;
-    if (p.Ctot % p.groups || (p.nsrc == 2 && p.C[0] % cpg)) { set_error("GroupNorm: groups straddle the concat boundary"); return SDDM_E_INVALID; }
+    if (p.Ctot % p.groups) { set_error("GroupNorm: %d channels do not divide into %d groups", p.Ctot, p.groups); return SDDM_E_INVALID; }
     if (cpg > 64) { set_error("GroupNorm: more than 64 channels per group"); return SDDM_E_INVALID; }
     SDDM_CUDA_TRY(launch_pdl(gn_finalize_kernel, dim3(p.groups, p.B), dim3(64), 0, st, p));
     SDDM_LAUNCH_CHECK();

@@ -159,6 +159,40 @@ def test_unet_nodes_vs_oracle(dev, prec):
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16", "bf16act"])
+@pytest.mark.parametrize("shape", ["two_levels_two_resblocks", "three_levels_wide", "batch_of_one"])
+def test_other_unet_configs_vs_oracle(dev, prec, shape):
+    """Shapes other than config_unet.json (different depth, res_blocks, channel widths, frame grid, batch sizes 1 / 3 / 5):
+    the op program, tile masks, ring plans and weight residency are all derived from the config."""
+    from sddm_b200.model.network import UNetModified2
+    if shape == "two_levels_two_resblocks":
+        cfg = dict(num_samples=64 + 31 * 32, in_channel=2, out_channel=1, inner_channel=32, norm_groups=32, channel_mults=(1, 2),
+                   res_blocks=2, dropout=0, segment_len=64, segment_stride=32)
+        B = 3
+    elif shape == "three_levels_wide":
+        cfg = dict(num_samples=128 + 63 * 64, in_channel=2, out_channel=1, inner_channel=64, norm_groups=32, channel_mults=(1, 2, 4),
+                   res_blocks=1, dropout=0, segment_len=128, segment_stride=64)
+        B = 5
+    else:
+        cfg = dict(UNET_CFG)
+        B = 1
+    sd = O.random_state_dict(cfg, seed=11)
+    net = UNetModified2(**cfg)
+    net.load_state_dict({k[len("noise_estimate_model."):]: v for k, v in sd.items()})
+    net = net.to(dev).eval()
+    net.precision = prec_id(prec)
+    Lc = cfg["num_samples"]
+    g = torch.Generator().manual_seed(5)
+    x = (0.1 * torch.randn(B, 1, Lc, generator=g)).clamp(-1, 1)
+    y = (0.4 * torch.randn(B, 1, Lc, generator=g)).clamp(-1, 1)
+    nl = torch.linspace(0.95, 0.9999, B).reshape(B, 1, 1)
+    ref = O.unet_forward(sd, cfg, x, y, nl)
+    out = net(x.to(dev), y.to(dev), nl.to(dev)).cpu()
+    e = rel_err(out, ref)
+    report(f"config[{shape}][{prec}] B={B}: eps_hat rel_err={e:.3e} (bar {EPS_BAR[prec]:.0e})")
+    assert e <= EPS_BAR[prec]
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16", "bf16act"])
 def test_unet_eps_vs_reference_golden(dev, golden, meta, prec):
     model, _ = make_model(dev)
     net = model.noise_estimate_model
