@@ -156,6 +156,15 @@ SDDM_API int sddm_frames(const float* sig, float* frames, int B, int n_samples, 
 /* replaces: SignalToFrames.overlapAdd (UNetModified2.py:30-41): [B,1,n_frames,F] -> [B,1,n]. */
 SDDM_API int sddm_overlap_add(const float* frames, float* sig, int B, int n_samples, int frame_len, int stride, void* stream);
 
+/* ---- STFT feature front-end (cfg 5) --------------------------------------------------------------- */
+/* replaces: prepare_spectrogram.py:20-55 = torchaudio Spectrogram / MelSpectrogram (torch.stft, centre = True, reflect padding,
+ * onesided, power 1, normalized = "window") followed by clamp((log10(S) - 1 + 5) / 5, 0, 1).
+ * wav: device [B, L] fp32; window: device [n_fft] (torch.hamming_window / hann_window, periodic); inv_norm = 1 / sqrt(sum w^2);
+ * mel_fb: NULL (linear spectrogram, n_out = n_fft/2 + 1) or device [n_fft/2 + 1, n_mels] triangular filterbank (n_out = n_mels);
+ * out: device [B, n_out, 1 + L / hop] fp32.  log_clamp = 0 returns the magnitudes themselves.  n_fft must be 1024. */
+SDDM_API int sddm_stft_features(const float* wav, int B, int L, int n_fft, int hop, const float* window, float inv_norm,
+                                const float* mel_fb, int n_mels, int log_clamp, float* out, void* stream);
+
 /* ---- introspection / test hooks ------------------------------------------------------------------- */
 /* number of kernel launches one sddm_eps call enqueues for this plan. */
 SDDM_API int sddm_plan_launches_per_eps(const sddm_plan* plan);

@@ -1,0 +1,176 @@
+// STFT feature front-end (cfg 5): magnitude spectrogram / mel spectrogram + log10 / clamp compression.
+//
+// reference: prepare_spectrogram.py:20-55 = torchaudio TT.Spectrogram(n_fft=1024, hop, window_fn, power=1, normalized=True)
+// -> torch.stft(center=True, pad_mode="reflect", onesided) / sqrt(sum w^2) -> abs  [-> MelScale (HTK triangular filterbank)]
+// -> clamp((log10(S) - 1 + 5) / 5, 0, 1).   Output layout [B][n_out][frames] as the reference's .npy files.
+//
+// HBM bound (reads 4 L bytes, writes ~8 L bytes per utterance of L samples, ~200 L flop).  One CTA = 32 consecutive frames of
+// one utterance, one warp per frame (4 frames per warp):
+//   * the 1024 windowed (reflect-padded) samples are packed into 512 complex points, 16 per lane: z[32 n1 + lane];
+//   * 512-point FFT as a four-step 16 x 32 decomposition: a 16-point radix-2 DIF in registers (over n1), the twiddle
+//     W512^(lane k1), then a 32-point radix-2 DIF ACROSS LANES with warp shuffles (over lane);
+//   * the spectrum is staged in shared memory (padded, conflict free) for the real-FFT post-processing
+//     X[k] = (Z[k] + conj Z[512-k]) / 2 - i/2 W1024^k (Z[k] - conj Z[512-k]),  k = 0..512;
+//   * magnitudes of the CTA's 32 frames are staged as a [513][32] tile so that global stores (and the mel filterbank
+//     contraction) run along the contiguous frame dimension.
+#include "kernels.cuh"
+#include "../../include/sddm_b200.h"
+
+namespace sddm {
+namespace {
+
+constexpr int NFFT = 1024, NBIN = NFFT / 2 + 1, FPB = 32;   // frames per CTA
+constexpr int ZPAD = 17 * 32;                              // padded 512-point spectrum: index (k & 15) + 17 * (k >> 4)
+constexpr int TILE_LD = FPB + 1;
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ int zidx(int k) { return (k & 15) + 17 * (k >> 4); }
+
+struct StftP {
+    const float* wav;      // [B][L]
+    const float* window;   // [1024]
+    const float* melfb;    // [513][n_mels] or nullptr
+    float* out;            // [B][n_out][frames]
+    int B, L, hop, frames, n_mels, log_clamp;
+    float inv_norm;        // 1 / sqrt(sum w^2)
+};
+
+__global__ void __launch_bounds__(256) stft_kernel(StftP p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* w512 = reinterpret_cast<float2*>(smem_raw);                 // [512]  exp(-2 pi i t / 512)
+    float2* w1024 = w512 + 512;                                         // [513]  exp(-2 pi i k / 1024)
+    float2* zbuf = w1024 + 520;                                         // [8 warps][ZPAD]
+    float* tile = reinterpret_cast<float*>(zbuf + 8 * ZPAD);            // [513][TILE_LD] magnitudes of the CTA's frames
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.y, m0 = blockIdx.x * FPB;
+    for (int t = tid; t < 512; t += 256) {
+        float s, c;
+        sincospif(-2.0f * (float)t / 512.0f, &s, &c);
+        w512[t] = make_float2(c, s);
+    }
+    for (int t = tid; t < NBIN; t += 256) {
+        float s, c;
+        sincospif(-2.0f * (float)t / 1024.0f, &s, &c);
+        w1024[t] = make_float2(c, s);
+    }
+    __syncthreads();
+    const float* x = p.wav + (int64_t)b * p.L;
+    float2* zb = zbuf + warp * ZPAD;
+    for (int f = 0; f < FPB / 8; ++f) {
+        const int ml = warp * (FPB / 8) + f, m = m0 + ml;
+        if (m < p.frames) {   // warp-uniform
+            // ---- load + window + pack: register n1 holds z[32 n1 + lane] = (x[64 n1 + 2 lane], x[64 n1 + 2 lane + 1])
+            float2 v[16];
+#pragma unroll
+            for (int n1 = 0; n1 < 16; ++n1) {
+                const int s0 = 64 * n1 + 2 * lane;
+                float xv[2];
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    int i = p.hop * m + s0 + q - NFFT / 2;   // centre = True, reflect padding
+                    if (i < 0) i = -i;
+                    if (i >= p.L) i = 2 * (p.L - 1) - i;
+                    xv[q] = __ldg(x + i) * __ldg(p.window + s0 + q);
+                }
+                v[n1] = make_float2(xv[0], xv[1]);
+            }
+            // ---- 16-point radix-2 DIF over the registers: afterwards register q holds Y[k1 = bitrev4(q)]
+#pragma unroll
+            for (int half = 8; half >= 1; half >>= 1) {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    if (q & half) continue;
+                    const float2 a = v[q], c = v[q + half];
+                    v[q] = make_float2(a.x + c.x, a.y + c.y);
+                    const float2 d = make_float2(a.x - c.x, a.y - c.y);
+                    const int e = (q & (half - 1)) * (8 / half);      // W16^e = W512^(32 e)
+                    v[q + half] = e == 0 ? d : cmul(d, w512[32 * e]);
+                }
+            }
+            // ---- twiddle W512^(lane * k1), then the 32-point radix-2 DIF across lanes: lane ends with k2 = bitrev5(lane)
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const int k1 = ((q & 1) << 3) | ((q & 2) << 1) | ((q & 4) >> 1) | ((q & 8) >> 3);
+                v[q] = cmul(v[q], w512[(lane * k1) & 511]);
+            }
+#pragma unroll
+            for (int half = 16; half >= 1; half >>= 1) {
+                const bool upper = (lane & half) != 0;
+                const float2 tw = w512[(lane & (half - 1)) * (16 / half) * 16];   // W_(2 half)^(lane mod half) = W512^(...)
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const float ox = __shfl_xor_sync(0xffffffffu, v[q].x, half), oy = __shfl_xor_sync(0xffffffffu, v[q].y, half);
+                    if (!upper) v[q] = make_float2(v[q].x + ox, v[q].y + oy);
+                    else v[q] = cmul(make_float2(ox - v[q].x, oy - v[q].y), tw);
+                }
+            }
+            const int k2 = (int)(__brev((unsigned)lane) >> 27);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const int k1 = ((q & 1) << 3) | ((q & 2) << 1) | ((q & 4) >> 1) | ((q & 8) >> 3);
+                zb[zidx(k1 + 16 * k2)] = v[q];
+            }
+            __syncwarp();
+            // ---- real-FFT post-processing + magnitude: bins k = lane + 32 r
+            for (int k = lane; k < NBIN; k += 32) {
+                const float2 zk = zb[zidx(k & 511)], zr = zb[zidx((512 - k) & 511)];
+                const float2 e = make_float2(0.5f * (zk.x + zr.x), 0.5f * (zk.y - zr.y));       // (Z[k] + conj Z[512-k]) / 2
+                const float2 d = make_float2(zk.x - zr.x, zk.y + zr.y);                         //  Z[k] - conj Z[512-k]
+                const float2 wd = cmul(w1024[k], d);
+                const float re = e.x + 0.5f * wd.y, im = e.y - 0.5f * wd.x;                     // e - i/2 * wd
+                tile[k * TILE_LD + ml] = sqrtf(re * re + im * im) * p.inv_norm;
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    const int nvalid = (p.frames - m0) < FPB ? (p.frames - m0) : FPB;
+    if (p.melfb == nullptr) {
+        float* o = p.out + (int64_t)b * NBIN * p.frames;
+        for (int i = tid; i < NBIN * FPB; i += 256) {
+            const int k = i / FPB, ml = i - k * FPB;
+            if (ml < nvalid) {
+                float s = tile[k * TILE_LD + ml];
+                if (p.log_clamp) s = fminf(fmaxf((log10f(s) - 1.0f + 5.0f) / 5.0f, 0.0f), 1.0f);
+                o[(int64_t)k * p.frames + m0 + ml] = s;
+            }
+        }
+    } else {   // MelScale: mel[j][m] = sum_k S[k][m] * fb[k][j], accumulated in ascending k
+        float* o = p.out + (int64_t)b * p.n_mels * p.frames;
+        for (int i = tid; i < p.n_mels * FPB; i += 256) {
+            const int j = i / FPB, ml = i - j * FPB;
+            if (ml < nvalid) {
+                float acc = 0.f;
+                for (int k = 0; k < NBIN; ++k) {
+                    const float wgt = __ldg(p.melfb + (int64_t)k * p.n_mels + j);
+                    if (wgt != 0.f) acc = fmaf(tile[k * TILE_LD + ml], wgt, acc);
+                }
+                if (p.log_clamp) acc = fminf(fmaxf((log10f(acc) - 1.0f + 5.0f) / 5.0f, 0.0f), 1.0f);
+                o[(int64_t)j * p.frames + m0 + ml] = acc;
+            }
+        }
+    }
+}
+
+}  // namespace
+}  // namespace sddm
+
+extern "C" SDDM_API int sddm_stft_features(const float* wav, int B, int L, int n_fft, int hop, const float* window, float inv_norm,
+                                           const float* mel_fb, int n_mels, int log_clamp, float* out, void* stream) {
+    using namespace sddm;
+    if (!wav || !window || !out || B <= 0) { set_error("stft: null buffer / bad batch"); return SDDM_E_INVALID; }
+    if (n_fft != NFFT) { set_error("stft: n_fft must be %d (config_diffwave.json window_length), got %d", NFFT, n_fft); return SDDM_E_INVALID; }
+    if (hop <= 0 || L <= n_fft / 2) { set_error("stft: hop must be positive and L > n_fft/2 (reflect padding), got hop=%d L=%d", hop, L); return SDDM_E_INVALID; }
+    if (mel_fb && n_mels <= 0) { set_error("stft: n_mels must be positive with a filterbank"); return SDDM_E_INVALID; }
+    StftP p{wav, window, mel_fb, out, B, L, hop, 1 + L / hop, mel_fb ? n_mels : 0, log_clamp, inv_norm};
+    const size_t smem = (512 + 520 + 8 * ZPAD) * sizeof(float2) + (size_t)NBIN * TILE_LD * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+        SDDM_CUDA_TRY(cudaFuncSetAttribute(stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    dim3 grid((p.frames + FPB - 1) / FPB, B);
+    stft_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(p);
+    SDDM_LAUNCH_CHECK();
+    return SDDM_OK;
+}
