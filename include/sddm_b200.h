@@ -161,9 +161,11 @@ SDDM_API int sddm_overlap_add(const float* frames, float* sig, int B, int n_samp
  * onesided, power 1, normalized = "window") followed by clamp((log10(S) - 1 + 5) / 5, 0, 1).
  * wav: device [B, L] fp32; window: device [n_fft] (torch.hamming_window / hann_window, periodic); inv_norm = 1 / sqrt(sum w^2);
  * mel_fb: NULL (linear spectrogram, n_out = n_fft/2 + 1) or device [n_fft/2 + 1, n_mels] triangular filterbank (n_out = n_mels);
+ * mel_lo / mel_hi: NULL or device int32 [n_mels], the band [lo, hi) of bins with non-zero weight per filter (skips the zeros);
  * out: device [B, n_out, 1 + L / hop] fp32.  log_clamp = 0 returns the magnitudes themselves.  n_fft must be 1024. */
 SDDM_API int sddm_stft_features(const float* wav, int B, int L, int n_fft, int hop, const float* window, float inv_norm,
-                                const float* mel_fb, int n_mels, int log_clamp, float* out, void* stream);
+                                const float* mel_fb, const int32_t* mel_lo, const int32_t* mel_hi, int n_mels, int log_clamp,
+                                float* out, void* stream);
 
 /* ---- introspection / test hooks ------------------------------------------------------------------- */
 /* number of kernel launches one sddm_eps call enqueues for this plan. */

@@ -62,8 +62,8 @@ SIGNATURES = {
     "sddm_enhance_host": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_int64, C.c_int]),
     "sddm_frames": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "sddm_overlap_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
-    "sddm_stft_features": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_int, C.c_int,
-                                     C.c_void_p, C.c_void_p]),
+    "sddm_stft_features": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "sddm_plan_launches_per_eps": (C.c_int, [C.c_void_p]),
     "sddm_plan_num_ops": (C.c_int, [C.c_void_p]),
     "sddm_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),

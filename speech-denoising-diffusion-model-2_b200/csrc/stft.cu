@@ -30,6 +30,8 @@ struct StftP {
     const float* wav;      // [B][L]
     const float* window;   // [1024]
     const float* melfb;    // [513][n_mels] or nullptr
+    const int* mel_lo;     // [n_mels] first bin with a non-zero weight (nullptr: 0)
+    const int* mel_hi;     // [n_mels] one past the last non-zero bin (nullptr: 513)
     float* out;            // [B][n_out][frames]
     int B, L, hop, frames, n_mels, log_clamp;
     float inv_norm;        // 1 / sqrt(sum w^2)
@@ -141,10 +143,8 @@ __global__ void __launch_bounds__(256) stft_kernel(StftP p) {
             const int j = i / FPB, ml = i - j * FPB;
             if (ml < nvalid) {
                 float acc = 0.f;
-                for (int k = 0; k < NBIN; ++k) {
-                    const float wgt = __ldg(p.melfb + (int64_t)k * p.n_mels + j);
-                    if (wgt != 0.f) acc = fmaf(tile[k * TILE_LD + ml], wgt, acc);
-                }
+                const int klo = p.mel_lo ? __ldg(p.mel_lo + j) : 0, khi = p.mel_hi ? __ldg(p.mel_hi + j) : NBIN;
+                for (int k = klo; k < khi; ++k) acc = fmaf(tile[k * TILE_LD + ml], __ldg(p.melfb + (int64_t)k * p.n_mels + j), acc);
                 if (p.log_clamp) acc = fminf(fmaxf((log10f(acc) - 1.0f + 5.0f) / 5.0f, 0.0f), 1.0f);
                 o[(int64_t)j * p.frames + m0 + ml] = acc;
             }
@@ -156,13 +156,14 @@ __global__ void __launch_bounds__(256) stft_kernel(StftP p) {
 }  // namespace sddm
 
 extern "C" SDDM_API int sddm_stft_features(const float* wav, int B, int L, int n_fft, int hop, const float* window, float inv_norm,
-                                           const float* mel_fb, int n_mels, int log_clamp, float* out, void* stream) {
+                                           const float* mel_fb, const int32_t* mel_lo, const int32_t* mel_hi, int n_mels, int log_clamp, float* out,
+                                           void* stream) {
     using namespace sddm;
     if (!wav || !window || !out || B <= 0) { set_error("stft: null buffer / bad batch"); return SDDM_E_INVALID; }
     if (n_fft != NFFT) { set_error("stft: n_fft must be %d (config_diffwave.json window_length), got %d", NFFT, n_fft); return SDDM_E_INVALID; }
     if (hop <= 0 || L <= n_fft / 2) { set_error("stft: hop must be positive and L > n_fft/2 (reflect padding), got hop=%d L=%d", hop, L); return SDDM_E_INVALID; }
     if (mel_fb && n_mels <= 0) { set_error("stft: n_mels must be positive with a filterbank"); return SDDM_E_INVALID; }
-    StftP p{wav, window, mel_fb, out, B, L, hop, 1 + L / hop, mel_fb ? n_mels : 0, log_clamp, inv_norm};
+    StftP p{wav, window, mel_fb, mel_fb ? mel_lo : nullptr, mel_fb ? mel_hi : nullptr, out, B, L, hop, 1 + L / hop, mel_fb ? n_mels : 0, log_clamp, inv_norm};
     const size_t smem = (512 + 520 + 8 * ZPAD) * sizeof(float2) + (size_t)NBIN * TILE_LD * sizeof(float);
     static bool attr = false;
     if (!attr) {

@@ -54,6 +54,12 @@ class Spectrogram:
             self._dev[key] = t.to(device=device, dtype=torch.float32).contiguous()
         return self._dev[key]
 
+    def _on_int(self, device, name, t):
+        key = (str(device), name)
+        if key not in self._dev:
+            self._dev[key] = t.to(device=device, dtype=torch.int32).contiguous()
+        return self._dev[key]
+
     def _run(self, waveform: torch.Tensor, fb: Optional[torch.Tensor], n_mels: int) -> torch.Tensor:
         if not waveform.is_cuda:
             raise RuntimeError("sddm_b200 Spectrogram needs a CUDA tensor (no CPU fallback)")
@@ -64,11 +70,20 @@ class Spectrogram:
         n_out = n_mels if fb is not None else self.n_fft // 2 + 1
         out = torch.empty((B, n_out, frames), device=x.device, dtype=torch.float32)
         win = self._on(x.device, "window", self.window)
-        fbd = self._on(x.device, "fb", fb) if fb is not None else None
+        fbd = lo = hi = None
+        if fb is not None:                       # band of non-zero weights per filter: the kernel skips the zeros
+            fbd = self._on(x.device, "fb", fb)
+            nz = fb != 0
+            first = torch.where(nz.any(0), nz.float().argmax(0), torch.zeros(fb.shape[1], dtype=torch.long))
+            last = torch.where(nz.any(0), fb.shape[0] - nz.flip(0).float().argmax(0), torch.zeros(fb.shape[1], dtype=torch.long))
+            lo = self._on_int(x.device, "lo", first)
+            hi = self._on_int(x.device, "hi", last)
         with torch.cuda.device(x.device):
             st = torch.cuda.current_stream().cuda_stream
             _lib.check(_lib.lib().sddm_stft_features(C.c_void_p(x.data_ptr()), B, L, self.n_fft, self.hop_length, C.c_void_p(win.data_ptr()),
                                                      C.c_float(self.inv_norm), C.c_void_p(fbd.data_ptr()) if fbd is not None else None,
+                                                     C.c_void_p(lo.data_ptr()) if lo is not None else None,
+                                                     C.c_void_p(hi.data_ptr()) if hi is not None else None,
                                                      n_mels, int(self.log_clamp), C.c_void_p(out.data_ptr()), C.c_void_p(st)))
         return out.reshape(tuple(shape[:-1]) + (n_out, frames))
 
