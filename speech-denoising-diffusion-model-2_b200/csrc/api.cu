@@ -285,7 +285,9 @@ static ConvP shape_probe(const sddm_plan* p, const Op& op) {
     c.Cin = 0;
     for (int i = 0; i < op.nsrc; ++i) { c.src[i].C = p->tensors[op.src[i]].C; c.Cin += c.src[i].C; }
     c.res_identity = op.res_kind == 1;
-    c.res_Cin = op.res_kind == 2 ? c.Cin : 0;
+    c.res_Cin = 0;   // channels of the raw block input read by the 1x1 res_conv
+    if (op.res_kind == 2)
+        for (int i = 0; i < op.gn_nsrc; ++i) c.res_Cin += p->tensors[op.gn_src[i]].C;
     return c;
 }
 

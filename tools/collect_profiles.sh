@@ -11,6 +11,8 @@ python tools/ncu_lines.py /tmp/top_src.csv 40 > profiles/r1_conv_tc_top_lines.tx
 python tools/ncu_roles.py /tmp/top_src.csv speech-denoising-diffusion-model-2_b200/csrc/conv_tc.cu >> profiles/r1_conv_tc_top_lines.txt
 cp gpurun_out/r1_trace.txt profiles/r1_pipeline_trace.txt
 cp gpurun_out/r1_umma_rate.txt profiles/r1_umma_rate.txt
+[ -f gpurun_out/r1_stft_bench.txt ] && cp gpurun_out/r1_stft_bench.txt profiles/r1_stft_bench.txt
+[ -f gpurun_out/r1_parity_report.txt ] && cp gpurun_out/r1_parity_report.txt profiles/r1_parity_report.txt
 python - <<'PY'
 import csv, json
 rows = list(csv.reader(open("profiles/r1_conv_tc_top_ncu_raw.csv")))
@@ -20,7 +22,7 @@ units = rows[1]
 def to_bytes(v, u):
     return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
 labels = ["conv:ups.14.block1", "conv:ups.14.block2"]      # -s 82 -c 2 of the second forward: conv launches 40, 41
-out = {"batch": 64, "source": "ncu --set full, profiles/r1_conv_tc_top_ncu_raw.csv", "dram_bytes_per_launch": {}, "ncu_duration_us": {}}
+out = {"batch": 64, "precision": "bf16act", "source": "ncu --set full, profiles/r1_conv_tc_top_ncu_raw.csv", "dram_bytes_per_launch": {}, "ncu_duration_us": {}}
 for lab, row in zip(labels, rows[2:]):
     out["dram_bytes_per_launch"][lab] = to_bytes(row[r], units[r]) + to_bytes(row[w], units[w])
     out["ncu_duration_us"][lab] = float(row[t])
