@@ -167,6 +167,55 @@ SDDM_API int sddm_stft_features(const float* wav, int B, int L, int n_fft, int h
                                 const float* mel_fb, const int32_t* mel_lo, const int32_t* mel_hi, int n_mels, int log_clamp,
                                 float* out, void* stream);
 
+/* ---- cfg 5: DiffWave denoiser + spectrogram-conditioned sampling loop --------------------------------- */
+/* replaces: DiffWave (model/diffwave.py:111-155) under SDDM_spectrogram.infer (model/model.py:206-257).
+ * Device layout is time-major ([B][T][64] residual stream); the conditioner path (SpectrogramUpsampler + the 30
+ * conditioner_projection 1x1 convs, all independent of the diffusion step) is evaluated ONCE per batch by
+ * sddm_dw_condition and cached in the workspace, so one eps_hat evaluation only reads it. */
+typedef struct sddm_dw_plan sddm_dw_plan;
+
+#define SDDM_DW_COND_SQRT_ALPHA_BAR 0   /* SDDM(noise_condition='sqrt_alpha_bar'): step value = sqrt_alpha_bar[t] */
+#define SDDM_DW_COND_TIME_STEP 1        /* config_diffwave.json: step value = t                                   */
+
+/* Mirrors DiffWave.__init__ kwargs (diffwave.py:112-131) + what SDDM_spectrogram needs (model.py:208-210). */
+typedef struct sddm_dw_config {
+    int32_t n_timestep;            /* T of the diffusion (config_diffwave.json: 200) */
+    int32_t freq_bins;             /* 513 */
+    int32_t residual_channels;     /* must be 64 */
+    int32_t residual_layers;       /* 30 */
+    int32_t dilation_cycle_length; /* 10 (dilation of layer i = 2^(i mod cycle), <= 2048) */
+    int32_t hop_samples;           /* must be 256 = the upsampler's 16 x 16 */
+    int32_t noise_condition;       /* SDDM_DW_COND_* */
+    int32_t precision;             /* SDDM_PREC_FP32 (CUDA cores) or SDDM_PREC_BF16 (tcgen05, bf16 residual stream + cache) */
+    int32_t reserved[4];
+} sddm_dw_config;
+
+SDDM_API int sddm_dw_plan_create(const sddm_dw_config* cfg, sddm_dw_plan** out);
+SDDM_API void sddm_dw_plan_destroy(sddm_dw_plan* plan);
+/* name = DiffWave state_dict key ("residual_layers.7.dilated_conv.weight", ...), host fp32, shape checked. */
+SDDM_API int sddm_dw_plan_load_weight(sddm_dw_plan* plan, const char* name, const void* data, const int64_t* shape, int ndim);
+SDDM_API int sddm_dw_plan_set_schedule(sddm_dw_plan* plan, const sddm_schedule* sch, int n);
+SDDM_API int sddm_dw_plan_finalize(sddm_dw_plan* plan);
+/* workspace for B utterances of `frames` spectrogram frames (audio length hop_samples * frames). */
+SDDM_API size_t sddm_dw_workspace_bytes(const sddm_dw_plan* plan, int B, int frames);
+
+/* replaces: SpectrogramUpsampler.forward (diffwave.py:54-61) + every ResidualBlock's conditioner_projection (:87).
+ * spec: device [B, freq_bins, frames] fp32.  Must precede sddm_dw_eps on the same workspace. */
+SDDM_API int sddm_dw_condition(sddm_dw_plan* plan, const float* spec, int B, int frames, void* ws, size_t ws_bytes, void* stream);
+/* replaces: DiffWave.forward (diffwave.py:133-155) for the conditioned workspace.  audio: device [B, 1, 256 * frames];
+ * diffusion_step: device [B] step values (as the module API allows) or NULL => the value SDDM_spectrogram.infer
+ * passes at step t (model.py:246-252). */
+SDDM_API int sddm_dw_eps(sddm_dw_plan* plan, const float* audio, const float* diffusion_step, int t, float* eps_out, int B,
+                         int frames, void* ws, size_t ws_bytes, void* stream);
+/* replaces: SDDM_spectrogram.infer (model.py:212-257, non-continuous): x_T ~ N(0,1), T x (eps_hat, p_transition).
+ * noises: NULL (Philox) or [T, B, L] (noises[0] -> x_T, noises[k] -> step t = T + 1 - k); eps_trace: NULL or [T, B, L]. */
+SDDM_API int sddm_dw_sample(sddm_dw_plan* plan, const float* spec, const float* noises, uint64_t seed, int64_t row0, float* out,
+                            float* eps_trace, int B, int frames, void* ws, size_t ws_bytes, void* stream);
+/* test hook: "upsampled" ([T, freq_bins] of utterance B-1), "x" (residual stream after the last eps call, [B, T, 64]),
+ * "skip" (sum of skips, [B, T, 64]), "cond<i>" (cached conditioner of layer i, [B, T, 128]) -> fp32 out; *n = element count. */
+SDDM_API int sddm_dw_debug_fetch(sddm_dw_plan* plan, const char* what, void* ws, int B, int frames, float* out, int64_t* n,
+                                 void* stream);
+
 /* ---- introspection / test hooks ------------------------------------------------------------------- */
 /* number of kernel launches one sddm_eps call enqueues for this plan. */
 SDDM_API int sddm_plan_launches_per_eps(const sddm_plan* plan);

@@ -32,6 +32,15 @@ SCHEDULE_FIELDS = ("betas", "alphas", "sqrt_alpha_bar", "predicted_noise_coeff",
                    "supportive_sigma_hat", "sqrt_delta", "c_xt", "c_yt", "c_epst", "sqrt_delta_estimated")
 
 
+class DwConfig(C.Structure):
+    _fields_ = [("n_timestep", C.c_int32), ("freq_bins", C.c_int32), ("residual_channels", C.c_int32),
+                ("residual_layers", C.c_int32), ("dilation_cycle_length", C.c_int32), ("hop_samples", C.c_int32),
+                ("noise_condition", C.c_int32), ("precision", C.c_int32), ("reserved", C.c_int32 * 4)]
+
+
+NOISE_CONDITIONS = {"sqrt_alpha_bar": 0, "time_step": 1}
+
+
 class Schedule(C.Structure):
     _fields_ = [(k, C.POINTER(C.c_float)) for k in SCHEDULE_FIELDS]
 
@@ -64,6 +73,19 @@ SIGNATURES = {
     "sddm_overlap_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "sddm_stft_features": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "sddm_dw_plan_create": (C.c_int, [C.POINTER(DwConfig), C.POINTER(C.c_void_p)]),
+    "sddm_dw_plan_destroy": (None, [C.c_void_p]),
+    "sddm_dw_plan_load_weight": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int]),
+    "sddm_dw_plan_set_schedule": (C.c_int, [C.c_void_p, C.POINTER(Schedule), C.c_int]),
+    "sddm_dw_plan_finalize": (C.c_int, [C.c_void_p]),
+    "sddm_dw_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
+    "sddm_dw_condition": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "sddm_dw_eps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
+                              C.c_void_p]),
+    "sddm_dw_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                 C.c_void_p, C.c_size_t, C.c_void_p]),
+    "sddm_dw_debug_fetch": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int64),
+                                      C.c_void_p]),
     "sddm_plan_launches_per_eps": (C.c_int, [C.c_void_p]),
     "sddm_plan_num_ops": (C.c_int, [C.c_void_p]),
     "sddm_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),

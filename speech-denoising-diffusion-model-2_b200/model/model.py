@@ -15,6 +15,7 @@ import torch
 from torch import nn
 
 from .diffusion import GaussianDiffusion
+from .diffwave import DiffWave
 from .unet_modified2 import UNetModified2
 
 
@@ -113,3 +114,29 @@ class SDDM(BaseModel):
             if continuous and t % every == 0:
                 samples.append(x_t)
         return samples if continuous else x_t
+
+
+class SDDM_spectrogram(SDDM):
+    """reference model/model.py:206-257: spectrogram-conditioned sampling (config_diffwave.json / config_wavegrad.json):
+    pure-noise start of length ``hop_samples * frames``, then T x (eps_hat, p_transition 'original')."""
+
+    def __init__(self, diffusion: GaussianDiffusion, noise_estimate_model: nn.Module, hop_samples: int,
+                 noise_condition="sqrt_alpha_bar"):
+        super().__init__(diffusion, noise_estimate_model, noise_condition)
+        self.hop_samples = hop_samples
+
+    @torch.no_grad()
+    def infer(self, condition, continuous=False, *, noises: Optional[torch.Tensor] = None, seed: Optional[int] = None,
+              row0: int = 0, return_trace: bool = False):
+        if not condition.is_cuda:
+            raise RuntimeError("SDDM_spectrogram.infer (sddm_b200) needs CUDA tensors: there is no CPU fallback")
+        if not isinstance(self.noise_estimate_model, DiffWave):
+            raise NotImplementedError("SDDM_spectrogram (sddm_b200) drives the DiffWave denoiser only")
+        if continuous:
+            raise NotImplementedError("continuous=True (intermediate samples) is not provided for the spectrogram models")
+        if self.hop_samples != 256:
+            raise ValueError("DiffWave's upsampler is 16 x 16: hop_samples must be 256, got %d" % self.hop_samples)
+        if seed is None and noises is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        plan = self.noise_estimate_model.get_plan(self.diffusion, self.noise_condition)
+        return plan.sample(condition, noises=noises, seed=0 if seed is None else int(seed), row0=row0, trace=return_trace)

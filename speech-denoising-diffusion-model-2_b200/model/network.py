@@ -1,5 +1,6 @@
 """Denoiser registry (reference model/network.py:1-12): ``config.init_obj('network', module_network, ...)`` finds
-the class by name.  Only the denoiser on the hot path of config_unet.json is provided."""
+the class by name.  The denoisers of config_unet.json (UNetModified2) and config_diffwave.json (DiffWave) are provided."""
+from .diffwave import DiffWave  # noqa: F401
 from .unet_modified2 import UNetModified2  # noqa: F401
 
-__all__ = ["UNetModified2"]
+__all__ = ["UNetModified2", "DiffWave"]

@@ -66,6 +66,28 @@ def cfg1_condition():
     return torch.nn.functional.pad(clip, (0, 2 * L - 32000)).view(2, 1, L)
 
 
+# cfg 5 (DiffWave) parity cases: "full" = config_diffwave.json's network on a short clip; "small" = fewer layers, odd frame
+# count, per-row diffusion steps.  Shared by tests/golden/make_golden_diffwave.py (reference side) and the tests.
+DIFFWAVE_CASES = {
+    "full": dict(freq_bins=513, residual_layers=30, dilation_cycle_length=10, B=2, frames=8, steps=[37.0, 37.0], seed=5,
+                 probe_layers=[0, 9, 29]),
+    "small": dict(freq_bins=513, residual_layers=6, dilation_cycle_length=3, B=3, frames=5, steps=[3.0, 57.0, 200.0], seed=6,
+                  probe_layers=[0, 5]),
+}
+
+
+def diffwave_test_module(case):
+    """Host mirror with the reference's default init under torch.manual_seed(0); the zero-initialised output_projection
+    weight (diffwave.py:131) is replaced by 0.1 * N(0,1) (seed 1) so that eps_hat depends on the whole network."""
+    from sddm_b200.model.network import DiffWave
+    torch.manual_seed(0)
+    net = DiffWave(num_samples=-1, num_timesteps=200, freq_bins=case["freq_bins"], residual_channels=64,
+                   residual_layers=case["residual_layers"], dilation_cycle_length=case["dilation_cycle_length"])
+    with torch.no_grad():
+        net.output_projection.weight.copy_(0.1 * torch.randn(net.output_projection.weight.shape, generator=torch.Generator().manual_seed(1)))
+    return net
+
+
 def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
     """max|a-b| / max|b| — the per-tensor error metric of BASELINE.md §3."""
     return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))

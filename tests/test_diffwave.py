@@ -1,0 +1,173 @@
+"""cfg 5: DiffWave denoiser + SDDM_spectrogram sampling loop.
+
+CPU (-m "not gpu"): the oracle restatement (oracle/diffwave_oracle.py) against goldens produced by the real reference modules
+(tests/golden/make_golden_diffwave.py), host-mirror surface.  GPU (-m gpu): the CUDA path through the C ABI (sddm_dw_*) against
+the same goldens and the oracle.  Tolerances: fp32 path 1e-3 of max (north_star's "TF32 mode" bar; measured ~1e-5), tcgen05
+bf16 path 2e-2 of max for eps_hat; final sample SI-SNR >= 40 dB.
+"""
+import math
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from conftest import DIFFWAVE_CASES, GOLDEN, diffwave_test_module, rel_err  # noqa: E402
+from oracle import diffwave_oracle as DO  # noqa: E402
+from oracle import sddm_oracle as O  # noqa: E402
+
+TOL = {"fp32": 1e-3, "bf16": 2e-2}
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return {k: torch.from_numpy(v) for k, v in np.load(os.path.join(GOLDEN, "diffwave.npz")).items()}
+
+
+def _sd(case):
+    return {k: v.detach().clone() for k, v in diffwave_test_module(case).state_dict().items()}
+
+
+def si_snr_db(est, ref):
+    est, ref = est.double().flatten(), ref.double().flatten()
+    s = (est @ ref) / (ref @ ref) * ref
+    return float(10 * torch.log10((s @ s) / ((est - s) @ (est - s))))
+
+
+# --------------------------------------------------------------------------------------------- CPU: oracle pinned to the reference
+@pytest.mark.parametrize("tag", list(DIFFWAVE_CASES))
+def test_oracle_forward_matches_reference(gold, tag):
+    case = DIFFWAVE_CASES[tag]
+    sd = _sd(case)
+    trace = {}
+    step = torch.tensor(case["steps"]).reshape(-1, 1, 1)
+    eps = DO.diffwave_forward(sd, gold[tag + ".spec"], gold[tag + ".audio"], step, case["residual_layers"], case["dilation_cycle_length"],
+                              trace=trace)
+    assert rel_err(eps, gold[tag + ".eps"]) < 2e-5
+    assert rel_err(trace["upsampled"][-1, :, ::29], gold[tag + ".up_last"]) < 1e-5
+    for i in case["probe_layers"]:
+        assert rel_err(trace["x%d" % i][:, ::4, ::3], gold[tag + ".x%d" % i]) < 2e-5
+
+
+@pytest.mark.parametrize("kind", ["time_step", "sqrt_alpha_bar"])
+def test_oracle_sampling_matches_reference(gold, kind):
+    case = DIFFWAVE_CASES["full"]
+    sched = O.make_schedule("linear", 6, 1e-4, 5e-2)
+    x0 = DO.sample_spectrogram(_sd(case), sched, gold["sample.spec"], gold["sample.noises"], 256, kind)
+    assert si_snr_db(x0, gold["sample.%s.x0" % kind]) > 60.0
+
+
+def test_embedding_vector_quirk():
+    v = DO.embedding_vector()
+    assert v.shape == (64,) and float(v[0]) == 1.0 and abs(float(v[-1]) - 10 ** ((63 / 64) * 4 / 63)) < 1e-6   # diffwave.py:28
+
+
+def test_mirror_surface():
+    from sddm_b200.model import model as M
+    from sddm_b200.model.diffusion import GaussianDiffusion
+    net = diffwave_test_module(DIFFWAVE_CASES["small"])
+    keys = list(net.state_dict().keys())
+    assert keys[0] == "input_projection.weight" and "residual_layers.5.output_residual.bias" in keys and keys[-1] == "output_projection.bias"
+    d = GaussianDiffusion(schedule="linear", n_timestep=6, linear_start=1e-4, linear_end=5e-2, device="cpu")
+    m = M.SDDM_spectrogram(d, net, hop_samples=256, noise_condition="time_step")
+    assert m.num_timesteps == 6 and m.p_transition == "original"
+    with pytest.raises(RuntimeError):
+        m.infer(torch.zeros(1, 513, 4))            # CPU tensors: no fallback
+    with pytest.raises(NotImplementedError):
+        M.SDDM_spectrogram(d, net, hop_samples=256, noise_condition="bogus")
+
+
+# --------------------------------------------------------------------------------------------- GPU: CUDA path through the C ABI
+def _gpu_module(case, prec):
+    from sddm_b200 import _lib
+    net = diffwave_test_module(case).cuda()
+    net.precision = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}[prec]
+    return net
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("tag", list(DIFFWAVE_CASES))
+def test_gpu_eps_vs_reference_golden(built_lib, gold, tag, prec):
+    case = DIFFWAVE_CASES[tag]
+    net = _gpu_module(case, prec)
+    spec, audio = gold[tag + ".spec"].cuda(), gold[tag + ".audio"].cuda()
+    step = torch.tensor(case["steps"]).reshape(-1, 1, 1).cuda()
+    eps = net(spec, audio, step).cpu()
+    B, frames = case["B"], case["frames"]
+    plan = net.get_plan()
+    T = 256 * frames
+    up = plan.fetch("upsampled", B, frames).reshape(T, case["freq_bins"]).t().cpu()
+    x = plan.fetch("x", B, frames).reshape(B, T, 64).permute(0, 2, 1).cpu()
+    e_up = rel_err(up[:, ::29], gold[tag + ".up_last"])
+    e_x = rel_err(x[:, ::4, ::3], gold[tag + ".x%d" % (case["residual_layers"] - 1)])
+    e = rel_err(eps, gold[tag + ".eps"])
+    print("diffwave %s %s: upsampler %.2e  x_last %.2e  eps %.2e" % (tag, prec, e_up, e_x, e))
+    assert e_up < (1e-5 if prec == "fp32" else 8e-3)
+    assert e_x < TOL[prec] and e < TOL[prec]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_gpu_conditioner_cache_vs_oracle(built_lib, gold, prec):
+    case = DIFFWAVE_CASES["small"]
+    net = _gpu_module(case, prec)
+    sd = _sd(case)
+    spec = gold["small.spec"]
+    plan = net.get_plan()
+    plan.condition(spec.cuda())
+    B, frames = case["B"], case["frames"]
+    up = DO.spectrogram_upsampler(sd, spec)
+    for l in (0, 5):
+        p = "residual_layers.%d." % l
+        want = torch.nn.functional.conv1d(up, sd[p + "conditioner_projection.weight"], sd[p + "conditioner_projection.bias"]) \
+            + sd[p + "dilated_conv.bias"][None, :, None]
+        got = plan.fetch("cond%d" % l, B, frames).reshape(B, 256 * frames, 128).permute(0, 2, 1).cpu()
+        assert rel_err(got, want) < (1e-5 if prec == "fp32" else 1e-2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("kind", ["time_step", "sqrt_alpha_bar"])
+def test_gpu_sampling_vs_reference_golden(built_lib, gold, kind, prec):
+    from sddm_b200.model import model as M
+    from sddm_b200.model.diffusion import GaussianDiffusion
+    case = DIFFWAVE_CASES["full"]
+    net = _gpu_module(case, prec)
+    d = GaussianDiffusion(schedule="linear", n_timestep=6, linear_start=1e-4, linear_end=5e-2, device="cuda")
+    m = M.SDDM_spectrogram(d, net, hop_samples=256, noise_condition=kind)
+    x0 = m.infer(gold["sample.spec"].cuda(), noises=gold["sample.noises"].cuda()).cpu()
+    snr = si_snr_db(x0, gold["sample.%s.x0" % kind])
+    print("diffwave sampling %s %s: SI-SNR vs reference %.1f dB" % (kind, prec, snr))
+    assert snr > (60.0 if prec == "fp32" else 40.0)
+
+
+@pytest.mark.gpu
+def test_gpu_edges(built_lib, gold):
+    """batch / frame-count edge cases against the oracle: one frame (T = 256 < the larger dilations: both taps outside),
+    batch of one, per-row steps; Philox sampling is deterministic per (seed, row0) and rows are batch invariant."""
+    from sddm_b200.model import model as M
+    from sddm_b200.model.diffusion import GaussianDiffusion
+    case = DIFFWAVE_CASES["full"]
+    sd = _sd(case)
+    g = torch.Generator().manual_seed(9)
+    for prec in ("fp32", "bf16"):
+        net = _gpu_module(case, prec)
+        for B, frames in ((1, 1), (2, 3)):
+            spec = torch.rand(B, 513, frames, generator=g) * 0.7
+            audio = torch.randn(B, 1, 256 * frames, generator=g)
+            step = torch.tensor([11.0, 150.0][:B]).reshape(B, 1, 1)
+            want = DO.diffwave_forward(sd, spec, audio, step)
+            got = net(spec.cuda(), audio.cuda(), step.cuda()).cpu()
+            assert rel_err(got, want) < TOL[prec], (prec, B, frames)
+    net = _gpu_module(case, "bf16")
+    d = GaussianDiffusion(schedule="linear", n_timestep=4, linear_start=1e-4, linear_end=5e-2, device="cuda")
+    m = M.SDDM_spectrogram(d, net, hop_samples=256, noise_condition="time_step")
+    spec = (torch.rand(3, 513, 2, generator=g) * 0.7).cuda()
+    a = m.infer(spec, seed=123)
+    b = m.infer(spec, seed=123)
+    c = m.infer(spec[1:2].contiguous(), seed=123, row0=1)
+    assert torch.equal(a, b) and torch.equal(a[1:2], c)
+    assert float(a.abs().max()) <= 1.0 and not torch.equal(a, m.infer(spec, seed=124))
