@@ -1,8 +1,528 @@
-// tcgen05 path of the DiffWave layer (placeholder until the kernels land).
+// tcgen05 / TMEM / TMA kernels of the DiffWave denoiser (cfg 5; reference model/diffwave.py:64-108), sm_100a.
+//
+// dw_layer_tc_kernel — one ResidualBlock over all time tiles (persistent CTAs, one per SM, tile = 128 samples of one utterance):
+//   operands   the residual stream is time-major bf16 [B][T][64]: a row is exactly one 128-byte swizzle atom, so ONE TMA box
+//              [128 t][64 c] (SWIZZLE_128B) IS a K-major UMMA operand.  The three taps of the dilated conv are three boxes at
+//              t0 - d, t0, t0 + d; rows outside [0, T) are zero filled by TMA (the conv's zero padding).
+//   MMA 1      acc1[128 x 128] = sum_tap X_tap[128 x 64] . Wd_tap^T          (12 tcgen05.mma, fp32 in TMEM)
+//   epilogue 1 + cached conditioner row (bf16, read straight from HBM) + diffusion-step bias -> sigmoid(gate) * tanh(filter)
+//              -> bf16 z tile written into shared memory in the same swizzled K-major layout = operand of MMA 2
+//   MMA 2      acc2[128 x 128] = z[128 x 64] . [W_res | W_skip]^T            (4 tcgen05.mma)
+//   epilogue 2 x_out = (x + acc2[:, :64] + b_res) / sqrt(2)  (x re-read from the centre box in shared memory, bf16 store);
+//              skip += acc2[:, 64:] + b_skip  (vectorised red.global.add.f32 — no read latency in the CTA)
+//   pipeline   warps 0-3 / 4-7: epilogue groups 0 / 1 (alternate tiles; group g owns operand stage g and TMEM columns
+//              [256 g, 256 g + 256)), warp 8: TMA producer, warp 9: MMA issuer.  MMA 2 of tile i-1 is issued after MMA 1 of
+//              tile i, so the tensor pipe works on one group's tile while the other group runs its epilogue.
+//   weights    Wd (48 KB) and [W_res | W_skip] (16 KB) stay resident in shared memory for the CTA's lifetime.
+//
+// dw_cond_tc_kernel — conditioner_projection of one layer for one utterance: [128 t x KP] . [128 n x KP]^T, 64-wide K chunks
+//   through a 4-stage TMA ring, + bias, bf16 output row [128] per time step (the cache the layer kernel reads).
+#include <cuda.h>
+
+#include <cstring>
+#include <map>
+#include <tuple>
+
 #include "../../include/sddm_b200.h"
 #include "diffwave.cuh"
 
 namespace sddm {
-int launch_dw_layer_tc(const DwLayerTc&, cudaStream_t) { set_error("DiffWave tcgen05 path not built"); return SDDM_E_INVALID; }
-int launch_dw_cond_tc(const DwCondTc&, cudaStream_t) { set_error("DiffWave tcgen05 path not built"); return SDDM_E_INVALID; }
+namespace {
+
+// ---- PTX wrappers -----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// bounded wait: a pipeline bug must surface as a trap (CUDA error), never as a hung GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try(bar, parity))
+        if (++spins > 40000000u) __trap();
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+                 "l"(map), "r"(bar), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+                 "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// shared-memory matrix descriptor, K-major, SWIZZLE_128B: rows of 128 bytes (64 bf16), 8-row groups 1024 bytes apart
+// (SBO), LBO unused for swizzled K-major layouts, bit 46 = descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B.
+// A K step of 16 elements inside the atom advances the start address by 32 bytes.
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor, kind::f16: D = fp32, A = B = bf16, both K-major, M = 128, N = n
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 ldg_nc128(const void* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void red_add_f32x4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float tanh_approx(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// ---- layer kernel ------------------------------------------------------------------------------------
+constexpr int kTile = 128;
+constexpr uint32_t kBox = kTile * DW_C * 2;             // 16 KB: one [128][64] bf16 operand box
+constexpr uint32_t kOffW1 = 0;                          // 3 boxes
+constexpr uint32_t kOffW2 = 3 * kBox;                   // 1 box
+constexpr uint32_t kOffA = 4 * kBox;                    // 2 stages x 3 boxes
+constexpr uint32_t kOffZ = 10 * kBox;                   // 2 boxes (one per epilogue group)
+constexpr uint32_t kOffB2 = 12 * kBox;                  // 128 floats
+constexpr uint32_t kOffBar = kOffB2 + 512;
+constexpr uint32_t kLayerSmem = kOffBar + 256 + 1024;   // + alignment slack
+constexpr int kLayerThreads = 320;
+enum { B_AFULL = 0, B_AEMPTY = 2, B_ACC1F = 4, B_ACC1E = 6, B_ZFULL = 8, B_ACC2F = 10, B_WFULL = 12, B_COUNT = 13 };
+
+struct alignas(64) LayerMaps {
+    CUtensorMap x, w1, w2;
+};
+
+__global__ void __launch_bounds__(kLayerThreads, 1) dw_layer_tc_kernel(const __grid_constant__ LayerMaps maps, DwLayerTc p, int ntiles,
+                                                                       int tiles_per_row) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char* gbase = smem_raw + (base - smem_u32(smem_raw));
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t bars = base + kOffBar;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + kOffBar + 128);
+    float* b2s = reinterpret_cast<float*>(gbase + kOffB2);
+    auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
+
+    if (tid == 0) {
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(bar(B_AFULL + s), 1);
+            mbar_init(bar(B_AEMPTY + s), 128);
+            mbar_init(bar(B_ACC1F + s), 1);
+            mbar_init(bar(B_ACC1E + s), 128);
+            mbar_init(bar(B_ZFULL + s), 128);
+            mbar_init(bar(B_ACC2F + s), 1);
+        }
+        mbar_init(bar(B_WFULL), 1);
+        fence_barrier_init();
+    }
+    if (tid < DW_N) b2s[tid] = p.b2[tid];
+    if (warp == 9) tmem_alloc(smem_u32(tmem_slot), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const int my_tiles = ntiles > (int)blockIdx.x ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    if (warp == 8) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            mbar_expect_tx(bar(B_WFULL), 4 * kBox);   // weights are not produced by the previous kernel: load before the PDL wait
+            for (int tap = 0; tap < 3; ++tap) tma_load_2d(base + kOffW1 + tap * kBox, &maps.w1, 0, tap * DW_N, bar(B_WFULL));
+            tma_load_2d(base + kOffW2, &maps.w2, 0, 0, bar(B_WFULL));
+        }
+        pdl_wait();
+        if (lane == 0) {
+            for (int i = 0; i < my_tiles; ++i) {
+                const int tile = blockIdx.x + i * gridDim.x;
+                const int b = tile / tiles_per_row, t0 = (tile - b * tiles_per_row) * kTile;
+                const int s = i & 1, n = i >> 1;
+                mbar_wait(bar(B_AEMPTY + s), (n & 1) ^ 1);
+                mbar_expect_tx(bar(B_AFULL + s), 3 * kBox);
+                const uint32_t dst = base + kOffA + s * 3 * kBox;
+                tma_load_3d(dst + kBox, &maps.x, 0, t0, b, bar(B_AFULL + s));            // centre first: also the residual input
+                tma_load_3d(dst, &maps.x, 0, t0 - p.dil, b, bar(B_AFULL + s));
+                tma_load_3d(dst + 2 * kBox, &maps.x, 0, t0 + p.dil, b, bar(B_AFULL + s));
+            }
+        }
+    } else if (warp == 9) {
+        // ================= MMA issuer =================
+        const uint32_t idesc = make_idesc(DW_N);
+        mbar_wait(bar(B_WFULL), 0);
+        for (int i = 0; i <= my_tiles; ++i) {
+            if (i < my_tiles) {
+                const int s = i & 1, n = i >> 1;
+                mbar_wait(bar(B_AFULL + s), n & 1);
+                mbar_wait(bar(B_ACC1E + s), (n & 1) ^ 1);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t a0 = base + kOffA + s * 3 * kBox, acc1 = tmem + 256u * s;
+#pragma unroll
+                    for (int tap = 0; tap < 3; ++tap)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma(acc1, make_desc_sw128(a0 + tap * kBox + k * 32), make_desc_sw128(base + kOffW1 + tap * kBox + k * 32), idesc,
+                                 (tap | k) != 0);
+                    umma_commit(bar(B_ACC1F + s));
+                }
+                __syncwarp();
+            }
+            if (i >= 1) {   // second GEMM of the previous tile (the other epilogue group's)
+                const int j = i - 1, s = j & 1, n = j >> 1;
+                mbar_wait(bar(B_ZFULL + s), n & 1);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t z0 = base + kOffZ + s * kBox, acc2 = tmem + 256u * s + 128u;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma(acc2, make_desc_sw128(z0 + k * 32), make_desc_sw128(base + kOffW2 + k * 32), idesc, k != 0);
+                    umma_commit(bar(B_ACC2F + s));
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ================= epilogue groups =================
+        pdl_wait();
+        const int g = warp >> 2, row = (warp & 3) * 32 + lane;
+        const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+        const uint32_t acc1 = tmem + 256u * g + lane_off, acc2 = acc1 + 128u;
+        const uint32_t zrow = base + kOffZ + g * kBox + row * 128, xrow = base + kOffA + g * 3 * kBox + kBox + row * 128;
+        const uint32_t sw = (uint32_t)(row & 7);
+        for (int i = g, n = 0; i < my_tiles; i += 2, ++n) {
+            const int tile = blockIdx.x + i * gridDim.x;
+            const int b = tile / tiles_per_row, t = (tile - b * tiles_per_row) * kTile + row;
+            const size_t grow = (size_t)b * p.T + t;
+            // ---- epilogue 1: gate
+            uint4 cv[16];
+            const uint4* cp = reinterpret_cast<const uint4*>(p.cond + grow * DW_N);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) cv[q] = ldg_nc128(cp + q);
+            const int v = (t < p.dil ? 1 : 0) | (t + p.dil >= p.T ? 2 : 0);
+            const float4* b1 = reinterpret_cast<const float4*>(p.bias1 + (size_t)b * p.bias1_row_stride + v * DW_N);
+            mbar_wait(bar(B_ACC1F + g), n & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float ga[32], fa[32];
+                tmem_ld32(acc1 + 32 * h, ga);
+                tmem_ld32(acc1 + 64 + 32 * h, fa);
+                if (h == 1) {   // every TMEM read of acc1 is done: MMA 1 of this group's next tile may overwrite it
+                    tc_fence_before();
+                    mbar_arrive(bar(B_ACC1E + g));
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {   // 8 channels per 16-byte chunk
+                    const uint4 cg = cv[4 * h + q], cf = cv[8 + 4 * h + q];
+                    const float4 bg0 = __ldg(b1 + 8 * h + 2 * q), bg1 = __ldg(b1 + 8 * h + 2 * q + 1);
+                    const float4 bf0 = __ldg(b1 + 16 + 8 * h + 2 * q), bf1 = __ldg(b1 + 16 + 8 * h + 2 * q + 1);
+                    const float cgs[8] = {bf16_lo(cg.x), bf16_hi(cg.x), bf16_lo(cg.y), bf16_hi(cg.y), bf16_lo(cg.z), bf16_hi(cg.z), bf16_lo(cg.w), bf16_hi(cg.w)};
+                    const float cfs[8] = {bf16_lo(cf.x), bf16_hi(cf.x), bf16_lo(cf.y), bf16_hi(cf.y), bf16_lo(cf.z), bf16_hi(cf.z), bf16_lo(cf.w), bf16_hi(cf.w)};
+                    const float bgs[8] = {bg0.x, bg0.y, bg0.z, bg0.w, bg1.x, bg1.y, bg1.z, bg1.w};
+                    const float bfs[8] = {bf0.x, bf0.y, bf0.z, bf0.w, bf1.x, bf1.y, bf1.z, bf1.w};
+                    float z[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float gt = ga[8 * q + e] + cgs[e] + bgs[e], ft = fa[8 * q + e] + cfs[e] + bfs[e];
+                        z[e] = fmaf(0.5f, tanh_approx(0.5f * gt), 0.5f) * tanh_approx(ft);     // sigmoid(g) * tanh(f)
+                    }
+                    uint4 o;
+                    o.x = pack_bf16(z[0], z[1]); o.y = pack_bf16(z[2], z[3]); o.z = pack_bf16(z[4], z[5]); o.w = pack_bf16(z[6], z[7]);
+                    sts128(zrow + ((((uint32_t)(4 * h + q)) ^ sw) << 4), o);
+                }
+            }
+            fence_async_smem();
+            mbar_arrive(bar(B_ZFULL + g));
+            // ---- epilogue 2: residual + skip
+            mbar_wait(bar(B_ACC2F + g), n & 1);
+            mbar_wait(bar(B_AFULL + g), n & 1);   // long complete; acquires the TMA-written centre box for this thread's reads
+            tc_fence_after();
+            __nv_bfloat16* xo = p.x_out + grow * DW_C;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float r[32];
+                tmem_ld32(acc2 + 32 * h, r);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint4 xv = lds128(xrow + ((((uint32_t)(4 * h + q)) ^ sw) << 4));
+                    const float xs[8] = {bf16_lo(xv.x), bf16_hi(xv.x), bf16_lo(xv.y), bf16_hi(xv.y), bf16_lo(xv.z), bf16_hi(xv.z), bf16_lo(xv.w), bf16_hi(xv.w)};
+                    float o[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) o[e] = (xs[e] + r[8 * q + e] + b2s[32 * h + 8 * q + e]) * 0.70710678118654752f;
+                    uint4 pk;
+                    pk.x = pack_bf16(o[0], o[1]); pk.y = pack_bf16(o[2], o[3]); pk.z = pack_bf16(o[4], o[5]); pk.w = pack_bf16(o[6], o[7]);
+                    *reinterpret_cast<uint4*>(xo + 32 * h + 8 * q) = pk;
+                }
+            }
+            mbar_arrive(bar(B_AEMPTY + g));   // the centre box has been read: the producer may refill this operand stage
+            float* sk = p.skip + grow * DW_C;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float r[32];
+                tmem_ld32(acc2 + 64 + 32 * h, r);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int c = 32 * h + 4 * q;
+                    const float a0 = r[4 * q] + b2s[DW_C + c], a1 = r[4 * q + 1] + b2s[DW_C + c + 1], a2 = r[4 * q + 2] + b2s[DW_C + c + 2],
+                                a3 = r[4 * q + 3] + b2s[DW_C + c + 3];
+                    if (p.first) *reinterpret_cast<float4*>(sk + c) = make_float4(a0, a1, a2, a3);
+                    else red_add_f32x4(sk + c, a0, a1, a2, a3);
+                }
+            }
+            tc_fence_before();
+        }
+    }
+    pdl_launch_dependents();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) tmem_dealloc(tmem, 512);
+}
+
+// ---- conditioner GEMM --------------------------------------------------------------------------------
+constexpr int kCondStages = 4;
+constexpr uint32_t kCondStage = 2 * kBox;                               // A box + B box
+constexpr uint32_t kCondOffBar = kCondStages * kCondStage;
+constexpr uint32_t kCondSmem = kCondOffBar + 256 + 1024;
+
+struct alignas(64) CondMaps {
+    CUtensorMap up, w;
+};
+
+__global__ void __launch_bounds__(192, 1) dw_cond_tc_kernel(const __grid_constant__ CondMaps maps, DwCondTc p, int nchunks) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char* gbase = smem_raw + (base - smem_u32(smem_raw));
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t bars = base + kCondOffBar;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + kCondOffBar + 128);
+    auto full = [&](int s) { return bars + 8u * (uint32_t)s; };
+    auto empty = [&](int s) { return bars + 8u * (uint32_t)(kCondStages + s); };
+    const uint32_t accf = bars + 8u * 2 * kCondStages;
+    if (tid == 0) {
+        for (int s = 0; s < kCondStages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+        mbar_init(accf, 1);
+        fence_barrier_init();
+    }
+    if (warp == 5) tmem_alloc(smem_u32(tmem_slot), 128);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const int t0 = blockIdx.x * kTile;
+    if (warp == 4) {
+        if (lane == 0) {
+            for (int c = 0; c < nchunks; ++c) {
+                const int s = c % kCondStages, n = c / kCondStages;
+                mbar_wait(empty(s), (n & 1) ^ 1);
+                mbar_expect_tx(full(s), kCondStage);
+                tma_load_2d(base + s * kCondStage, &maps.up, c * 64, t0, full(s));
+                tma_load_2d(base + s * kCondStage + kBox, &maps.w, c * 64, 0, full(s));
+            }
+        }
+    } else if (warp == 5) {
+        const uint32_t idesc = make_idesc(DW_N);
+        for (int c = 0; c < nchunks; ++c) {
+            const int s = c % kCondStages, n = c / kCondStages;
+            mbar_wait(full(s), n & 1);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t a0 = base + s * kCondStage;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma(tmem, make_desc_sw128(a0 + k * 32), make_desc_sw128(a0 + kBox + k * 32), idesc, (c | k) != 0);
+                umma_commit(empty(s));
+                if (c == nchunks - 1) umma_commit(accf);
+            }
+            __syncwarp();
+        }
+    } else {
+        const int row = warp * 32 + lane;
+        mbar_wait(accf, 0);
+        tc_fence_after();
+        __nv_bfloat16* o = p.out + (size_t)(t0 + row) * DW_N;
+        const uint32_t acc = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            float r[32];
+            tmem_ld32(acc + 32 * h, r);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float v[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = r[8 * q + e] + __ldg(p.bias + 32 * h + 8 * q + e);
+                uint4 pk;
+                pk.x = pack_bf16(v[0], v[1]); pk.y = pack_bf16(v[2], v[3]); pk.z = pack_bf16(v[4], v[5]); pk.w = pack_bf16(v[6], v[7]);
+                *reinterpret_cast<uint4*>(o + 32 * h + 8 * q) = pk;
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 5) tmem_dealloc(tmem, 128);
+}
+
+// ---- host ----------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !f) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        fn = reinterpret_cast<EncodeTiledFn>(f);
+    }
+    return fn;
+}
+
+// bf16 matrix [d2][rows][cols] (cols innermost, row pitch `ld` elements) with a [128][64] box, 128-byte swizzle, zero fill
+int encode_bf16(CUtensorMap* m, const void* base, int cols, int ld, long long rows, int d2) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { set_error("diffwave tc: cuTensorMapEncodeTiled is unavailable"); return SDDM_E_CUDA; }
+    const cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)d2};
+    const cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)rows * ld * 2};
+    const cuuint32_t box[3] = {64, 128, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, d2 > 0 ? 3 : 2, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("diffwave tc: cuTensorMapEncodeTiled failed (%d) for [%d][%lld][%d]", (int)r, d2, rows, cols); return SDDM_E_CUDA; }
+    return SDDM_OK;
+}
+
+int num_sms() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+}  // namespace
+
+int launch_dw_layer_tc(const DwLayerTc& p, cudaStream_t st) {
+    if (p.T % kTile) { set_error("diffwave tc: T must be a multiple of %d", kTile); return SDDM_E_INVALID; }
+    static bool attr = false;
+    if (!attr) {
+        SDDM_CUDA_TRY(cudaFuncSetAttribute(dw_layer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLayerSmem));
+        attr = true;
+    }
+    // tensor maps depend only on (buffers, shape): cache them (one sampling run re-launches the same 30 layers T_steps times)
+    static std::map<std::tuple<const void*, const void*, const void*, int, int>, LayerMaps> cache;
+    const auto key = std::make_tuple((const void*)p.x_in, (const void*)p.w1, (const void*)p.w2, p.B, p.T);
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+        if (cache.size() > 4096) cache.clear();
+        LayerMaps m;
+        int rc = encode_bf16(&m.x, p.x_in, DW_C, DW_C, p.T, p.B);
+        if (rc) return rc;
+        if ((rc = encode_bf16(&m.w1, p.w1, DW_C, DW_C, 3 * DW_N, 0))) return rc;
+        if ((rc = encode_bf16(&m.w2, p.w2, DW_C, DW_C, DW_N, 0))) return rc;
+        it = cache.emplace(key, m).first;
+    }
+    const int tiles_per_row = p.T / kTile, ntiles = p.B * tiles_per_row;
+    const int grid = ntiles < num_sms() ? ntiles : num_sms();
+    SDDM_CUDA_TRY(launch_pdl(dw_layer_tc_kernel, dim3(grid), dim3(kLayerThreads), kLayerSmem, st, it->second, p, ntiles, tiles_per_row));
+    count_launch();
+    return SDDM_OK;
+}
+
+int launch_dw_cond_tc(const DwCondTc& p, cudaStream_t st) {
+    if (p.T % kTile || p.KP % 64) { set_error("diffwave tc: T %% 128 and KP %% 64 must be 0"); return SDDM_E_INVALID; }
+    static bool attr = false;
+    if (!attr) {
+        SDDM_CUDA_TRY(cudaFuncSetAttribute(dw_cond_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCondSmem));
+        attr = true;
+    }
+    CondMaps m;
+    int rc = encode_bf16(&m.up, p.up, p.KP, p.KP, p.T, 0);
+    if (rc) return rc;
+    if ((rc = encode_bf16(&m.w, p.w, p.KP, p.KP, DW_N, 0))) return rc;
+    dw_cond_tc_kernel<<<p.T / kTile, 192, kCondSmem, st>>>(m, p, p.KP / 64);
+    SDDM_LAUNCH_CHECK();
+    return SDDM_OK;
+}
+
 }  // namespace sddm
