@@ -3,7 +3,8 @@
 // Layout in HBM (one row = one utterance of T = 256 * frames samples), time-major so that a time tile is a dense
 // [rows = time][K = channels] operand:
 //   x     [B][T][64]      residual stream (fp32; bf16 on the tcgen05 path, two buffers ping-pong)
-//   skip  [B][T][64]      running sum of the skip branches, fp32
+//   skip  [B][T][64]      running sum of the skip branches, fp32 (fp32 path) |  z cache [L][B][T][64] bf16 (tcgen05 path: the gated
+//                         activations of every layer; the skip branch is linear in them and is contracted once at the end)
 //   cond  [L][B][T][128]  conditioner_projection(upsampled spectrogram) + its bias + the dilated_conv bias, for every layer:
 //                         independent of the diffusion step, so it is computed once per batch (sddm_dw_condition) and only
 //                         READ by the T_steps x L layer evaluations (1.23 GB per 10 s utterance in bf16; the B200 has room)
@@ -348,7 +349,8 @@ struct sddm_dw_plan {
            o_b2 = 0, o_wsp = 0, o_bsp = 0, o_wo = 0, o_inw = 0, o_inb = 0, o_u1w = 0, o_u2w = 0;
     float u1b = 0.f, u2b = 0.f, bo = 0.f;
     // offsets into d_bf16 (tcgen05 path)
-    size_t h_w1 = 0, h_w2 = 0, h_wc = 0;
+    size_t h_w1 = 0, h_w2 = 0, h_wc = 0, h_ws = 0, h_wsp = 0;
+    size_t o_b2r = 0, o_bsum = 0;   // tcgen05 path: residual biases [L][64], sum of the skip biases [64]
     // which workspace holds a valid conditioner cache
     const void* cond_ws = nullptr;
     int cond_B = 0, cond_frames = 0;
@@ -369,8 +371,8 @@ DwLayout dw_layout(const sddm_dw_plan* p, int B, int frames) {
     auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 1024); return r; };
     l.x0 = take(BT * DW_C * esz);
     l.x1 = take(p->tc ? BT * DW_C * esz : 0);
-    l.z = take(p->tc ? 0 : BT * DW_C * 4);
-    l.skip = take(BT * DW_C * 4);
+    l.z = take(p->tc ? (size_t)p->L * BT * DW_C * 2 : BT * DW_C * 4);   // tcgen05 path: z cache of every layer
+    l.skip = take(p->tc ? 0 : BT * DW_C * 4);
     l.cond = take((size_t)p->L * BT * DW_N * esz);
     l.u1 = take((size_t)B * 16 * frames * p->F * 4);
     l.up = take(T * p->KP * esz);
@@ -457,13 +459,20 @@ int dw_forward(sddm_dw_plan* p, const float* audio, const float* step_dev, float
             q.cond = at<__nv_bfloat16>(ws, lay.cond) + (size_t)l * B * T * DW_N;
             q.bias1 = bias1 + (size_t)l * 4 * DW_N; q.bias1_row_stride = L * 4 * DW_N;
             q.w1 = p->d_bf16 + p->h_w1 + (size_t)l * 3 * DW_N * DW_C;
-            q.w2 = p->d_bf16 + p->h_w2 + (size_t)l * DW_N * DW_C;
-            q.b2 = W + p->o_b2 + (size_t)l * DW_N;
-            q.skip = skip; q.first = l == 0;
+            q.w2 = p->d_bf16 + p->h_w2 + (size_t)l * DW_C * DW_C;
+            q.b2 = W + p->o_b2r + (size_t)l * DW_C;
+            q.zc = at<__nv_bfloat16>(ws, lay.z) + (size_t)l * B * T * DW_C;
             q.B = B; q.T = T; q.dil = 1 << (l % p->cfg.dilation_cycle_length);
             int rc = launch_dw_layer_tc(q, st);
             if (rc) return rc;
         }
+        DwFinalTc f{};
+        f.zc = at<__nv_bfloat16>(ws, lay.z);
+        f.ws = p->d_bf16 + p->h_ws; f.wsp = p->d_bf16 + p->h_wsp;
+        f.bsum = W + p->o_bsum; f.bsp = W + p->o_bsp; f.wo = W + p->o_wo;
+        f.bo = p->bo; f.inv_sqrt_layers = (float)(1.0 / std::sqrt((double)L));
+        f.eps = eps_out; f.L = L; f.B = B; f.T = T;
+        return launch_dw_final_tc(f, st);
     }
     GemmP f{};
     f.A = skip; f.lda = DW_C; f.T = T; f.ntaps = 1; f.dil = 0; f.Kper = DW_C;
@@ -627,11 +636,16 @@ SDDM_API int sddm_dw_plan_finalize(sddm_dw_plan* p) {
         w2.resize((size_t)L * DW_C * DW_N);
     }
     bc.resize((size_t)L * DW_N);
-    std::vector<__nv_bfloat16> hw1, hw2, hwc;
+    std::vector<__nv_bfloat16> hw1, hw2, hwc, hws, hwsp;
+    std::vector<float> b2r((size_t)L * DW_C), bsum(DW_C, 0.f);
     if (p->tc) {
         hw1.resize((size_t)L * 3 * DW_N * DW_C);
-        hw2.resize((size_t)L * DW_N * DW_C);
+        hw2.resize((size_t)L * DW_C * DW_C);
+        hws.resize((size_t)L * DW_C * DW_C);
+        hwsp.resize((size_t)DW_C * DW_C);
         hwc.assign((size_t)L * DW_N * KP, __float2bfloat16(0.f));
+        const auto& w = W("skip_projection.weight");
+        for (size_t i = 0; i < hwsp.size(); ++i) hwsp[i] = __float2bfloat16(w[i]);   // [n][c]; the 1 / sqrt(L) is applied to the operand
     }
     for (int l = 0; l < L; ++l) {
         const std::string k = "residual_layers." + std::to_string(l) + ".";
@@ -646,7 +660,12 @@ SDDM_API int sddm_dw_plan_finalize(sddm_dw_plan* p) {
         memcpy(&wp[(size_t)l * DW_C * DW_EMB], W(k + "diffusion_projection.weight").data(), sizeof(float) * DW_C * DW_EMB);
         memcpy(&bp[(size_t)l * DW_C], W(k + "diffusion_projection.bias").data(), sizeof(float) * DW_C);
         memcpy(&wd[(size_t)l * DW_N * DW_C * 3], dw.data(), sizeof(float) * DW_N * DW_C * 3);
-        for (int n = 0; n < DW_C; ++n) { b2[(size_t)l * DW_N + n] = rb[n]; b2[(size_t)l * DW_N + DW_C + n] = sb[n]; }
+        for (int n = 0; n < DW_C; ++n) {
+            b2[(size_t)l * DW_N + n] = rb[n];
+            b2[(size_t)l * DW_N + DW_C + n] = sb[n];
+            b2r[(size_t)l * DW_C + n] = rb[n];
+            bsum[n] += sb[n];
+        }
         for (int np = 0; np < DW_N; ++np) {
             const int n = p->tc ? np : gate_perm(np);
             bc[(size_t)l * DW_N + np] = cb[n] + db[n];
@@ -666,17 +685,21 @@ SDDM_API int sddm_dw_plan_finalize(sddm_dw_plan* p) {
             for (int c = 0; c < DW_C; ++c) {
                 const float v = n < DW_C ? rw[(size_t)n * DW_C + c] : sw[(size_t)(n - DW_C) * DW_C + c];
                 if (!p->tc) w2[((size_t)l * DW_C + c) * DW_N + n] = v;
-                else hw2[((size_t)l * DW_N + n) * DW_C + c] = __float2bfloat16(v);
+                else if (n < DW_C) hw2[((size_t)l * DW_C + n) * DW_C + c] = __float2bfloat16(v);
+                else hws[((size_t)l * DW_C + (n - DW_C)) * DW_C + c] = __float2bfloat16(v);
             }
     }
     p->o_wp = put(wp); p->o_bp = put(bp); p->o_wd = put(wd); p->o_b2 = put(b2); p->o_bc = put(bc);
+    p->o_b2r = put(b2r); p->o_bsum = put(bsum);
     if (!p->tc) { p->o_w1 = put(w1); p->o_wc = put(wc); p->o_w2 = put(w2); }
     SDDM_CUDA_TRY(cudaMalloc(&p->d_f32, f.size() * sizeof(float)));
     SDDM_CUDA_TRY(cudaMemcpy(p->d_f32, f.data(), f.size() * sizeof(float), cudaMemcpyHostToDevice));
     if (p->tc) {
-        p->h_w1 = 0; p->h_w2 = hw1.size(); p->h_wc = hw1.size() + hw2.size();
+        p->h_w1 = 0; p->h_w2 = hw1.size(); p->h_ws = p->h_w2 + hw2.size(); p->h_wsp = p->h_ws + hws.size(); p->h_wc = p->h_wsp + hwsp.size();
         h = hw1;
         h.insert(h.end(), hw2.begin(), hw2.end());
+        h.insert(h.end(), hws.begin(), hws.end());
+        h.insert(h.end(), hwsp.begin(), hwsp.end());
         h.insert(h.end(), hwc.begin(), hwc.end());
         SDDM_CUDA_TRY(cudaMalloc(&p->d_bf16, h.size() * sizeof(__nv_bfloat16)));
         SDDM_CUDA_TRY(cudaMemcpy(p->d_bf16, h.data(), h.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
@@ -805,7 +828,10 @@ SDDM_API int sddm_dw_debug_fetch(sddm_dw_plan* p, const char* what, void* ws, in
     bool is16 = p->tc;
     if (w == "upsampled") { rows = T; cols = p->F; ld = p->KP; off = lay.up; }
     else if (w == "x") { rows = B * T; cols = DW_C; ld = DW_C; off = (p->tc && (p->L & 1)) ? lay.x1 : lay.x0; }
-    else if (w == "skip") { rows = B * T; cols = DW_C; ld = DW_C; off = lay.skip; is16 = false; }
+    else if (w == "skip") {
+        if (p->tc) { set_error("the tcgen05 path keeps the per-layer z cache instead of a skip sum"); return SDDM_E_INVALID; }
+        rows = B * T; cols = DW_C; ld = DW_C; off = lay.skip; is16 = false;
+    }
     else if (w.rfind("cond", 0) == 0) {
         const int l = atoi(w.c_str() + 4);
         if (l < 0 || l >= p->L) { set_error("no such layer: %s", what); return SDDM_E_INVALID; }
