@@ -344,6 +344,7 @@ struct sddm_dw_plan {
     std::vector<float> sch[12];
     float* d_f32 = nullptr;
     __nv_bfloat16* d_bf16 = nullptr;
+    float* d_bias1_table = nullptr;   // [T+1][L][4][128]: bias1 of every diffusion step of the schedule (sampling never recomputes it)
     // offsets into d_f32
     size_t o_vec = 0, o_ew1 = 0, o_eb1 = 0, o_ew2 = 0, o_eb2 = 0, o_wp = 0, o_bp = 0, o_wd = 0, o_w1 = 0, o_wc = 0, o_bc = 0, o_w2 = 0,
            o_b2 = 0, o_wsp = 0, o_bsp = 0, o_wo = 0, o_inw = 0, o_inb = 0, o_u1w = 0, o_u2w = 0;
@@ -412,17 +413,27 @@ int launch_gemm(const GemmP& g, int B, cudaStream_t st) {
 }
 
 // one eps_hat evaluation on a conditioned workspace
-int dw_forward(sddm_dw_plan* p, const float* audio, const float* step_dev, float step_scalar, float* eps_out, int B, int frames, void* ws,
+// step_dev: per-row step values (module API) or nullptr => row t of the precomputed table serves every batch row
+int dw_forward(sddm_dw_plan* p, const float* audio, const float* step_dev, int t, float* eps_out, int B, int frames, void* ws,
                cudaStream_t st) {
     const DwLayout lay = dw_layout(p, B, frames);
     const int T = p->cfg.hop_samples * frames, L = p->L;
     const float* W = p->d_f32;
-    float* h2 = at<float>(ws, lay.h2);
-    float* bias1 = at<float>(ws, lay.bias1);
-    dw_embed_kernel<<<B, 512, 0, st>>>(step_dev, step_scalar, W + p->o_vec, W + p->o_ew1, W + p->o_eb1, W + p->o_ew2, W + p->o_eb2, h2);
-    SDDM_LAUNCH_CHECK();
-    dw_bias1_kernel<<<dim3(L, B), 128, 0, st>>>(h2, W + p->o_wp, W + p->o_bp, W + p->o_wd, bias1, L, p->tc ? 0 : 1);
-    SDDM_LAUNCH_CHECK();
+    const float* bias1;
+    int bias1_stride;
+    if (step_dev) {
+        float* h2 = at<float>(ws, lay.h2);
+        float* b1 = at<float>(ws, lay.bias1);
+        dw_embed_kernel<<<B, 512, 0, st>>>(step_dev, 0.f, W + p->o_vec, W + p->o_ew1, W + p->o_eb1, W + p->o_ew2, W + p->o_eb2, h2);
+        SDDM_LAUNCH_CHECK();
+        dw_bias1_kernel<<<dim3(L, B), 128, 0, st>>>(h2, W + p->o_wp, W + p->o_bp, W + p->o_wd, b1, L, p->tc ? 0 : 1);
+        SDDM_LAUNCH_CHECK();
+        bias1 = b1;
+        bias1_stride = L * 4 * DW_N;
+    } else {
+        bias1 = p->d_bias1_table + (size_t)t * L * 4 * DW_N;
+        bias1_stride = 0;
+    }
     const int64_t n16 = (int64_t)B * T * 16;
     float* skip = at<float>(ws, lay.skip);
     if (!p->tc) {
@@ -436,7 +447,7 @@ int dw_forward(sddm_dw_plan* p, const float* audio, const float* step_dev, float
             g.A = x; g.lda = DW_C; g.T = T; g.ntaps = 3; g.dil = dil; g.Kper = DW_C;
             g.W = W + p->o_w1 + (size_t)l * 3 * DW_C * DW_N; g.K = 3 * DW_C; g.N = DW_N;
             g.cond = at<float>(ws, lay.cond) + (size_t)l * B * T * DW_N;
-            g.bias1 = bias1 + (size_t)l * 4 * DW_N; g.bias1_stride = L * 4 * DW_N;
+            g.bias1 = bias1 + (size_t)l * 4 * DW_N; g.bias1_stride = bias1_stride;
             g.out = z;
             int rc = launch_gemm<EPI_GATE>(g, B, st);
             if (rc) return rc;
@@ -457,7 +468,7 @@ int dw_forward(sddm_dw_plan* p, const float* audio, const float* step_dev, float
             q.x_in = (l & 1) ? xb : xa;
             q.x_out = (l & 1) ? xa : xb;
             q.cond = at<__nv_bfloat16>(ws, lay.cond) + (size_t)l * B * T * DW_N;
-            q.bias1 = bias1 + (size_t)l * 4 * DW_N; q.bias1_row_stride = L * 4 * DW_N;
+            q.bias1 = bias1 + (size_t)l * 4 * DW_N; q.bias1_row_stride = bias1_stride;
             q.w1 = p->d_bf16 + p->h_w1 + (size_t)l * 3 * DW_N * DW_C;
             q.w2 = p->d_bf16 + p->h_w2 + (size_t)l * DW_C * DW_C;
             q.b2 = W + p->o_b2r + (size_t)l * DW_C;
@@ -557,6 +568,7 @@ SDDM_API void sddm_dw_plan_destroy(sddm_dw_plan* p) {
     if (!p) return;
     if (p->d_f32) cudaFree(p->d_f32);
     if (p->d_bf16) cudaFree(p->d_bf16);
+    if (p->d_bias1_table) cudaFree(p->d_bias1_table);
     delete p;
 }
 
@@ -704,7 +716,24 @@ SDDM_API int sddm_dw_plan_finalize(sddm_dw_plan* p) {
         SDDM_CUDA_TRY(cudaMalloc(&p->d_bf16, h.size() * sizeof(__nv_bfloat16)));
         SDDM_CUDA_TRY(cudaMemcpy(p->d_bf16, h.data(), h.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
     }
-    SDDM_CUDA_TRY(cudaDeviceSynchronize());
+    {   // bias1 of every step of the schedule (diffwave.py:33-45,86 evaluated at the value SDDM_spectrogram.infer passes)
+        const int n = p->T + 1;
+        std::vector<float> steps(n);
+        for (int t = 0; t < n; ++t) steps[t] = dw_step_value(p, t);
+        float *d_steps = nullptr, *d_h2 = nullptr;
+        SDDM_CUDA_TRY(cudaMalloc(&d_steps, n * sizeof(float)));
+        SDDM_CUDA_TRY(cudaMalloc(&d_h2, (size_t)n * DW_EMB * sizeof(float)));
+        SDDM_CUDA_TRY(cudaMalloc(&p->d_bias1_table, (size_t)n * L * 4 * DW_N * sizeof(float)));
+        SDDM_CUDA_TRY(cudaMemcpy(d_steps, steps.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+        const float* Wt = p->d_f32;
+        dw_embed_kernel<<<n, 512>>>(d_steps, 0.f, Wt + p->o_vec, Wt + p->o_ew1, Wt + p->o_eb1, Wt + p->o_ew2, Wt + p->o_eb2, d_h2);
+        SDDM_LAUNCH_CHECK();
+        dw_bias1_kernel<<<dim3(L, n), 128>>>(d_h2, Wt + p->o_wp, Wt + p->o_bp, Wt + p->o_wd, p->d_bias1_table, L, p->tc ? 0 : 1);
+        SDDM_LAUNCH_CHECK();
+        SDDM_CUDA_TRY(cudaDeviceSynchronize());
+        cudaFree(d_steps);
+        cudaFree(d_h2);
+    }
     p->host_w.clear();
     p->finalized = true;
     return SDDM_OK;
@@ -776,12 +805,8 @@ SDDM_API int sddm_dw_eps(sddm_dw_plan* p, const float* audio, const float* diffu
     if ((rc = dw_check_ws(p, B, frames, ws, ws_bytes))) return rc;
     if ((rc = dw_check_conditioned(p, ws, B, frames))) return rc;
     if (!audio || !eps_out) { set_error("null buffer"); return SDDM_E_INVALID; }
-    float sv = 0.f;
-    if (!diffusion_step) {
-        if (t < 0 || t > p->T) { set_error("t=%d out of range [0, %d]", t, p->T); return SDDM_E_INVALID; }
-        sv = dw_step_value(p, t);
-    }
-    return dw_forward(p, audio, diffusion_step, sv, eps_out, B, frames, ws, (cudaStream_t)stream);
+    if (!diffusion_step && (t < 0 || t > p->T)) { set_error("t=%d out of range [0, %d]", t, p->T); return SDDM_E_INVALID; }
+    return dw_forward(p, audio, diffusion_step, t, eps_out, B, frames, ws, (cudaStream_t)stream);
 }
 
 SDDM_API int sddm_dw_sample(sddm_dw_plan* p, const float* spec, const float* noises, uint64_t seed, int64_t row0, float* out, float* eps_trace,
@@ -798,7 +823,7 @@ SDDM_API int sddm_dw_sample(sddm_dw_plan* p, const float* spec, const float* noi
     if ((rc = launch_x_T_coef(SDDM_VAR_ORIGINAL, 0.f, 1.f, nullptr, noises, seed, row0, x, B, Ls, st))) return rc;   // model.py:216
     for (int t = T; t >= 1; --t) {
         float* e = eps_trace ? eps_trace + (size_t)(T - t) * BL : eps;
-        if ((rc = dw_forward(p, x, nullptr, dw_step_value(p, t), e, B, frames, ws, st))) return rc;
+        if ((rc = dw_forward(p, x, nullptr, t, e, B, frames, ws, st))) return rc;
         PostP pp{};
         pp.eps_in = e;
         pp.x_in = x;
