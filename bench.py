@@ -5,6 +5,8 @@ a batch of 64 VoiceBank-DEMAND-shaped utterance-chunks per GPU, synthetic audio,
 
     python bench.py [--gpus N --steps K --warmup W]                 # our arm (one rank per GPU under torchrun)
     python bench.py --impl reference [...]                           # the reference algorithm on the host CPU cores
+    python bench.py --workload cfg5 [...]                             # BASELINE.json configs[4]: DiffWave, 8 x 10 s utterances per GPU,
+                                                                      # 200 steps (same JSON contract; not the headline)
 
 One "step" = one full enhancement (x_T init + 100 x [eps_hat, posterior update]) of the rank's 64-row batch.
 Prints ONE JSON line on rank 0.
@@ -139,6 +141,184 @@ def run_reference(args):
             "cpu_baseline": {"value": v, "unit": "utt/s", "cores": r["threads"], "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------
+# cfg 5: DiffWave (config_diffwave.json) on 10 s utterances, spectrogram from the STFT front-end, 200 reverse steps
+# ------------------------------------------------------------------------------------------------------
+DW_SECONDS, DW_STEPS, DW_FRAMES = 10.0, 200, 626
+DW_WORKLOAD = ("cfg5: DiffWave (config_diffwave.json) full 200-step sampling, %d utterances x 10 s (spec [513,626] from the STFT "
+               "front-end, 160256 samples) per GPU")
+
+
+def dw_cpu_rate(frames=40, threads=None):
+    """utterances/s of the CPU port (oracle) from a bounded sample: one eps_hat on `frames` of 626 frames of one utterance,
+    scaled linearly in time (the network is fully convolutional) and to 200 steps."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import diffwave_oracle as DO
+    from sddm_b200.model.network import DiffWave
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    net = DiffWave(freq_bins=513)
+    sd = {k: v.detach() for k, v in net.state_dict().items()}
+    g = torch.Generator().manual_seed(3)
+    spec, audio = torch.rand(1, 513, frames, generator=g) * 0.7, torch.randn(1, 1, 256 * frames, generator=g)
+    with torch.no_grad():
+        DO.diffwave_forward(sd, spec, audio, torch.full((1, 1, 1), 100.0))
+        t0 = time.perf_counter()
+        n = 0
+        while n < 3 or time.perf_counter() - t0 < 5.0:
+            DO.diffwave_forward(sd, spec, audio, torch.full((1, 1, 1), 100.0 - n))
+            n += 1
+        per = (time.perf_counter() - t0) / n
+    full = per * DW_FRAMES / frames * DW_STEPS
+    return dict(value=1.0 / full, seconds_full=full, threads=threads,
+                sample="%d eps_hat evaluations on %d of %d frames of one utterance, scaled to 626 frames x 200 steps" % (n, frames, DW_FRAMES))
+
+
+def run_reference_diffwave(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    vals = [dw_cpu_rate() for _ in range(max(1, min(args.steps, 5)))]
+    v = statistics.median(r["value"] for r in vals)
+    r = vals[-1]
+    line = {"impl": "reference", "metric": "utterances_per_sec", "value": v, "unit": "utt/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * args.batch_cfg5 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": DW_WORKLOAD % args.batch_cfg5, "note": "reference algorithm (oracle port, torch CPU ATen kernels) on host cores"},
+            "rtf": 1.0 / (v * DW_SECONDS),
+            "cpu_baseline": {"value": v, "unit": "utt/s", "cores": r["threads"], "kind": "port", "sample": r["sample"]},
+            "e2e": {"value": v, "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def run_diffwave(args):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
+    from sddm_b200 import PREC_BF16, PREC_FP32, _lib, prepare_spectrogram as PS
+    from sddm_b200.model.diffusion import GaussianDiffusion
+    from sddm_b200.model.model import SDDM_spectrogram
+    from sddm_b200.model.network import DiffWave
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    torch.manual_seed(0)
+    net = DiffWave(freq_bins=513)
+    with torch.no_grad():   # the reference zero-initialises this weight (diffwave.py:131): make eps_hat depend on the network
+        net.output_projection.weight.copy_(0.1 * torch.randn(net.output_projection.weight.shape))
+    prec = "fp32" if args.precision == "fp32" else "bf16"
+    net.precision = PREC_FP32 if prec == "fp32" else PREC_BF16
+    d = GaussianDiffusion("linear", DW_STEPS, 1e-4, 0.02, device=dev)
+    model = SDDM_spectrogram(d, net, hop_samples=256, noise_condition="time_step").to(dev).eval()
+    B, Lw = args.batch_cfg5, int(DW_SECONDS * SR)
+    wav = (0.1 * torch.randn(B, Lw, generator=torch.Generator().manual_seed(2000 + rank))).to(dev)
+    spec = PS.Spectrogram(n_fft=1024, hop_length=256, window_fn=torch.hamming_window, log_clamp=True)(wav).contiguous()
+    frames, Ls = spec.shape[-1], 256 * spec.shape[-1]
+    spec_host = spec.cpu().pin_memory()
+    out_host = torch.empty(B, 1, Ls).pin_memory()
+    plan = net.get_plan(d, "time_step")
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for s in range(steps):
+            fn(s)
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def step_resident(s):
+        model.infer(spec, seed=s, row0=rank * B)
+
+    def step_e2e(s):
+        x = spec_host.to(dev, non_blocking=True)                        # H2D of the spectrograms from pinned memory
+        y = model.infer(x, seed=s, row0=rank * B)
+        out_host.copy_(y, non_blocking=True)                            # D2H of the generated waveforms
+        torch.cuda.current_stream().synchronize()
+
+    for s in range(max(3, args.warmup)):
+        step_resident(s)
+    step_e2e(0)
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = _lib.launch_count()
+    ms = timed(step_resident, args.steps)
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    prof = None
+    if rank == 0 and world == 1 and prec == "bf16":
+        plan.profile(True)
+        timed(step_resident, 1)
+        prof = plan.profile_report()
+        plan.profile(False)
+    ms_e2e = timed(step_e2e, args.steps)
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+    total = B * world * args.steps
+    value, e2e = total / (ms / 1e3), total / (ms_e2e / 1e3)
+    pk = peaks()
+    line = {"metric": "utterances_per_sec", "value": value, "unit": "utt/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": prec, "data": "synthetic",
+            "config": {"workload": DW_WORKLOAD % B, "batch_per_gpu": B, "reverse_steps": DW_STEPS, "noise": "in-kernel Philox4x32-10",
+                       "weights": "config-shaped random init (torch.manual_seed(0)); output_projection.weight 0.1 N(0,1) instead of zeros",
+                       "precision": prec, "noise_condition": "time_step",
+                       "l2": "per-layer working set (%.0f MB) >> 126 MB L2; no flush needed" % (B * Ls * 640 / 1e6),
+                       "conditioner": "upsampler + 30 conditioner projections evaluated once per step of this bench (inside the timed region) and cached"},
+            "rtf": 1.0 / (value * DW_SECONDS),
+            "e2e": {"value": e2e, "unit": "utt/s", "h2d_bytes_per_step": B * 513 * frames * 4, "d2h_bytes_per_step": B * Ls * 4,
+                    "rtf": 1.0 / (e2e * DW_SECONDS)},
+            "gpu_launches": int(launches), "clocks": clocks, "peaks": pk["source"]}
+    if prof and prof["layer"][1]:
+        lay_ms, lay_n = prof["layer"]
+        head_ms, head_n = prof["head"]
+        dur = lay_ms * 1e-3 / lay_n
+        alg = B * Ls * 640.0
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "top_kernel_traffic.json")) as f:
+                tj = json.load(f)
+            if tj.get("diffwave_batch") == B:
+                traffic = tj.get("diffwave_layer_dram_bytes_per_launch")
+        except Exception:
+            pass
+        line["kernels"] = {"dw_layer_tc": {"avg_us": dur * 1e6, "launches": lay_n, "gbs": alg / dur / 1e9, "share": lay_ms / (ms / args.steps)},
+                           "dw_final_tc": {"avg_us": 1e3 * head_ms / max(1, head_n), "launches": head_n,
+                                           "gbs": B * Ls * (128.0 * 30 + 4) / (head_ms * 1e-3 / max(1, head_n)) / 1e9, "share": head_ms / (ms / args.steps)}}
+        line["roofline"] = {"kernel": "dw_layer_tc_kernel", "bound": "hbm", "achieved": alg / dur / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                            "frac": alg / dur / 1e9 / pk["hbm"], "traffic": traffic, "avg_launch_us": dur * 1e6,
+                            "share_of_step": lay_ms / (ms / args.steps), "algorithmic_bytes_per_launch": alg,
+                            "algorithmic_bytes_per_sample": 640, "arith_intensity_flop_per_byte": 2.0 * (192 * 128 + 64 * 64) / 640.0}
+    if world == 1 and not args.no_cpu_baseline:
+        r = dw_cpu_rate()
+        line["cpu_baseline"] = {"value": r["value"], "unit": "utt/s", "cores": r["threads"], "kind": "port", "sample": r["sample"]}
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -293,8 +473,12 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("SDDM_B200_PRECISION", "bf16act"), choices=["bf16", "fp32", "bf16act"])
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg5"], help="cfg2 = the headline (UNetModified2); cfg5 = DiffWave")
+    ap.add_argument("--batch-cfg5", type=int, default=8, help="10 s utterances per GPU for --workload cfg5")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload == "cfg5":
+        (run_reference_diffwave if args.impl == "reference" else run_diffwave)(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -211,6 +211,10 @@ SDDM_API int sddm_dw_eps(sddm_dw_plan* plan, const float* audio, const float* di
  * noises: NULL (Philox) or [T, B, L] (noises[0] -> x_T, noises[k] -> step t = T + 1 - k); eps_trace: NULL or [T, B, L]. */
 SDDM_API int sddm_dw_sample(sddm_dw_plan* plan, const float* spec, const float* noises, uint64_t seed, int64_t row0, float* out,
                             float* eps_trace, int B, int frames, void* ws, size_t ws_bytes, void* stream);
+/* per-launch CUDA-event timing of the tcgen05 path (bench roofline): enable resets the totals; kind 0 = residual-layer kernel,
+ * kind 1 = skip / output head.  Both calls synchronise the device. */
+SDDM_API int sddm_dw_profile_enable(sddm_dw_plan* plan, int on);
+SDDM_API int sddm_dw_profile_read(sddm_dw_plan* plan, int kind, double* total_ms, int64_t* launches);
 /* test hook: "upsampled" ([T, freq_bins] of utterance B-1), "x" (residual stream after the last eps call, [B, T, 64]),
  * "skip" (sum of skips, [B, T, 64]), "cond<i>" (cached conditioner of layer i, [B, T, 128]) -> fp32 out; *n = element count. */
 SDDM_API int sddm_dw_debug_fetch(sddm_dw_plan* plan, const char* what, void* ws, int B, int frames, float* out, int64_t* n,

@@ -344,6 +344,11 @@ struct sddm_dw_plan {
     std::vector<float> sch[12];
     float* d_f32 = nullptr;
     __nv_bfloat16* d_bf16 = nullptr;
+    // per-launch CUDA-event timing of the layer / head kernels (bench roofline; off by default)
+    bool prof_on = false;
+    std::vector<cudaEvent_t> prof_ev;
+    std::vector<int> prof_kind;   // 0 layer, 1 head
+    size_t prof_used = 0;
     float* d_bias1_table = nullptr;   // [T+1][L][4][128]: bias1 of every diffusion step of the schedule (sampling never recomputes it)
     // offsets into d_f32
     size_t o_vec = 0, o_ew1 = 0, o_eb1 = 0, o_ew2 = 0, o_eb2 = 0, o_wp = 0, o_bp = 0, o_wd = 0, o_w1 = 0, o_wc = 0, o_bc = 0, o_w2 = 0,
@@ -413,6 +418,27 @@ int launch_gemm(const GemmP& g, int B, cudaStream_t st) {
 }
 
 // one eps_hat evaluation on a conditioned workspace
+int dw_prof_mark(sddm_dw_plan* p, int kind, bool begin, cudaStream_t st) {
+    if (!p->prof_on) return SDDM_OK;
+    if (begin) {
+        if (p->prof_used + 2 > p->prof_ev.size()) {
+            for (int i = 0; i < 2; ++i) {
+                cudaEvent_t e;
+                SDDM_CUDA_TRY(cudaEventCreate(&e));
+                p->prof_ev.push_back(e);
+            }
+            p->prof_kind.push_back(kind);
+        } else {
+            p->prof_kind[p->prof_used / 2] = kind;
+        }
+        SDDM_CUDA_TRY(cudaEventRecord(p->prof_ev[p->prof_used], st));
+    } else {
+        SDDM_CUDA_TRY(cudaEventRecord(p->prof_ev[p->prof_used + 1], st));
+        p->prof_used += 2;
+    }
+    return SDDM_OK;
+}
+
 // step_dev: per-row step values (module API) or nullptr => row t of the precomputed table serves every batch row
 int dw_forward(sddm_dw_plan* p, const float* audio, const float* step_dev, int t, float* eps_out, int B, int frames, void* ws,
                cudaStream_t st) {
@@ -474,8 +500,10 @@ int dw_forward(sddm_dw_plan* p, const float* audio, const float* step_dev, int t
             q.b2 = W + p->o_b2r + (size_t)l * DW_C;
             q.zc = at<__nv_bfloat16>(ws, lay.z) + (size_t)l * B * T * DW_C;
             q.B = B; q.T = T; q.dil = 1 << (l % p->cfg.dilation_cycle_length);
-            int rc = launch_dw_layer_tc(q, st);
+            int rc = dw_prof_mark(p, 0, true, st);
             if (rc) return rc;
+            if ((rc = launch_dw_layer_tc(q, st))) return rc;
+            if ((rc = dw_prof_mark(p, 0, false, st))) return rc;
         }
         DwFinalTc f{};
         f.zc = at<__nv_bfloat16>(ws, lay.z);
@@ -483,7 +511,10 @@ int dw_forward(sddm_dw_plan* p, const float* audio, const float* step_dev, int t
         f.bsum = W + p->o_bsum; f.bsp = W + p->o_bsp; f.wo = W + p->o_wo;
         f.bo = p->bo; f.inv_sqrt_layers = (float)(1.0 / std::sqrt((double)L));
         f.eps = eps_out; f.L = L; f.B = B; f.T = T;
-        return launch_dw_final_tc(f, st);
+        int rc = dw_prof_mark(p, 1, true, st);
+        if (rc) return rc;
+        if ((rc = launch_dw_final_tc(f, st))) return rc;
+        return dw_prof_mark(p, 1, false, st);
     }
     GemmP f{};
     f.A = skip; f.lda = DW_C; f.T = T; f.ntaps = 1; f.dil = 0; f.Kper = DW_C;
@@ -569,6 +600,7 @@ SDDM_API void sddm_dw_plan_destroy(sddm_dw_plan* p) {
     if (p->d_f32) cudaFree(p->d_f32);
     if (p->d_bf16) cudaFree(p->d_bf16);
     if (p->d_bias1_table) cudaFree(p->d_bias1_table);
+    for (cudaEvent_t e : p->prof_ev) cudaEventDestroy(e);
     delete p;
 }
 
@@ -836,6 +868,31 @@ SDDM_API int sddm_dw_sample(sddm_dw_plan* p, const float* spec, const float* noi
         dw_step_coefs(p, t, k8);
         if ((rc = launch_post_coef(pp, k8, st))) return rc;
     }
+    return SDDM_OK;
+}
+
+SDDM_API int sddm_dw_profile_enable(sddm_dw_plan* p, int on) {
+    if (!p) { set_error("null plan"); return SDDM_E_INVALID; }
+    SDDM_CUDA_TRY(cudaDeviceSynchronize());
+    p->prof_on = on != 0;
+    p->prof_used = 0;
+    return SDDM_OK;
+}
+
+SDDM_API int sddm_dw_profile_read(sddm_dw_plan* p, int kind, double* total_ms, int64_t* launches) {
+    if (!p || !total_ms || !launches) { set_error("null argument"); return SDDM_E_INVALID; }
+    SDDM_CUDA_TRY(cudaDeviceSynchronize());
+    double tot = 0.0;
+    int64_t n = 0;
+    for (size_t i = 0; i + 1 < p->prof_used; i += 2) {
+        if (p->prof_kind[i / 2] != kind) continue;
+        float ms = 0.f;
+        SDDM_CUDA_TRY(cudaEventElapsedTime(&ms, p->prof_ev[i], p->prof_ev[i + 1]));
+        tot += ms;
+        ++n;
+    }
+    *total_ms = tot;
+    *launches = n;
     return SDDM_OK;
 }
 

@@ -174,6 +174,20 @@ class DiffWavePlan:
         self._cond_key = (spec.data_ptr(), spec._version, B, frames)
         return (out, eps_tr) if trace else out
 
+    def profile(self, on: bool) -> None:
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().sddm_dw_profile_enable(self._h, int(on)))
+
+    def profile_report(self):
+        """{'layer': (total_ms, launches), 'head': (...)} of the tcgen05 kernels since profile(True)."""
+        out = {}
+        with torch.cuda.device(self.device):
+            for kind, name in ((0, "layer"), (1, "head")):
+                ms, n = C.c_double(), C.c_int64()
+                _lib.check(_lib.lib().sddm_dw_profile_read(self._h, kind, C.byref(ms), C.byref(n)))
+                out[name] = (ms.value, n.value)
+        return out
+
     def fetch(self, what: str, B: int, frames: int) -> torch.Tensor:
         """Debug: 'upsampled' [T,F] (last utterance), 'x' / 'skip' [B,T,64], 'cond<i>' [B,T,128] as fp32."""
         n = C.c_int64()
