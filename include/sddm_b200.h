@@ -220,6 +220,39 @@ SDDM_API int sddm_dw_profile_read(sddm_dw_plan* plan, int kind, double* total_ms
 SDDM_API int sddm_dw_debug_fetch(sddm_dw_plan* plan, const char* what, void* ws, int B, int frames, float* out, int64_t* n,
                                  void* stream);
 
+/* ---- cfg 4: WaveGrad denoiser + spectrogram-conditioned sampling loop -------------------------------- */
+/* replaces: WaveGrad (model/wavegrad.py:140-179; the architecture has no constructor arguments: 5 DBlocks / FiLMs / UBlocks,
+ * 128 mel bins, 300 samples per frame) under SDDM_spectrogram.infer (model/model.py:206-257).  fp32 CUDA-core path. */
+typedef struct sddm_wg_plan sddm_wg_plan;
+
+typedef struct sddm_wg_config {
+    int32_t n_timestep;       /* T of the diffusion (config_wavegrad.json: 1000) */
+    int32_t hop_samples;      /* must be 300 = 5 * 5 * 3 * 2 * 2 */
+    int32_t noise_condition;  /* SDDM_DW_COND_* (config_wavegrad.json: sqrt_alpha_bar, the SDDM default) */
+    int32_t precision;        /* must be SDDM_PREC_FP32 */
+    int32_t reserved[4];
+} sddm_wg_config;
+
+SDDM_API int sddm_wg_plan_create(const sddm_wg_config* cfg, sddm_wg_plan** out);
+SDDM_API void sddm_wg_plan_destroy(sddm_wg_plan* plan);
+/* name = WaveGrad state_dict key ("upsample.2.block3.1.weight", ...) or "film.<i>.encoding.frequencies" (the
+ * PositionalEncoding frequency vector exp(-ln(1e4) k / (dim/2)), wavegrad.py:45-46); host fp32, shape checked. */
+SDDM_API int sddm_wg_plan_load_weight(sddm_wg_plan* plan, const char* name, const void* data, const int64_t* shape, int ndim);
+SDDM_API int sddm_wg_plan_set_schedule(sddm_wg_plan* plan, const sddm_schedule* sch, int n);
+SDDM_API int sddm_wg_plan_finalize(sddm_wg_plan* plan);
+SDDM_API size_t sddm_wg_workspace_bytes(const sddm_wg_plan* plan, int B, int frames);
+/* replaces: WaveGrad.forward (wavegrad.py:167-179).  spec: device [B, 128, frames]; audio: device [B, 300 * frames];
+ * noise_level: device [B] or NULL => the value SDDM_spectrogram.infer passes at step t; eps_out: device [B, 300 * frames]. */
+SDDM_API int sddm_wg_eps(sddm_wg_plan* plan, const float* spec, const float* audio, const float* noise_level, int t, float* eps_out,
+                         int B, int frames, void* ws, size_t ws_bytes, void* stream);
+/* replaces: SDDM_spectrogram.infer (model.py:212-257, non-continuous) around WaveGrad; buffers as sddm_dw_sample. */
+SDDM_API int sddm_wg_sample(sddm_wg_plan* plan, const float* spec, const float* noises, uint64_t seed, int64_t row0, float* out,
+                            float* eps_trace, int B, int frames, void* ws, size_t ws_bytes, void* stream);
+/* test hook: activation "d0".."d4" (downsample outputs) / "u0".."u4" (upsample outputs) of the last sddm_wg_eps call on this
+ * workspace -> out [B, L, C] fp32 (time-major); shape2 receives {L, C}. */
+SDDM_API int sddm_wg_debug_fetch(sddm_wg_plan* plan, const char* what, void* ws, int B, int frames, float* out, int64_t* shape2,
+                                 void* stream);
+
 /* ---- introspection / test hooks ------------------------------------------------------------------- */
 /* number of kernel launches one sddm_eps call enqueues for this plan. */
 SDDM_API int sddm_plan_launches_per_eps(const sddm_plan* plan);

@@ -38,6 +38,11 @@ class DwConfig(C.Structure):
                 ("noise_condition", C.c_int32), ("precision", C.c_int32), ("reserved", C.c_int32 * 4)]
 
 
+class WgConfig(C.Structure):
+    _fields_ = [("n_timestep", C.c_int32), ("hop_samples", C.c_int32), ("noise_condition", C.c_int32), ("precision", C.c_int32),
+                ("reserved", C.c_int32 * 4)]
+
+
 NOISE_CONDITIONS = {"sqrt_alpha_bar": 0, "time_step": 1}
 
 
@@ -87,6 +92,18 @@ SIGNATURES = {
     "sddm_dw_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "sddm_dw_profile_read": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "sddm_dw_debug_fetch": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int64),
+                                      C.c_void_p]),
+    "sddm_wg_plan_create": (C.c_int, [C.POINTER(WgConfig), C.POINTER(C.c_void_p)]),
+    "sddm_wg_plan_destroy": (None, [C.c_void_p]),
+    "sddm_wg_plan_load_weight": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int]),
+    "sddm_wg_plan_set_schedule": (C.c_int, [C.c_void_p, C.POINTER(Schedule), C.c_int]),
+    "sddm_wg_plan_finalize": (C.c_int, [C.c_void_p]),
+    "sddm_wg_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
+    "sddm_wg_eps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                              C.c_size_t, C.c_void_p]),
+    "sddm_wg_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                 C.c_void_p, C.c_size_t, C.c_void_p]),
+    "sddm_wg_debug_fetch": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int64),
                                       C.c_void_p]),
     "sddm_plan_launches_per_eps": (C.c_int, [C.c_void_p]),
     "sddm_plan_num_ops": (C.c_int, [C.c_void_p]),

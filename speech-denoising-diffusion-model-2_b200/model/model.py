@@ -16,6 +16,7 @@ from torch import nn
 
 from .diffusion import GaussianDiffusion
 from .diffwave import DiffWave
+from .wavegrad import WaveGrad
 from .unet_modified2 import UNetModified2
 
 
@@ -118,7 +119,9 @@ class SDDM(BaseModel):
 
 class SDDM_spectrogram(SDDM):
     """reference model/model.py:206-257: spectrogram-conditioned sampling (config_diffwave.json / config_wavegrad.json):
-    pure-noise start of length ``hop_samples * frames``, then T x (eps_hat, p_transition 'original')."""
+    pure-noise start of length ``hop_samples * frames``, then T x (eps_hat, p_transition 'original').  With WaveGrad the
+    shipped reference wrapper raises (it hands [B,1,T] to WaveGrad.forward, which needs [B,T]): here the loop
+    runs, with that one squeeze."""
 
     def __init__(self, diffusion: GaussianDiffusion, noise_estimate_model: nn.Module, hop_samples: int,
                  noise_condition="sqrt_alpha_bar"):
@@ -130,12 +133,15 @@ class SDDM_spectrogram(SDDM):
               row0: int = 0, return_trace: bool = False):
         if not condition.is_cuda:
             raise RuntimeError("SDDM_spectrogram.infer (sddm_b200) needs CUDA tensors: there is no CPU fallback")
-        if not isinstance(self.noise_estimate_model, DiffWave):
-            raise NotImplementedError("SDDM_spectrogram (sddm_b200) drives the DiffWave denoiser only")
+        net = self.noise_estimate_model
+        if not isinstance(net, (DiffWave, WaveGrad)):
+            raise NotImplementedError("SDDM_spectrogram (sddm_b200) drives the DiffWave and WaveGrad denoisers")
         if continuous:
             raise NotImplementedError("continuous=True (intermediate samples) is not provided for the spectrogram models")
-        if self.hop_samples != 256:
-            raise ValueError("DiffWave's upsampler is 16 x 16: hop_samples must be 256, got %d" % self.hop_samples)
+        want_hop = 256 if isinstance(net, DiffWave) else 300
+        if self.hop_samples != want_hop:
+            raise ValueError("%s upsamples a spectrogram frame to %d samples: hop_samples must be %d, got %d"
+                             % (type(net).__name__, want_hop, want_hop, self.hop_samples))
         if seed is None and noises is None:
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())
         plan = self.noise_estimate_model.get_plan(self.diffusion, self.noise_condition)

@@ -88,6 +88,27 @@ def diffwave_test_module(case):
     return net
 
 
+# cfg 4 (WaveGrad) parity cases (the network has no constructor arguments): spectrogram frames F -> 300 F samples
+WAVEGRAD_CASES = {
+    "b2f4": dict(B=2, frames=4, levels=[0.3, 0.9], seed=11),
+    "b1f7": dict(B=1, frames=7, levels=[0.62], seed=12),
+}
+
+
+def wavegrad_test_module():
+    """Host mirror with the reference's default init under torch.manual_seed(0); the zero-initialised biases
+    (wavegrad.py:16,63-64) are replaced by 0.05 * N(0,1) (seed 1) so that every bias path is exercised."""
+    from sddm_b200.model.network import WaveGrad
+    torch.manual_seed(0)
+    net = WaveGrad()
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for k, v in net.state_dict().items():
+            if k.endswith(".bias"):
+                v.copy_(0.05 * torch.randn(v.shape, generator=g))
+    return net
+
+
 def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
     """max|a-b| / max|b| — the per-tensor error metric of BASELINE.md §3."""
     return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))

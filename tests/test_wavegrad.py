@@ -1,0 +1,109 @@
+"""cfg 4: WaveGrad denoiser + SDDM_spectrogram sampling loop (fp32 CUDA-core path).
+
+CPU (-m "not gpu"): oracle/wavegrad_oracle.py against goldens of the real reference modules (tests/golden/make_golden_wavegrad.py),
+host-mirror surface.  GPU (-m gpu): the CUDA path through the C ABI (sddm_wg_*).  Tolerance 1e-3 of max for eps_hat and every
+block output (measured ~1e-6), final sample SI-SNR >= 60 dB.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from conftest import GOLDEN, WAVEGRAD_CASES, rel_err, wavegrad_test_module  # noqa: E402
+from oracle import sddm_oracle as O  # noqa: E402
+from oracle import wavegrad_oracle as WO  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return {k: torch.from_numpy(v) for k, v in np.load(os.path.join(GOLDEN, "wavegrad.npz")).items()}
+
+
+@pytest.fixture(scope="module")
+def sd():
+    return {k: v.detach().clone() for k, v in wavegrad_test_module().state_dict().items()}
+
+
+def si_snr_db(est, ref):
+    est, ref = est.double().flatten(), ref.double().flatten()
+    s = (est @ ref) / (ref @ ref) * ref
+    return float(10 * torch.log10((s @ s) / ((est - s) @ (est - s))))
+
+
+@pytest.mark.parametrize("tag", list(WAVEGRAD_CASES))
+def test_oracle_forward_matches_reference(gold, sd, tag):
+    case = WAVEGRAD_CASES[tag]
+    trace = {}
+    eps = WO.wavegrad_forward(sd, gold[tag + ".spec"], gold[tag + ".audio"], torch.tensor(case["levels"]), trace=trace)
+    assert rel_err(eps.reshape(-1), gold[tag + ".eps"].reshape(-1)) < 2e-5
+    for k in ("d0", "d2", "d4", "u0", "u2", "u4"):
+        assert rel_err(trace[k][:, ::5, ::3], gold[tag + "." + k]) < 2e-5
+
+
+def test_oracle_sampling_matches_reference(gold, sd):
+    x0 = WO.sample_spectrogram(sd, O.make_schedule("linear", 4, 1e-4, 5e-2), gold["sample.spec"], gold["sample.noises"])
+    assert si_snr_db(x0, gold["sample.x0"]) > 60.0
+
+
+def test_mirror_surface():
+    from sddm_b200.model import model as M
+    from sddm_b200.model.diffusion import GaussianDiffusion
+    net = wavegrad_test_module()
+    keys = list(net.state_dict().keys())
+    assert keys[0] == "downsample.0.weight" and "film.4.output_conv.bias" in keys and keys[-1] == "last_conv.bias"
+    assert 15_800_000 < sum(p.numel() for p in net.parameters()) < 16_000_000       # 15.92 M parameters
+    d = GaussianDiffusion(schedule="linear", n_timestep=4, linear_start=1e-4, linear_end=5e-2, device="cpu")
+    m = M.SDDM_spectrogram(d, net, hop_samples=300)
+    assert m.noise_condition == "sqrt_alpha_bar"
+    with pytest.raises(RuntimeError):
+        m.infer(torch.zeros(1, 128, 3))             # CPU tensors: no fallback
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", list(WAVEGRAD_CASES))
+def test_gpu_eps_vs_reference_golden(built_lib, gold, tag):
+    case = WAVEGRAD_CASES[tag]
+    net = wavegrad_test_module().cuda()
+    B, F = case["B"], case["frames"]
+    eps = net(gold[tag + ".spec"].cuda(), gold[tag + ".audio"].cuda(), torch.tensor(case["levels"]).cuda()).cpu()
+    assert eps.shape == gold[tag + ".eps"].shape                      # torch.squeeze quirk: [T] when B == 1
+    plan = net.get_plan()
+    errs = {}
+    for k in ("d0", "d1", "d2", "d3", "d4", "u0", "u1", "u2", "u3", "u4"):
+        errs[k] = rel_err(plan.fetch(k, B, F).cpu()[:, ::5, ::3], gold[tag + "." + k])
+    e = rel_err(eps.reshape(-1), gold[tag + ".eps"].reshape(-1))
+    print("wavegrad %s: eps %.2e  blocks %s" % (tag, e, " ".join("%s %.1e" % kv for kv in errs.items())))
+    assert e < 1e-3 and max(errs.values()) < 1e-3
+
+
+@pytest.mark.gpu
+def test_gpu_sampling_vs_reference_golden(built_lib, gold):
+    from sddm_b200.model import model as M
+    from sddm_b200.model.diffusion import GaussianDiffusion
+    net = wavegrad_test_module().cuda()
+    d = GaussianDiffusion(schedule="linear", n_timestep=4, linear_start=1e-4, linear_end=5e-2, device="cuda")
+    m = M.SDDM_spectrogram(d, net, hop_samples=300)
+    x0 = m.infer(gold["sample.spec"].cuda(), noises=gold["sample.noises"].cuda()).cpu()
+    snr = si_snr_db(x0, gold["sample.x0"])
+    print("wavegrad sampling: SI-SNR vs reference %.1f dB" % snr)
+    assert snr > 60.0
+    a = m.infer(gold["sample.spec"].cuda(), seed=5)
+    b = m.infer(gold["sample.spec"].cuda(), seed=5)
+    c = m.infer(gold["sample.spec"][1:2].contiguous().cuda(), seed=5, row0=1)
+    assert torch.equal(a, b) and torch.equal(a[1:2], c) and float(a.abs().max()) <= 1.0
+
+
+@pytest.mark.gpu
+def test_gpu_ragged_lengths_vs_oracle(built_lib, sd):
+    """frame counts whose level lengths are not multiples of the 64-row tile (1 frame: L = 300, 150, 75, 25, 5)."""
+    net = wavegrad_test_module().cuda()
+    g = torch.Generator().manual_seed(21)
+    for B, F in ((1, 1), (3, 2), (2, 11)):
+        spec, audio = torch.rand(B, 128, F, generator=g), torch.randn(B, 300 * F, generator=g)
+        lv = torch.rand(B, generator=g)
+        want = WO.wavegrad_forward(sd, spec, audio, lv)
+        got = net.get_plan().eps(spec.cuda(), audio.cuda(), noise_level=lv.cuda()).cpu()
+        assert rel_err(got, want) < 1e-3, (B, F)
