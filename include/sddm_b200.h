@@ -222,14 +222,14 @@ SDDM_API int sddm_dw_debug_fetch(sddm_dw_plan* plan, const char* what, void* ws,
 
 /* ---- cfg 4: WaveGrad denoiser + spectrogram-conditioned sampling loop -------------------------------- */
 /* replaces: WaveGrad (model/wavegrad.py:140-179; the architecture has no constructor arguments: 5 DBlocks / FiLMs / UBlocks,
- * 128 mel bins, 300 samples per frame) under SDDM_spectrogram.infer (model/model.py:206-257).  fp32 CUDA-core path. */
+ * 128 mel bins, 300 samples per frame) under SDDM_spectrogram.infer (model/model.py:206-257). */
 typedef struct sddm_wg_plan sddm_wg_plan;
 
 typedef struct sddm_wg_config {
     int32_t n_timestep;       /* T of the diffusion (config_wavegrad.json: 1000) */
     int32_t hop_samples;      /* must be 300 = 5 * 5 * 3 * 2 * 2 */
     int32_t noise_condition;  /* SDDM_DW_COND_* (config_wavegrad.json: sqrt_alpha_bar, the SDDM default) */
-    int32_t precision;        /* must be SDDM_PREC_FP32 */
+    int32_t precision;        /* SDDM_PREC_FP32 (CUDA cores) or SDDM_PREC_BF16 (tcgen05 convs, bf16 activations) */
     int32_t reserved[4];
 } sddm_wg_config;
 

@@ -16,6 +16,7 @@
 
 #include "../../include/sddm_b200.h"
 #include "kernels.cuh"
+#include "wavegrad.cuh"
 
 namespace sddm {
 namespace {
@@ -136,6 +137,59 @@ __global__ void __launch_bounds__(256) wg_first_kernel(const float* __restrict__
     }
 }
 
+// tcgen05 path: the same conv, stored as the two bf16 operand tensors its consumers read (raw and leaky_relu'd), channels
+// zero-padded from 32 to 64 (one 128-byte TMA / UMMA swizzle atom per row)
+__global__ void __launch_bounds__(256) wg_first_kernel_tc(const float* __restrict__ audio, const float* __restrict__ w, const float* __restrict__ bias,
+                                                          __nv_bfloat16* __restrict__ raw16, __nv_bfloat16* __restrict__ act16, int B, int L) {
+    const int64_t total = (int64_t)B * L * 16;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i & 15) * 4;
+        const int64_t row = i >> 4;
+        const int b = (int)(row / L), t = (int)(row - (int64_t)b * L);
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (c < 32) {
+            float a[5];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                const int tt = t + k - 2;
+                a[k] = (tt >= 0 && tt < L) ? __ldg(audio + (int64_t)b * L + tt) : 0.f;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float s = 0.f;
+#pragma unroll
+                for (int k = 0; k < 5; ++k) s = fmaf(__ldg(w + (c + q) * 5 + k), a[k], s);
+                v[q] = s + __ldg(bias + c + q);
+            }
+        }
+        __nv_bfloat162 r0 = __floats2bfloat162_rn(v[0], v[1]), r1 = __floats2bfloat162_rn(v[2], v[3]);
+        __nv_bfloat162 a0 = __floats2bfloat162_rn(lrelu02(v[0]), lrelu02(v[1])), a1 = __floats2bfloat162_rn(lrelu02(v[2]), lrelu02(v[3]));
+        uint2 pr, pa;
+        pr.x = *reinterpret_cast<uint32_t*>(&r0); pr.y = *reinterpret_cast<uint32_t*>(&r1);
+        pa.x = *reinterpret_cast<uint32_t*>(&a0); pa.y = *reinterpret_cast<uint32_t*>(&a1);
+        reinterpret_cast<uint2*>(raw16)[i] = pr;
+        reinterpret_cast<uint2*>(act16)[i] = pa;
+    }
+}
+
+__global__ void __launch_bounds__(256) wg_transpose_spec_tc(const float* __restrict__ spec, __nv_bfloat16* __restrict__ out, int B, int C, int F) {
+    const int64_t total = (int64_t)B * C * F;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const int64_t r = i / C;
+        const int f = (int)(r % F), b = (int)(r / F);
+        out[i] = __float2bfloat16_rn(__ldg(spec + ((int64_t)b * C + c) * F + f));
+    }
+}
+
+__global__ void __launch_bounds__(256) wg_bf16_to_f32(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int64_t rows, int cols, int ld) {
+    const int64_t total = rows * cols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / cols;
+        dst[i] = __bfloat162float(src[r * ld + (int)(i - r * cols)]);
+    }
+}
+
 // last_conv: Conv1d(128, 1, 3, padding = 1) (wavegrad.py:165); one warp per output sample, lanes over channels
 __global__ void __launch_bounds__(256) wg_last_kernel(const float* __restrict__ x /* [B][L][128] */, const float* __restrict__ w /* [3][128] */,
                                                       float bias, float* __restrict__ out, int B, int L) {
@@ -211,6 +265,9 @@ struct sddm_wg_plan {
     bool have_sched = false, finalized = false;
     std::vector<float> sch[5];
     float* d_f32 = nullptr;
+    __nv_bfloat16* d_bf16 = nullptr;          // tcgen05 path: [N][taps * Cin] K-major packs (polyphase-combined for the up-sampling convs)
+    std::map<std::string, size_t> tc_w;      // module key -> offset into d_bf16
+    bool tc = false;
     size_t o_first_w = 0, o_first_b = 0, o_last_w = 0, o_freq = 0;
     float last_b = 0.f;
     PeDims pe{};
@@ -236,14 +293,20 @@ struct WgRun {
     cudaStream_t st;
     size_t off = 0;
     int rc = SDDM_OK;
-    std::map<std::string, std::pair<float*, std::pair<int, int>>> named;   // name -> (ptr, (L, C))
+    struct Named { void* ptr; int L, C, ld, is16; };
+    std::map<std::string, Named> named;
 
     float* alloc(size_t L, size_t C) {
         const size_t o = off;
-        off = align_up(off + (size_t)B * L * C * sizeof(float), 256);
+        off = align_up(off + (size_t)B * L * C * sizeof(float), 1024);
         return reinterpret_cast<float*>(ws + o);   // ws may be null in a sizing run: the value is then only an offset, never dereferenced
     }
-    void name(const char* n, float* ptr, int L, int C) { named[n] = {ptr, {L, C}}; }
+    void name(const char* n, void* ptr, int L, int C, int ld = 0, int is16 = 0) { named[n] = Named{ptr, L, C, ld ? ld : C, is16}; }
+    __nv_bfloat16* alloc16(size_t L, size_t ld) {
+        const size_t o = off;
+        off = align_up(off + (size_t)B * L * ld * 2, 1024);
+        return reinterpret_cast<__nv_bfloat16*>(ws + o);
+    }
 
     float* conv(const std::string& key, const float* in, int Lin, int L, int up, int down, const float* film, int pre, int dil, int post,
                 const float* pe, const float* add) {
@@ -261,8 +324,101 @@ struct WgRun {
         return out;
     }
 
-    // returns eps pointer semantics through eps_out
     int forward(const float* spec, const float* audio, const float* level_dev, float level_scalar, float* eps_out) {
+        return p->tc ? forward_tc(spec, audio, level_dev, level_scalar, eps_out) : forward_fp32(spec, audio, level_dev, level_scalar, eps_out);
+    }
+
+    // ---- tcgen05 path ------------------------------------------------------------------------------------
+    struct Act { __nv_bfloat16* raw16; __nv_bfloat16* act16; float* raw32; int L, C, ld; };
+
+    // one conv launch; `a` is the operand tensor (already in consumer form), decim: row-strided (nearest down-sampled) view
+    void tc(const std::string& key, const __nv_bfloat16* a, int a_ld, int a_L, int decim, int rows, const int* toff, int ntaps, int phases,
+            const float* add, int add_div, int add_rows, const float* film, int act_mode, bool post_pe, const float* pe, Act& o, int want) {
+        // want bits: 1 raw32, 2 raw16, 4 act16
+        const ConvW& w = p->convs.at(key);
+        const int H = w.Cout;
+        o.L = phases * rows; o.C = H; o.ld = H < 64 ? 64 : H;
+        o.raw32 = (want & 1) ? alloc(o.L, H) : nullptr;
+        o.raw16 = (want & 2) ? alloc16(o.L, o.ld) : nullptr;
+        o.act16 = (want & 4) ? alloc16(o.L, o.ld) : nullptr;
+        if (dry || rc) return;
+        WgTcConv c{};
+        c.a = a; c.a_row_pitch = (long long)a_ld * decim; c.a_batch_pitch = (long long)a_L * a_ld; c.rows = rows; c.Cin = a_ld;
+        c.ntaps = ntaps;
+        for (int i = 0; i < ntaps; ++i) c.toff[i] = toff[i];
+        c.w = p->d_bf16 + p->tc_w.at(key); c.Ntot = phases * H;
+        c.bias = p->d_f32 + w.b_off; c.H = H; c.phases = phases; c.L_out = o.L;
+        c.add = add; c.add_div = add_div; c.add_rows = add_rows; c.film = film; c.act_mode = (want & 4) ? act_mode : 0;
+        c.post_lrelu = post_pe ? 1 : 0; c.pe = pe; c.pe_stride = p->pe_total;
+        c.raw32 = o.raw32; c.raw16 = o.raw16; c.act16 = o.act16; c.ld16 = o.ld; c.B = B;
+        rc = launch_wg_conv_tc(c, st);
+    }
+
+    int forward_tc(const float* spec, const float* audio, const float* level_dev, float level_scalar, float* eps_out) {
+        const int T = WG_HOP * frames;
+        const float* W = dry ? nullptr : p->d_f32;
+        float* pe = alloc(1, p->pe_total);
+        __nv_bfloat16* spec_t = alloc16(frames, WG_MELS);
+        Act d[5], film[5];
+        d[0].L = T; d[0].C = 32; d[0].ld = 64; d[0].raw32 = nullptr;
+        d[0].raw16 = alloc16(T, 64);
+        d[0].act16 = alloc16(T, 64);
+        if (!dry) {
+            wg_pe_kernel<<<B, 256, 0, st>>>(level_dev, level_scalar, W + p->o_freq, pe, p->pe, p->pe_total);
+            count_launch();
+            wg_transpose_spec_tc<<<grid_1d((int64_t)B * WG_MELS * frames, 256), 256, 0, st>>>(spec, spec_t, B, WG_MELS, frames);
+            count_launch();
+            wg_first_kernel_tc<<<grid_1d((int64_t)B * T * 16, 256), 256, 0, st>>>(audio, W + p->o_first_w, W + p->o_first_b, d[0].raw16, d[0].act16, B, T);
+            count_launch();
+        }
+        const int t1[1] = {0}, t3[3] = {-1, 0, 1};
+        for (int i = 0; i < 5; ++i) {
+            if (i > 0) {
+                const int f = kDown[i - 1][2], Lin = d[i - 1].L, L = Lin / f, ld = d[i - 1].ld;
+                const std::string k = "downsample." + std::to_string(i) + ".";
+                Act r, a, c;
+                tc(k + "residual_dense", d[i - 1].raw16, ld, Lin, f, L, t1, 1, 1, nullptr, 1, 0, nullptr, 0, false, nullptr, r, 1);
+                tc(k + "conv.0", d[i - 1].act16, ld, Lin, f, L, t3, 3, 1, nullptr, 1, 0, nullptr, 1, false, nullptr, a, 4);
+                const int t2[3] = {-2, 0, 2}, t4[3] = {-4, 0, 4};
+                tc(k + "conv.1", a.act16, a.ld, L, 1, L, t2, 3, 1, nullptr, 1, 0, nullptr, 1, false, nullptr, c, 4);
+                tc(k + "conv.2", c.act16, c.ld, L, 1, L, t4, 3, 1, r.raw32, 1, L, nullptr, 1, false, nullptr, d[i], i < 4 ? 6 : 2);
+            }
+            const std::string k = "film." + std::to_string(i) + ".";
+            Act fa;
+            tc(k + "input_conv", d[i].raw16, d[i].ld, d[i].L, 1, d[i].L, t3, 3, 1, nullptr, 1, 0, nullptr, 0, true, pe + p->pe.off[i], fa, 2);
+            tc(k + "output_conv", fa.raw16, fa.ld, fa.L, 1, fa.L, t3, 3, 1, nullptr, 1, 0, nullptr, 0, false, nullptr, film[i], 1);
+            char nm[8];
+            snprintf(nm, sizeof nm, "d%d", i);
+            name(nm, d[i].raw16, d[i].L, d[i].C, d[i].ld, 1);
+        }
+        Act x;
+        tc("first_conv", spec_t, WG_MELS, frames, 1, frames, t3, 3, 1, nullptr, 1, 0, nullptr, 1, false, nullptr, x, 6);
+        for (int i = 0; i < 5; ++i) {
+            const int f = kUp[i][2], Lx = x.L, L = Lx * f;
+            const float* fl = film[4 - i].raw32;
+            const std::string k = "upsample." + std::to_string(i) + ".";
+            Act b1, q, xs, r3, xo;
+            tc(k + "block1", x.raw16, x.ld, Lx, 1, Lx, t1, 1, 1, nullptr, 1, 0, nullptr, 0, false, nullptr, b1, 1);
+            tc(k + "block2.0", x.act16, x.ld, Lx, 1, Lx, t3, 3, f, nullptr, 1, 0, fl, 2, false, nullptr, q, 4);
+            const int ta[3] = {-kUp[i][4], 0, kUp[i][4]}, tb[3] = {-kUp[i][5], 0, kUp[i][5]}, tcx[3] = {-kUp[i][6], 0, kUp[i][6]};
+            tc(k + "block2.1", q.act16, q.ld, L, 1, L, ta, 3, 1, b1.raw32, f, Lx, fl, 2, false, nullptr, xs, 5);
+            tc(k + "block3.0", xs.act16, xs.ld, L, 1, L, tb, 3, 1, nullptr, 1, 0, fl, 2, false, nullptr, r3, 4);
+            tc(k + "block3.1", r3.act16, r3.ld, L, 1, L, tcx, 3, 1, xs.raw32, 1, L, nullptr, 1, false, nullptr, xo, i < 4 ? 6 : 1);
+            x = xo;
+            char nm[8];
+            snprintf(nm, sizeof nm, "u%d", i);
+            if (i < 4) name(nm, x.raw16, L, x.C, x.ld, 1);
+            else name(nm, x.raw32, L, x.C, x.C, 0);
+        }
+        if (!dry && !rc) {
+            wg_last_kernel<<<grid_1d(((int64_t)B * T + 7) / 8, 1), 256, 0, st>>>(x.raw32, W + p->o_last_w, p->last_b, eps_out, B, T);
+            count_launch();
+            if (cudaPeekAtLastError() != cudaSuccess) { set_error("wavegrad launch failed: %s", cudaGetErrorString(cudaGetLastError())); rc = SDDM_E_CUDA; }
+        }
+        return rc;
+    }
+
+    int forward_fp32(const float* spec, const float* audio, const float* level_dev, float level_scalar, float* eps_out) {
         const int T = WG_HOP * frames;
         const float* W = dry ? nullptr : p->d_f32;
         float* pe = alloc(1, p->pe_total);
@@ -371,12 +527,13 @@ SDDM_API int sddm_wg_plan_create(const sddm_wg_config* cfg, sddm_wg_plan** out) 
     if (!cfg || !out) { set_error("null argument"); return SDDM_E_INVALID; }
     *out = nullptr;
     if (cfg->hop_samples != WG_HOP) { set_error("hop_samples must be %d (WaveGrad's 5*5*3*2*2 upsampling), got %d", WG_HOP, cfg->hop_samples); return SDDM_E_INVALID; }
-    if (cfg->precision != SDDM_PREC_FP32) { set_error("WaveGrad runs the fp32 path only (precision must be SDDM_PREC_FP32), got %d", cfg->precision); return SDDM_E_INVALID; }
+    if (cfg->precision != SDDM_PREC_FP32 && cfg->precision != SDDM_PREC_BF16) { set_error("WaveGrad precision must be SDDM_PREC_FP32 or SDDM_PREC_BF16, got %d", cfg->precision); return SDDM_E_INVALID; }
     if (cfg->n_timestep < 1) { set_error("n_timestep must be positive"); return SDDM_E_INVALID; }
     if (cfg->noise_condition != SDDM_DW_COND_SQRT_ALPHA_BAR && cfg->noise_condition != SDDM_DW_COND_TIME_STEP) { set_error("unknown noise_condition %d", cfg->noise_condition); return SDDM_E_INVALID; }
     sddm_wg_plan* p = new sddm_wg_plan();
     p->cfg = *cfg;
     p->T = cfg->n_timestep;
+    p->tc = cfg->precision == SDDM_PREC_BF16;
     p->expect["downsample.0.weight"] = {32, 1, 5};
     p->expect["downsample.0.bias"] = {32};
     for (int i = 1; i <= 4; ++i) {
@@ -417,6 +574,7 @@ SDDM_API int sddm_wg_plan_create(const sddm_wg_config* cfg, sddm_wg_plan** out) 
 SDDM_API void sddm_wg_plan_destroy(sddm_wg_plan* p) {
     if (!p) return;
     if (p->d_f32) cudaFree(p->d_f32);
+    if (p->d_bf16) cudaFree(p->d_bf16);
     delete p;
 }
 
@@ -483,6 +641,33 @@ SDDM_API int sddm_wg_plan_finalize(sddm_wg_plan* p) {
                 for (int k = 0; k < c.K; ++k) v[((size_t)k * c.Cin + ci) * c.Cout + n] = w[((size_t)n * c.Cin + ci) * c.K + k];
         c.w_off = put(v);
         c.b_off = put(p->host_w[kv.first + ".bias"]);
+    }
+    if (p->tc) {   // [N][taps * CinP] bf16, K-major; 32-channel inputs zero-padded to 64; up-sampling convs in polyphase form
+        std::vector<__nv_bfloat16> h;
+        for (auto& kv : p->convs) {
+            const ConvW& c = kv.second;
+            const auto& w = p->host_w[kv.first + ".weight"];   // [Cout][Cin][K]
+            const int cinp = c.Cin < 64 ? 64 : c.Cin;
+            int phases = 1;
+            if (kv.first.size() > 9 && kv.first.compare(kv.first.size() - 8, 8, "block2.0") == 0) phases = kUp[kv.first[9] - '0'][2];
+            const int ktot = c.K * cinp, ntot = phases * c.Cout;
+            std::vector<float> m((size_t)ntot * ktot, 0.f);
+            for (int ph = 0; ph < phases; ++ph)
+                for (int k = 0; k < c.K; ++k) {
+                    // tap k reads up-sampled index t + k - K/2 (dilation 1 on these layers); t = phases * s + ph -> source row s + o
+                    const int num = ph + k - c.K / 2;
+                    const int o = phases == 1 ? 0 : (num >= 0 ? num / phases : -((-num + phases - 1) / phases));
+                    const int gt = phases == 1 ? k : o + 1;
+                    for (int n = 0; n < c.Cout; ++n)
+                        for (int ci = 0; ci < c.Cin; ++ci)
+                            m[((size_t)ph * c.Cout + n) * ktot + (size_t)gt * cinp + ci] += w[((size_t)n * c.Cin + ci) * c.K + k];
+                }
+            while (h.size() % 512) h.push_back(__float2bfloat16(0.f));   // 1024-byte aligned packs (TMA base alignment)
+            p->tc_w[kv.first] = h.size();
+            for (float v : m) h.push_back(__float2bfloat16(v));
+        }
+        SDDM_CUDA_TRY(cudaMalloc(&p->d_bf16, h.size() * sizeof(__nv_bfloat16)));
+        SDDM_CUDA_TRY(cudaMemcpy(p->d_bf16, h.data(), h.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
     }
     SDDM_CUDA_TRY(cudaMalloc(&p->d_f32, f.size() * sizeof(float)));
     SDDM_CUDA_TRY(cudaMemcpy(p->d_f32, f.data(), f.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -552,10 +737,17 @@ SDDM_API int sddm_wg_debug_fetch(sddm_wg_plan* p, const char* what, void* ws, in
     r.forward(nullptr, nullptr, nullptr, 0.f, nullptr);
     auto it = r.named.find(what);
     if (it == r.named.end()) { set_error("unknown debug tensor '%s'", what); return SDDM_E_INVALID; }
-    shape2[0] = it->second.second.first;
-    shape2[1] = it->second.second.second;
+    const auto& nm = it->second;
+    shape2[0] = nm.L;
+    shape2[1] = nm.C;
     if (!out) return SDDM_OK;
-    SDDM_CUDA_TRY(cudaMemcpyAsync(out, it->second.first, (size_t)B * shape2[0] * shape2[1] * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    const int64_t rows = (int64_t)B * nm.L;
+    if (nm.is16) {
+        wg_bf16_to_f32<<<grid_1d(rows * nm.C, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(nm.ptr), out, rows, nm.C, nm.ld);
+        SDDM_LAUNCH_CHECK();
+    } else {
+        SDDM_CUDA_TRY(cudaMemcpyAsync(out, nm.ptr, (size_t)rows * nm.C * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    }
     return SDDM_OK;
 }
 

@@ -1,7 +1,8 @@
 """``WaveGrad`` — host mirror of reference model/wavegrad.py:140-179 (config_wavegrad.json's denoiser).
 
 Parameter container only (same layers, names, initialisers and construction order as the reference, so ``state_dict``
-and default initialisation match); ``forward`` runs the CUDA plan (``sddm_wg_*`` in include/sddm_b200.h).
+and default initialisation match); ``forward`` runs the CUDA plan (``sddm_wg_*`` in include/sddm_b200.h): fp32 CUDA-core
+parity path or the tcgen05 bf16 path.
 """
 from __future__ import annotations
 
@@ -13,7 +14,7 @@ import torch
 from torch import nn
 
 from .. import _lib
-from ..plan import _f32c, _ptr
+from ..plan import _f32c, _ptr, default_precision
 
 
 class _Holder(nn.Module):
@@ -82,15 +83,15 @@ class WaveGradPlan:
     HOP, N_MELS = 300, 128
 
     def __init__(self, weights: Dict[str, torch.Tensor], tables: Dict[str, np.ndarray], n_timestep: int, noise_condition: str,
-                 device: torch.device):
+                 precision: int, device: torch.device):
         if device.type != "cuda":
             raise RuntimeError("sddm_b200 needs a CUDA device (no CPU fallback); got %s" % device)
         if noise_condition not in _lib.NOISE_CONDITIONS:
             raise NotImplementedError(noise_condition)
-        self.device, self.T = device, int(n_timestep)
+        self.device, self.T, self.precision = device, int(n_timestep), precision
         lib = _lib.lib()
         c = _lib.WgConfig(n_timestep=n_timestep, hop_samples=self.HOP, noise_condition=_lib.NOISE_CONDITIONS[noise_condition],
-                          precision=_lib.PREC_FP32)
+                          precision=precision)
         h = C.c_void_p()
         _lib.check(lib.sddm_wg_plan_create(C.byref(c), C.byref(h)))
         self._h = h
@@ -199,6 +200,7 @@ class WaveGrad(nn.Module):
                                        UBlock(256, 128, 2, [1, 2, 4, 8]), UBlock(128, 128, 2, [1, 2, 4, 8])])
         self.first_conv = Conv1d(128, 768, 3, padding=1)
         self.last_conv = Conv1d(128, 1, 3, padding=1)
+        self.precision: Optional[int] = None     # None -> SDDM_B200_PRECISION env / default
         self._plans: Dict[tuple, WaveGradPlan] = {}
 
     def _param_version(self):
@@ -212,15 +214,17 @@ class WaveGrad(nn.Module):
         self._plans = {}
         return super().load_state_dict(*a, **k)
 
-    def get_plan(self, diffusion=None, noise_condition: str = "sqrt_alpha_bar") -> WaveGradPlan:
+    def get_plan(self, diffusion=None, noise_condition: str = "sqrt_alpha_bar", precision: Optional[int] = None) -> WaveGradPlan:
         dev = next(self.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("WaveGrad (sddm_b200) must live on a CUDA device: call .to('cuda') first; there is no CPU fallback")
+        prec = precision if precision is not None else (self.precision if self.precision is not None else default_precision())
+        prec = _lib.PREC_FP32 if prec == _lib.PREC_FP32 else _lib.PREC_BF16      # bf16act == bf16 for this denoiser
         tables = diffusion.host_tables() if diffusion is not None else None
-        key = (id(tables), noise_condition, str(dev), self._param_version())
+        key = (id(tables), noise_condition, prec, str(dev), self._param_version())
         plan = self._plans.get(key)
         if plan is None:
-            self._plans = {k: v for k, v in self._plans.items() if k[3] == key[3]}
+            self._plans = {k: v for k, v in self._plans.items() if k[4] == key[4]}
             if diffusion is not None:
                 T = diffusion.num_timesteps
             else:
@@ -230,7 +234,7 @@ class WaveGrad(nn.Module):
                 count = f.encoding.dim // 2
                 step = torch.arange(count, dtype=torch.float32) / count
                 weights["film.%d.encoding.frequencies" % i] = torch.exp(-np.log(1e4) * step)
-            plan = WaveGradPlan(weights, tables, T, noise_condition, dev)
+            plan = WaveGradPlan(weights, tables, T, noise_condition, prec, dev)
             self._plans[key] = plan
         return plan
 

@@ -1,8 +1,8 @@
 """cfg 4: WaveGrad denoiser + SDDM_spectrogram sampling loop (fp32 CUDA-core path).
 
 CPU (-m "not gpu"): oracle/wavegrad_oracle.py against goldens of the real reference modules (tests/golden/make_golden_wavegrad.py),
-host-mirror surface.  GPU (-m gpu): the CUDA path through the C ABI (sddm_wg_*).  Tolerance 1e-3 of max for eps_hat and every
-block output (measured ~1e-6), final sample SI-SNR >= 60 dB.
+host-mirror surface.  GPU (-m gpu): the CUDA paths through the C ABI (sddm_wg_*).  Tolerance for eps_hat and every block output:
+fp32 path 1e-3 of max (measured ~1e-6), tcgen05 bf16 path 2e-2; final sample SI-SNR >= 60 / 40 dB.
 """
 import os
 import sys
@@ -62,11 +62,22 @@ def test_mirror_surface():
         m.infer(torch.zeros(1, 128, 3))             # CPU tensors: no fallback
 
 
-@pytest.mark.gpu
-@pytest.mark.parametrize("tag", list(WAVEGRAD_CASES))
-def test_gpu_eps_vs_reference_golden(built_lib, gold, tag):
-    case = WAVEGRAD_CASES[tag]
+TOL = {"fp32": 1e-3, "bf16": 2e-2}
+
+
+def _gpu_module(prec):
+    from sddm_b200 import _lib
     net = wavegrad_test_module().cuda()
+    net.precision = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}[prec]
+    return net
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("tag", list(WAVEGRAD_CASES))
+def test_gpu_eps_vs_reference_golden(built_lib, gold, tag, prec):
+    case = WAVEGRAD_CASES[tag]
+    net = _gpu_module(prec)
     B, F = case["B"], case["frames"]
     eps = net(gold[tag + ".spec"].cuda(), gold[tag + ".audio"].cuda(), torch.tensor(case["levels"]).cuda()).cpu()
     assert eps.shape == gold[tag + ".eps"].shape                      # torch.squeeze quirk: [T] when B == 1
@@ -75,21 +86,22 @@ def test_gpu_eps_vs_reference_golden(built_lib, gold, tag):
     for k in ("d0", "d1", "d2", "d3", "d4", "u0", "u1", "u2", "u3", "u4"):
         errs[k] = rel_err(plan.fetch(k, B, F).cpu()[:, ::5, ::3], gold[tag + "." + k])
     e = rel_err(eps.reshape(-1), gold[tag + ".eps"].reshape(-1))
-    print("wavegrad %s: eps %.2e  blocks %s" % (tag, e, " ".join("%s %.1e" % kv for kv in errs.items())))
-    assert e < 1e-3 and max(errs.values()) < 1e-3
+    print("wavegrad %s %s: eps %.2e  blocks %s" % (tag, prec, e, " ".join("%s %.1e" % kv for kv in errs.items())))
+    assert e < TOL[prec] and max(errs.values()) < TOL[prec]
 
 
 @pytest.mark.gpu
-def test_gpu_sampling_vs_reference_golden(built_lib, gold):
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_gpu_sampling_vs_reference_golden(built_lib, gold, prec):
     from sddm_b200.model import model as M
     from sddm_b200.model.diffusion import GaussianDiffusion
-    net = wavegrad_test_module().cuda()
+    net = _gpu_module(prec)
     d = GaussianDiffusion(schedule="linear", n_timestep=4, linear_start=1e-4, linear_end=5e-2, device="cuda")
     m = M.SDDM_spectrogram(d, net, hop_samples=300)
     x0 = m.infer(gold["sample.spec"].cuda(), noises=gold["sample.noises"].cuda()).cpu()
     snr = si_snr_db(x0, gold["sample.x0"])
-    print("wavegrad sampling: SI-SNR vs reference %.1f dB" % snr)
-    assert snr > 60.0
+    print("wavegrad sampling %s: SI-SNR vs reference %.1f dB" % (prec, snr))
+    assert snr > (60.0 if prec == "fp32" else 40.0)
     a = m.infer(gold["sample.spec"].cuda(), seed=5)
     b = m.infer(gold["sample.spec"].cuda(), seed=5)
     c = m.infer(gold["sample.spec"][1:2].contiguous().cuda(), seed=5, row0=1)
@@ -99,11 +111,12 @@ def test_gpu_sampling_vs_reference_golden(built_lib, gold):
 @pytest.mark.gpu
 def test_gpu_ragged_lengths_vs_oracle(built_lib, sd):
     """frame counts whose level lengths are not multiples of the 64-row tile (1 frame: L = 300, 150, 75, 25, 5)."""
-    net = wavegrad_test_module().cuda()
     g = torch.Generator().manual_seed(21)
-    for B, F in ((1, 1), (3, 2), (2, 11)):
-        spec, audio = torch.rand(B, 128, F, generator=g), torch.randn(B, 300 * F, generator=g)
-        lv = torch.rand(B, generator=g)
-        want = WO.wavegrad_forward(sd, spec, audio, lv)
-        got = net.get_plan().eps(spec.cuda(), audio.cuda(), noise_level=lv.cuda()).cpu()
-        assert rel_err(got, want) < 1e-3, (B, F)
+    for prec in ("fp32", "bf16"):
+        net = _gpu_module(prec)
+        for B, F in ((1, 1), (3, 2), (2, 11)):
+            spec, audio = torch.rand(B, 128, F, generator=g), torch.randn(B, 300 * F, generator=g)
+            lv = torch.rand(B, generator=g)
+            want = WO.wavegrad_forward(sd, spec, audio, lv)
+            got = net.get_plan().eps(spec.cuda(), audio.cuda(), noise_level=lv.cuda()).cpu()
+            assert rel_err(got, want) < TOL[prec], (prec, B, F)
