@@ -1,11 +1,11 @@
 // tcgen05 / TMEM / TMA convolution of the WaveGrad denoiser (cfg 4; reference model/wavegrad.py:52-137), sm_100a.
 //
 // Every Conv1d is a GEMM tile [128 time rows] x [128 output columns] accumulated in TMEM over (tap, 64-channel chunk) steps.
-// Both operands arrive by TMA in the 128-byte-swizzled K-major layout (3-stage ring, 32 KB per stage): the activation box is
+// Both operands arrive by TMA in the 128-byte-swizzled K-major layout (5-stage ring, 32 KB per stage): the activation box is
 // a window of a time-major bf16 tensor shifted by the tap offset (zero filled outside = the padding), the weight box a slice
 // of the pre-packed [N][K] matrix.  Everything the reference applies between two convs (leaky_relu, the FiLM affine,
 // nearest-neighbour resampling) is moved to the producer's epilogue or into the view / the polyphase weight packing, so
-// the main loop is pure TMA -> tcgen05.mma.  Two CTAs per SM: one runs its epilogue while the other streams its K loop.
+// the main loop is pure TMA -> tcgen05.mma.  Persistent CTAs, two TMEM accumulator stages, two epilogue groups.
 #include <cstring>
 #include <map>
 #include <tuple>
@@ -18,10 +18,12 @@ namespace {
 
 constexpr int kTileM = 128, kTileN = 128;
 constexpr uint32_t kBoxBytes = 128 * 64 * 2;          // 16 KB
-constexpr int kStages = 3;
+constexpr int kStages = 5;
 constexpr uint32_t kStageBytes = 2 * kBoxBytes;
-constexpr uint32_t kOffBars = kStages * kStageBytes;
-constexpr uint32_t kSmem = kOffBars + 128 + 1024;
+constexpr uint32_t kOffTile = kStages * kStageBytes;          // 8 transposition tiles (one per epilogue warp), 4608 B each
+constexpr uint32_t kOffBars = kOffTile + 8 * 4608;
+constexpr uint32_t kSmem = kOffBars + 256 + 1024;
+constexpr int kThreads = 320;
 
 struct alignas(64) WgMaps {
     CUtensorMap a, w;
@@ -29,131 +31,167 @@ struct alignas(64) WgMaps {
 
 __device__ __forceinline__ float lrelu02(float v) { return v > 0.f ? v : 0.2f * v; }
 
-__global__ void __launch_bounds__(192, 2) wg_conv_tc_kernel(const __grid_constant__ WgMaps maps, WgTcConv p) {
+// Persistent CTA (one per SM): warps 0-3 / 4-7 = epilogue groups 0 / 1 (alternate tiles, TMEM columns [128 g, 128 g + 128)),
+// warp 8 = TMA producer, warp 9 = MMA issuer.  The operand ring runs ahead across tile boundaries, so the loads and MMAs of the
+// next tiles overlap the (global-memory-latency-bound) epilogues of the previous two.
+__global__ void __launch_bounds__(kThreads, 1) wg_conv_tc_kernel(const __grid_constant__ WgMaps maps, WgTcConv p, int tiles_n, int tiles_m, int ntiles) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char* gbase = smem_raw + (base - smem_u32(smem_raw));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t bars = base + kOffBars;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + kOffBars + 64);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + kOffBars + 192);
     auto full = [&](int s) { return bars + 8u * (uint32_t)s; };
     auto empty = [&](int s) { return bars + 8u * (uint32_t)(kStages + s); };
-    const uint32_t accf = bars + 8u * 2 * kStages;
+    auto accf = [&](int g) { return bars + 8u * (uint32_t)(2 * kStages + g); };
+    auto acce = [&](int g) { return bars + 8u * (uint32_t)(2 * kStages + 2 + g); };
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
-        mbar_init(accf, 1);
+        for (int g = 0; g < 2; ++g) { mbar_init(accf(g), 1); mbar_init(acce(g), 128); }
         fence_barrier_init();
     }
-    if (warp == 5) tmem_alloc(smem_u32(tmem_slot), 128);
+    if (warp == 9) tmem_alloc(smem_u32(tmem_slot), 256);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const int n0 = blockIdx.x * kTileN, s0 = blockIdx.y * kTileM, b = blockIdx.z;
+    const int my_tiles = ntiles > (int)blockIdx.x ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     const int cchunks = p.Cin / 64, nchunks = p.ntaps * cchunks;
-    if (warp == 4) {
+    // tile index -> (n tile fastest, m tile, batch): CTAs that run concurrently share activation rows in L2
+    auto tile_of = [&](int i, int& n0, int& s0, int& b) {
+        const int tile = blockIdx.x + i * gridDim.x;
+        const int tn = tile % tiles_n, r = tile / tiles_n;
+        n0 = tn * kTileN; s0 = (r % tiles_m) * kTileM; b = r / tiles_m;
+    };
+    if (warp == 8) {
         pdl_wait();
         if (lane == 0) {
-            for (int c = 0; c < nchunks; ++c) {
-                const int st = c % kStages, n = c / kStages;
-                const int tap = c / cchunks, cc = c - tap * cchunks;
-                mbar_wait(empty(st), (n & 1) ^ 1);
-                mbar_expect_tx(full(st), kStageBytes);
-                tma_load_3d(base + st * kStageBytes, &maps.a, cc * 64, s0 + p.toff[tap], b, full(st));
-                tma_load_2d(base + st * kStageBytes + kBoxBytes, &maps.w, tap * p.Cin + cc * 64, n0, full(st));
+            int c = 0;
+            for (int i = 0; i < my_tiles; ++i) {
+                int n0, s0, b;
+                tile_of(i, n0, s0, b);
+                for (int k = 0; k < nchunks; ++k, ++c) {
+                    const int st = c % kStages, n = c / kStages;
+                    const int tap = k / cchunks, cc = k - tap * cchunks;
+                    mbar_wait(empty(st), (n & 1) ^ 1);
+                    mbar_expect_tx(full(st), kStageBytes);
+                    tma_load_3d(base + st * kStageBytes, &maps.a, cc * 64, s0 + p.toff[tap], b, full(st));
+                    tma_load_2d(base + st * kStageBytes + kBoxBytes, &maps.w, tap * p.Cin + cc * 64, n0, full(st));
+                }
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == 9) {
         const uint32_t idesc = make_idesc(kTileN);
-        for (int c = 0; c < nchunks; ++c) {
-            const int st = c % kStages, n = c / kStages;
-            mbar_wait(full(st), n & 1);
+        int c = 0;
+        for (int i = 0; i < my_tiles; ++i) {
+            const int g = i & 1, ng = i >> 1;
+            mbar_wait(acce(g), (ng & 1) ^ 1);
             tc_fence_after();
-            if (elect_one()) {
-                const uint32_t a0 = base + st * kStageBytes;
+            for (int k = 0; k < nchunks; ++k, ++c) {
+                const int st = c % kStages, n = c / kStages;
+                mbar_wait(full(st), n & 1);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t a0 = base + st * kStageBytes;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma(tmem, make_desc_sw128(a0 + k * 32), make_desc_sw128(a0 + kBoxBytes + k * 32), idesc, (c | k) != 0);
-                umma_commit(empty(st));
-                if (c == nchunks - 1) umma_commit(accf);
+                    for (int kk = 0; kk < 4; ++kk)
+                        umma(tmem + 128u * g, make_desc_sw128(a0 + kk * 32), make_desc_sw128(a0 + kBoxBytes + kk * 32), idesc, (k | kk) != 0);
+                    umma_commit(empty(st));
+                    if (k == nchunks - 1) umma_commit(accf(g));
+                }
+                __syncwarp();
             }
-            __syncwarp();
         }
     } else {
         pdl_wait();
-        const int s = s0 + warp * 32 + lane;
-        const uint32_t acc = tmem + ((uint32_t)(warp * 32) << 16);
-        mbar_wait(accf, 0);
+        const int g = warp >> 2, wq = warp & 3;
+        const uint32_t acc = tmem + 128u * g + ((uint32_t)(wq * 32) << 16);
+        // Transposition tile of this warp (32 rows x 32 columns, pitch 36 floats): TMEM hands every thread one ROW, but global
+        // memory wants a warp access to cover whole 128-byte row segments (8 lanes x 16 B per row, 4 rows per instruction) —
+        // row-per-thread accesses cost 32 L1 wavefronts per instruction.
+        const uint32_t tile = base + kOffTile + (uint32_t)warp * 4608u;
+        const int rsub = lane >> 3, cl = 4 * (lane & 7);
+        for (int i = g, ng = 0; i < my_tiles; i += 2, ++ng) {
+        int n0, s0t, b;
+        tile_of(i, n0, s0t, b);
+        const int s0 = s0t + wq * 32 - warp * 32;   // so that s0 + warp * 32 is this warp's first row
+        mbar_wait(accf(g), ng & 1);
         tc_fence_after();
 #pragma unroll 1
         for (int h = 0; h < 4; ++h) {
             float v[32];
-            __syncwarp();                    // reconverge after the guarded stores of the previous chunk
-            tmem_ld32(acc + 32 * h, v);      // warp-collective: every lane takes part, stores are guarded below
+            __syncwarp();                    // the previous chunk's tile reads are done (and the warp is converged for the collective)
+            tmem_ld32(acc + 32 * h, v);
+            if (h == 3) {                    // the accumulator stage has been read completely: the MMAs of this group's next tile may start
+                tc_fence_before();
+                mbar_arrive(acce(g));
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                sts128(tile + lane * 144 + q * 16, make_uint4(__float_as_uint(v[4 * q]), __float_as_uint(v[4 * q + 1]), __float_as_uint(v[4 * q + 2]),
+                                                                  __float_as_uint(v[4 * q + 3])));
+            __syncwarp();
             const int j0 = n0 + 32 * h;
             if (j0 >= p.Ntot) {              // beyond the GEMM's N: only the zero padding of a narrower-than-ld16 bf16 tensor remains
-                if (p.phases == 1 && j0 < p.ld16 && s < p.L_out) {
-                    const size_t row = (size_t)b * p.L_out + s;
-                    const uint4 z = make_uint4(0, 0, 0, 0);
-                    for (int q = 0; q < 4; ++q) {
-                        if (p.raw16) *reinterpret_cast<uint4*>(p.raw16 + row * p.ld16 + j0 + 8 * q) = z;
-                        if (p.act16) *reinterpret_cast<uint4*>(p.act16 + row * p.ld16 + j0 + 8 * q) = z;
+                if (p.phases == 1 && j0 < p.ld16) {
+                    for (int it = 0; it < 8; ++it) {
+                        const int sr = s0 + warp * 32 + it * 4 + rsub;
+                        if (sr >= p.L_out || sr >= p.rows) continue;
+                        const size_t row = (size_t)b * p.L_out + sr;
+                        if (p.raw16) *reinterpret_cast<uint2*>(p.raw16 + row * p.ld16 + j0 + cl) = make_uint2(0, 0);
+                        if (p.act16) *reinterpret_cast<uint2*>(p.act16 + row * p.ld16 + j0 + cl) = make_uint2(0, 0);
                     }
                 }
                 continue;
             }
-            const int phase = j0 / p.H, c0 = j0 - phase * p.H;
-            const int t = p.phases * s + phase;
-            if (t >= p.L_out || s >= p.rows) continue;
-            const size_t row = (size_t)b * p.L_out + t;
+            const int phase = j0 / p.H, c0 = j0 - phase * p.H + cl;
+            const float4 bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + c0));
+            float4 pe4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.post_lrelu) pe4 = __ldg(reinterpret_cast<const float4*>(p.pe + (size_t)b * p.pe_stride + c0));
+            // all global loads of the chunk are issued before the first use (8 row groups x up to 3 tensors in flight per thread)
+            float4 ad[8], sh[8], sc[8];
+            bool ok[8];
+            size_t rowi[8];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] += __ldg(p.bias + c0 + i);
-            if (p.post_lrelu) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = lrelu02(v[i]) + __ldg(p.pe + (size_t)b * p.pe_stride + c0 + i);
-            }
-            if (p.add) {
-                const float4* ap = reinterpret_cast<const float4*>(p.add + ((size_t)b * p.add_rows + t / p.add_div) * p.H + c0);
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const float4 a = __ldg(ap + q);
-                    v[4 * q] += a.x; v[4 * q + 1] += a.y; v[4 * q + 2] += a.z; v[4 * q + 3] += a.w;
-                }
-            }
-            if (p.raw32) {
-                float4* o = reinterpret_cast<float4*>(p.raw32 + row * p.H + c0);
-#pragma unroll
-                for (int q = 0; q < 8; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-            }
-            if (p.raw16) {
-                uint4* o = reinterpret_cast<uint4*>(p.raw16 + row * p.ld16 + c0);
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    o[q] = make_uint4(pack_bf16(v[8 * q], v[8 * q + 1]), pack_bf16(v[8 * q + 2], v[8 * q + 3]), pack_bf16(v[8 * q + 4], v[8 * q + 5]),
-                                      pack_bf16(v[8 * q + 6], v[8 * q + 7]));
-            }
-            if (p.act_mode) {
-                if (p.act_mode == 2) {
-                    const float4* sh = reinterpret_cast<const float4*>(p.film + row * 2 * p.H + c0);
-                    const float4* sc = reinterpret_cast<const float4*>(p.film + row * 2 * p.H + p.H + c0);
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float4 a = __ldg(sh + q), m = __ldg(sc + q);
-                        v[4 * q] = fmaf(m.x, v[4 * q], a.x); v[4 * q + 1] = fmaf(m.y, v[4 * q + 1], a.y);
-                        v[4 * q + 2] = fmaf(m.z, v[4 * q + 2], a.z); v[4 * q + 3] = fmaf(m.w, v[4 * q + 3], a.w);
+            for (int it = 0; it < 8; ++it) {
+                const int sr = s0 + warp * 32 + it * 4 + rsub;
+                const int t = p.phases * sr + phase;
+                ok[it] = sr < p.rows && t < p.L_out;
+                rowi[it] = (size_t)b * p.L_out + t;
+                ad[it] = sh[it] = sc[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ok[it]) {
+                    if (p.add) ad[it] = __ldg(reinterpret_cast<const float4*>(p.add + ((size_t)b * p.add_rows + t / p.add_div) * p.H + c0));
+                    if (p.act_mode == 2) {
+                        sh[it] = __ldg(reinterpret_cast<const float4*>(p.film + rowi[it] * 2 * p.H + c0));
+                        sc[it] = __ldg(reinterpret_cast<const float4*>(p.film + rowi[it] * 2 * p.H + p.H + c0));
                     }
                 }
-                uint4* o = reinterpret_cast<uint4*>(p.act16 + row * p.ld16 + c0);
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    o[q] = make_uint4(pack_bf16(lrelu02(v[8 * q]), lrelu02(v[8 * q + 1])), pack_bf16(lrelu02(v[8 * q + 2]), lrelu02(v[8 * q + 3])),
-                                      pack_bf16(lrelu02(v[8 * q + 4]), lrelu02(v[8 * q + 5])), pack_bf16(lrelu02(v[8 * q + 6]), lrelu02(v[8 * q + 7])));
             }
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                if (!ok[it]) continue;
+                const size_t row = rowi[it];
+                const uint4 u = lds128(tile + (it * 4 + rsub) * 144 + (lane & 7) * 16);
+                float4 x = make_float4(__uint_as_float(u.x) + bias4.x, __uint_as_float(u.y) + bias4.y, __uint_as_float(u.z) + bias4.z,
+                                       __uint_as_float(u.w) + bias4.w);
+                if (p.post_lrelu) x = make_float4(lrelu02(x.x) + pe4.x, lrelu02(x.y) + pe4.y, lrelu02(x.z) + pe4.z, lrelu02(x.w) + pe4.w);
+                x.x += ad[it].x; x.y += ad[it].y; x.z += ad[it].z; x.w += ad[it].w;
+                if (p.raw32) *reinterpret_cast<float4*>(p.raw32 + row * p.H + c0) = x;
+                if (p.raw16) *reinterpret_cast<uint2*>(p.raw16 + row * p.ld16 + c0) = make_uint2(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w));
+                if (p.act_mode) {
+                    if (p.act_mode == 2)
+                        x = make_float4(fmaf(sc[it].x, x.x, sh[it].x), fmaf(sc[it].y, x.y, sh[it].y), fmaf(sc[it].z, x.z, sh[it].z), fmaf(sc[it].w, x.w, sh[it].w));
+                    *reinterpret_cast<uint2*>(p.act16 + row * p.ld16 + c0) =
+                        make_uint2(pack_bf16(lrelu02(x.x), lrelu02(x.y)), pack_bf16(lrelu02(x.z), lrelu02(x.w)));
+                }
+            }
+        }
         }
         tc_fence_before();
     }
     __syncthreads();
     pdl_launch_dependents();
-    if (warp == 5) tmem_dealloc(tmem, 128);
+    if (warp == 9) tmem_dealloc(tmem, 256);
 }
 
 }  // namespace
@@ -176,9 +214,9 @@ int launch_wg_conv_tc(const WgTcConv& p, cudaStream_t st) {
         if ((rc = encode_bf16_view(&m.w, p.w, p.ntaps * p.Cin, (long long)p.ntaps * p.Cin, p.Ntot, 0, 0, 128))) return rc;
         it = cache.emplace(key, m).first;
     }
-    dim3 grid((p.Ntot + kTileN - 1) / kTileN, (p.rows + kTileM - 1) / kTileM, p.B);
-    // a narrower-than-ld16 output also needs its padding columns written: they live in the same (only) N tile
-    SDDM_CUDA_TRY(launch_pdl(wg_conv_tc_kernel, grid, dim3(192), kSmem, st, it->second, p));
+    const int tiles_n = (p.Ntot + kTileN - 1) / kTileN, tiles_m = (p.rows + kTileM - 1) / kTileM, ntiles = tiles_n * tiles_m * p.B;
+    const int grid = ntiles < num_sms() ? ntiles : num_sms();
+    SDDM_CUDA_TRY(launch_pdl(wg_conv_tc_kernel, dim3(grid), dim3(kThreads), kSmem, st, it->second, p, tiles_n, tiles_m, ntiles));
     count_launch();
     return SDDM_OK;
 }

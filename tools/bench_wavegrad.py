@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--frames", type=int, default=107)
     ap.add_argument("--eps-iters", type=int, default=5)
     ap.add_argument("--cpu", action="store_true")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     args = ap.parse_args()
     import torch
     import __graft_entry__ as ge
@@ -28,6 +29,8 @@ def main():
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
     net = WaveGrad()
+    from sddm_b200 import PREC_BF16, PREC_FP32
+    net.precision = PREC_FP32 if args.precision == "fp32" else PREC_BF16
     d = GaussianDiffusion("linear", 1000, 1e-6, 1e-2, device=dev)
     model = SDDM_spectrogram(d, net, hop_samples=300).to(dev).eval()
     B, F = args.batch, args.frames
@@ -45,8 +48,9 @@ def main():
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.eps_iters
     gflop = 93.94 * F / 107.0 * B
-    out = dict(workload="WaveGrad cfg4: %d utterances, spec [128,%d], T=%d, 1000 steps, fp32 CUDA cores" % (B, F, T), eps_ms=ms,
-               tflops=gflop / ms, sampling_s_estimated=ms, utt_per_s_estimated=B / ms, rtf_estimated=ms / (B * T / 16000.0))
+    out = dict(workload="WaveGrad cfg4: %d utterances, spec [128,%d], T=%d, 1000 steps, %s" % (B, F, T, args.precision), eps_ms=ms,
+               tflops=gflop / ms, sampling_s_estimated=ms, utt_per_s_estimated=B / ms, rtf_estimated=ms / (B * T / 16000.0),
+               note="tflops counts the reference's 93.94 GFLOP per utterance-step; the polyphase / low-resolution forms execute fewer")
     if args.cpu:
         from oracle import wavegrad_oracle as WO
         sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
