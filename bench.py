@@ -5,6 +5,7 @@ a batch of 64 VoiceBank-DEMAND-shaped utterance-chunks per GPU, synthetic audio,
 
     python bench.py [--gpus N --steps K --warmup W]                 # our arm (one rank per GPU under torchrun)
     python bench.py --impl reference [...]                           # the reference algorithm on the host CPU cores
+    python bench.py --workload cfg4 [...]                             # BASELINE.json configs[3]: WaveGrad, 8 x 2 s utterances per GPU, 1000 steps
     python bench.py --workload cfg5 [...]                             # BASELINE.json configs[4]: DiffWave, 8 x 10 s utterances per GPU,
                                                                       # 200 steps (same JSON contract; not the headline)
 
@@ -141,6 +142,164 @@ def run_reference(args):
             "cpu_baseline": {"value": v, "unit": "utt/s", "cores": r["threads"], "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------
+# cfg 4: WaveGrad (config_wavegrad.json), spec [128, 107] -> 32 100 samples, 1000 reverse steps
+# ------------------------------------------------------------------------------------------------------
+WG_FRAMES, WG_STEPS, WG_SECONDS = 107, 1000, 107 * 300 / 16000.0
+WG_WORKLOAD = "cfg4: WaveGrad (config_wavegrad.json) full 1000-step sampling, %d utterances x 2.0 s (mel spec [128,107], 32100 samples) per GPU"
+
+
+def wg_cpu_rate(threads=None):
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import wavegrad_oracle as WO
+    from sddm_b200.model.network import WaveGrad
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    net = WaveGrad()
+    sd = {k: v.detach() for k, v in net.state_dict().items()}
+    g = torch.Generator().manual_seed(3)
+    spec, audio = torch.rand(1, 128, WG_FRAMES, generator=g), torch.randn(1, 300 * WG_FRAMES, generator=g)
+    with torch.no_grad():
+        WO.wavegrad_forward(sd, spec, audio, torch.tensor([0.5]))
+        t0 = time.perf_counter()
+        n = 0
+        while n < 3 or time.perf_counter() - t0 < 8.0:
+            WO.wavegrad_forward(sd, spec, audio, torch.tensor([0.5]))
+            n += 1
+        per = (time.perf_counter() - t0) / n
+    return dict(value=1.0 / (per * WG_STEPS), threads=threads, sample="%d eps_hat evaluations of one utterance, scaled to 1000 steps" % n)
+
+
+def run_reference_wavegrad(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    vals = [wg_cpu_rate() for _ in range(max(1, min(args.steps, 5)))]
+    v = statistics.median(r["value"] for r in vals)
+    r = vals[-1]
+    line = {"impl": "reference", "metric": "utterances_per_sec", "value": v, "unit": "utt/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * args.batch_cfg5 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": WG_WORKLOAD % args.batch_cfg5, "note": "reference algorithm (oracle port, torch CPU ATen kernels) on host cores"},
+            "rtf": 1.0 / (v * WG_SECONDS),
+            "cpu_baseline": {"value": v, "unit": "utt/s", "cores": r["threads"], "kind": "port", "sample": r["sample"]},
+            "e2e": {"value": v, "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def run_wavegrad(args):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
+    from sddm_b200 import PREC_BF16, PREC_FP32, _lib
+    from sddm_b200.model.diffusion import GaussianDiffusion
+    from sddm_b200.model.model import SDDM_spectrogram
+    from sddm_b200.model.network import WaveGrad
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    torch.manual_seed(0)
+    net = WaveGrad()
+    prec = "fp32" if args.precision == "fp32" else "bf16"
+    net.precision = PREC_FP32 if prec == "fp32" else PREC_BF16
+    d = GaussianDiffusion("linear", WG_STEPS, 1e-6, 1e-2, device=dev)
+    model = SDDM_spectrogram(d, net, hop_samples=300).to(dev).eval()
+    B, Ls = args.batch_cfg5, 300 * WG_FRAMES
+    spec_host = torch.rand(B, 128, WG_FRAMES, generator=torch.Generator().manual_seed(3000 + rank)).pin_memory()
+    spec = spec_host.to(dev)
+    out_host = torch.empty(B, 1, Ls).pin_memory()
+    plan = net.get_plan(d)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for s in range(steps):
+            fn(s)
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def step_resident(s):
+        model.infer(spec, seed=s, row0=rank * B)
+
+    def step_e2e(s):
+        x = spec_host.to(dev, non_blocking=True)
+        y = model.infer(x, seed=s, row0=rank * B)
+        out_host.copy_(y, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for s in range(max(3, args.warmup)):
+        step_resident(s)
+    step_e2e(0)
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = _lib.launch_count()
+    ms = timed(step_resident, args.steps)
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    prof = None
+    if rank == 0 and world == 1 and prec == "bf16":
+        plan.profile(True)
+        timed(step_resident, 1)
+        prof = plan.profile_report()
+        plan.profile(False)
+    ms_e2e = timed(step_e2e, args.steps)
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+    total = B * world * args.steps
+    value, e2e = total / (ms / 1e3), total / (ms_e2e / 1e3)
+    pk = peaks()
+    line = {"metric": "utterances_per_sec", "value": value, "unit": "utt/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": prec, "data": "synthetic",
+            "config": {"workload": WG_WORKLOAD % B, "batch_per_gpu": B, "reverse_steps": WG_STEPS, "noise": "in-kernel Philox4x32-10",
+                       "weights": "config-shaped random init (torch.manual_seed(0))", "precision": prec, "noise_condition": "sqrt_alpha_bar",
+                       "l2": "activations of one eps_hat (~%.0f MB) >> 126 MB L2; no flush needed" % (B * 180.0)},
+            "rtf": 1.0 / (value * WG_SECONDS),
+            "e2e": {"value": e2e, "unit": "utt/s", "h2d_bytes_per_step": B * 128 * WG_FRAMES * 4, "d2h_bytes_per_step": B * Ls * 4,
+                    "rtf": 1.0 / (e2e * WG_SECONDS)},
+            "gpu_launches": int(launches), "clocks": clocks, "peaks": pk["source"]}
+    if prof and prof[1]:
+        tot_ms, n, flops, byts = prof
+        dur = tot_ms * 1e-3 / n
+        line["kernels"] = {"wg_conv_tc": {"avg_us": dur * 1e6, "launches": n, "tflops": flops / (tot_ms * 1e-3) / 1e12,
+                                          "gbs": byts / (tot_ms * 1e-3) / 1e9, "share": tot_ms / (ms / args.steps)}}
+        line["roofline"] = {"kernel": "wg_conv_tc_kernel (all %d conv launches of one sampling run)" % n, "bound": "tensor",
+                            "achieved": flops / (tot_ms * 1e-3) / 1e12, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                            "frac": flops / (tot_ms * 1e-3) / 1e12 / pk["bf16_sustained"], "traffic": None, "avg_launch_us": dur * 1e6,
+                            "share_of_step": tot_ms / (ms / args.steps), "executed_flops_per_launch": flops / n,
+                            "algorithmic_bytes_per_launch": byts / n, "arith_intensity_flop_per_byte": flops / max(byts, 1.0),
+                            "note": "flops = GEMM work executed (polyphase up-sampling convs include their zero blocks)"}
+    if world == 1 and not args.no_cpu_baseline:
+        r = wg_cpu_rate()
+        line["cpu_baseline"] = {"value": r["value"], "unit": "utt/s", "cores": r["threads"], "kind": "port", "sample": r["sample"]}
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -473,10 +632,12 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("SDDM_B200_PRECISION", "bf16act"), choices=["bf16", "fp32", "bf16act"])
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg5"], help="cfg2 = the headline (UNetModified2); cfg5 = DiffWave")
-    ap.add_argument("--batch-cfg5", type=int, default=8, help="10 s utterances per GPU for --workload cfg5")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4", "cfg5"], help="cfg2 = the headline (UNetModified2); cfg4 = WaveGrad; cfg5 = DiffWave")
+    ap.add_argument("--batch-cfg5", type=int, default=8, help="utterances per GPU for --workload cfg4 / cfg5")
     args = ap.parse_args()
-    if args.workload == "cfg5":
+    if args.workload == "cfg4":
+        (run_reference_wavegrad if args.impl == "reference" else run_wavegrad)(args)
+    elif args.workload == "cfg5":
         (run_reference_diffwave if args.impl == "reference" else run_diffwave)(args)
     elif args.impl == "reference":
         run_reference(args)

@@ -248,6 +248,10 @@ SDDM_API int sddm_wg_eps(sddm_wg_plan* plan, const float* spec, const float* aud
 /* replaces: SDDM_spectrogram.infer (model.py:212-257, non-continuous) around WaveGrad; buffers as sddm_dw_sample. */
 SDDM_API int sddm_wg_sample(sddm_wg_plan* plan, const float* spec, const float* noises, uint64_t seed, int64_t row0, float* out,
                             float* eps_trace, int B, int frames, void* ws, size_t ws_bytes, void* stream);
+/* per-launch CUDA-event timing of the tcgen05 conv launches (bench roofline): enable resets the totals; read returns the summed
+ * duration, the number of launches, the GEMM flops they executed and their algorithmic bytes.  Both calls synchronise the device. */
+SDDM_API int sddm_wg_profile_enable(sddm_wg_plan* plan, int on);
+SDDM_API int sddm_wg_profile_read(sddm_wg_plan* plan, double* total_ms, int64_t* launches, double* flops, double* bytes);
 /* test hook: activation "d0".."d4" (downsample outputs) / "u0".."u4" (upsample outputs) of the last sddm_wg_eps call on this
  * workspace -> out [B, L, C] fp32 (time-major); shape2 receives {L, C}. */
 SDDM_API int sddm_wg_debug_fetch(sddm_wg_plan* plan, const char* what, void* ws, int B, int frames, float* out, int64_t* shape2,

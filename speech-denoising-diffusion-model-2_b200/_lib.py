@@ -103,6 +103,8 @@ SIGNATURES = {
                               C.c_size_t, C.c_void_p]),
     "sddm_wg_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                  C.c_void_p, C.c_size_t, C.c_void_p]),
+    "sddm_wg_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
+    "sddm_wg_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "sddm_wg_debug_fetch": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int64),
                                       C.c_void_p]),
     "sddm_plan_launches_per_eps": (C.c_int, [C.c_void_p]),

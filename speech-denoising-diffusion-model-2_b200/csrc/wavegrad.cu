@@ -272,6 +272,11 @@ struct sddm_wg_plan {
     float last_b = 0.f;
     PeDims pe{};
     int pe_total = 0;
+    // per-launch CUDA-event timing of the tcgen05 conv launches (bench roofline; off by default)
+    bool prof_on = false;
+    std::vector<cudaEvent_t> prof_ev;
+    size_t prof_used = 0;
+    double prof_flops = 0.0, prof_bytes = 0.0;   // executed GEMM flops / algorithmic operand + result bytes of the timed launches
 };
 
 namespace sddm {
@@ -351,7 +356,20 @@ struct WgRun {
         c.add = add; c.add_div = add_div; c.add_rows = add_rows; c.film = film; c.act_mode = (want & 4) ? act_mode : 0;
         c.post_lrelu = post_pe ? 1 : 0; c.pe = pe; c.pe_stride = p->pe_total;
         c.raw32 = o.raw32; c.raw16 = o.raw16; c.act16 = o.act16; c.ld16 = o.ld; c.B = B;
+        if (p->prof_on) {
+            if (p->prof_used + 2 > p->prof_ev.size())
+                for (int i = 0; i < 2; ++i) { cudaEvent_t e; cudaEventCreate(&e); p->prof_ev.push_back(e); }
+            cudaEventRecord(p->prof_ev[p->prof_used], st);
+        }
         rc = launch_wg_conv_tc(c, st);
+        if (p->prof_on) {
+            cudaEventRecord(p->prof_ev[p->prof_used + 1], st);
+            p->prof_used += 2;
+            p->prof_flops += 2.0 * B * rows * (double)c.Ntot * ntaps * a_ld;
+            p->prof_bytes += (double)B * (rows * (double)a_ld * 2 + (double)o.L * H * ((want & 1 ? 4 : 0) + (want & 2 ? 2 : 0) + (want & 4 ? 2 : 0) +
+                                                                                        (add ? 4.0 / add_div : 0) + (film && act_mode == 2 ? 8 : 0))) +
+                             (double)c.Ntot * ntaps * a_ld * 2;
+        }
     }
 
     int forward_tc(const float* spec, const float* audio, const float* level_dev, float level_scalar, float* eps_out) {
@@ -575,6 +593,7 @@ SDDM_API void sddm_wg_plan_destroy(sddm_wg_plan* p) {
     if (!p) return;
     if (p->d_f32) cudaFree(p->d_f32);
     if (p->d_bf16) cudaFree(p->d_bf16);
+    for (cudaEvent_t e : p->prof_ev) cudaEventDestroy(e);
     delete p;
 }
 
@@ -726,6 +745,31 @@ SDDM_API int sddm_wg_sample(sddm_wg_plan* p, const float* spec, const float* noi
         const float k8[8] = {p->sch[3][t], sqrtf(p->sch[1][t]), p->sch[4][t], 0.f, 1.f, 0.f, 0.f, 0.f};
         if ((rc = launch_post_coef(pp, k8, st))) return rc;
     }
+    return SDDM_OK;
+}
+
+SDDM_API int sddm_wg_profile_enable(sddm_wg_plan* p, int on) {
+    if (!p) { set_error("null plan"); return SDDM_E_INVALID; }
+    SDDM_CUDA_TRY(cudaDeviceSynchronize());
+    p->prof_on = on != 0;
+    p->prof_used = 0;
+    p->prof_flops = p->prof_bytes = 0.0;
+    return SDDM_OK;
+}
+
+SDDM_API int sddm_wg_profile_read(sddm_wg_plan* p, double* total_ms, int64_t* launches, double* flops, double* bytes) {
+    if (!p || !total_ms || !launches || !flops || !bytes) { set_error("null argument"); return SDDM_E_INVALID; }
+    SDDM_CUDA_TRY(cudaDeviceSynchronize());
+    double tot = 0.0;
+    for (size_t i = 0; i + 1 < p->prof_used; i += 2) {
+        float ms = 0.f;
+        SDDM_CUDA_TRY(cudaEventElapsedTime(&ms, p->prof_ev[i], p->prof_ev[i + 1]));
+        tot += ms;
+    }
+    *total_ms = tot;
+    *launches = (int64_t)(p->prof_used / 2);
+    *flops = p->prof_flops;
+    *bytes = p->prof_bytes;
     return SDDM_OK;
 }
 

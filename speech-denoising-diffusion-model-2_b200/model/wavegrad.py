@@ -177,6 +177,17 @@ class WaveGradPlan:
                                                  _ptr(eps_tr), B, frames, _ptr(ws), ws.numel(), C.c_void_p(st)))
         return (out, eps_tr) if trace else out
 
+    def profile(self, on: bool) -> None:
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().sddm_wg_profile_enable(self._h, int(on)))
+
+    def profile_report(self):
+        """(total_ms, launches, executed_flops, algorithmic_bytes) of the tcgen05 conv launches since profile(True)."""
+        ms, n, fl, by = C.c_double(), C.c_int64(), C.c_double(), C.c_double()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().sddm_wg_profile_read(self._h, C.byref(ms), C.byref(n), C.byref(fl), C.byref(by)))
+        return ms.value, n.value, fl.value, by.value
+
     def fetch(self, what: str, B: int, frames: int) -> torch.Tensor:
         """Debug: activation 'd0'..'d4' / 'u0'..'u4' of the last eps call as [B, C, L]."""
         shape = (C.c_int64 * 2)()
