@@ -2,8 +2,9 @@
 
 The reference ``InferDataset`` zero-pads every utterance to a multiple of T = num_samples and views it as
 ``[n_chunk, 1, T]``; ``infer_data_collate`` concatenates the chunks of several utterances along dim 0 and carries an
-index tensor (utterance id per chunk); infer.py:81-120 regroups rows by that index.  Audio file decoding is out of
-scope here (torchaudio.load needs torchcodec, absent): datasets are built from in-memory waveforms or ``.npy`` files.
+index tensor (utterance id per chunk); infer.py:81-120 regroups rows by that index.  The reference decodes audio with
+torchaudio.load (needs torchcodec, absent in this image): here waveforms come from memory, ``.npy`` files or PCM / float
+``.wav`` files read and written with scipy.io.wavfile (``load_wave`` / ``save_wave``).
 """
 from __future__ import annotations
 
@@ -14,6 +15,40 @@ from typing import List, Sequence, Tuple
 import numpy as np
 import torch
 import torch.nn.functional as F
+
+
+def load_wave(path, sample_rate: int = None) -> torch.Tensor:
+    """``.npy`` (float waveform) or ``.wav`` (int16 / int32 / uint8 PCM scaled to [-1, 1) as torchaudio.load does, or float) ->
+    float32 [1, n].  A sample-rate mismatch raises (the reference resamples nothing either: data_loaders.py:108-111)."""
+    path = str(path)
+    if path.endswith(".npy"):
+        return torch.as_tensor(np.load(path), dtype=torch.float32).reshape(1, -1)
+    from scipy.io import wavfile
+    sr, data = wavfile.read(path)
+    if sample_rate is not None and sr != sample_rate:
+        raise ValueError("%s: sample rate %d != %d" % (path, sr, sample_rate))
+    if data.ndim > 1:
+        data = data[:, 0]
+    if data.dtype == np.int16:
+        x = data.astype(np.float32) / 32768.0
+    elif data.dtype == np.int32:
+        x = data.astype(np.float32) / 2147483648.0
+    elif data.dtype == np.uint8:
+        x = (data.astype(np.float32) - 128.0) / 128.0
+    else:
+        x = data.astype(np.float32)
+    return torch.from_numpy(np.ascontiguousarray(x)).reshape(1, -1)
+
+
+def save_wave(path, wave: torch.Tensor, sample_rate: int = 16000) -> None:
+    """float32 waveform [1, n] / [n] -> 16-bit PCM ``.wav`` (what torchaudio.save writes for float input), or ``.npy``."""
+    x = wave.detach().to("cpu", torch.float32).reshape(-1).numpy()
+    path = str(path)
+    if path.endswith(".npy"):
+        np.save(path, x)
+        return
+    from scipy.io import wavfile
+    wavfile.write(path, sample_rate, np.clip(np.round(x * 32768.0), -32768, 32767).astype(np.int16))
 
 
 def chunk_waveform(wave: torch.Tensor, T: int) -> torch.Tensor:
@@ -37,7 +72,7 @@ class InferDataset(torch.utils.data.Dataset):
     @staticmethod
     def _load(x):
         if isinstance(x, (str, Path)):
-            x = np.load(x)
+            return load_wave(x)
         return torch.as_tensor(x, dtype=torch.float32).reshape(1, -1)
 
     def __len__(self):

@@ -3,7 +3,10 @@
 ``build_model(config)`` performs infer.py:36-51 (registry construction through ``ConfigParser.init_obj``, ``.to(device)``,
 ``.eval()``, optional checkpoint ``state_dict``); ``enhance_batch`` is the per-batch body infer.py:72-77 minus file IO;
 ``enhance_utterances`` adds the chunk / regroup steps around it (infer.py:81-120) and the multi-GPU row sharding.
-Run as ``python -m sddm_b200.infer -c config_unet.json [-r checkpoint.pth] --npy noisy1.npy noisy2.npy ...``.
+``generate_from_spectrograms`` is the same for the spectrogram-conditioned models (config_diffwave.json / config_wavegrad.json).
+Run as ``python -m sddm_b200.infer -c configs/config_unet.json [-r checkpoint.pth] --inputs noisy1.wav noisy2.npy ...``
+(waveforms for SDDM; ``[bins, frames]`` spectrogram ``.npy`` files — or, for DiffWave, ``.wav`` files that go through the STFT
+front-end — for SDDM_spectrogram).
 """
 from __future__ import annotations
 
@@ -64,19 +67,59 @@ def enhance_utterances(model, waves: Sequence[torch.Tensor], batch_chunks: int =
     return module_data.regroup(full, index, [int(w.numel()) for w in waves])
 
 
-def main(config, npy_files: Sequence[str], out_dir: Optional[str] = None):
+@torch.no_grad()
+def generate_from_spectrograms(model, specs: Sequence[torch.Tensor], batch: int = 8, seed: int = 0, rank: int = 0,
+                               world: int = 1) -> List[torch.Tensor]:
+    """SDDM_spectrogram.infer over a list of [bins, frames] spectrograms: utterances are sharded contiguously over the ranks
+    (no communication inside the loop), equal-length neighbours are batched, Philox is keyed by the GLOBAL utterance id.
+    Returns this rank's waveforms ([1, hop * frames] each) in utterance order, with None for utterances of other ranks."""
+    device = next(model.parameters()).device
+    lo, hi = shard_bounds(len(specs), world, rank)
+    outs: List[Optional[torch.Tensor]] = [None] * len(specs)
+    i = lo
+    while i < hi:
+        j = i + 1
+        while j < hi and j - i < batch and specs[j].shape == specs[i].shape:
+            j += 1
+        x = torch.stack([torch.as_tensor(s, dtype=torch.float32) for s in specs[i:j]]).to(device, non_blocking=True)
+        y = model.infer(x, seed=seed, row0=i)
+        for k in range(i, j):
+            outs[k] = y[k - i].reshape(1, -1)
+        i = j
+    return outs
+
+
+def main(config, inputs: Sequence[str], out_dir: Optional[str] = None):
+    import os
+    import pathlib
     import numpy as np
     logger = config.get_logger("infer")
     model = build_model(config)
     logger.info(model)
-    waves = [torch.from_numpy(np.load(f).astype("float32")).reshape(-1) for f in npy_files]
-    bs = config.config.get("infer_data_loader", {}).get("args", {}).get("batch_size", 64)
-    outs = enhance_utterances(model, waves, batch_chunks=max(1, int(bs)))
-    out_path = (config.save_dir / "samples" / "output") if out_dir is None else __import__("pathlib").Path(out_dir)
+    sr = config.config.get("sample_rate", 16000)
+    bs = max(1, int(config.config.get("infer_data_loader", {}).get("args", {}).get("batch_size", 64)))
+    if isinstance(model, module_arch.SDDM_spectrogram):
+        from . import prepare_spectrogram as PS
+        device = next(model.parameters()).device
+        specs = []
+        for f in inputs:
+            if f.endswith(".npy"):
+                specs.append(torch.from_numpy(np.load(f).astype("float32")))
+            else:   # DiffWave: wav -> hamming STFT magnitude, log / clamp compressed (prepare_spectrogram.py:20-41)
+                cfg = config.config.get("spectrogram", {"window_length": 1024, "hop_samples": 256})
+                tr = PS.Spectrogram(n_fft=cfg["window_length"], hop_length=cfg["hop_samples"], window_fn=torch.hamming_window, log_clamp=True)
+                specs.append(tr(module_data.load_wave(f, sr).to(device))[0].cpu())
+        outs = generate_from_spectrograms(model, specs, batch=bs)
+    else:
+        waves = [module_data.load_wave(f, sr).reshape(-1) for f in inputs]
+        outs = enhance_utterances(model, waves, batch_chunks=bs)
+    out_path = (config.save_dir / "samples" / "output") if out_dir is None else pathlib.Path(out_dir)
     out_path.mkdir(parents=True, exist_ok=True)
-    for f, o in zip(npy_files, outs):
-        np.save(out_path / (__import__("os").path.basename(f)), o.cpu().numpy())
-    logger.info("enhanced %d utterances -> %s", len(outs), out_path)
+    for f, o in zip(inputs, outs):
+        stem = os.path.basename(f)
+        stem = stem[:-4] if stem.endswith((".wav", ".npy")) else stem
+        module_data.save_wave(out_path / (stem + (".npy" if f.endswith(".npy") and not isinstance(model, module_arch.SDDM_spectrogram) else ".wav")), o, sr)
+    logger.info("processed %d utterances -> %s", len(outs), out_path)
 
 
 if __name__ == "__main__":
@@ -84,7 +127,8 @@ if __name__ == "__main__":
     args.add_argument("-c", "--config", default=None, type=str, help="config file path (default: None)")
     args.add_argument("-r", "--resume", default=None, type=str, help="path to latest checkpoint (default: None)")
     args.add_argument("-d", "--device", default=None, type=str, help="indices of GPUs to enable (default: all)")
-    args.add_argument("--npy", nargs="+", default=[], help="noisy utterances as .npy float32 waveforms")
+    args.add_argument("--inputs", "--npy", nargs="+", default=[], dest="inputs",
+                      help="noisy utterances (.wav / .npy waveforms) or, for SDDM_spectrogram, spectrograms (.npy [bins, frames])")
     args.add_argument("--out", default=None, type=str)
     parsed = args.parse_args()
-    main(ConfigParser.from_args(parsed), parsed.npy, parsed.out)
+    main(ConfigParser.from_args(parsed), parsed.inputs, parsed.out)

@@ -171,3 +171,24 @@ def test_gpu_edges(built_lib, gold):
     c = m.infer(spec[1:2].contiguous(), seed=123, row0=1)
     assert torch.equal(a, b) and torch.equal(a[1:2], c)
     assert float(a.abs().max()) <= 1.0 and not torch.equal(a, m.infer(spec, seed=124))
+
+
+@pytest.mark.gpu
+def test_gpu_generate_from_spectrograms_sharding_invariance(built_lib):
+    """infer.generate_from_spectrograms: ragged utterance lists, and the result of every utterance is independent of how the
+    list is sharded over ranks / grouped into batches (Philox keyed by the global utterance id)."""
+    from sddm_b200 import infer as I
+    from sddm_b200.model import model as M
+    from sddm_b200.model.diffusion import GaussianDiffusion
+    net = _gpu_module(DIFFWAVE_CASES["small"], "bf16")
+    d = GaussianDiffusion(schedule="linear", n_timestep=3, linear_start=1e-4, linear_end=5e-2, device="cuda")
+    m = M.SDDM_spectrogram(d, net, hop_samples=256, noise_condition="time_step")
+    g = torch.Generator().manual_seed(4)
+    specs = [torch.rand(513, f, generator=g) * 0.7 for f in (3, 3, 2, 5, 5)]
+    full = I.generate_from_spectrograms(m, specs, batch=4, seed=9)
+    assert [o.shape[-1] for o in full] == [256 * f for f in (3, 3, 2, 5, 5)]
+    parts = [I.generate_from_spectrograms(m, specs, batch=1, seed=9, rank=r, world=2) for r in range(2)]
+    for k in range(len(specs)):
+        mine = parts[0][k] if parts[0][k] is not None else parts[1][k]
+        assert (parts[0][k] is None) != (parts[1][k] is None)
+        assert torch.equal(mine, full[k]), k
