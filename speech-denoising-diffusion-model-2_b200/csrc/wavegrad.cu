@@ -338,7 +338,7 @@ struct WgRun {
 
     // one conv launch; `a` is the operand tensor (already in consumer form), decim: row-strided (nearest down-sampled) view
     void tc(const std::string& key, const __nv_bfloat16* a, int a_ld, int a_L, int decim, int rows, const int* toff, int ntaps, int phases,
-            const float* add, int add_div, int add_rows, const float* film, int act_mode, bool post_pe, const float* pe, Act& o, int want) {
+            const float* add, int add_div, int add_rows, const __nv_bfloat16* film, int act_mode, bool post_pe, const float* pe, Act& o, int want) {
         // want bits: 1 raw32, 2 raw16, 4 act16
         const ConvW& w = p->convs.at(key);
         const int H = w.Cout;
@@ -367,7 +367,7 @@ struct WgRun {
             p->prof_used += 2;
             p->prof_flops += 2.0 * B * rows * (double)c.Ntot * ntaps * a_ld;
             p->prof_bytes += (double)B * (rows * (double)a_ld * 2 + (double)o.L * H * ((want & 1 ? 4 : 0) + (want & 2 ? 2 : 0) + (want & 4 ? 2 : 0) +
-                                                                                        (add ? 4.0 / add_div : 0) + (film && act_mode == 2 ? 8 : 0))) +
+                                                                                        (add ? 4.0 / add_div : 0) + (film && act_mode == 2 ? 4 : 0))) +
                              (double)c.Ntot * ntaps * a_ld * 2;
         }
     }
@@ -404,7 +404,7 @@ struct WgRun {
             const std::string k = "film." + std::to_string(i) + ".";
             Act fa;
             tc(k + "input_conv", d[i].raw16, d[i].ld, d[i].L, 1, d[i].L, t3, 3, 1, nullptr, 1, 0, nullptr, 0, true, pe + p->pe.off[i], fa, 2);
-            tc(k + "output_conv", fa.raw16, fa.ld, fa.L, 1, fa.L, t3, 3, 1, nullptr, 1, 0, nullptr, 0, false, nullptr, film[i], 1);
+            tc(k + "output_conv", fa.raw16, fa.ld, fa.L, 1, fa.L, t3, 3, 1, nullptr, 1, 0, nullptr, 0, false, nullptr, film[i], 2);   // bf16 [L][2H]: shift | scale
             char nm[8];
             snprintf(nm, sizeof nm, "d%d", i);
             name(nm, d[i].raw16, d[i].L, d[i].C, d[i].ld, 1);
@@ -413,7 +413,7 @@ struct WgRun {
         tc("first_conv", spec_t, WG_MELS, frames, 1, frames, t3, 3, 1, nullptr, 1, 0, nullptr, 1, false, nullptr, x, 6);
         for (int i = 0; i < 5; ++i) {
             const int f = kUp[i][2], Lx = x.L, L = Lx * f;
-            const float* fl = film[4 - i].raw32;
+            const __nv_bfloat16* fl = film[4 - i].raw16;
             const std::string k = "upsample." + std::to_string(i) + ".";
             Act b1, q, xs, r3, xo;
             tc(k + "block1", x.raw16, x.ld, Lx, 1, Lx, t1, 1, 1, nullptr, 1, 0, nullptr, 0, false, nullptr, b1, 1);

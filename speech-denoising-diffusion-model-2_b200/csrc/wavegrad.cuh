@@ -21,7 +21,7 @@ struct WgTcConv {
     int H, phases, L_out;              // Ntot = phases * H; output rows L_out (<= phases * rows)
     const float* add; int add_div;     // nullable fp32 [B][ceil(L_out / add_div)][H]: + add[t / add_div][c]
     int add_rows;                      // rows per batch of `add`
-    const float* film;                 // nullable fp32 [B][L_out][2 H]
+    const __nv_bfloat16* film;         // nullable bf16 [B][L_out][2 H]: FiLM shift | scale
     int act_mode;                      // act16 = 0: not stored, 1: leaky_relu(v), 2: leaky_relu(film_shift + film_scale * v)
     int post_lrelu; const float* pe; int pe_stride;   // v = leaky_relu(v) + pe[b][c]  (FiLM.input_conv)
     float* raw32; __nv_bfloat16* raw16; __nv_bfloat16* act16;   // nullable outputs [B][L_out][ld]; ld16 for the bf16 ones, H for raw32

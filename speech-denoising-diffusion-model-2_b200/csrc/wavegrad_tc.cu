@@ -149,7 +149,8 @@ __global__ void __launch_bounds__(kThreads, 1) wg_conv_tc_kernel(const __grid_co
             float4 pe4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (p.post_lrelu) pe4 = __ldg(reinterpret_cast<const float4*>(p.pe + (size_t)b * p.pe_stride + c0));
             // all global loads of the chunk are issued before the first use (8 row groups x up to 3 tensors in flight per thread)
-            float4 ad[8], sh[8], sc[8];
+            float4 ad[8];
+            uint2 sh[8], sc[8];
             bool ok[8];
             size_t rowi[8];
 #pragma unroll
@@ -158,12 +159,13 @@ __global__ void __launch_bounds__(kThreads, 1) wg_conv_tc_kernel(const __grid_co
                 const int t = p.phases * sr + phase;
                 ok[it] = sr < p.rows && t < p.L_out;
                 rowi[it] = (size_t)b * p.L_out + t;
-                ad[it] = sh[it] = sc[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                ad[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                sh[it] = sc[it] = make_uint2(0u, 0u);
                 if (ok[it]) {
                     if (p.add) ad[it] = __ldg(reinterpret_cast<const float4*>(p.add + ((size_t)b * p.add_rows + t / p.add_div) * p.H + c0));
                     if (p.act_mode == 2) {
-                        sh[it] = __ldg(reinterpret_cast<const float4*>(p.film + rowi[it] * 2 * p.H + c0));
-                        sc[it] = __ldg(reinterpret_cast<const float4*>(p.film + rowi[it] * 2 * p.H + p.H + c0));
+                        sh[it] = __ldg(reinterpret_cast<const uint2*>(p.film + rowi[it] * 2 * p.H + c0));
+                        sc[it] = __ldg(reinterpret_cast<const uint2*>(p.film + rowi[it] * 2 * p.H + p.H + c0));
                     }
                 }
             }
@@ -180,7 +182,8 @@ __global__ void __launch_bounds__(kThreads, 1) wg_conv_tc_kernel(const __grid_co
                 if (p.raw16) *reinterpret_cast<uint2*>(p.raw16 + row * p.ld16 + c0) = make_uint2(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w));
                 if (p.act_mode) {
                     if (p.act_mode == 2)
-                        x = make_float4(fmaf(sc[it].x, x.x, sh[it].x), fmaf(sc[it].y, x.y, sh[it].y), fmaf(sc[it].z, x.z, sh[it].z), fmaf(sc[it].w, x.w, sh[it].w));
+                        x = make_float4(fmaf(bf16_lo(sc[it].x), x.x, bf16_lo(sh[it].x)), fmaf(bf16_hi(sc[it].x), x.y, bf16_hi(sh[it].x)),
+                                        fmaf(bf16_lo(sc[it].y), x.z, bf16_lo(sh[it].y)), fmaf(bf16_hi(sc[it].y), x.w, bf16_hi(sh[it].y)));
                     *reinterpret_cast<uint2*>(p.act16 + row * p.ld16 + c0) =
                         make_uint2(pack_bf16(lrelu02(x.x), lrelu02(x.y)), pack_bf16(lrelu02(x.z), lrelu02(x.w)));
                 }
