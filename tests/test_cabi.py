@@ -102,3 +102,40 @@ def test_no_cpu_fallback(built_lib):
         d.p_transition(x, 3, x)
     with pytest.raises((SddmError, RuntimeError)):
         Plan(net.cfg, dict(net.state_dict()), d.host_tables(), 100, 0, torch.device("cuda"))
+
+
+def test_diffwave_and_wavegrad_plan_validation(built_lib):
+    """sddm_dw_* / sddm_wg_* argument and call-order checks (no device work)."""
+    from sddm_b200._lib import DwConfig, WgConfig
+    lib = built_lib
+    good = dict(n_timestep=200, freq_bins=513, residual_channels=64, residual_layers=30, dilation_cycle_length=10, hop_samples=256,
+                noise_condition=1, precision=0)
+    h = C.c_void_p()
+    assert lib.sddm_dw_plan_create(C.byref(DwConfig(**good)), C.byref(h)) == 0 and h.value
+    w = torch.zeros(128, 64, 3)
+    assert lib.sddm_dw_plan_load_weight(h, b"residual_layers.29.dilated_conv.weight", C.c_void_p(w.data_ptr()), (C.c_int64 * 3)(128, 64, 3), 3) == 0
+    assert lib.sddm_dw_plan_load_weight(h, b"residual_layers.30.dilated_conv.weight", C.c_void_p(w.data_ptr()), (C.c_int64 * 3)(128, 64, 3), 3) == -1
+    assert lib.sddm_dw_plan_load_weight(h, b"residual_layers.0.dilated_conv.weight", C.c_void_p(w.data_ptr()), (C.c_int64 * 3)(128, 64, 5), 3) == -1
+    assert lib.sddm_dw_plan_finalize(h) == -2 and b"schedule" in lib.sddm_last_error()
+    assert lib.sddm_dw_eps(h, None, None, 1, None, 1, 4, None, 0, None) == -2
+    lib.sddm_dw_plan_destroy(h)
+    for over, msg in ((dict(residual_channels=128), b"residual_channels"), (dict(hop_samples=300), b"hop_samples"),
+                      (dict(precision=2), b"precision"), (dict(noise_condition=5), b"noise_condition"), (dict(residual_layers=0), b"residual_layers")):
+        h2 = C.c_void_p()
+        assert lib.sddm_dw_plan_create(C.byref(DwConfig(**{**good, **over})), C.byref(h2)) == -1, over
+        assert msg in lib.sddm_last_error(), (over, lib.sddm_last_error())
+    wg = dict(n_timestep=1000, hop_samples=300, noise_condition=0, precision=0)
+    h = C.c_void_p()
+    assert lib.sddm_wg_plan_create(C.byref(WgConfig(**wg)), C.byref(h)) == 0 and h.value
+    w = torch.zeros(512, 768, 3)
+    assert lib.sddm_wg_plan_load_weight(h, b"upsample.0.block2.0.weight", C.c_void_p(w.data_ptr()), (C.c_int64 * 3)(512, 768, 3), 3) == 0
+    assert lib.sddm_wg_plan_load_weight(h, b"upsample.0.block2.0.weight", C.c_void_p(w.data_ptr()), (C.c_int64 * 3)(512, 512, 3), 3) == -1
+    assert lib.sddm_wg_plan_load_weight(h, b"upsample.5.block1.weight", C.c_void_p(w.data_ptr()), (C.c_int64 * 3)(512, 768, 3), 3) == -1
+    assert lib.sddm_wg_plan_finalize(h) == -2
+    assert lib.sddm_wg_workspace_bytes(h, 2, 4) > 0                    # sizing needs no device
+    assert lib.sddm_wg_eps(h, None, None, None, 1, None, 1, 4, None, 0, None) == -2
+    lib.sddm_wg_plan_destroy(h)
+    for over, msg in ((dict(hop_samples=256), b"hop_samples"), (dict(precision=2), b"precision"), (dict(n_timestep=0), b"n_timestep")):
+        h2 = C.c_void_p()
+        assert lib.sddm_wg_plan_create(C.byref(WgConfig(**{**wg, **over})), C.byref(h2)) == -1, over
+        assert msg in lib.sddm_last_error(), (over, lib.sddm_last_error())
