@@ -137,6 +137,15 @@ SDDM_API int sddm_x_T_raw(int variant, float a, float b, const float* cond, cons
 SDDM_API int sddm_p_step_raw(int variant, const float* k8, float* x_t, const float* eps, const float* cond, const float* z,
                     uint64_t seed, int64_t row0, int t, int T, int B, int L, void* stream);
 
+/* replaces: GaussianDiffusion.q_stochastic / q_stochastic_conditional (diffusion.py:225-279), the forward-diffusion draw of the
+ * training step SDDM.forward (model/model.py:29-48).  coef: device [B][4] per-row scalars
+ *   mode 0: {sqrt_alpha_bar_sample, sqrt(1 - sample^2), -, -}            x_t = c0 x_0 + c1 z
+ *   mode 1: {sqrt_alpha_bar[t], m[t] sqrt_alpha_bar[t], sqrt_delta[t], 1 / sqrt(1 - alpha_bar[t])}
+ *           x_t = (c0 x_0 + c1 (y - x_0)) + c2 z;  combined_noise = c3 (c1 (y - x_0) + c2 z)
+ * noise: injected N(0,1) [B,1,L] or NULL => Philox (seed, row0 + row, draw 0), written to noise_out when that is not NULL. */
+SDDM_API int sddm_q_sample_raw(int mode, const float* coef, const float* x0, const float* y, const float* noise, uint64_t seed, int64_t row0,
+                      float* x_t, float* combined_noise, float* noise_out, int B, int L, void* stream);
+
 /* replaces: SDDM.infer (model/model.py:50-124, non-continuous branch): x_T init + T x (eps_hat, update).
  * noises: NULL (Philox) or injected [T, B, L] (noises[0] -> x_T, noises[k] -> step t = T + 1 - k).
  * eps_trace: NULL or [T, B, L] receiving eps_hat of step t at index T - t (verification mode).

@@ -12,6 +12,7 @@ reference-layout ``state_dict``) of the reference algorithm:
 * x_T initialisation ........ /root/reference/model/diffusion.py:281-300
 * posterior updates ......... /root/reference/model/diffusion.py:164-222
 * sampling loop ............. /root/reference/model/model.py:50-124
+* forward diffusion ......... /root/reference/model/diffusion.py:225-279 (q_stochastic*, the draw of the training step)
 * UNetModified2 denoiser .... /root/reference/model/UNetModified2.py:5-269
 * SI-SNR .................... /root/reference/model/metric.py:5-34
 
@@ -291,6 +292,31 @@ def sample(sd: Dict[str, Tensor], cfg: dict, sch: Dict[str, Tensor], condition: 
         if trace is not None:
             trace.setdefault("x", {})[t - 1] = x
     return x
+
+
+# --------------------------------------------------------------------------------------
+# forward diffusion of the training step  (diffusion.py:225-279; the random draws are arguments)
+# --------------------------------------------------------------------------------------
+def q_stochastic(sch, x_0: Tensor, noise: Tensor, t: Tensor, random_step: Optional[Tensor]):
+    """t: int64 [B] in [1, T]; random_step: float [B] in [0, 1) or None (= t_is_integer).  Returns (x_t, sample, t + step)."""
+    shape = [x_0.shape[0]] + [1] * (x_0.ndim - 1)
+    if random_step is None:
+        sample, random_step = sch["sqrt_alpha_bar"][t], 0
+    else:
+        l_a, l_b = sch["sqrt_alpha_bar"][t - 1], sch["sqrt_alpha_bar"][t]
+        sample = l_a + random_step * (l_b - l_a)
+    sample = sample.view(shape)
+    x_t = sample * x_0 + torch.sqrt(1.0 - torch.square(sample)) * noise
+    return x_t, sample, (t + random_step).view(shape)
+
+
+def q_stochastic_conditional(sch, x_0: Tensor, y: Tensor, noise: Tensor, t: Tensor):
+    """t: int64 [B,1,1].  Returns (x_t, combined_noise, sqrt_alpha_bar[t])."""
+    gaussian_noise = sch["sqrt_delta"][t] * noise
+    noise_from_condition = sch["m"][t] * sch["sqrt_alpha_bar"][t] * (y - x_0)
+    x_t = sch["sqrt_alpha_bar"][t] * x_0 + noise_from_condition + gaussian_noise
+    combined = 1.0 / (torch.sqrt(1.0 - sch["alpha_bar"][t])) * (noise_from_condition + gaussian_noise)
+    return x_t, combined, sch["sqrt_alpha_bar"][t]
 
 
 def sisnr(s_hat: Tensor, s: Tensor) -> Tensor:                                  # model/metric.py:5-34

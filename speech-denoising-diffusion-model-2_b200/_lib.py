@@ -71,6 +71,8 @@ SIGNATURES = {
                                C.c_int, C.c_int, C.c_void_p]),
     "sddm_p_step_raw": (C.c_int, [C.c_int, C.POINTER(C.c_float), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
                                   C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "sddm_q_sample_raw": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "sddm_sample": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p,
                               C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "sddm_enhance_host": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_int64, C.c_int]),

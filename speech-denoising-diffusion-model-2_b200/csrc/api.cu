@@ -905,6 +905,14 @@ int sddm_p_step_raw(int variant, const float* k8, float* x_t, const float* eps, 
     return launch_post_coef(pp, k8, (cudaStream_t)stream);
 }
 
+int sddm_q_sample_raw(int mode, const float* coef, const float* x0, const float* y, const float* noise, uint64_t seed, int64_t row0,
+                      float* x_t, float* combined_noise, float* noise_out, int B, int L, void* stream) {
+    if (mode != 0 && mode != 1) { set_error("unknown q_transition mode %d", mode); return SDDM_E_INVALID; }
+    if (!coef || !x0 || !x_t || B <= 0 || L <= 0 || L % 4) { set_error("bad buffer / batch / length (L must be a multiple of 4)"); return SDDM_E_INVALID; }
+    if (mode == 1 && (!y || !combined_noise)) { set_error("the conditional q_transition needs the condition and a combined-noise output"); return SDDM_E_INVALID; }
+    return launch_q_sample(mode, coef, x0, y, noise, seed, row0, x_t, combined_noise, noise_out, B, L, (cudaStream_t)stream);
+}
+
 int sddm_sample(sddm_plan* p, int variant, const float* cond, const float* noises, uint64_t seed, int64_t row0, float* out,
                 float* eps_trace, float* x_trace, int B, void* ws, size_t ws_bytes, void* stream) {
     int rc = check_ready(p);

@@ -29,6 +29,10 @@ struct PostP {
 // k8 = {c2, sqrt(alpha_t), noise std, gamma, 1-gamma, c_xt, c_yt, c_epst} of step t (host scalars)
 int launch_post_coef(const PostP& p, const float* k8, cudaStream_t st);
 
+// forward diffusion q(x_t | x_0) with per-row coefficients (diffusion.py:225-279); see q_sample_kernel
+int launch_q_sample(int mode, const float* coef, const float* x0, const float* y, const float* z, uint64_t seed, int64_t row0, float* x_t,
+                    float* combined, float* z_out, int B, int L, cudaStream_t st);
+
 int launch_frames(const float* sig, float* frames, int B, int n, int F, int hop, cudaStream_t st);
 int launch_overlap_add(const float* frames, float* sig, int B, int n, int F, int hop, cudaStream_t st);
 

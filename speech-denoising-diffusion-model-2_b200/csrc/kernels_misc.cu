@@ -121,6 +121,54 @@ int launch_post_coef(const PostP& p, const float* k8, cudaStream_t st) {
 }
 
 // ===================================================================================================
+// forward diffusion q(x_t | x_0)                        reference: model/diffusion.py:225-279
+//   mode 0 (q_stochastic):             x_t = a x_0 + b z                     coef[row] = {a, b, -, -}
+//   mode 1 (q_stochastic_conditional): g = sd z; c = (m sab) (y - x_0); x_t = (sab x_0 + c) + g; combined = k (c + g)
+//                                                                             coef[row] = {sab, m sab, sd, k = 1 / sqrt(1 - alpha_bar)}
+// every product / sum rounded separately, as the reference's eager ops do
+// ===================================================================================================
+__global__ void __launch_bounds__(256) q_sample_kernel(int mode, const float4* __restrict__ coef, const float4* __restrict__ x0,
+                                                       const float4* __restrict__ y, const float4* __restrict__ z, uint64_t seed, int64_t row0,
+                                                       float4* __restrict__ x_t, float4* __restrict__ combined, float4* __restrict__ z_out, int B, int L4) {
+    const int64_t total = (int64_t)B * L4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int row = (int)(i / L4), e4 = (int)(i - (int64_t)row * L4);
+        const float4 k = __ldg(coef + row), a = x0[i];
+        const float4 n = z ? z[i] : philox_normal4(seed, (uint32_t)e4, (uint64_t)(row0 + row), 0u);
+        if (z_out) z_out[i] = n;
+        float4 o;
+        if (mode == 0) {
+            o.x = __fadd_rn(__fmul_rn(k.x, a.x), __fmul_rn(k.y, n.x));
+            o.y = __fadd_rn(__fmul_rn(k.x, a.y), __fmul_rn(k.y, n.y));
+            o.z = __fadd_rn(__fmul_rn(k.x, a.z), __fmul_rn(k.y, n.z));
+            o.w = __fadd_rn(__fmul_rn(k.x, a.w), __fmul_rn(k.y, n.w));
+        } else {
+            const float4 c = y[i];
+            const float av[4] = {a.x, a.y, a.z, a.w}, cv[4] = {c.x, c.y, c.z, c.w}, nv[4] = {n.x, n.y, n.z, n.w};
+            float ov[4], mv[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float g = __fmul_rn(k.z, nv[q]);
+                const float nc = __fmul_rn(k.y, __fsub_rn(cv[q], av[q]));
+                ov[q] = __fadd_rn(__fadd_rn(__fmul_rn(k.x, av[q]), nc), g);
+                mv[q] = __fmul_rn(k.w, __fadd_rn(nc, g));
+            }
+            o = make_float4(ov[0], ov[1], ov[2], ov[3]);
+            combined[i] = make_float4(mv[0], mv[1], mv[2], mv[3]);
+        }
+        x_t[i] = o;
+    }
+}
+
+int launch_q_sample(int mode, const float* coef, const float* x0, const float* y, const float* z, uint64_t seed, int64_t row0, float* x_t,
+                    float* combined, float* z_out, int B, int L, cudaStream_t st) {
+    q_sample_kernel<<<grid_for((int64_t)B * (L / 4), 256), 256, 0, st>>>(mode, (const float4*)coef, (const float4*)x0, (const float4*)y, (const float4*)z,
+                                                                       seed, row0, (float4*)x_t, (float4*)combined, (float4*)z_out, B, L / 4);
+    SDDM_LAUNCH_CHECK();
+    return SDDM_OK;
+}
+
+// ===================================================================================================
 // framing helpers                                       reference: model/UNetModified2.py:5-41
 // ===================================================================================================
 __global__ void __launch_bounds__(256) frames_kernel(const float* __restrict__ sig, float* __restrict__ fr, int B, int n,

@@ -182,11 +182,60 @@ class GaussianDiffusion(nn.Module):
     def p_transition_conditional(self, x_t, t, predicted_noise, condition, noise=None, seed=None):
         return self._step("conditional", x_t, t, predicted_noise, condition, noise, seed)
 
-    def q_stochastic(self, x_0, noise, t_is_integer=False):
-        raise NotImplementedError("q_stochastic belongs to the training step (SURVEY.md §8f row 1), not built yet")
+    # -- forward diffusion (the draw of the training step SDDM.forward) -------------------------------
+    def _q(self, mode, coef, x_0, y, noise, seed, row0):
+        _need_cuda(x_0, y, noise)
+        x0, yy, z = _prep(x_0), _prep(y), _prep(noise)
+        B, L = x0.shape[0], x0.numel() // x0.shape[0]
+        x_t = torch.empty_like(x0)
+        comb = torch.empty_like(x0) if mode == 1 else None
+        z_out = torch.empty_like(x0) if z is None else None
+        coef = coef.to(x0.device, torch.float32).contiguous()
+        with torch.cuda.device(x0.device):
+            st = torch.cuda.current_stream().cuda_stream
+            _lib.check(_lib.lib().sddm_q_sample_raw(mode, _ptr(coef), _ptr(x0), _ptr(yy), _ptr(z), _seed(seed), int(row0), _ptr(x_t), _ptr(comb),
+                                                    _ptr(z_out), B, L, C.c_void_p(st)))
+        return x_t, comb, (z if z is not None else z_out)
 
-    def q_stochastic_conditional(self, x_0, y, noise):
-        raise NotImplementedError("q_stochastic_conditional belongs to the training step (SURVEY.md §8f), not built yet")
+    @torch.no_grad()
+    def q_stochastic(self, x_0, noise, t_is_integer=False, *, t=None, random_step=None, seed=None, row0=0, return_noise=False):
+        """reference :225-251.  Returns (x_t, sqrt_alpha_bar_sample [B,1,..], t + random_step [B,1,..]).  The per-row scalars
+        are drawn / gathered with the reference's own torch ops on B-element tensors; the [B,1,T] work is one CUDA kernel.
+        Extensions (keyword-only): fixed ``t`` / ``random_step`` draws (tests), ``noise=None`` => in-kernel Philox."""
+        b = x_0.shape[0]
+        shape = [b] + [1] * (x_0.ndim - 1)
+        dev = x_0.device
+        if t is None:
+            t = torch.randint(1, self.num_timesteps + 1, [b], device=dev)
+        t = t.to(dev).reshape(b)
+        if t_is_integer:
+            sample = self.sqrt_alpha_bar[t]
+            random_step = 0
+        else:
+            l_a, l_b = self.sqrt_alpha_bar[t - 1], self.sqrt_alpha_bar[t]
+            if random_step is None:
+                random_step = torch.rand(b, device=dev)
+            random_step = random_step.to(dev).reshape(b)
+            sample = l_a + random_step * (l_b - l_a)
+        coef = torch.stack([sample, torch.sqrt(1.0 - torch.square(sample)), torch.zeros_like(sample), torch.zeros_like(sample)], dim=1)
+        x_t, _, z = self._q(0, coef, x_0, None, noise, seed, row0)
+        out = (x_t.reshape(x_0.shape), sample.view(shape), (t + random_step).view(shape))
+        return out + (z.reshape(x_0.shape),) if return_noise else out
+
+    @torch.no_grad()
+    def q_stochastic_conditional(self, x_0, y, noise, *, t=None, seed=None, row0=0, return_noise=False):
+        """reference :253-279.  Returns (x_t, combined_noise, sqrt_alpha_bar[t] [B,1,..])."""
+        b = x_0.shape[0]
+        shape = [b] + [1] * (x_0.ndim - 1)
+        dev = x_0.device
+        if t is None:
+            t = torch.randint(1, self.num_timesteps + 1, tuple(shape), device=dev)
+        t = t.to(dev).reshape(b)
+        sab = self.sqrt_alpha_bar[t]
+        coef = torch.stack([sab, self.m[t] * sab, self.sqrt_delta[t], 1.0 / torch.sqrt(1.0 - self.alpha_bar[t])], dim=1)
+        x_t, comb, z = self._q(1, coef, x_0, y, noise, seed, row0)
+        out = (x_t.reshape(x_0.shape), comb.reshape(x_0.shape), sab.view(shape))
+        return out + (z.reshape(x_0.shape),) if return_noise else out
 
 
 def _seed(seed):

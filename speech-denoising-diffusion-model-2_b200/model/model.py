@@ -48,10 +48,20 @@ class SDDM(BaseModel):
         if q_transition not in ("original", "conditional"):
             raise NotImplementedError
 
-    # train step -- SURVEY.md §8f row 1 (needs backward kernels); not part of the inference hot path yet
-    def forward(self, target, condition):
-        raise NotImplementedError("SDDM.forward is the training step (q_stochastic + backward); this build covers the "
-                                  "inference hot path SDDM.infer only")
+    # train step, forward half (reference :29-48): forward-diffusion draw + eps_hat; returns (predicted, noise) for the loss.
+    # Inference-mode only: there are no backward kernels, so no gradients flow.
+    @torch.no_grad()
+    def forward(self, target, condition, *, seed: Optional[int] = None):
+        if not target.is_cuda:
+            raise RuntimeError("SDDM.forward (sddm_b200) needs CUDA tensors: there is no CPU fallback")
+        if self.q_transition == "original":
+            x_t, noise_level, t, noise = self.diffusion.q_stochastic(target, None, seed=seed, return_noise=True)
+            level = noise_level if self.noise_condition == "sqrt_alpha_bar" else t
+            predicted = self.noise_estimate_model(condition, x_t, level)
+        else:
+            x_t, noise, noise_level = self.diffusion.q_stochastic_conditional(target, condition, None, seed=seed)
+            predicted = self.noise_estimate_model(condition, x_t, noise_level)
+        return predicted, noise
 
     def _fused_ok(self) -> bool:
         return isinstance(self.noise_estimate_model, UNetModified2) and self.noise_condition == "sqrt_alpha_bar"

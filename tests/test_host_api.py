@@ -106,7 +106,7 @@ def test_reference_error_behaviour():
             SDDM(d, net, **kw)
     with pytest.raises(AssertionError):
         UNetModified2(num_samples=16449)                             # UNetModified2.py:13
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="no CPU fallback"):           # the training-step forward runs on the GPU only
         SDDM(d, net).forward(torch.zeros(1, 1, L), torch.zeros(1, 1, L))
 
 
