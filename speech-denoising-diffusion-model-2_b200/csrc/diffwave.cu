@@ -914,6 +914,11 @@ SDDM_API int sddm_dw_debug_fetch(sddm_dw_plan* p, const char* what, void* ws, in
         if (p->tc) { set_error("the tcgen05 path keeps the per-layer z cache instead of a skip sum"); return SDDM_E_INVALID; }
         rows = B * T; cols = DW_C; ld = DW_C; off = lay.skip; is16 = false;
     }
+    else if (w[0] == 'z') {   // gated activation: tcgen05 path "z<l>" (z cache of layer l), fp32 path "z" (the last layer evaluated)
+        const int l = p->tc ? atoi(w.c_str() + 1) : 0;
+        if (l < 0 || l >= p->L) { set_error("no such layer: %s", what); return SDDM_E_INVALID; }
+        rows = B * T; cols = DW_C; ld = DW_C; off = lay.z + (p->tc ? (size_t)l * B * T * DW_C * 2 : 0);
+    }
     else if (w.rfind("cond", 0) == 0) {
         const int l = atoi(w.c_str() + 4);
         if (l < 0 || l >= p->L) { set_error("no such layer: %s", what); return SDDM_E_INVALID; }

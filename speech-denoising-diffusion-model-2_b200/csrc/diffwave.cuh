@@ -27,6 +27,7 @@ struct DwLayerTc {
     const __nv_bfloat16* w2;      // [64][64]    K-major (n = residual channel, c)
     const float* b2;              // [64] output_residual bias
     int B, T, dil;
+    int opaque_zero;              // must be 0 (see the release of the operand / conditioner buffers in the kernel)
 };
 int launch_dw_layer_tc(const DwLayerTc& p, cudaStream_t st);
 

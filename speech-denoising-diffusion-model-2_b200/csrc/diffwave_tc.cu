@@ -150,6 +150,7 @@ __global__ void __launch_bounds__(kLayerThreads, 1) dw_layer_tc_kernel(const __g
         const uint32_t zbox = base + kOffZ + g * kBox, zrow = zbox + row * 128, xrow = base + kOffA + g * 3 * kBox + row * 128;
         const uint32_t crow = base + kOffCond + row * 128;
         const uint32_t sw = (uint32_t)(row & 7);
+        const uint32_t zmask = (uint32_t)p.opaque_zero;   // always 0, but only the host knows
         for (int i = g, n = 0; i < my_tiles; i += 2, ++n) {
             const int tile = blockIdx.x + i * gridDim.x;
             const int b = tile / tiles_per_row, t0 = (tile - b * tiles_per_row) * kTile, t = t0 + row;
@@ -161,15 +162,25 @@ __global__ void __launch_bounds__(kLayerThreads, 1) dw_layer_tc_kernel(const __g
                 cv[q] = lds128(crow + ((((uint32_t)q) ^ sw) << 4));
                 cv[8 + q] = lds128(crow + kBox + ((((uint32_t)q) ^ sw) << 4));
             }
-            mbar_arrive(bar(B_CEMPTY));            // the shared conditioner buffer may be refilled for the next tile
+            // Release only once the loads have RETURNED: ld.shared is asynchronous and mbarrier.arrive does not wait for it, so an
+            // arrive issued right behind the loads lets the producer's TMA refill overtake loads still queued in the shared-memory
+            // pipe (seen as rare corrupted tiles at > 8 tiles per CTA).  Folding one word of every load into the barrier address
+            // (masked by a zero the compiler cannot see) makes the arrive data-dependent on all of them.
+            uint32_t dep = 0;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) dep ^= cv[q].x;
+            mbar_arrive(bar(B_CEMPTY) + (dep & zmask));   // the shared conditioner buffer may be refilled for the next tile
             const int v = (t < p.dil ? 1 : 0) | (t + p.dil >= p.T ? 2 : 0);
             const float4* b1 = reinterpret_cast<const float4*>(p.bias1 + (size_t)b * p.bias1_row_stride + v * DW_N);
             mbar_wait(bar(B_AFULL + g), n & 1);    // acquires the TMA-written centre box for this thread's reads
             uint4 xv[8];                           // this row of the layer input, for the residual connection of epilogue 2
 #pragma unroll
             for (int q = 0; q < 8; ++q) xv[q] = lds128(xrow + ((((uint32_t)q) ^ sw) << 4));
+            dep = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) dep ^= xv[q].x;
             mbar_wait(bar(B_ACC1F + g), n & 1);
-            mbar_arrive(bar(B_AEMPTY + g));        // MMA 1 has consumed the three boxes and x is in registers: refill the stage
+            mbar_arrive(bar(B_AEMPTY + g) + (dep & zmask));   // MMA 1 has consumed the three boxes and x IS in registers: refill the stage
             tc_fence_after();
             if (leader) bulk_wait_read_0();        // the x_out store of this group's previous tile has finished reading the z box
             group_bar(1 + g);

@@ -192,3 +192,25 @@ def test_gpu_generate_from_spectrograms_sharding_invariance(built_lib):
         mine = parts[0][k] if parts[0][k] is not None else parts[1][k]
         assert (parts[0][k] is None) != (parts[1][k] is None)
         assert torch.equal(mine, full[k]), k
+
+
+@pytest.mark.gpu
+def test_gpu_full_size_bf16_vs_fp32_and_row_invariance(built_lib):
+    """BASELINE cfg 5 size (10 s utterances: spec [513, 626], T = 160 256): the tcgen05 path agrees with the fp32 path on eps_hat
+    (the fp32 path is the one pinned to the reference at small sizes), rows do not depend on their batch neighbours, and
+    repeated evaluation is bit-identical."""
+    case = DIFFWAVE_CASES["full"]
+    g = torch.Generator().manual_seed(12)
+    B, frames = 2, 626
+    spec = (torch.rand(B, 513, frames, generator=g) * 0.7).cuda()
+    audio = torch.randn(B, 1, 256 * frames, generator=g).cuda()
+    step = torch.tensor([150.0, 20.0]).reshape(B, 1, 1).cuda()
+    ref = _gpu_module(case, "fp32")(spec, audio, step)
+    net = _gpu_module(case, "bf16")
+    got = net(spec, audio, step)
+    e = rel_err(got.cpu(), ref.cpu())
+    print("diffwave full size: bf16 vs fp32 eps %.2e" % e)
+    assert e < 2e-2
+    assert torch.equal(got, net(spec, audio, step))
+    one = net(spec[1:2].contiguous(), audio[1:2].contiguous(), step[1:2].contiguous())
+    assert torch.equal(one, got[1:2])

@@ -120,3 +120,23 @@ def test_gpu_ragged_lengths_vs_oracle(built_lib, sd):
             want = WO.wavegrad_forward(sd, spec, audio, lv)
             got = net.get_plan().eps(spec.cuda(), audio.cuda(), noise_level=lv.cuda()).cpu()
             assert rel_err(got, want) < TOL[prec], (prec, B, F)
+
+
+@pytest.mark.gpu
+def test_gpu_full_size_bf16_vs_fp32_and_row_invariance(built_lib):
+    """BASELINE cfg 4 size (spec [128, 107], 32 100 samples): tcgen05 path vs the fp32 path (pinned to the reference at small
+    sizes), batch-row invariance, determinism."""
+    g = torch.Generator().manual_seed(13)
+    B, F = 3, 107
+    spec = torch.rand(B, 128, F, generator=g).cuda()
+    audio = torch.randn(B, 300 * F, generator=g).cuda()
+    lv = torch.tensor([0.95, 0.5, 0.1]).cuda()
+    ref = _gpu_module("fp32").get_plan().eps(spec, audio, noise_level=lv)
+    net = _gpu_module("bf16")
+    got = net.get_plan().eps(spec, audio, noise_level=lv)
+    e = rel_err(got.cpu(), ref.cpu())
+    print("wavegrad full size: bf16 vs fp32 eps %.2e" % e)
+    assert e < 2e-2
+    assert torch.equal(got, net.get_plan().eps(spec, audio, noise_level=lv))
+    one = net.get_plan().eps(spec[2:3].contiguous(), audio[2:3].contiguous(), noise_level=lv[2:3].contiguous())
+    assert torch.equal(one, got[2:3])
