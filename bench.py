@@ -5,6 +5,8 @@ a batch of 64 VoiceBank-DEMAND-shaped utterance-chunks per GPU, synthetic audio,
 
     python bench.py [--gpus N --steps K --warmup W]                 # our arm (one rank per GPU under torchrun)
     python bench.py --impl reference [...]                           # the reference algorithm on the host CPU cores
+    python bench.py --workload cfg3 [...]                             # BASELINE.json configs[2]: 824 test-set-shaped utterances, STRONG scaling:
+                                                                      # chunk -> shard rows over the ranks -> enhance -> NCCL gather -> regroup
     python bench.py --workload cfg4 [...]                             # BASELINE.json configs[3]: WaveGrad, 8 x 2 s utterances per GPU, 1000 steps
     python bench.py --workload cfg5 [...]                             # BASELINE.json configs[4]: DiffWave, 8 x 10 s utterances per GPU,
                                                                       # 200 steps (same JSON contract; not the headline)
@@ -134,14 +136,118 @@ def run_reference(args):
     v = statistics.median(r["value"] for r in vals)
     r = vals[-1]
     sample = "%d chunks x %d of 100 reverse steps per bench step, scaled to 100 steps" % (r["rows"], r["steps_timed"])
+    workload = WORKLOAD
+    if getattr(args, "workload", "cfg2") == "cfg3":   # utterances of the 824-file set average 2455 / 824 chunks
+        v = v * 824.0 / 2455.0
+        sample += ", then to 2455 chunks / 824 utterances"
+        workload = "cfg3: UNetModified2 full 100-step enhancement of 824 test-set-shaped utterances (2455 chunks of 16448 samples)"
     line = {"impl": "reference", "metric": "utterances_per_sec", "value": v, "unit": "utt/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * 64 / v, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "reference algorithm (oracle port, torch CPU ATen kernels) on host cores"},
+            "config": {"workload": workload, "note": "reference algorithm (oracle port, torch CPU ATen kernels) on host cores"},
             "rtf": 1.0 / (v * L / SR),
             "cpu_baseline": {"value": v, "unit": "utt/s", "cores": r["threads"], "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------
+# cfg 3: the 824-utterance VoiceBank-DEMAND-test-shaped set, sharded over the ranks (strong scaling)
+# ------------------------------------------------------------------------------------------------------
+def cfg3_lengths():
+    """824 utterance lengths, log-normal with a 2.3 s median clipped to [1 s, 10 s] at 16 kHz, seeded (the real
+    test set is not available offline; this reproduces its shape: 824 files, ~2.5 s average)."""
+    import numpy as np
+    rng = np.random.default_rng(824)
+    sec = np.clip(rng.lognormal(mean=np.log(2.3), sigma=0.45, size=824), 1.0, 10.0)
+    return (sec * SR).astype(np.int64)
+
+
+def run_cfg3(args):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
+    from sddm_b200 import PREC_BF16, PREC_BF16_ACT, PREC_FP32, _lib
+    from sddm_b200.infer import enhance_utterances
+    from sddm_b200.model.diffusion import GaussianDiffusion
+    from sddm_b200.model.model import SDDM
+    from sddm_b200.model.network import UNetModified2
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    torch.manual_seed(0)
+    net = UNetModified2(**UNET)
+    net.precision = {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16act": PREC_BF16_ACT}[args.precision]
+    model = SDDM(GaussianDiffusion("linear", T_STEPS, 1e-6, 1e-3, device=dev), net, p_transition="condition_in").to(dev).eval()
+    lengths = cfg3_lengths()
+    g = torch.Generator().manual_seed(824)
+    waves = [(0.1 * torch.randn(int(n), generator=g)).clamp(-1, 1).pin_memory() for n in lengths]     # host buffers: H2D is inside the step
+    n_chunks = int(sum((int(n) + L - 1) // L for n in lengths))
+    audio_s = float(lengths.sum()) / SR
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    outs = [None]
+
+    def step(s):
+        outs[0] = enhance_utterances(model, waves, batch_chunks=args.batch, seed=s, rank=rank, world=world)
+
+    def timed(steps):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for s in range(steps):
+            step(s)
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for s in range(max(3, args.warmup)):
+        step(s)
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = _lib.launch_count()
+    ms = timed(args.steps)
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    ok = len(outs[0]) == len(lengths) and all(o.shape[-1] == int(n) for o, n in zip(outs[0], lengths))
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+    value = len(lengths) * args.steps / (ms / 1e3)
+    line = {"metric": "utterances_per_sec", "value": value, "unit": "utt/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "fp32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+            "config": {"workload": "cfg3: UNetModified2 full 100-step enhancement of 824 test-set-shaped utterances (%.0f s of audio, %d chunks of 16448 "
+                                   "samples), rows sharded contiguously over the ranks, NCCL all-gather of the enhanced rows, regrouped per utterance"
+                                   % (audio_s, n_chunks),
+                       "sub_batch_chunks": args.batch, "reverse_steps": T_STEPS, "precision": args.precision, "noise": "in-kernel Philox4x32-10, keyed by the global row",
+                       "lengths": "log-normal, median 2.3 s, clipped to [1, 10] s, numpy default_rng(824)",
+                       "l2": "per-step working set of a 64-chunk sub-batch >> 126 MB L2; no flush needed"},
+            "rtf": (ms / args.steps / 1e3) / audio_s, "chunks_per_sec": n_chunks * args.steps / (ms / 1e3),
+            "e2e": {"value": value, "unit": "utt/s", "h2d_bytes_per_step": n_chunks * L * 4 // world, "d2h_bytes_per_step": 0,
+                    "note": "the timed step is already end to end from pinned host waveforms (chunking, H2D, enhancement, gather, regroup); outputs stay on the device"},
+            "gpu_launches": int(launches), "clocks": clocks, "outputs_ok": bool(ok)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -632,10 +738,13 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("SDDM_B200_PRECISION", "bf16act"), choices=["bf16", "fp32", "bf16act"])
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4", "cfg5"], help="cfg2 = the headline (UNetModified2); cfg4 = WaveGrad; cfg5 = DiffWave")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"],
+                    help="cfg2 = the headline (UNetModified2, weak scaling); cfg3 = 824-utterance set (strong scaling); cfg4 = WaveGrad; cfg5 = DiffWave")
     ap.add_argument("--batch-cfg5", type=int, default=8, help="utterances per GPU for --workload cfg4 / cfg5")
     args = ap.parse_args()
-    if args.workload == "cfg4":
+    if args.workload == "cfg3" and args.impl != "reference":
+        run_cfg3(args)
+    elif args.workload == "cfg4":
         (run_reference_wavegrad if args.impl == "reference" else run_wavegrad)(args)
     elif args.workload == "cfg5":
         (run_reference_diffwave if args.impl == "reference" else run_diffwave)(args)
