@@ -78,6 +78,12 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+def quiet_nccl():
+    """NCCL_DEBUG=VERSION (set on some boxes) makes NCCL print its version on STDOUT, next to the one JSON line this script owes."""
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
+
+
 def synth_batch(rows, seed):
     import torch
     return (0.1 * torch.randn(rows, 1, L, generator=torch.Generator().manual_seed(seed))).clamp(-1, 1)
@@ -173,6 +179,7 @@ def run_cfg3(args):
         ge.build()
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        quiet_nccl()
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         dist.barrier()
@@ -306,6 +313,7 @@ def run_wavegrad(args):
         ge.build()
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        quiet_nccl()
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         dist.barrier()
@@ -469,6 +477,7 @@ def run_diffwave(args):
         ge.build()
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        quiet_nccl()
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         dist.barrier()
@@ -599,6 +608,7 @@ def run_ours(args):
         ge.build()
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        quiet_nccl()
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         dist.barrier()
