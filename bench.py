@@ -7,7 +7,7 @@ a batch of 64 VoiceBank-DEMAND-shaped utterance-chunks per GPU, synthetic audio,
     python bench.py --impl reference [...]                           # the reference algorithm on the host CPU cores
     python bench.py --workload cfg3 [...]                             # BASELINE.json configs[2]: 824 test-set-shaped utterances, STRONG scaling:
                                                                       # chunk -> shard rows over the ranks -> enhance -> NCCL gather -> regroup
-    python bench.py --workload cfg4 [...]                             # BASELINE.json configs[3]: WaveGrad, 8 x 2 s utterances per GPU, 1000 steps
+    python bench.py --workload cfg4 [...]                             # BASELINE.json configs[3]: WaveGrad, 32 x 2 s utterances per GPU, 1000 steps
     python bench.py --workload cfg5 [...]                             # BASELINE.json configs[4]: DiffWave, 8 x 10 s utterances per GPU,
                                                                       # 200 steps (same JSON contract; not the headline)
 
@@ -750,8 +750,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"],
                     help="cfg2 = the headline (UNetModified2, weak scaling); cfg3 = 824-utterance set (strong scaling); cfg4 = WaveGrad; cfg5 = DiffWave")
-    ap.add_argument("--batch-cfg5", type=int, default=8, help="utterances per GPU for --workload cfg4 / cfg5")
+    ap.add_argument("--batch-cfg5", type=int, default=None, help="utterances per GPU for --workload cfg4 (default 32) / cfg5 (default 8)")
     args = ap.parse_args()
+    if args.batch_cfg5 is None:
+        args.batch_cfg5 = 32 if args.workload == "cfg4" else 8
     if args.workload == "cfg3" and args.impl != "reference":
         run_cfg3(args)
     elif args.workload == "cfg4":
