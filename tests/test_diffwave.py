@@ -21,6 +21,15 @@ from oracle import sddm_oracle as O  # noqa: E402
 TOL = {"fp32": 1e-3, "bf16": 2e-2}
 
 
+def report(line):
+    """print + append to gpurun_out/parity_report.txt (copied to profiles/ at the end of a round)."""
+    print(line)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    os.makedirs(os.path.join(root, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(root, "gpurun_out", "parity_report.txt"), "a") as f:
+        f.write(line + "\n")
+
+
 @pytest.fixture(scope="module")
 def gold():
     return {k: torch.from_numpy(v) for k, v in np.load(os.path.join(GOLDEN, "diffwave.npz")).items()}
@@ -104,7 +113,7 @@ def test_gpu_eps_vs_reference_golden(built_lib, gold, tag, prec):
     e_up = rel_err(up[:, ::29], gold[tag + ".up_last"])
     e_x = rel_err(x[:, ::4, ::3], gold[tag + ".x%d" % (case["residual_layers"] - 1)])
     e = rel_err(eps, gold[tag + ".eps"])
-    print("diffwave %s %s: upsampler %.2e  x_last %.2e  eps %.2e" % (tag, prec, e_up, e_x, e))
+    report("diffwave %s %s: upsampler %.2e  x_last %.2e  eps %.2e" % (tag, prec, e_up, e_x, e))
     assert e_up < (1e-5 if prec == "fp32" else 8e-3)
     assert e_x < TOL[prec] and e < TOL[prec]
 
@@ -140,7 +149,7 @@ def test_gpu_sampling_vs_reference_golden(built_lib, gold, kind, prec):
     m = M.SDDM_spectrogram(d, net, hop_samples=256, noise_condition=kind)
     x0 = m.infer(gold["sample.spec"].cuda(), noises=gold["sample.noises"].cuda()).cpu()
     snr = si_snr_db(x0, gold["sample.%s.x0" % kind])
-    print("diffwave sampling %s %s: SI-SNR vs reference %.1f dB" % (kind, prec, snr))
+    report("diffwave sampling %s %s: SI-SNR vs reference %.1f dB" % (kind, prec, snr))
     assert snr > (60.0 if prec == "fp32" else 40.0)
 
 
@@ -209,7 +218,7 @@ def test_gpu_full_size_bf16_vs_fp32_and_row_invariance(built_lib):
     net = _gpu_module(case, "bf16")
     got = net(spec, audio, step)
     e = rel_err(got.cpu(), ref.cpu())
-    print("diffwave full size: bf16 vs fp32 eps %.2e" % e)
+    report("diffwave full size: bf16 vs fp32 eps %.2e" % e)
     assert e < 2e-2
     assert torch.equal(got, net(spec, audio, step))
     one = net(spec[1:2].contiguous(), audio[1:2].contiguous(), step[1:2].contiguous())

@@ -17,6 +17,15 @@ from oracle import sddm_oracle as O  # noqa: E402
 from oracle import wavegrad_oracle as WO  # noqa: E402
 
 
+def report(line):
+    """print + append to gpurun_out/parity_report.txt (copied to profiles/ at the end of a round)."""
+    print(line)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    os.makedirs(os.path.join(root, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(root, "gpurun_out", "parity_report.txt"), "a") as f:
+        f.write(line + "\n")
+
+
 @pytest.fixture(scope="module")
 def gold():
     return {k: torch.from_numpy(v) for k, v in np.load(os.path.join(GOLDEN, "wavegrad.npz")).items()}
@@ -86,7 +95,7 @@ def test_gpu_eps_vs_reference_golden(built_lib, gold, tag, prec):
     for k in ("d0", "d1", "d2", "d3", "d4", "u0", "u1", "u2", "u3", "u4"):
         errs[k] = rel_err(plan.fetch(k, B, F).cpu()[:, ::5, ::3], gold[tag + "." + k])
     e = rel_err(eps.reshape(-1), gold[tag + ".eps"].reshape(-1))
-    print("wavegrad %s %s: eps %.2e  blocks %s" % (tag, prec, e, " ".join("%s %.1e" % kv for kv in errs.items())))
+    report("wavegrad %s %s: eps %.2e  blocks %s" % (tag, prec, e, " ".join("%s %.1e" % kv for kv in errs.items())))
     assert e < TOL[prec] and max(errs.values()) < TOL[prec]
 
 
@@ -100,7 +109,7 @@ def test_gpu_sampling_vs_reference_golden(built_lib, gold, prec):
     m = M.SDDM_spectrogram(d, net, hop_samples=300)
     x0 = m.infer(gold["sample.spec"].cuda(), noises=gold["sample.noises"].cuda()).cpu()
     snr = si_snr_db(x0, gold["sample.x0"])
-    print("wavegrad sampling %s: SI-SNR vs reference %.1f dB" % (prec, snr))
+    report("wavegrad sampling %s: SI-SNR vs reference %.1f dB" % (prec, snr))
     assert snr > (60.0 if prec == "fp32" else 40.0)
     a = m.infer(gold["sample.spec"].cuda(), seed=5)
     b = m.infer(gold["sample.spec"].cuda(), seed=5)
@@ -135,7 +144,7 @@ def test_gpu_full_size_bf16_vs_fp32_and_row_invariance(built_lib):
     net = _gpu_module("bf16")
     got = net.get_plan().eps(spec, audio, noise_level=lv)
     e = rel_err(got.cpu(), ref.cpu())
-    print("wavegrad full size: bf16 vs fp32 eps %.2e" % e)
+    report("wavegrad full size: bf16 vs fp32 eps %.2e" % e)
     assert e < 2e-2
     assert torch.equal(got, net.get_plan().eps(spec, audio, noise_level=lv))
     one = net.get_plan().eps(spec[2:3].contiguous(), audio[2:3].contiguous(), noise_level=lv[2:3].contiguous())
