@@ -78,10 +78,23 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def quiet_nccl():
-    """NCCL_DEBUG=VERSION (set on some boxes) makes NCCL print its version on STDOUT, next to the one JSON line this script owes."""
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"
+def init_distributed(local):
+    """init_process_group + first barrier with file descriptor 1 pointing at stderr: NCCL prints its version banner (NCCL_DEBUG >=
+    VERSION, possibly from /etc/nccl.conf) on STDOUT when the first communicator is created, next to the one JSON line this script owes."""
+    import torch
+    import torch.distributed as dist
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
+        torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
 
 
 def synth_batch(rows, seed):
@@ -179,10 +192,7 @@ def run_cfg3(args):
         ge.build()
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        quiet_nccl()
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        dist.barrier()
+        init_distributed(local)
     from sddm_b200 import PREC_BF16, PREC_BF16_ACT, PREC_FP32, _lib
     from sddm_b200.infer import enhance_utterances
     from sddm_b200.model.diffusion import GaussianDiffusion
@@ -313,10 +323,7 @@ def run_wavegrad(args):
         ge.build()
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        quiet_nccl()
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        dist.barrier()
+        init_distributed(local)
     from sddm_b200 import PREC_BF16, PREC_FP32, _lib
     from sddm_b200.model.diffusion import GaussianDiffusion
     from sddm_b200.model.model import SDDM_spectrogram
@@ -477,10 +484,7 @@ def run_diffwave(args):
         ge.build()
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        quiet_nccl()
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        dist.barrier()
+        init_distributed(local)
     from sddm_b200 import PREC_BF16, PREC_FP32, _lib, prepare_spectrogram as PS
     from sddm_b200.model.diffusion import GaussianDiffusion
     from sddm_b200.model.model import SDDM_spectrogram
@@ -608,10 +612,7 @@ def run_ours(args):
         ge.build()
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        quiet_nccl()
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        dist.barrier()
+        init_distributed(local)
     from sddm_b200 import PREC_BF16, PREC_BF16_ACT, PREC_FP32, _lib
     from sddm_b200.infer import enhance_batch
     from sddm_b200.model.diffusion import GaussianDiffusion
