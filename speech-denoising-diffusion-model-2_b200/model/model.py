@@ -146,13 +146,27 @@ class SDDM_spectrogram(SDDM):
         net = self.noise_estimate_model
         if not isinstance(net, (DiffWave, WaveGrad)):
             raise NotImplementedError("SDDM_spectrogram (sddm_b200) drives the DiffWave and WaveGrad denoisers")
-        if continuous:
-            raise NotImplementedError("continuous=True (intermediate samples) is not provided for the spectrogram models")
         want_hop = 256 if isinstance(net, DiffWave) else 300
         if self.hop_samples != want_hop:
             raise ValueError("%s upsamples a spectrogram frame to %d samples: hop_samples must be %d, got %d"
                              % (type(net).__name__, want_hop, want_hop, self.hop_samples))
         if seed is None and noises is None:
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())
-        plan = self.noise_estimate_model.get_plan(self.diffusion, self.noise_condition)
-        return plan.sample(condition, noises=noises, seed=0 if seed is None else int(seed), row0=row0, trace=return_trace)
+        seed = 0 if seed is None else int(seed)
+        plan = net.get_plan(self.diffusion, self.noise_condition)
+        if not continuous:
+            return plan.sample(condition, noises=noises, seed=seed, row0=row0, trace=return_trace)
+        # continuous=True (reference :230-244): the intermediate x_t every `sample_inter` steps, one eps call + one update kernel per step
+        assert condition.shape[0] == 1, "Batch size must be 1 to do continuous sampling"
+        d, T, B = self.diffusion, self.num_timesteps, condition.shape[0]
+        every = 1 | (T // 100)
+        Ls = self.hop_samples * condition.shape[-1]
+        z = (lambda k: None) if noises is None else (lambda k: noises[k].reshape(B, 1, Ls))
+        x_t = d._x_T("original", torch.empty(B, 1, Ls, device=condition.device), z(0), seed)      # pure-noise start (:216)
+        samples = [condition]
+        for t in range(T, 0, -1):
+            predicted = plan.eps(condition, x_t, t=t).reshape(x_t.shape)
+            x_t = d.p_transition(x_t, t, predicted, noise=z(T + 1 - t) if t > 1 else None, seed=seed + t)
+            if t % every == 0:
+                samples.append(x_t)
+        return samples

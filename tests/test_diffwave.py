@@ -223,3 +223,23 @@ def test_gpu_full_size_bf16_vs_fp32_and_row_invariance(built_lib):
     assert torch.equal(got, net(spec, audio, step))
     one = net(spec[1:2].contiguous(), audio[1:2].contiguous(), step[1:2].contiguous())
     assert torch.equal(one, got[1:2])
+
+
+@pytest.mark.gpu
+def test_gpu_continuous_sampling_matches_fused_loop(built_lib):
+    """SDDM_spectrogram.infer(continuous=True) (reference model.py:230-244): the condition followed by the intermediate x_t of
+    every `1 | T // 100`-th step; with injected noise its last sample equals the fused sampler's result."""
+    from sddm_b200.model import model as M
+    from sddm_b200.model.diffusion import GaussianDiffusion
+    net = _gpu_module(DIFFWAVE_CASES["small"], "fp32")
+    d = GaussianDiffusion(schedule="linear", n_timestep=4, linear_start=1e-4, linear_end=5e-2, device="cuda")
+    m = M.SDDM_spectrogram(d, net, hop_samples=256, noise_condition="time_step")
+    g = torch.Generator().manual_seed(3)
+    spec = (torch.rand(1, 513, 3, generator=g) * 0.7).cuda()
+    noises = torch.randn(4, 1, 1, 768, generator=g).cuda()
+    samples = m.infer(spec, continuous=True, noises=noises)
+    assert len(samples) == 5 and samples[0] is spec and all(s.shape == (1, 1, 768) for s in samples[1:])
+    fused = m.infer(spec, noises=noises)
+    assert rel_err(samples[-1].cpu(), fused.cpu()) < 1e-5
+    with pytest.raises(AssertionError):
+        m.infer(torch.cat([spec, spec]), continuous=True)
