@@ -37,44 +37,79 @@ struct StftP {
     float inv_norm;        // 1 / sqrt(sum w^2)
 };
 
-__global__ void __launch_bounds__(256) stft_kernel(StftP p) {
+// W16^e = exp(-2 pi i e / 16), e = 0..7: the twiddles of the in-register 16-point DIF (compile-time constants)
+__device__ __forceinline__ float2 w16(int e) {
+    constexpr float c[8] = {1.0f, 0.92387953251128674f, 0.70710678118654752f, 0.38268343236508977f, 0.0f, -0.38268343236508977f,
+                            -0.70710678118654752f, -0.92387953251128674f};
+    constexpr float sn[8] = {0.0f, -0.38268343236508977f, -0.70710678118654752f, -0.92387953251128674f, -1.0f, -0.92387953251128674f,
+                             -0.70710678118654752f, -0.38268343236508977f};
+    return make_float2(c[e], sn[e]);
+}
+
+__global__ void __launch_bounds__(256, 2) stft_kernel(StftP p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* w512 = reinterpret_cast<float2*>(smem_raw);                 // [512]  exp(-2 pi i t / 512)
-    float2* w1024 = w512 + 512;                                         // [513]  exp(-2 pi i k / 1024)
-    float2* zbuf = w1024 + 520;                                         // [8 warps][ZPAD]
+    float2* w1024 = reinterpret_cast<float2*>(smem_raw);                // [513]  exp(-2 pi i k / 1024)   (real-FFT post-processing)
+    float* win = reinterpret_cast<float*>(w1024 + 520);                 // [1024] window
+    float2* zbuf = reinterpret_cast<float2*>(win + NFFT);               // [8 warps][ZPAD]
     float* tile = reinterpret_cast<float*>(zbuf + 8 * ZPAD);            // [513][TILE_LD] magnitudes of the CTA's frames
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.y, m0 = blockIdx.x * FPB;
-    for (int t = tid; t < 512; t += 256) {
-        float s, c;
-        sincospif(-2.0f * (float)t / 512.0f, &s, &c);
-        w512[t] = make_float2(c, s);
-    }
     for (int t = tid; t < NBIN; t += 256) {
-        float s, c;
-        sincospif(-2.0f * (float)t / 1024.0f, &s, &c);
-        w1024[t] = make_float2(c, s);
+        float sv, cv;
+        sincospif(-2.0f * (float)t / 1024.0f, &sv, &cv);
+        w1024[t] = make_float2(cv, sv);
+    }
+    for (int t = tid; t < NFFT; t += 256) win[t] = __ldg(p.window + t);
+    // per-lane twiddles, computed once: W512^(lane k1(q)) between the two FFT stages, and for stage s (half = 16 >> s) of the
+    // cross-lane DIF the factor applied to the UPPER lane of a butterfly, W_(2 half)^(lane mod half) (1 for the lower lane)
+    float2 tw1[16], tws[4];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        const int k1 = ((q & 1) << 3) | ((q & 2) << 1) | ((q & 4) >> 1) | ((q & 8) >> 3);
+        float sv, cv;
+        sincospif(-2.0f * (float)((lane * k1) & 511) / 512.0f, &sv, &cv);
+        tw1[q] = make_float2(cv, sv);
+    }
+#pragma unroll
+    for (int st = 0; st < 4; ++st) {
+        const int half = 16 >> st;
+        float sv, cv;
+        sincospif(-2.0f * (float)((lane & (half - 1)) * (16 / half) * 16) / 512.0f, &sv, &cv);
+        tws[st] = (lane & half) ? make_float2(cv, sv) : make_float2(1.0f, 0.0f);
     }
     __syncthreads();
     const float* x = p.wav + (int64_t)b * p.L;
     float2* zb = zbuf + warp * ZPAD;
+    const int k2 = (int)(__brev((unsigned)lane) >> 27);
+    const int zlo = (lane & 15) + 17 * (lane >> 4);   // zidx(lane + 32 r) = zlo + 34 r
     for (int f = 0; f < FPB / 8; ++f) {
         const int ml = warp * (FPB / 8) + f, m = m0 + ml;
         if (m < p.frames) {   // warp-uniform
             // ---- load + window + pack: register n1 holds z[32 n1 + lane] = (x[64 n1 + 2 lane], x[64 n1 + 2 lane + 1])
             float2 v[16];
+            const int i0 = p.hop * m - NFFT / 2;
+            if (i0 >= 0 && i0 + NFFT <= p.L && ((i0 | (int)((uintptr_t)x >> 2)) & 1) == 0) {   // interior frame, 8-byte aligned pairs
+                const float2* xp = reinterpret_cast<const float2*>(x + i0) + lane;
+                const float2* wp = reinterpret_cast<const float2*>(win) + lane;
 #pragma unroll
-            for (int n1 = 0; n1 < 16; ++n1) {
-                const int s0 = 64 * n1 + 2 * lane;
-                float xv[2];
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    int i = p.hop * m + s0 + q - NFFT / 2;   // centre = True, reflect padding
-                    if (i < 0) i = -i;
-                    if (i >= p.L) i = 2 * (p.L - 1) - i;
-                    xv[q] = __ldg(x + i) * __ldg(p.window + s0 + q);
+                for (int n1 = 0; n1 < 16; ++n1) {
+                    const float2 xv = __ldg(xp + 32 * n1), wv = wp[32 * n1];
+                    v[n1] = make_float2(xv.x * wv.x, xv.y * wv.y);
                 }
-                v[n1] = make_float2(xv[0], xv[1]);
+            } else {
+#pragma unroll
+                for (int n1 = 0; n1 < 16; ++n1) {
+                    const int s0 = 64 * n1 + 2 * lane;
+                    float xv[2];
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        int i = i0 + s0 + q;   // centre = True, reflect padding
+                        if (i < 0) i = -i;
+                        if (i >= p.L) i = 2 * (p.L - 1) - i;
+                        xv[q] = __ldg(x + i) * win[s0 + q];
+                    }
+                    v[n1] = make_float2(xv[0], xv[1]);
+                }
             }
             // ---- 16-point radix-2 DIF over the registers: afterwards register q holds Y[k1 = bitrev4(q)]
 #pragma unroll
@@ -85,28 +120,24 @@ __global__ void __launch_bounds__(256) stft_kernel(StftP p) {
                     const float2 a = v[q], c = v[q + half];
                     v[q] = make_float2(a.x + c.x, a.y + c.y);
                     const float2 d = make_float2(a.x - c.x, a.y - c.y);
-                    const int e = (q & (half - 1)) * (8 / half);      // W16^e = W512^(32 e)
-                    v[q + half] = e == 0 ? d : cmul(d, w512[32 * e]);
+                    const int e = (q & (half - 1)) * (8 / half);      // W16^e
+                    v[q + half] = e == 0 ? d : (e == 4 ? make_float2(d.y, -d.x) : cmul(d, w16(e)));
                 }
             }
-            // ---- twiddle W512^(lane * k1), then the 32-point radix-2 DIF across lanes: lane ends with k2 = bitrev5(lane)
+            // ---- twiddle W512^(lane * k1), then the 32-point radix-2 DIF ACROSS LANES: lane ends with k2 = bitrev5(lane)
 #pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                const int k1 = ((q & 1) << 3) | ((q & 2) << 1) | ((q & 4) >> 1) | ((q & 8) >> 3);
-                v[q] = cmul(v[q], w512[(lane * k1) & 511]);
-            }
+            for (int q = 0; q < 16; ++q) v[q] = cmul(v[q], tw1[q]);
 #pragma unroll
-            for (int half = 16; half >= 1; half >>= 1) {
-                const bool upper = (lane & half) != 0;
-                const float2 tw = w512[(lane & (half - 1)) * (16 / half) * 16];   // W_(2 half)^(lane mod half) = W512^(...)
+            for (int st = 0; st < 5; ++st) {
+                const int half = 16 >> st;
+                const float sgn = (lane & half) ? -1.0f : 1.0f;      // lower lane: v + o; upper lane: (o - v) * twiddle
 #pragma unroll
                 for (int q = 0; q < 16; ++q) {
                     const float ox = __shfl_xor_sync(0xffffffffu, v[q].x, half), oy = __shfl_xor_sync(0xffffffffu, v[q].y, half);
-                    if (!upper) v[q] = make_float2(v[q].x + ox, v[q].y + oy);
-                    else v[q] = cmul(make_float2(ox - v[q].x, oy - v[q].y), tw);
+                    const float2 a = make_float2(fmaf(v[q].x, sgn, ox), fmaf(v[q].y, sgn, oy));
+                    v[q] = st < 4 ? cmul(a, tws[st < 4 ? st : 0]) : a;   // the last stage's twiddle is 1
                 }
             }
-            const int k2 = (int)(__brev((unsigned)lane) >> 27);
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
                 const int k1 = ((q & 1) << 3) | ((q & 2) << 1) | ((q & 4) >> 1) | ((q & 8) >> 3);
@@ -114,8 +145,11 @@ __global__ void __launch_bounds__(256) stft_kernel(StftP p) {
             }
             __syncwarp();
             // ---- real-FFT post-processing + magnitude: bins k = lane + 32 r
-            for (int k = lane; k < NBIN; k += 32) {
-                const float2 zk = zb[zidx(k & 511)], zr = zb[zidx((512 - k) & 511)];
+#pragma unroll 4
+            for (int r = 0; r < 17; ++r) {
+                const int k = lane + 32 * r;
+                if (k >= NBIN) break;
+                const float2 zk = zb[k < 512 ? zlo + 34 * r : 0], zr = zb[zidx((512 - k) & 511)];
                 const float2 e = make_float2(0.5f * (zk.x + zr.x), 0.5f * (zk.y - zr.y));       // (Z[k] + conj Z[512-k]) / 2
                 const float2 d = make_float2(zk.x - zr.x, zk.y + zr.y);                         //  Z[k] - conj Z[512-k]
                 const float2 wd = cmul(w1024[k], d);
@@ -129,12 +163,12 @@ __global__ void __launch_bounds__(256) stft_kernel(StftP p) {
     const int nvalid = (p.frames - m0) < FPB ? (p.frames - m0) : FPB;
     if (p.melfb == nullptr) {
         float* o = p.out + (int64_t)b * NBIN * p.frames;
-        for (int i = tid; i < NBIN * FPB; i += 256) {
-            const int k = i / FPB, ml = i - k * FPB;
-            if (ml < nvalid) {
-                float s = tile[k * TILE_LD + ml];
-                if (p.log_clamp) s = fminf(fmaxf((log10f(s) - 1.0f + 5.0f) / 5.0f, 0.0f), 1.0f);
-                o[(int64_t)k * p.frames + m0 + ml] = s;
+        const int ml = tid & 31;
+        if (ml < nvalid) {
+            for (int k = tid >> 5; k < NBIN; k += 8) {   // a warp writes one 128-byte row segment of bin k
+                float sv = tile[k * TILE_LD + ml];
+                if (p.log_clamp) sv = fminf(fmaxf(fmaf(__log2f(sv), 0.0602059991327962f, 0.8f), 0.0f), 1.0f);   // (log10(s) - 1 + 5) / 5
+                o[(int64_t)k * p.frames + m0 + ml] = sv;
             }
         }
     } else {   // MelScale: mel[j][m] = sum_k S[k][m] * fb[k][j], accumulated in ascending k
@@ -164,7 +198,7 @@ extern "C" SDDM_API int sddm_stft_features(const float* wav, int B, int L, int n
     if (hop <= 0 || L <= n_fft / 2) { set_error("stft: hop must be positive and L > n_fft/2 (reflect padding), got hop=%d L=%d", hop, L); return SDDM_E_INVALID; }
     if (mel_fb && n_mels <= 0) { set_error("stft: n_mels must be positive with a filterbank"); return SDDM_E_INVALID; }
     StftP p{wav, window, mel_fb, mel_fb ? mel_lo : nullptr, mel_fb ? mel_hi : nullptr, out, B, L, hop, 1 + L / hop, mel_fb ? n_mels : 0, log_clamp, inv_norm};
-    const size_t smem = (512 + 520 + 8 * ZPAD) * sizeof(float2) + (size_t)NBIN * TILE_LD * sizeof(float);
+    const size_t smem = (520 + 8 * ZPAD) * sizeof(float2) + (size_t)NFFT * sizeof(float) + (size_t)NBIN * TILE_LD * sizeof(float);
     static bool attr = false;
     if (!attr) {
         SDDM_CUDA_TRY(cudaFuncSetAttribute(stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
