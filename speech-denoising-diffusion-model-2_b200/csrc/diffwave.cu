@@ -781,6 +781,7 @@ SDDM_API int sddm_dw_condition(sddm_dw_plan* p, const float* spec, int B, int fr
     if (rc) return rc;
     if ((rc = dw_check_ws(p, B, frames, ws, ws_bytes))) return rc;
     if (!spec) { set_error("null spectrogram"); return SDDM_E_INVALID; }
+    if (16 * frames + 1 > 65535 || B > 65535) { set_error("utterance too long / batch too large for one launch (frames=%d, B=%d; limits 4095 frames, 65535 rows)", frames, B); return SDDM_E_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
     const DwLayout lay = dw_layout(p, B, frames);
     const int T = p->cfg.hop_samples * frames, W1 = 16 * frames, F = p->F, KP = p->KP, L = p->L;

@@ -525,6 +525,7 @@ WgLayout wg_layout(const sddm_wg_plan* p, int B, int frames) {
 
 int wg_check_ws(const sddm_wg_plan* p, int B, int frames, const void* ws, size_t ws_bytes) {
     if (B <= 0 || frames <= 0) { set_error("batch and frame count must be positive (B=%d frames=%d)", B, frames); return SDDM_E_INVALID; }
+    if (B > 65535 || (long long)frames * WG_HOP > (1ll << 30)) { set_error("batch too large / utterance too long (B=%d frames=%d)", B, frames); return SDDM_E_INVALID; }
     if (!ws) { set_error("null workspace"); return SDDM_E_INVALID; }
     if (reinterpret_cast<uintptr_t>(ws) % 256) { set_error("workspace must be 256-byte aligned"); return SDDM_E_INVALID; }
     const size_t need = wg_layout(p, B, frames).total;
