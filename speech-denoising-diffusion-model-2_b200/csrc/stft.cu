@@ -171,14 +171,24 @@ __global__ void __launch_bounds__(256, 2) stft_kernel(StftP p) {
                 o[(int64_t)k * p.frames + m0 + ml] = sv;
             }
         }
-    } else {   // MelScale: mel[j][m] = sum_k S[k][m] * fb[k][j], accumulated in ascending k
+    } else {   // MelScale: mel[j][m] = sum_k S[k][m] * fb[k][j]
         float* o = p.out + (int64_t)b * p.n_mels * p.frames;
         for (int i = tid; i < p.n_mels * FPB; i += 256) {
             const int j = i / FPB, ml = i - j * FPB;
             if (ml < nvalid) {
-                float acc = 0.f;
                 const int klo = p.mel_lo ? __ldg(p.mel_lo + j) : 0, khi = p.mel_hi ? __ldg(p.mel_hi + j) : NBIN;
-                for (int k = klo; k < khi; ++k) acc = fmaf(tile[k * TILE_LD + ml], __ldg(p.melfb + (int64_t)k * p.n_mels + j), acc);
+                // four independent partial sums: the filterbank loads (L1 hits, ~40 cycles each) would otherwise serialise the loop
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                int k = klo;
+                const float* fb = p.melfb + j;
+                for (; k + 3 < khi; k += 4) {
+                    a0 = fmaf(tile[k * TILE_LD + ml], __ldg(fb + (int64_t)k * p.n_mels), a0);
+                    a1 = fmaf(tile[(k + 1) * TILE_LD + ml], __ldg(fb + (int64_t)(k + 1) * p.n_mels), a1);
+                    a2 = fmaf(tile[(k + 2) * TILE_LD + ml], __ldg(fb + (int64_t)(k + 2) * p.n_mels), a2);
+                    a3 = fmaf(tile[(k + 3) * TILE_LD + ml], __ldg(fb + (int64_t)(k + 3) * p.n_mels), a3);
+                }
+                for (; k < khi; ++k) a0 = fmaf(tile[k * TILE_LD + ml], __ldg(fb + (int64_t)k * p.n_mels), a0);
+                float acc = (a0 + a1) + (a2 + a3);
                 if (p.log_clamp) acc = fminf(fmaxf((log10f(acc) - 1.0f + 5.0f) / 5.0f, 0.0f), 1.0f);
                 o[(int64_t)j * p.frames + m0 + ml] = acc;
             }
