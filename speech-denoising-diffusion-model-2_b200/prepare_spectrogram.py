@@ -73,11 +73,13 @@ class Spectrogram:
         fbd = lo = hi = None
         if fb is not None:                       # band of non-zero weights per filter: the kernel skips the zeros
             fbd = self._on(x.device, "fb", fb)
-            nz = fb != 0
-            first = torch.where(nz.any(0), nz.float().argmax(0), torch.zeros(fb.shape[1], dtype=torch.long))
-            last = torch.where(nz.any(0), fb.shape[0] - nz.flip(0).float().argmax(0), torch.zeros(fb.shape[1], dtype=torch.long))
-            lo = self._on_int(x.device, "lo", first)
-            hi = self._on_int(x.device, "hi", last)
+            if (str(x.device), "lo") not in self._dev:      # computed once per device: this runs on the host, ahead of every launch otherwise
+                nz = fb != 0
+                first = torch.where(nz.any(0), nz.float().argmax(0), torch.zeros(fb.shape[1], dtype=torch.long))
+                last = torch.where(nz.any(0), fb.shape[0] - nz.flip(0).float().argmax(0), torch.zeros(fb.shape[1], dtype=torch.long))
+                self._on_int(x.device, "lo", first)
+                self._on_int(x.device, "hi", last)
+            lo, hi = self._dev[(str(x.device), "lo")], self._dev[(str(x.device), "hi")]
         with torch.cuda.device(x.device):
             st = torch.cuda.current_stream().cuda_stream
             _lib.check(_lib.lib().sddm_stft_features(C.c_void_p(x.data_ptr()), B, L, self.n_fft, self.hop_length, C.c_void_p(win.data_ptr()),
