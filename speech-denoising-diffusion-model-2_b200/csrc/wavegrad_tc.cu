@@ -20,10 +20,12 @@ constexpr int kTileM = 128, kTileN = 128;
 constexpr uint32_t kBoxBytes = 128 * 64 * 2;          // 16 KB
 constexpr int kStages = 5;
 constexpr uint32_t kStageBytes = 2 * kBoxBytes;
-constexpr uint32_t kOffTile = kStages * kStageBytes;          // 8 transposition tiles (one per epilogue warp), 4608 B each
-constexpr uint32_t kOffBars = kOffTile + 8 * 4608;
+constexpr int kGroups = 3;                                     // epilogue groups = TMEM accumulator stages
+constexpr uint32_t kOffTile = kStages * kStageBytes;          // one transposition tile per epilogue warp, 4608 B each
+constexpr uint32_t kOffBars = kOffTile + 4 * kGroups * 4608;
 constexpr uint32_t kSmem = kOffBars + 256 + 1024;
-constexpr int kThreads = 320;
+constexpr int kThreads = (4 * kGroups + 2) * 32;
+constexpr int kProdWarp = 4 * kGroups, kMmaWarp = 4 * kGroups + 1;
 
 struct alignas(64) WgMaps {
     CUtensorMap a, w;
@@ -31,8 +33,8 @@ struct alignas(64) WgMaps {
 
 __device__ __forceinline__ float lrelu02(float v) { return v > 0.f ? v : 0.2f * v; }
 
-// Persistent CTA (one per SM): warps 0-3 / 4-7 = epilogue groups 0 / 1 (alternate tiles, TMEM columns [128 g, 128 g + 128)),
-// warp 8 = TMA producer, warp 9 = MMA issuer.  The operand ring runs ahead across tile boundaries, so the loads and MMAs of the
+// Persistent CTA (one per SM): warps 4g .. 4g+3 = epilogue group g of kGroups (tiles round robin, TMEM columns [128 g, 128 g + 128)),
+// then one TMA producer warp and one MMA issuer warp.  The operand ring runs ahead across tile boundaries, so the loads and MMAs of the
 // next tiles overlap the (global-memory-latency-bound) epilogues of the previous two.
 __global__ void __launch_bounds__(kThreads, 1) wg_conv_tc_kernel(const __grid_constant__ WgMaps maps, WgTcConv p, int tiles_n, int tiles_m, int ntiles) {
     extern __shared__ unsigned char smem_raw[];
@@ -44,13 +46,13 @@ __global__ void __launch_bounds__(kThreads, 1) wg_conv_tc_kernel(const __grid_co
     auto full = [&](int s) { return bars + 8u * (uint32_t)s; };
     auto empty = [&](int s) { return bars + 8u * (uint32_t)(kStages + s); };
     auto accf = [&](int g) { return bars + 8u * (uint32_t)(2 * kStages + g); };
-    auto acce = [&](int g) { return bars + 8u * (uint32_t)(2 * kStages + 2 + g); };
+    auto acce = [&](int g) { return bars + 8u * (uint32_t)(2 * kStages + kGroups + g); };
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
-        for (int g = 0; g < 2; ++g) { mbar_init(accf(g), 1); mbar_init(acce(g), 128); }
+        for (int g = 0; g < kGroups; ++g) { mbar_init(accf(g), 1); mbar_init(acce(g), 128); }
         fence_barrier_init();
     }
-    if (warp == 9) tmem_alloc(smem_u32(tmem_slot), 256);
+    if (warp == kMmaWarp) tmem_alloc(smem_u32(tmem_slot), 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -63,7 +65,7 @@ __global__ void __launch_bounds__(kThreads, 1) wg_conv_tc_kernel(const __grid_co
         const int tn = tile % tiles_n, r = tile / tiles_n;
         n0 = tn * kTileN; s0 = (r % tiles_m) * kTileM; b = r / tiles_m;
     };
-    if (warp == 8) {
+    if (warp == kProdWarp) {
         pdl_wait();
         if (lane == 0) {
             int c = 0;
@@ -80,11 +82,11 @@ __global__ void __launch_bounds__(kThreads, 1) wg_conv_tc_kernel(const __grid_co
                 }
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == kMmaWarp) {
         const uint32_t idesc = make_idesc(kTileN);
         int c = 0;
         for (int i = 0; i < my_tiles; ++i) {
-            const int g = i & 1, ng = i >> 1;
+            const int g = i % kGroups, ng = i / kGroups;
             mbar_wait(acce(g), (ng & 1) ^ 1);
             tc_fence_after();
             for (int k = 0; k < nchunks; ++k, ++c) {
@@ -111,7 +113,7 @@ __global__ void __launch_bounds__(kThreads, 1) wg_conv_tc_kernel(const __grid_co
         // row-per-thread accesses cost 32 L1 wavefronts per instruction.
         const uint32_t tile = base + kOffTile + (uint32_t)warp * 4608u;
         const int rsub = lane >> 3, cl = 4 * (lane & 7);
-        for (int i = g, ng = 0; i < my_tiles; i += 2, ++ng) {
+        for (int i = g, ng = 0; i < my_tiles; i += kGroups, ++ng) {
         int n0, s0t, b;
         tile_of(i, n0, s0t, b);
         const int s0 = s0t + wq * 32 - warp * 32;   // so that s0 + warp * 32 is this warp's first row
@@ -194,7 +196,7 @@ __global__ void __launch_bounds__(kThreads, 1) wg_conv_tc_kernel(const __grid_co
     }
     __syncthreads();
     pdl_launch_dependents();
-    if (warp == 9) tmem_dealloc(tmem, 256);
+    if (warp == kMmaWarp) tmem_dealloc(tmem, 512);
 }
 
 }  // namespace
