@@ -1,12 +1,12 @@
 // cfg 4: WaveGrad denoiser (reference model/wavegrad.py:20-179) + SDDM_spectrogram.infer (model/model.py:206-257).
 //
-// First correct path: fp32 on CUDA cores.  Activations are time-major [B][L][C]; every Conv1d of the network (k = 1 / 3,
+// fp32 path (this file): CUDA cores.  Activations are time-major [B][L][C]; every Conv1d of the network (k = 1 / 3,
 // any dilation) is ONE launch of a tiled GEMM whose operand loader fuses everything the reference applies to the conv input:
 //   nearest-neighbour F.interpolate (x factor or / factor: an index map), the FiLM affine shift + scale * x, leaky_relu(0.2)
 //   and the zero padding (applied last, in the post-activation domain),
 // and whose epilogue fuses bias, the FiLM-branch leaky_relu + positional encoding, and the block's residual add.
-// 54 launches per eps_hat instead of the reference's ~200 eager kernels; the tcgen05 version of the wide layers
-// (512 -> 512 at K = 1536 is a proper tensor-pipe-bound GEMM) is the next step for this row.
+// 56 launches per eps_hat instead of the reference's ~200 eager kernels.  With precision = SDDM_PREC_BF16 the 52 conv launches run
+// wavegrad_tc.cu's tcgen05 kernel instead (forward_tc below: activations stored in the form their consumers read).
 #include <cmath>
 #include <cstdio>
 #include <cstring>
