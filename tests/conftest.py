@@ -112,3 +112,34 @@ def wavegrad_test_module():
 def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
     """max|a-b| / max|b| — the per-tensor error metric of BASELINE.md §3."""
     return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+
+
+# BASELINE-size parity inputs, shared by tests/golden/make_golden_fullsize.py (reference side) and the -m gpu tests
+CFG2_GOLDEN_ROWS = (0, 31, 63)
+
+
+def cfg2_inputs():
+    """SURVEY.md §8d cfg 2: 64 chunks clip(0.1 N(0,1)), seed 0; injected noises [100, 64, 1, L], seed 1234."""
+    cond = (0.1 * torch.randn(64, 1, L, generator=torch.Generator().manual_seed(0))).clamp(-1, 1)
+    noises = torch.randn(100, 64, 1, L, generator=torch.Generator().manual_seed(1234))
+    return cond, noises
+
+
+def cfg5_fullsize_inputs():
+    """cfg 5 size: 10 s utterances, spec [513, 626], 160 256 samples; per-row diffusion steps."""
+    g = torch.Generator().manual_seed(12)
+    B, frames = 2, 626
+    spec = torch.rand(B, 513, frames, generator=g) * 0.7
+    audio = torch.randn(B, 1, 256 * frames, generator=g)
+    step = torch.tensor([150.0, 20.0]).reshape(B, 1, 1)
+    return spec, audio, step
+
+
+def cfg4_fullsize_inputs():
+    """cfg 4 size: spec [128, 107], 32 100 samples; per-row noise levels."""
+    g = torch.Generator().manual_seed(13)
+    B, F = 3, 107
+    spec = torch.rand(B, 128, F, generator=g)
+    audio = torch.randn(B, 300 * F, generator=g)
+    lv = torch.tensor([0.95, 0.5, 0.1])
+    return spec, audio, lv

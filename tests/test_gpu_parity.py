@@ -11,7 +11,7 @@ import time
 import pytest
 import torch
 
-from conftest import L, ROOT, UNET_CFG, cfg1_condition, rel_err, seed0_state_dict
+from conftest import CFG2_GOLDEN_ROWS, L, ROOT, UNET_CFG, cfg1_condition, cfg2_inputs, rel_err, seed0_state_dict
 
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import sddm_oracle as O  # noqa: E402
@@ -155,7 +155,7 @@ def test_unet_nodes_vs_oracle(dev, prec):
     e = rel_err(out, ref)
     report(f"node[{prec}] eps_hat rel_err={e:.3e} (bar {EPS_BAR[prec]:.0e}), worst node {worst:.3e}")
     assert e <= EPS_BAR[prec]
-    assert worst <= (1e-3 if prec == "fp32" else 6e-2)
+    assert worst <= (1e-3 if prec == "fp32" else 3e-2)
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16", "bf16act"])
@@ -229,7 +229,7 @@ def test_sampling_cfg1_vs_reference_golden(dev, golden, prec):
     snr = float(O.sisnr(out.cpu(), g["out"]))
     report(f"sampling cfg1[{prec}]: eps err t=100 {e100:.3e}, t=50 {e50:.3e}, t=1 {e1:.3e}; final SI-SNR {snr:.1f} dB, "
            f"max err {rel_err(out.cpu(), g['out']):.3e}")
-    assert e100 <= EPS_BAR[prec]
+    assert e100 <= EPS_BAR[prec] and e50 <= EPS_BAR[prec] and e1 <= EPS_BAR[prec]
     assert snr >= (60.0 if prec == "fp32" else SNR_BAR)
     assert float(out.abs().max()) <= 1.0
 
@@ -277,22 +277,35 @@ def test_batch_invariance_determinism_and_host_api(dev):
     assert all(torch.equal(a, b) for a, b in zip(outs, outs2))
 
 
-def test_full_size_cfg2(dev):
-    """BASELINE cfg 2: 64 chunks, full 100-step schedule.  Size-independent checks: the bf16 (tcgen05) and fp32 modes
-    agree to >= 40 dB SI-SNR on every row with the same injected noise, rows 0-1 reproduce a 2-row run bit for bit,
-    output is clamped to [-1, 1]."""
+def test_full_size_cfg2(dev, golden):
+    """BASELINE cfg 2: 64 chunks, full 100-step schedule, every persistent CTA working through many tiles.
+    Pinned to the REFERENCE: rows 0 / 31 / 63 of the batch were run through the reference's SDDM.infer with the same injected
+    noise (tests/golden/make_golden_fullsize.py); their per-step eps_hat (t = 100 / 50 / 1) and final waveforms must match
+    within the north_star bars in every precision mode.  Size-independent checks on top: the bf16 (tcgen05) and fp32 modes agree
+    to >= 40 dB SI-SNR on every row, rows 0-1 reproduce a 2-row run bit for bit, output is clamped to [-1, 1]."""
     model, _ = make_model(dev)
     net = model.noise_estimate_model
-    cond = (0.1 * torch.randn(64, 1, L, generator=torch.Generator().manual_seed(0))).clamp(-1, 1).to(dev)
-    noises = torch.randn(100, 64, 1, L, generator=torch.Generator().manual_seed(1234)).to(dev)
+    cond, noises = cfg2_inputs()
+    cond, noises = cond.to(dev), noises.to(dev)
+    gold = golden("fullsize.npz")
+    rows = list(CFG2_GOLDEN_ROWS)
+    assert gold["cfg2.rows"].tolist() == rows
     outs = {}
     for prec in ("fp32", "bf16", "bf16act"):
         net.precision = prec_id(prec)
         torch.cuda.synchronize()
         t0 = time.time()
-        outs[prec] = model.infer(cond, noises=noises)
+        out, eps_tr, _ = model.infer(cond, noises=noises, return_trace=True)
         torch.cuda.synchronize()
-        report(f"cfg2[{prec}]: 64 chunks x 100 steps in {time.time() - t0:.3f} s")
+        outs[prec] = out
+        report(f"cfg2[{prec}]: 64 chunks x 100 steps in {time.time() - t0:.3f} s (with traces)")
+        errs = {t: rel_err(eps_tr[100 - t][rows].cpu(), gold[f"cfg2.eps_t{t}"]) for t in (100, 50, 1)}
+        snrs = [float(O.sisnr(out[r:r + 1].cpu(), gold["cfg2.out"][i:i + 1])) for i, r in enumerate(rows)]
+        report(f"cfg2[{prec}] rows {rows} vs REFERENCE golden: eps err t=100 {errs[100]:.3e}, t=50 {errs[50]:.3e}, t=1 {errs[1]:.3e}; "
+               f"final SI-SNR {min(snrs):.1f} dB (min over rows), max err {rel_err(out[rows].cpu(), gold['cfg2.out']):.3e}")
+        assert max(errs.values()) <= EPS_BAR[prec], (prec, errs)
+        assert min(snrs) >= (60.0 if prec == "fp32" else SNR_BAR), (prec, snrs)
+        del eps_tr
         two = model.infer(cond[:2], noises=noises[:, :2].contiguous())
         assert torch.equal(two, outs[prec][:2]), prec
         assert float(outs[prec].abs().max()) <= 1.0 and torch.isfinite(outs[prec]).all()

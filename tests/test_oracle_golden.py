@@ -120,3 +120,32 @@ def test_random_state_dict_layout(meta):
     sd = O.random_state_dict(dict(UNET_CFG), seed=3)
     ref = {k: v["shape"] for k, v in meta["weights_seed0"].items() if k.startswith("noise_estimate_model.")}
     assert {k: list(v.shape) for k, v in sd.items()} == ref
+
+
+def test_oracles_vs_reference_at_baseline_sizes(golden):
+    """The three oracles against reference outputs at BASELINE's full sizes (tests/golden/make_golden_fullsize.py):
+    cfg 2 rows 0/31/63 at t = 100 (x_T + one eps_hat), cfg 4 at F = 107, cfg 5 on one 10 s utterance."""
+    import diffwave_oracle as DO
+    import wavegrad_oracle as WO
+    from conftest import (CFG2_GOLDEN_ROWS, DIFFWAVE_CASES, cfg2_inputs, cfg4_fullsize_inputs, cfg5_fullsize_inputs,
+                          diffwave_test_module, wavegrad_test_module)
+    g = golden("fullsize.npz")
+    sd, _ = seed0_state_dict()
+    cond, noises = cfg2_inputs()
+    rows = list(CFG2_GOLDEN_ROWS)
+    sch = O.make_schedule("linear", 100, 1e-6, 1e-3)
+    with torch.no_grad():
+        x = O.get_x_T(sch, 100, cond[rows], noises[0][rows])
+        eps = O.unet_forward(sd, dict(UNET_CFG), cond[rows], x, sch["sqrt_alpha_bar"][100] * torch.ones(3, 1, 1))
+    assert rel_err(eps, g["cfg2.eps_t100"]) < 1e-5
+    del noises
+    spec, audio, lv = cfg4_fullsize_inputs()
+    wsd = {k: v.detach() for k, v in wavegrad_test_module().state_dict().items()}
+    with torch.no_grad():
+        e4 = WO.wavegrad_forward(wsd, spec[:2], audio[:2], lv[:2])
+    assert rel_err(e4.reshape(g["cfg4.eps_rows01"].shape), g["cfg4.eps_rows01"]) < 1e-5
+    spec, audio, step = cfg5_fullsize_inputs()
+    dsd = {k: v.detach() for k, v in diffwave_test_module(DIFFWAVE_CASES["full"]).state_dict().items()}
+    with torch.no_grad():
+        e5 = DO.diffwave_forward(dsd, spec[:1], audio[:1], step[:1])
+    assert rel_err(e5, g["cfg5.eps_row0"]) < 1e-5
