@@ -103,70 +103,147 @@ def synth_batch(rows, seed):
 
 
 # ------------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference algorithm (the reference itself is pure PyTorch and cannot travel
-# to the GPU box; the oracle runs the same ATen CPU kernels: mkldnn conv, native_group_norm, ...)
+# reference arms.  The reference is pure Python (no setup.py, nothing to pip-install): __graft_entry__.build() copies its import
+# closure (model/ base/ utils/ logger/) to baseline/_ref/ (git-ignored, travels to the GPU box); when that copy is present the
+# arms below run the reference's OWN modules (kind "reference"), else the oracle port (same ATen kernels, kind "port").
 # ------------------------------------------------------------------------------------------------------
-def cpu_reference_rate(budget_s, rows=2, threads=None):
-    """utterance-chunks/s of full 100-step sampling on the host cores, measured on a bounded sample:
-    `rows` chunks x as many reverse steps as fit in ~budget_s (each step costs the same), scaled to 100 steps."""
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+
+def reference_sddm(n_timestep, device):
+    """(kind, model): SDDM(GaussianDiffusion(linear 1e-6..1e-3, n_timestep), UNetModified2(config_unet.json), 'condition_in') built
+    from the reference's own classes (reference infer.py:36-42), default init under torch.manual_seed(0)."""
     import torch
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import sddm_oracle as O
-    from sddm_b200.model.network import UNetModified2
+    if os.path.isdir(os.path.join(REF_DIR, "model")):
+        if REF_DIR not in sys.path:
+            sys.path.insert(0, REF_DIR)
+        import model.diffusion as rd
+        import model.model as rm
+        import model.network as rn
+        torch.manual_seed(0)
+        net = rn.UNetModified2(**UNET)
+        diff = rd.GaussianDiffusion(schedule="linear", n_timestep=n_timestep, linear_start=1e-6, linear_end=1e-3, device=device)
+        return "reference", rm.SDDM(diff, net, p_transition="condition_in").to(device).eval()
+    return "port", None
+
+
+class _PortSDDM:
+    """oracle port of SDDM.infer for a k-step schedule (used only when baseline/_ref is absent)."""
+
+    def __init__(self, n_timestep):
+        import torch
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import sddm_oracle as O
+        from sddm_b200.model.network import UNetModified2
+        torch.manual_seed(0)
+        net = UNetModified2(**UNET)
+        self.O, self.T = O, n_timestep
+        self.sd = {"noise_estimate_model." + k: v.detach() for k, v in net.state_dict().items()}
+        self.sch = O.make_schedule("linear", n_timestep, 1e-6, 1e-3)
+
+    def infer(self, cond):
+        import torch
+        O = self.O
+        x = O.get_x_T(self.sch, self.T, cond, torch.randn_like(cond))
+        for t in range(self.T, 0, -1):
+            eps = O.unet_forward(self.sd, dict(UNET), cond, x, self.sch["sqrt_alpha_bar"][t] * torch.ones(cond.shape[0], 1, 1))
+            x = O.p_transition(self.sch, x, t, eps, torch.randn_like(cond), "condition_in")
+        return x
+
+
+def cpu_reference(rows, k, n_runs, warmup=0, threads=None):
+    """Times `n_runs` CPU runs of the reference's SDDM.infer on the real `rows`-chunk batch with a k-step schedule (every reverse
+    step costs the same: k of the 100 steps is a bounded sample of the workload).  Nothing is extrapolated over rows."""
+    import torch
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
-    torch.manual_seed(0)
-    net = UNetModified2(**UNET)
-    sd = {"noise_estimate_model." + k: v.detach() for k, v in net.state_dict().items()}
-    sch = O.make_schedule("linear", T_STEPS, 1e-6, 1e-3)
-    cond = synth_batch(rows, 1)
-    g = torch.Generator().manual_seed(2)
-    x = O.get_x_T(sch, T_STEPS, cond, torch.randn(cond.shape, generator=g))
-    cfg = dict(UNET)
-
-    def one_step(x, t):
-        eps = O.unet_forward(sd, cfg, cond, x, sch["sqrt_alpha_bar"][t] * torch.ones(rows, 1, 1))
-        return O.p_transition(sch, x, t, eps, torch.randn(cond.shape, generator=g), "condition_in")
-
+    kind, model = reference_sddm(k, "cpu")
+    if model is None:
+        model = _PortSDDM(k)
+    cond = synth_batch(rows, 1000)
+    times = []
     with torch.no_grad():
-        x = one_step(x, T_STEPS)                      # warm-up (allocator, mkldnn primitive cache)
-        t0 = time.perf_counter()
-        x = one_step(x, T_STEPS - 1)
-        per = time.perf_counter() - t0
-        n = max(2, min(T_STEPS - 2, int(budget_s / max(per, 1e-3))))
-        t0 = time.perf_counter()
-        for k in range(n):
-            x = one_step(x, T_STEPS - 2 - k)
-        dt = time.perf_counter() - t0
-    per_step = dt / n
-    full = per_step * T_STEPS                       # seconds for `rows` chunks, all 100 steps
-    return dict(value=rows / full, seconds_full=full, steps_timed=n, rows=rows, threads=threads)
+        for i in range(warmup + n_runs):
+            t0 = time.perf_counter()
+            model.infer(cond)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    return dict(kind=kind, times=times, rows=rows, k=k, threads=threads)
+
+
+def cpu_probe_step_seconds(rows):
+    """seconds of one reverse step on `rows` chunks (one 1-step run after a warm-up run)."""
+    r = cpu_reference(rows, 1, 1, warmup=1)
+    return r["times"][0], r["kind"]
 
 
 def run_reference(args):
+    """bench.py --impl reference: the reference's own CPU implementation on all host cores, on the SAME 64-chunk batch; one bench step
+    = SDDM.infer with k reverse steps, k sized so that (steps + warmup) runs end within ~150 s; value = rows / (t * 100 / k)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    vals = []
-    for _ in range(max(0, args.warmup)):
-        cpu_reference_rate(2.0)
-    for _ in range(max(1, args.steps)):
-        vals.append(cpu_reference_rate(max(2.0, 90.0 / max(1, args.steps))))
-    v = statistics.median(r["value"] for r in vals)
-    r = vals[-1]
-    sample = "%d chunks x %d of 100 reverse steps per bench step, scaled to 100 steps" % (r["rows"], r["steps_timed"])
-    workload = WORKLOAD
-    if getattr(args, "workload", "cfg2") == "cfg3":   # utterances of the 824-file set average 2455 / 824 chunks
-        v = v * 824.0 / 2455.0
-        sample += ", then to 2455 chunks / 824 utterances"
-        workload = "cfg3: UNetModified2 full 100-step enhancement of 824 test-set-shaped utterances (2455 chunks of 16448 samples)"
+    rows = args.batch
+    per, kind = cpu_probe_step_seconds(rows)
+    n = max(1, args.steps) + max(0, args.warmup)
+    k = max(1, min(T_STEPS, int(args.ref_budget / (n * max(per, 1e-3)))))
+    r = cpu_reference(rows, k, max(1, args.steps), warmup=max(0, args.warmup))
+    ms = 1e3 * statistics.mean(r["times"])
+    v = rows / (ms / 1e3 * T_STEPS / k)
+    sample = "%d chunks (the real batch) x %d of 100 reverse steps per bench step through SDDM.infer (k-step schedule); utt/s = rows / (t x 100 / %d)" % (rows, k, k)
     line = {"impl": "reference", "metric": "utterances_per_sec", "value": v, "unit": "utt/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * 64 / v, "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": workload, "note": "reference algorithm (oracle port, torch CPU ATen kernels) on host cores"},
+            "config": {"workload": WORKLOAD, "rows": rows, "reverse_steps_run": k, "reverse_steps_full": T_STEPS,
+                       "note": ("the reference's own modules (baseline/_ref copy of /root/reference)" if kind == "reference" else
+                                "oracle port of the reference (torch CPU ATen kernels)") + " on the host cores; ms_per_step is the measured time of one bounded bench step"},
             "rtf": 1.0 / (v * L / SR),
-            "cpu_baseline": {"value": v, "unit": "utt/s", "cores": r["threads"], "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": v, "unit": "utt/s", "cores": r["threads"], "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def gpu_eager_reference(rows, runs=3, warmup=1, device="cuda:0"):
+    """The reference's own PyTorch path on THIS GPU ("the kernel to beat"): reference modules .to(cuda), cudnn.benchmark = True
+    (reference infer.py:17), default TF32 convolutions, full 100-step SDDM.infer on the same batch; CUDA events, 1 warm-up + 3 runs."""
+    import torch
+    kind, model = reference_sddm(T_STEPS, device)
+    if model is None:
+        return None
+    torch.backends.cudnn.benchmark = True
+    cond = synth_batch(rows, 1000).to(device)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + runs):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            model.infer(cond)
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= warmup:
+                times.append(e0.elapsed_time(e1))
+    best, med = min(times), statistics.median(times)
+    del model
+    torch.cuda.empty_cache()
+    return {"value": rows / (med / 1e3), "unit": "utt/s", "best": rows / (best / 1e3), "ms_median": med, "ms_best": best, "runs": runs, "warmup": warmup,
+            "rows": rows, "kind": "reference modules, PyTorch eager + cuDNN (cudnn.benchmark=True, conv TF32 = %s), fp32 tensors"
+                                  % torch.backends.cudnn.allow_tf32, "torch": torch.__version__, "cudnn": torch.backends.cudnn.version()}
+
+
+def run_reference_gpu(args):
+    """bench.py --impl reference-gpu: the same JSON contract, measured on the reference's CUDA-eager path (one GPU)."""
+    import torch
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    g = gpu_eager_reference(args.batch, runs=max(1, args.steps), warmup=max(1, args.warmup))
+    if g is None:
+        print(json.dumps({"impl": "reference-gpu", "unavailable": "baseline/_ref (copy of the reference modules) is absent"}))
+        return
+    line = {"impl": "reference-gpu", "metric": "utterances_per_sec", "value": g["value"], "unit": "utt/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": g["ms_median"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32",
+            "data": "synthetic", "config": {"workload": WORKLOAD, "note": g["kind"]}, "rtf": 1.0 / (g["value"] * L / SR), "gpu_eager_baseline": g,
+            "e2e": {"value": g["value"], "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
 
 
@@ -614,7 +691,6 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         init_distributed(local)
     from sddm_b200 import PREC_BF16, PREC_BF16_ACT, PREC_FP32, _lib
-    from sddm_b200.infer import enhance_batch
     from sddm_b200.model.diffusion import GaussianDiffusion
     from sddm_b200.model.model import SDDM
     from sddm_b200.model.network import UNetModified2
@@ -653,10 +729,9 @@ def run_ours(args):
         model.infer(cond, seed=s, row0=rank * B)
 
     def step_e2e(s):
-        x = cond_host.to(dev, non_blocking=True)                        # H2D from pinned memory, inside the timed region
-        y = enhance_batch(model, x, seed=s, row0=rank * B)
-        out_host.copy_(y, non_blocking=True)                            # D2H of the enhanced batch
-        torch.cuda.current_stream().synchronize()
+        # the reference-facing C-ABI call with HOST buffers (sddm_enhance_host): H2D from pinned memory, the full loop and the
+        # D2H of the enhanced batch all happen inside the library, inside the timed region; it returns after its stream has drained
+        plan.enhance_host(cond_host, "condition_in", seed=s, row0=rank * B, max_rows=B, out=out_host)
 
     for s in range(max(3, args.warmup)):
         step_resident(s)
@@ -728,11 +803,18 @@ def run_ours(args):
                             "share_of_step": top["ms"] / tot, "arith_intensity_flop_per_byte": ai,
                             "algorithmic_bytes_per_launch": top["bytes_per_row"] * B,
                             "algorithmic_flops_per_launch": top["flops_per_row"] * B}
+    if world == 1 and not args.no_gpu_baseline:
+        del model, plan
+        torch.cuda.empty_cache()
+        line["gpu_eager_baseline"] = gpu_eager_reference(B, device="cuda:%d" % local)
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_rate(args.cpu_budget)
-        line["cpu_baseline"] = {"value": r["value"], "unit": "utt/s", "cores": r["threads"], "kind": "port",
-                                "sample": "%d chunks x %d of 100 reverse steps (%.1f s of CPU work), scaled to 100 steps"
-                                          % (r["rows"], r["steps_timed"], r["seconds_full"] * r["steps_timed"] / T_STEPS)}
+        per, _ = cpu_probe_step_seconds(B)
+        k = max(1, min(T_STEPS, int(args.cpu_budget / max(per, 1e-3))))
+        r = cpu_reference(B, k, 1)
+        v = B / (r["times"][0] * T_STEPS / k)
+        line["cpu_baseline"] = {"value": v, "unit": "utt/s", "cores": r["threads"], "kind": r["kind"],
+                                "sample": "%d chunks (the real batch) x %d of 100 reverse steps through SDDM.infer with a %d-step schedule "
+                                          "(%.1f s of CPU work); utt/s = rows / (t x 100 / %d)" % (B, k, k, r["times"][0], k)}
     print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -744,23 +826,27 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--precision", default=os.environ.get("SDDM_B200_PRECISION", "bf16act"), choices=["bf16", "fp32", "bf16act"])
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the reference's CUDA-eager run (gpu_eager_baseline)")
+    ap.add_argument("--ref-budget", type=float, default=150.0, help="--impl reference: seconds of CPU work for all (steps + warmup) bench steps")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"],
                     help="cfg2 = the headline (UNetModified2, weak scaling); cfg3 = 824-utterance set (strong scaling); cfg4 = WaveGrad; cfg5 = DiffWave")
     ap.add_argument("--batch-cfg5", type=int, default=None, help="utterances per GPU for --workload cfg4 (default 32) / cfg5 (default 8)")
     args = ap.parse_args()
     if args.batch_cfg5 is None:
         args.batch_cfg5 = 32 if args.workload == "cfg4" else 8
-    if args.workload == "cfg3" and args.impl != "reference":
+    if args.workload == "cfg3" and args.impl == "ours":
         run_cfg3(args)
     elif args.workload == "cfg4":
         (run_reference_wavegrad if args.impl == "reference" else run_wavegrad)(args)
     elif args.workload == "cfg5":
         (run_reference_diffwave if args.impl == "reference" else run_diffwave)(args)
+    elif args.impl == "reference-gpu":
+        run_reference_gpu(args)
     elif args.impl == "reference":
         run_reference(args)
     else:
