@@ -14,6 +14,8 @@
 
 namespace sddm {
 
+constexpr int kMaxRows = 65536;   // batch rows per call (size of the plan-owned GroupNorm arrival counters)
+
 static thread_local char g_err[1024] = "";
 static std::atomic<uint64_t> g_launches{0};
 
@@ -51,6 +53,7 @@ struct Op {
     size_t gamma_off = 0, beta_off = 0;   // offsets into the packed fp32 arena
     size_t ss_off = 0;                    // per-sample float offset of [scale(Ctot), shift(Ctot)]
     int Ctot = 0;
+    bool gn_fused = false;                // finalised by the preceding producer kernel (gn_fuse.cuh): no launch of its own
     // CONV / FINAL
     int src[2] = {-1, -1};
     int nsrc = 0;
@@ -63,6 +66,9 @@ struct Op {
     int res_kind = 0;   // 0 none, 1 identity, 2 1x1 conv
     size_t resw_off = 0, reswtc_off = 0, resb_off = 0;
     bool use_tc = false;
+    bool use_row = false;                 // conv_row.cu (128-wide level, bf16 activations); STEM / CONV / FINAL
+    size_t wrow_off = 0;                  // bf16 arena offset of the row-kernel weight image (main chunks, then res_conv chunks)
+    uint32_t wrow_bytes = 0;
     // introspection (bench roofline): algorithmic work per batch row
     std::string label;
     double flops = 0.0, bytes = 0.0;
@@ -94,6 +100,7 @@ struct sddm_plan {
     float* d_f32 = nullptr;
     __nv_bfloat16* d_bf16 = nullptr;
     float* d_temb_table = nullptr;   // [T+1][E]
+    unsigned int* d_gn_counters = nullptr;   // [kMaxRows] arrival counters of the fused GroupNorm finalisation (all zero between kernels)
     size_t off_freq = 0, off_w1 = 0, off_b1 = 0, off_w2 = 0, off_b2 = 0, off_wn = 0, off_bn = 0;
     size_t off_stem_w = 0, off_stem_b = 0, off_final_w = 0;
     float final_bias = 0.f;
@@ -241,6 +248,33 @@ static std::vector<__nv_bfloat16> pack_conv_tc(const std::vector<float>& w, int 
     return o;
 }
 
+// row kernel (conv_row.cu): [Cout][Cin][3][3] -> bf16 [Cin/16][kx][2][n][8] with n = ky * 32 + cout (Cout = 32, 96 rows) or
+// n = ky (Cout = 1, padded to 16 rows): per (16-channel chunk, kx) a K-major no-swizzle UMMA B operand (LBO = rows * 16 B, SBO = 128 B)
+static std::vector<__nv_bfloat16> pack_conv_row(const std::vector<float>& w, int cout, int cin) {
+    const int rows = cout == 1 ? 16 : 96;
+    std::vector<__nv_bfloat16> o((size_t)(cin / 16) * 3 * 2 * rows * 8, __float2bfloat16(0.f));
+    for (int ci = 0; ci < cin; ++ci)
+        for (int ky = 0; ky < 3; ++ky)
+            for (int kx = 0; kx < 3; ++kx)
+                for (int co = 0; co < cout; ++co) {
+                    const int c16 = ci / 16, half = (ci % 16) / 8, e = ci % 8, n = cout == 1 ? ky : ky * 32 + co;
+                    o[((((size_t)c16 * 3 + kx) * 2 + half) * rows + n) * 8 + e] = __float2bfloat16(w[((size_t)co * cin + ci) * 9 + ky * 3 + kx]);
+                }
+    return o;
+}
+
+// stem on the row kernel: one K16 chunk whose slots are [cond hi, x_t hi, cond lo, x_t lo, 0...]: the bf16 weight of input
+// channel c multiplies both halves of the split waveform sample
+static std::vector<__nv_bfloat16> pack_stem_row(const std::vector<float>& w, int cout) {
+    std::vector<__nv_bfloat16> o((size_t)3 * 2 * 96 * 8, __float2bfloat16(0.f));
+    for (int ky = 0; ky < 3; ++ky)
+        for (int kx = 0; kx < 3; ++kx)
+            for (int co = 0; co < cout; ++co)
+                for (int e = 0; e < 4; ++e)
+                    o[(((size_t)kx * 2 + 0) * 96 + ky * 32 + co) * 8 + e] = __float2bfloat16(w[((size_t)co * 2 + (e & 1)) * 9 + ky * 3 + kx]);
+    return o;
+}
+
 static int new_tensor(sddm_plan* p, const std::string& name, int C, int H, int W) {
     TensorInfo t{name, C, H, W, 0, 0, 0};
     p->tensors.push_back(t);
@@ -288,6 +322,7 @@ static ConvP shape_probe(const sddm_plan* p, const Op& op) {
     c.res_Cin = 0;   // channels of the raw block input read by the 1x1 res_conv
     if (op.res_kind == 2)
         for (int i = 0; i < op.gn_nsrc; ++i) c.res_Cin += p->tensors[op.gn_src[i]].C;
+    c.act16 = p->cfg.precision == SDDM_PREC_BF16_ACT;
     return c;
 }
 
@@ -297,6 +332,8 @@ static int build_program(sddm_plan* p, Arena& a) {
     const bool act16 = c.precision == SDDM_PREC_BF16_ACT;
     const double esz = act16 ? 2.0 : 4.0;
     bool act16_ok = true;
+    const char* no_row = getenv("SDDM_NO_ROW_KERNEL");   // A/B switch: keep every layer on conv_tc.cu / the CUDA-core stem and final conv
+    const bool use_row_kernels = act16 && !(no_row && no_row[0] == '1');
     size_t ss_cursor = 0;   // relative; rebased after tensors are laid out
     int temb_cursor = 0;
     std::vector<int> feats;
@@ -309,8 +346,20 @@ static int build_program(sddm_plan* p, Arena& a) {
                           (probe.res_identity ? (double)probe.Cout * probe.Hout * probe.Wout : 0.0) +
                           (double)probe.res_Cin * probe.Hin * probe.Win);   // the 1x1 res_conv re-reads the raw block input
         op.use_tc = want_tc && conv_tc_supported(probe);
+        op.use_row = want_tc && use_row_kernels && conv_row_supported(probe);
         if (act16 && !op.use_tc) act16_ok = false;
-        p->tensors[op.out].nparts = op.use_tc ? conv_tc_nparts(probe.Hout, probe.Wout) : conv_fp32_nparts(probe.Hout, probe.Wout);
+        p->tensors[op.out].nparts = op.use_row ? conv_row_nparts(probe.Hout)
+                                               : (op.use_tc ? conv_tc_nparts(probe.Hout, probe.Wout) : conv_fp32_nparts(probe.Hout, probe.Wout));
+    };
+    // row-kernel weight image of a convolution op: main chunks, then the 1x1 res_conv chunks ([Cin/16][1][2][32][8] = pack_conv_tc with k = 1)
+    auto fill_row_w = [&](Op& op, const std::string& wkey, int cout, int cin, const std::string& reskey, int res_cin) {
+        std::vector<__nv_bfloat16> img = pack_conv_row(W_(p, wkey + ".weight"), cout, cin);
+        if (res_cin) {
+            const std::vector<__nv_bfloat16> r = pack_conv_tc(W_(p, reskey + ".weight"), cout, res_cin, 1);
+            img.insert(img.end(), r.begin(), r.end());
+        }
+        op.wrow_off = a.put_h(img);
+        op.wrow_bytes = (uint32_t)(img.size() * sizeof(__nv_bfloat16));
     };
     auto emit_res = [&](const NodeDesc& nd, std::vector<int> srcs) {
         const int gn1 = emit_gn(p, a, srcs, nd.key + ".block1.block.0", &ss_cursor);
@@ -326,6 +375,7 @@ static int build_program(sddm_plan* p, Arena& a) {
         c1.temb_off = temb_cursor;
         temb_cursor += nd.cout;
         set_tc(c1, nd.key + ".block1");
+        if (c1.use_row) fill_row_w(c1, nd.key + ".block1.block.3", nd.cout, nd.cin, "", 0);
         p->ops.push_back(c1);
         const int gn2 = emit_gn(p, a, {h}, nd.key + ".block2.block.0", &ss_cursor);
         const int out = new_tensor(p, nd.key, nd.cout, H, W);
@@ -351,6 +401,7 @@ static int build_program(sddm_plan* p, Arena& a) {
             c2.gn_src[0] = srcs[0];
         }
         set_tc(c2, nd.key + ".block2");
+        if (c2.use_row) fill_row_w(c2, nd.key + ".block2.block.3", nd.cout, nd.cout, nd.key + ".res_conv", c2.res_kind == 2 ? nd.cin : 0);
         p->ops.push_back(c2);
         return out;
     };
@@ -364,6 +415,7 @@ static int build_program(sddm_plan* p, Arena& a) {
         cv.out = out;
         fill_conv_op(p, a, cv, nd.key + ".conv", nd.cout, nd.cin, want_tc);
         set_tc(cv, nd.key + ".conv");
+        if (cv.use_row) fill_row_w(cv, nd.key + ".conv", nd.cout, nd.cin, "", 0);
         p->ops.push_back(cv);
         return out;
     };
@@ -407,9 +459,15 @@ static int build_program(sddm_plan* p, Arena& a) {
                 p->off_stem_w = a.put(pk);
                 p->off_stem_b = a.put(W_(p, "downs.0.bias"));
                 cur = new_tensor(p, nd.key, nd.cout, H, W);
-                p->tensors[cur].nparts = stem_nparts(H, W);
                 Op op;
                 op.kind = Op::STEM;
+                op.use_row = use_row_kernels && W == 128 && H % 16 == 0 && nd.cout == 32;
+                p->tensors[cur].nparts = op.use_row ? conv_row_nparts(H) : stem_nparts(H, W);
+                if (op.use_row) {
+                    const std::vector<__nv_bfloat16> img = pack_stem_row(w, nd.cout);
+                    op.wrow_off = a.put_h(img);
+                    op.wrow_bytes = (uint32_t)(img.size() * sizeof(__nv_bfloat16));
+                }
                 op.out = cur;
                 op.label = "stem:downs.0";
                 op.flops = 2.0 * 18.0 * nd.cout * H * W;
@@ -457,6 +515,12 @@ static int build_program(sddm_plan* p, Arena& a) {
         op.in_gn = true;
         op.in_ss_off = p->ops[gnf].ss_off;
         op.label = "final_conv";
+        op.use_row = use_row_kernels && p->W == 128 && p->H % 16 == 0 && C == 32;
+        if (op.use_row) {
+            const std::vector<__nv_bfloat16> img = pack_conv_row(w, 1, C);
+            op.wrow_off = a.put_h(img);
+            op.wrow_bytes = (uint32_t)(img.size() * sizeof(__nv_bfloat16));
+        }
         op.flops = 2.0 * 9.0 * C * p->H * p->W;
         op.bytes = esz * (double)C * p->H * p->W + 4.0 * (double)p->H * p->W;
         p->ops.push_back(op);
@@ -481,7 +545,16 @@ static int build_program(sddm_plan* p, Arena& a) {
         if (op.in_gn) op.in_ss_off += ss_base;
     }
     p->floats_per_sample = off;
-    p->launches_per_eps = (int)p->ops.size() + 1;   // + the overlap-add / posterior kernel
+    // a GroupNorm whose newest source comes out of a tcgen05 convolution or the stem is finalised inside that producer
+    int fused = 0;
+    for (size_t i = 1; i < p->ops.size(); ++i) {
+        Op& g = p->ops[i];
+        const Op& prev = p->ops[i - 1];
+        if (g.kind != Op::GN || !want_tc) continue;
+        const bool producer_ok = prev.kind == Op::STEM || (prev.kind == Op::CONV && prev.use_tc);
+        if (producer_ok && prev.out == g.gn_src[0]) { g.gn_fused = true; ++fused; }
+    }
+    p->launches_per_eps = (int)p->ops.size() - fused + 1;   // + the overlap-add / posterior kernel
     return SDDM_OK;
 }
 
@@ -530,12 +603,33 @@ static int prof_mark(sddm_plan* p, int op, bool begin, cudaStream_t st) {
     return SDDM_OK;
 }
 
+// descriptor of a GroupNorm op for the producer-side finalisation (the producer of gn_src[0] runs it)
+static void fill_gn_fuse(const sddm_plan* p, const Op& op, int B, void* ws, int expect, GnFuse* g) {
+    g->nsrc = op.gn_nsrc;
+    for (int i = 0; i < op.gn_nsrc; ++i) {
+        const TensorInfo& t = p->tensors[op.gn_src[i]];
+        g->parts[i] = sect(p, ws, t.parts_off, B);
+        g->C[i] = t.C;
+        g->nparts[i] = t.nparts;
+    }
+    const TensorInfo& t0 = p->tensors[op.gn_src[0]];
+    g->gamma = p->d_f32 + op.gamma_off;
+    g->beta = p->d_f32 + op.beta_off;
+    g->scale = sect(p, ws, op.ss_off, B);
+    g->shift = g->scale + (size_t)op.Ctot * B;
+    g->Ctot = op.Ctot; g->groups = p->cfg.norm_groups; g->HW = t0.H * t0.W; g->eps = 1e-5f;
+    g->counter = p->d_gn_counters;
+    g->expect = expect;
+}
+
 // one UNetModified2 forward up to the final conv frames (ws.frames); temb: device pointer, row stride
 static int run_unet(sddm_plan* p, const float* cond, const float* x_t, const float* temb, int temb_stride, int B, void* ws,
                     cudaStream_t st) {
     const sddm_config& c = p->cfg;
     for (size_t oi = 0; oi < p->ops.size(); ++oi) {
         const Op& op = p->ops[oi];
+        if (op.kind == Op::GN && op.gn_fused) continue;
+        const Op* fuse = (oi + 1 < p->ops.size() && p->ops[oi + 1].kind == Op::GN && p->ops[oi + 1].gn_fused) ? &p->ops[oi + 1] : nullptr;
         int rc = prof_mark(p, (int)oi, true, st);
         if (rc != SDDM_OK) return rc;
         switch (op.kind) {
@@ -544,7 +638,8 @@ static int run_unet(sddm_plan* p, const float* cond, const float* x_t, const flo
                 StemP sp{cond, x_t, p->d_f32 + p->off_stem_w, p->d_f32 + p->off_stem_b, sect(p, ws, o.data_off, B),
                          sect(p, ws, o.parts_off, B), B, c.num_samples, o.H, o.W, c.segment_stride, o.C, o.nparts};
                 sp.act16 = c.precision == SDDM_PREC_BF16_ACT;
-                rc = launch_stem(sp, st);
+                if (fuse) { sp.gn_on = 1; fill_gn_fuse(p, *fuse, B, ws, op.use_row ? conv_row_arrivals(o.H) : o.nparts, &sp.gn); }
+                rc = op.use_row ? launch_stem_row(sp, p->d_bf16 + op.wrow_off, op.wrow_bytes, st) : launch_stem(sp, st);
                 break;
             }
             case Op::GN: {
@@ -608,11 +703,23 @@ static int run_unet(sddm_plan* p, const float* cond, const float* x_t, const flo
                 cp.nparts = o.nparts;
                 cp.B = B;
                 cp.act16 = c.precision == SDDM_PREC_BF16_ACT;
-                rc = op.use_tc ? launch_conv_tc(cp, st) : launch_conv_fp32(cp, st);
+                if (fuse && op.use_tc) { cp.gn_on = 1; fill_gn_fuse(p, *fuse, B, ws, op.use_row ? conv_row_arrivals(o.H) : conv_tc_tiles(o.H, o.W), &cp.gn); }
+                if (op.use_row) rc = launch_conv_row(cp, p->d_bf16 + op.wrow_off, op.wrow_bytes, nullptr, 0.f, st);
+                else rc = op.use_tc ? launch_conv_tc(cp, st) : launch_conv_fp32(cp, st);
                 break;
             }
             case Op::FINAL: {
                 const TensorInfo& t = p->tensors[op.src[0]];
+                if (op.use_row) {
+                    ConvP cp{};
+                    cp.nsrc = 1; cp.Cin = t.C; cp.Cout = 1;
+                    cp.src[0].x = sect(p, ws, t.data_off, B); cp.src[0].C = t.C;
+                    cp.src[0].scale = sect(p, ws, op.in_ss_off, B);
+                    cp.src[0].shift = cp.src[0].scale + (size_t)t.C * B;
+                    cp.Hin = cp.Hout = t.H; cp.Win = cp.Wout = t.W; cp.mode = CONV_S1; cp.B = B; cp.act16 = 1;
+                    rc = launch_conv_row(cp, p->d_bf16 + op.wrow_off, op.wrow_bytes, sect(p, ws, p->off_frames, B), p->final_bias, st);
+                    break;
+                }
                 FinalP f{};
                 f.x = sect(p, ws, t.data_off, B);
                 f.scale = sect(p, ws, op.in_ss_off, B);
@@ -712,6 +819,7 @@ void sddm_plan_destroy(sddm_plan* p) {
     cudaFree(p->d_f32);
     cudaFree(p->d_bf16);
     cudaFree(p->d_temb_table);
+    cudaFree(p->d_gn_counters);
     cudaFree(p->d_cond);
     cudaFree(p->d_out);
     cudaFree(p->d_ws);
@@ -793,6 +901,8 @@ int sddm_plan_finalize(sddm_plan* p) {
              p->d_f32 + p->off_wn, p->d_f32 + p->off_bn, p->d_temb_table, T1, p->cfg.inner_channel, p->E};
     rc = launch_temb(tp, nullptr);
     if (rc != SDDM_OK) { cudaFree(d_nl); return rc; }
+    SDDM_CUDA_TRY(cudaMalloc(&p->d_gn_counters, kMaxRows * sizeof(unsigned int)));
+    SDDM_CUDA_TRY(cudaMemset(p->d_gn_counters, 0, kMaxRows * sizeof(unsigned int)));
     SDDM_CUDA_TRY(cudaDeviceSynchronize());
     cudaFree(d_nl);
     p->host_w.clear();
@@ -808,7 +918,7 @@ size_t sddm_workspace_bytes(const sddm_plan* p, int B) {
 int sddm_plan_launches_per_eps(const sddm_plan* p) { return (p && p->finalized) ? p->launches_per_eps : 0; }
 
 static int check_ws(const sddm_plan* p, int B, const void* ws, size_t ws_bytes) {
-    if (B <= 0) { set_error("batch must be positive"); return SDDM_E_INVALID; }
+    if (B <= 0 || B > kMaxRows) { set_error("batch must be in [1, %d]", kMaxRows); return SDDM_E_INVALID; }
     if (!ws || ws_bytes < sddm_workspace_bytes(p, B)) { set_error("workspace too small: %zu < %zu", ws_bytes, sddm_workspace_bytes(p, B)); return SDDM_E_WORKSPACE; }
     if ((uintptr_t)ws % 256) { set_error("workspace must be 256-byte aligned"); return SDDM_E_INVALID; }
     return SDDM_OK;

@@ -47,6 +47,22 @@ struct ConvSrc {
     int C;
 };
 
+// GroupNorm of the CONSUMER, finalised by the producer kernel's last-arriving CTA per sample (gn_fuse.cuh)
+struct GnFuse {
+    const float* parts[2];   // partial statistics of every source of the consumer's GroupNorm (this kernel's output first)
+    int C[2];
+    int nparts[2];
+    int nsrc;
+    const float* gamma;      // [Ctot]
+    const float* beta;
+    float* scale;            // [B][Ctot]
+    float* shift;
+    int Ctot, groups, HW;
+    float eps;
+    unsigned int* counter;   // [B], zero outside the kernel
+    int expect;              // arrivals per sample = tiles per sample of the producer
+};
+
 enum ConvMode { CONV_S1 = 0, CONV_S2 = 1, CONV_UP = 2 };  // 3x3 pad 1: stride 1 | stride 2 | nearest x2 then stride 1
 
 struct ConvP {
@@ -75,6 +91,8 @@ struct ConvP {
     int nparts;
     int B;
     int act16;     // activations (every src / res_src / out tensor) are bf16 in HBM instead of fp32 (tcgen05 path only)
+    int gn_on;     // tcgen05 path: finalise the consumer's GroupNorm in this kernel (gn below), no gn_finalize launch
+    GnFuse gn;
 };
 
 int launch_conv_fp32(const ConvP& p, cudaStream_t st);
@@ -82,6 +100,12 @@ int launch_conv_tc(const ConvP& p, cudaStream_t st);   // tcgen05 path; requires
 bool conv_tc_supported(const ConvP& p);
 int conv_fp32_nparts(int Hout, int Wout);
 int conv_tc_nparts(int Hout, int Wout);
+int conv_tc_tiles(int Hout, int Wout);
+// row-streaming tcgen05 kernel of the 128-wide level (conv_row.cu): bf16 activations, Cout = 32 (or 1: the final Block -> frames)
+bool conv_row_supported(const ConvP& p);
+int conv_row_nparts(int H);      // partial-statistics slots per sample: (H / 16) blocks x 2 groups x 4 warps
+int conv_row_arrivals(int H);    // arrivals per sample of the fused GroupNorm finalisation
+int launch_conv_row(const ConvP& p, const __nv_bfloat16* w_row, uint32_t w_bytes, float* frames, float final_bias, cudaStream_t st);   // tiles per sample (= arrivals per sample of the fused GroupNorm finalisation)
 
 // ---------------------------------------------------------------------------------------------------
 // programmatic dependent launch (PDL): a kernel launched with launch_pdl() may start while its predecessor in the stream

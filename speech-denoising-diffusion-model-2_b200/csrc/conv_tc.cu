@@ -32,6 +32,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "gn_fuse.cuh"
 #include "../../include/sddm_b200.h"
 
 namespace sddm {
@@ -244,7 +245,8 @@ struct SmemHdr {
     uint64_t tmem_full[2], tmem_empty[2];
     uint64_t res_full[kEpiGroups][4];
     uint32_t tmem_base;
-    uint32_t pad[15];
+    uint32_t gn_last[kEpiGroups];
+    uint32_t pad[13];
     float addv[kEpiGroups][256];
 };
 constexpr uint32_t kHdrBytes = 3072;
@@ -469,6 +471,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
                     }
                     float2* dst = reinterpret_cast<float2*>(p.parts) + ((int64_t)t.n * p.nparts + t.trem * 4 + w4) * p.Cout + cb * 32 + lane;
                     *dst = make_float2(s1, s2);
+                }
+            }
+            if (p.gn_on) {   // publish this tile's partials; the group that completes sample n finalises the consumer's GroupNorm
+                __threadfence();
+                group_bar(bar_id);
+                if (leader) hdr->gn_last[e] = atomicAdd(p.gn.counter + t.n, 1u) == (unsigned)(p.gn.expect - 1) ? 1u : 0u;
+                group_bar(bar_id);
+                if (hdr->gn_last[e]) {
+                    __threadfence();
+                    gn_fused_finalize(p.gn, t.n, m, kEpiGroupThreads);
+                    if (leader) p.gn.counter[t.n] = 0u;
                 }
             }
         }
@@ -1080,6 +1093,7 @@ bool conv_tc_supported(const ConvP& p) {
 }
 
 int conv_tc_nparts(int Hout, int Wout) { return ((Hout + TH - 1) / TH) * ((Wout + TW - 1) / TW) * 4; }
+int conv_tc_tiles(int Hout, int Wout) { return ((Hout + TH - 1) / TH) * ((Wout + TW - 1) / TW); }
 
 int launch_conv_tc(const ConvP& p, cudaStream_t st) {
     if (!conv_tc_supported(p) || !p.w_tc) { set_error("conv tc: unsupported shape Cin=%d Cout=%d mode=%d", p.Cin, p.Cout, p.mode); return SDDM_E_INVALID; }

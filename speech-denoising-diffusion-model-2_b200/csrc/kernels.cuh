@@ -58,8 +58,11 @@ struct StemP {
     float* parts;        // [B][nparts][CO][2], nparts = tiles per sample (16 x 8 pixels each)
     int B, L, H, W, hop, CO, nparts;
     int act16;           // out is bf16 [B][H][W][CO]
+    int gn_on;           // finalise the consumer's GroupNorm in this kernel (gn_fuse.cuh)
+    GnFuse gn;
 };
 int launch_stem(const StemP& p, cudaStream_t st);
+int launch_stem_row(const StemP& p, const __nv_bfloat16* w_row, uint32_t w_bytes, cudaStream_t st);   // conv_row.cu
 int stem_nparts(int H, int W);
 
 // GroupNorm finalize: partial sums -> per-(sample, channel) scale / shift

@@ -2,6 +2,7 @@
 // overlap-add, framing helpers, noise-level embedding, stem (framing + cat + conv 2->C), GroupNorm
 // finalize and the final Block (GN + Swish + conv C->1).  All fp32, all coalesced / vectorised.
 #include "kernels.cuh"
+#include "gn_fuse.cuh"
 #include "../../include/sddm_b200.h"
 
 namespace sddm {
@@ -268,6 +269,7 @@ __global__ void __launch_bounds__(256) stem_kernel(StemP p) {
     constexpr int PASSES = 128 / PPP;
     __shared__ float sin_[2][18][10];
     __shared__ float red[8][CO][2];
+    __shared__ int gn_last;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int cg = tid % CG, pl = tid / CG;
     float4 w[18];
@@ -347,6 +349,17 @@ __global__ void __launch_bounds__(256) stem_kernel(StemP p) {
 #pragma unroll
             for (int wq = 0; wq < 8; ++wq) { a += red[wq][tid][0]; b += red[wq][tid][1]; }
             *reinterpret_cast<float2*>(p.parts + (((int64_t)n * p.nparts + tile) * CO + tid) * 2) = make_float2(a, b);
+        }
+        if (p.gn_on) {   // publish the tile's partials; the last tile of sample n finalises the consumer's GroupNorm
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) gn_last = atomicAdd(p.gn.counter + n, 1u) == (unsigned)(p.gn.expect - 1);
+            __syncthreads();
+            if (gn_last) {
+                __threadfence();
+                if (tid < 128) gn_fused_finalize(p.gn, n, tid, 128);
+                if (tid == 0) p.gn.counter[n] = 0u;
+            }
         }
     }
 }
