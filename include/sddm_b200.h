@@ -284,6 +284,11 @@ SDDM_API int sddm_debug_umma_probe(int variant, int N, int K, float* max_err_hos
 /* pipeline trace of the tcgen05 conv kernel: enable != 0 starts recording (next 64 conv launches, CTA 0 of each: cycles per
  * role spent waiting on each barrier); enable == 0 copies the [64][48] int64 counters to host_out and stops. */
 SDDM_API int sddm_debug_tc_trace(int enable, long long* host_out);
+/* the same for the row-streaming kernel of the 128-wide level (conv_row.cu): [64][32] int64 counters per launch:
+ * [0..7] / [8..15] epilogue group 0 / 1: total, wait acc_full, TMEM loads, store-buffer wait, residual wait, barrier 1, barrier 2, rows;
+ * [16..20] MMA warp: total, wait weights, wait acc_empty, wait full_a, rows; [21..22] raw loader: total, wait raw_empty;
+ * [24..27] / [28..31] transform group 0 / 1: total, wait raw_full, wait empty_a, work */
+SDDM_API int sddm_debug_row_trace(int enable, long long* host_out);
 /* issue-rate microbenchmark: average cycles per back-to-back tcgen05.mma (M 128, K 16, bf16, shared-memory operands) */
 SDDM_API int sddm_debug_umma_rate(int N, int reps, int nA, int geo, float* cycles_per_mma);
 

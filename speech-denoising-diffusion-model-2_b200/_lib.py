@@ -117,6 +117,7 @@ SIGNATURES = {
     "sddm_debug_fetch": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]),
     "sddm_debug_umma_probe": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "sddm_debug_tc_trace": (C.c_int, [C.c_int, C.c_void_p]),
+    "sddm_debug_row_trace": (C.c_int, [C.c_int, C.c_void_p]),
     "sddm_debug_umma_rate": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
 }
 

@@ -551,8 +551,13 @@ static int build_program(sddm_plan* p, Arena& a) {
         Op& g = p->ops[i];
         const Op& prev = p->ops[i - 1];
         if (g.kind != Op::GN || !want_tc) continue;
-        const bool producer_ok = prev.kind == Op::STEM || (prev.kind == Op::CONV && prev.use_tc);
-        if (producer_ok && prev.out == g.gn_src[0]) { g.gn_fused = true; ++fused; }
+        // Only the row kernels fuse: their CTAs own contiguous row runs, so a sample is finalised by one of <= 3 CTAs.  With the
+        // round-robin tile schedule of conv_tc.cu the CTA that finalises sample n falls behind and is then the last to arrive for
+        // sample n + 1, n + 2, ... too: all finalisations serialise on one CTA (measured: 57 -> 606 us for ups.10.conv).
+        const bool producer_ok = (prev.kind == Op::STEM || prev.kind == Op::CONV) && prev.use_row;
+        bool small = true;   // the last-arriving CTA walks every partial of the sample: keep that walk short
+        for (int k = 0; k < g.gn_nsrc; ++k) small = small && p->tensors[g.gn_src[k]].nparts <= 256;
+        if (producer_ok && small && prev.out == g.gn_src[0]) { g.gn_fused = true; ++fused; }
     }
     p->launches_per_eps = (int)p->ops.size() - fused + 1;   // + the overlap-add / posterior kernel
     return SDDM_OK;
@@ -703,7 +708,7 @@ static int run_unet(sddm_plan* p, const float* cond, const float* x_t, const flo
                 cp.nparts = o.nparts;
                 cp.B = B;
                 cp.act16 = c.precision == SDDM_PREC_BF16_ACT;
-                if (fuse && op.use_tc) { cp.gn_on = 1; fill_gn_fuse(p, *fuse, B, ws, op.use_row ? conv_row_arrivals(o.H) : conv_tc_tiles(o.H, o.W), &cp.gn); }
+                if (fuse) { cp.gn_on = 1; fill_gn_fuse(p, *fuse, B, ws, op.use_row ? conv_row_arrivals(o.H) : conv_tc_tiles(o.H, o.W), &cp.gn); }
                 if (op.use_row) rc = launch_conv_row(cp, p->d_bf16 + op.wrow_off, op.wrow_bytes, nullptr, 0.f, st);
                 else rc = op.use_tc ? launch_conv_tc(cp, st) : launch_conv_fp32(cp, st);
                 break;

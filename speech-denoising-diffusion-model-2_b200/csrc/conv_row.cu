@@ -47,8 +47,9 @@ constexpr int PLANE = 134;                   // operand slots (16 B) per k8 plan
 constexpr uint32_t kAStage = 4u * PLANE * 16u;            // 8576 B: one 32-channel operand row
 constexpr uint32_t kRawStage = 8192u + 256u;              // bf16 row slab + scale / shift tail
 constexpr uint32_t kOutTile = 8192u;                      // 128 px x 32 ch bf16 staging row (64B swizzle)
-constexpr int kMaxRing = 8, kMaxSlots = 5;
+constexpr int kNR = 6, kNA = 6, kNS = 5;                  // ring depths: raw slabs, operand slabs, accumulator slots (compile time: cheap % and /)
 constexpr size_t kSmemCap = 232448 - 1024;
+enum RowKind { ROW_ACT = 0, ROW_STEM = 1, ROW_FINAL = 2 };
 
 struct alignas(64) RowMaps {
     CUtensorMap src[2];    // main sources (concat order), box 32 ch x (128 | 64) px
@@ -58,34 +59,29 @@ struct alignas(64) RowMaps {
 
 struct RowArgs {
     int B, H, nblocks;          // 16-row blocks in the whole batch
-    int stem, final_out, up;
-    int n_main, n_res, ksteps;  // 32-channel slabs per input row: main conv / 1x1 res_conv; K16 steps per main slab
     int C0, rC0;                // channels of source 0 (concat boundary) of the main / res inputs
-    int Cin, affine;
+    int Cin;
     const float* scale; const float* shift;     // [B][Cin] GroupNorm of the input
     const __nv_bfloat16* w;                      // packed: main chunks, then res chunks
     uint32_t w_bytes;
-    int n_cols;                 // N of the main MMAs: 96 (or 16 for the final Block)
     const float* bias; const float* temb; int temb_stride; const float* res_bias;
-    int res_identity;
     const float* cond; const float* x_t; int L, hop;   // stem
     float* parts; int nparts;   // [B][nparts][32][2]
     float* frames; float final_bias;
     int gn_on; GnFuse gn;
-    int NR, NA, NS, NOUT, NRES, slot_cols, tmem_cols;
     uint32_t off_w, off_raw, off_a, off_out, off_res;
+    long long* trace;           // debug: per-role wait / busy cycle counters of CTA 0 (nullptr = off), 32 counters per launch
 };
 
 struct RowHdr {
-    uint64_t raw_full[kMaxRing], raw_empty[kMaxRing];
-    uint64_t full_a[kMaxRing], empty_a[kMaxRing];
-    uint64_t acc_full[kMaxSlots], acc_empty[kMaxSlots];
+    uint64_t raw_full[kNR], raw_empty[kNR];
+    uint64_t full_a[kNA], empty_a[kNA];
+    uint64_t acc_full[kNS], acc_empty[kNS];
     uint64_t res_full[kEpi][2];
     uint64_t w_full;
     uint32_t tmem_base;
     uint32_t gn_last[kEpi];
-    uint32_t pad[5];
-    float addv[kEpi][32];
+    alignas(16) float addv[kEpi][32];
 };
 constexpr uint32_t kHdr = 1024;
 static_assert(sizeof(RowHdr) <= kHdr, "header too large");
@@ -104,38 +100,68 @@ __device__ __forceinline__ bool seg_at(int H, int b0, int b1, int k, Seg& s) {
     return true;
 }
 
+__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, bool tr, long long& acc) {
+    if (!tr) { mbar_wait(bar, parity); return; }
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    acc += clock64() - t0;
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+
+// KIND: ROW_ACT (bf16 activation rows in, 32 channels out), ROW_STEM (waveform windows in), ROW_FINAL (1 channel out -> frames)
+// NMAIN / NRES: 32-channel slabs per input row of the 3x3 conv / the 1x1 res_conv; UP: nearest x2 of a [H/2][64] input;
+// AFF: GroupNorm-apply + Swish on the main slabs; RESID: identity residual added in the epilogue
+template <int KIND, int NMAIN, int NRES, bool UP, bool AFF, bool RESID>
 __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const RowArgs a, const __grid_constant__ RowMaps maps) {
+    constexpr int NSLAB = NMAIN + NRES;
+    constexpr int KSTEPS = KIND == ROW_STEM ? 1 : 2;                 // K16 steps per main slab
+    constexpr int NCOLS = KIND == ROW_FINAL ? 16 : 96;               // N of the main MMAs
+    constexpr int SLOT = KIND == ROW_FINAL ? 32 : 96;                // TMEM columns per accumulator slot
+    constexpr uint32_t TMEM_COLS = KIND == ROW_FINAL ? 256u : 512u;
+    constexpr uint32_t W_CHUNK = (uint32_t)NCOLS * 32u;              // bytes per (k16, kx) weight chunk: 2 halves x N rows x 16 B
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t dyn = smem_u32(smem_dyn), base = (dyn + 1023u) & ~1023u;
     RowHdr* hdr = reinterpret_cast<RowHdr*>(smem_dyn + (base - dyn));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int nslab = a.n_main + a.n_res;
     pdl_launch_dependents();
 
-    // contiguous run of blocks of this CTA
+    // contiguous run of blocks of this CTA, and its number of input rows (= accumulator items)
     const int q = a.nblocks / (int)gridDim.x, rem = a.nblocks - q * (int)gridDim.x;
     const int b0 = (int)blockIdx.x * q + ((int)blockIdx.x < rem ? (int)blockIdx.x : rem);
     const int b1 = b0 + q + ((int)blockIdx.x < rem ? 1 : 0);
+    int nitems = 0;
+    {
+        Seg s;
+        for (int k = 0; seg_at(a.H, b0, b1, k, s); ++k) nitems += s.r1 - s.r0 + 1;
+    }
 
     if (tid == 0) {
-        for (int i = 0; i < kMaxRing; ++i) {
-            mbar_init(smem_u32(&hdr->raw_full[i]), 1); mbar_init(smem_u32(&hdr->raw_empty[i]), kGrp);
-            mbar_init(smem_u32(&hdr->full_a[i]), kGrp); mbar_init(smem_u32(&hdr->empty_a[i]), 1);
-        }
-        for (int i = 0; i < kMaxSlots; ++i) { mbar_init(smem_u32(&hdr->acc_full[i]), 1); mbar_init(smem_u32(&hdr->acc_empty[i]), 12); }
+        for (int i = 0; i < kNR; ++i) { mbar_init(smem_u32(&hdr->raw_full[i]), 1); mbar_init(smem_u32(&hdr->raw_empty[i]), kGrp); }
+        for (int i = 0; i < kNA; ++i) { mbar_init(smem_u32(&hdr->full_a[i]), kGrp); mbar_init(smem_u32(&hdr->empty_a[i]), 1); }
+        for (int i = 0; i < kNS; ++i) { mbar_init(smem_u32(&hdr->acc_full[i]), 1); mbar_init(smem_u32(&hdr->acc_empty[i]), 12); }
         for (int e = 0; e < kEpi; ++e) for (int k = 0; k < 2; ++k) mbar_init(smem_u32(&hdr->res_full[e][k]), 1);
         mbar_init(smem_u32(&hdr->w_full), 1);
         fence_barrier_init();
     }
-    if (warp == kMma) tmem_alloc(smem_u32(&hdr->tmem_base), (uint32_t)a.tmem_cols);
+    if (warp == kMma) tmem_alloc(smem_u32(&hdr->tmem_base), TMEM_COLS);
     // operand ring: zero once - the x halo slots (0 and 129) of every plane are never written again (stem: plane 1 stays zero too)
-    for (uint32_t i = (uint32_t)tid; i < (uint32_t)a.NA * kAStage / 16u; i += kRowThreads)
+    for (uint32_t i = (uint32_t)tid; i < (uint32_t)kNA * kAStage / 16u; i += kRowThreads)
         sts128(base + a.off_a + i * 16u, make_uint4(0u, 0u, 0u, 0u));
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = hdr->tmem_base;
+    const bool tr = a.trace != nullptr && blockIdx.x == 0;
+    long long tw[6] = {0, 0, 0, 0, 0, 0};
+    const long long t_begin = tr ? clock64() : 0;
 
     if (warp < 8) {
         // ============================== epilogue: group e owns the output rows with y & 1 == e ===========================
@@ -143,137 +169,146 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const RowArgs 
         const int e = warp >> 2, w4 = warp & 3, m = tid & 127;
         const int bar_id = 1 + e;
         const bool leader = m == 0;
-        const bool has_res = a.res_identity != 0;
-        const uint32_t obuf0 = base + a.off_out + (uint32_t)(e * a.NOUT) * kOutTile;
+        const uint32_t obuf0 = base + a.off_out + (uint32_t)(e * 2) * kOutTile;
         const uint32_t rbuf0 = base + a.off_res + (uint32_t)(e * 2) * kOutTile;
         const uint32_t addv_u32 = smem_u32(hdr->addv[e]);
         const uint32_t lane_tm = tmem_base + ((uint32_t)(w4 * 32) << 16);
+        const uint32_t swz = (uint32_t)((m >> 1) & 3);       // 64B swizzle of this thread's staging / residual row
         const int c2 = lane & 15, hrow = lane >> 4;
         float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;   // statistics of this group's rows of the current block (2 channels per lane)
-        int ob = 0;                                          // rows stored so far (staging buffer parity)
-        int rq = 0;                                          // residual rows consumed so far
-        // residual prefetch runs one row ahead: the (n, y) sequence of this group
+        int ob = 0;                                          // rows stored so far (staging / residual buffer parity)
+        // identity residual: TMA prefetch two rows ahead along this group's (n, y) sequence
         int pk = 0, py = -1, pn = 0, pend = 0, pissued = 0;
         Seg ps{};
-        auto res_next = [&]() -> bool {   // advance (pk, py) to this group's next output row; false when exhausted
-            for (;;) {
+        auto res_issue = [&]() {
+            for (;;) {   // advance (pk, py) to this group's next output row
                 if (py < 0) {
-                    if (!seg_at(a.H, b0, b1, pk, ps)) return false;
+                    if (!seg_at(a.H, b0, b1, pk, ps)) return;
                     py = ps.ya + ((ps.ya & 1) == e ? 0 : 1);
                     pend = ps.yb; pn = ps.n;
                 } else {
                     py += 2;
                 }
-                if (py < pend) return true;
+                if (py < pend) break;
                 py = -1; ++pk;
             }
-        };
-        auto res_issue = [&]() {
-            if (!res_next()) return;
             const uint32_t bar = smem_u32(&hdr->res_full[e][pissued & 1]);
             mbar_expect_tx(bar, kOutTile);
             tma_load_4d(rbuf0 + (uint32_t)(pissued & 1) * kOutTile, &maps.rsrc[0], 0, 0, py, pn, bar);
             ++pissued;
         };
-        if (has_res && leader) res_issue();
+        if (RESID && leader) { res_issue(); res_issue(); }
         int item_base = 0;
         Seg s;
         for (int k = 0; seg_at(a.H, b0, b1, k, s); item_base += s.r1 - s.r0 + 1, ++k) {
-            // per-channel additive term of this sample: bias (+ noise-level embedding row) (+ res_conv bias)
-            group_bar(bar_id);
-            if (m < 32 && !a.final_out) {
-                float v = __ldg(a.bias + m);
-                if (a.temb) v += __ldg(a.temb + (int64_t)s.n * a.temb_stride + m);
-                if (a.n_res) v += __ldg(a.res_bias + m);
-                hdr->addv[e][m] = v;
+            if (KIND != ROW_FINAL) {
+                // per-channel additive term of this sample: bias (+ noise-level embedding row) (+ res_conv bias)
+                group_bar(bar_id);
+                if (m < 32) {
+                    float v = __ldg(a.bias + m);
+                    if (a.temb) v += __ldg(a.temb + (int64_t)s.n * a.temb_stride + m);
+                    if (NRES) v += __ldg(a.res_bias + m);
+                    hdr->addv[e][m] = v;
+                }
+                group_bar(bar_id);
             }
-            group_bar(bar_id);
             for (int y = s.ya + ((s.ya & 1) == e ? 0 : 1); y < s.yb; y += 2) {
                 const bool vA = y - 1 >= s.r0, vC = y + 1 <= s.r1;
-                const int iB = item_base + (y - s.r0), iA = iB - 1, iC = iB + 1;
-                const int last = vC ? iC : iB;
-                mbar_wait(smem_u32(&hdr->acc_full[last % a.NS]), (uint32_t)(last / a.NS) & 1u);
+                const int iB = item_base + (y - s.r0), last = vC ? iB + 1 : iB;
+                const int slB = iB % kNS, slA = (iB + kNS - 1) % kNS, slC = (iB + 1) % kNS;
+                mbar_wait_t(smem_u32(&hdr->acc_full[last % kNS]), (uint32_t)(last / kNS) & 1u, tr, tw[0]);
                 tc_fence_after();
-                // arrivals owed to the three accumulator slots (see header: rows outside [ya, yb) never arrive)
-                const int first = y == s.ya, lastrow = y == s.yb - 1;
-                // (an input row r is read by the output rows r - 1, r, r + 1; those outside [ya, yb) never come, so the first / last
-                //  row of the segment arrives in their place: every slot sees exactly 3 arrivals x 4 warps)
+                // arrivals owed to the three accumulator slots: an input row r is read by the output rows r - 1, r, r + 1; those
+                // outside [ya, yb) never come, so the first / last row of the segment arrives in their place (3 x 4 warps per slot)
+                const bool first = y == s.ya, lastrow = y == s.yb - 1;
                 const uint32_t nA = first ? 3u : 1u, nB = 1u + (first ? 1u : 0u) + (lastrow ? 1u : 0u), nC = lastrow ? 3u : 1u;
-                if (a.final_out) {
+                const long long te0 = tr ? clock64() : 0;
+                if (KIND == ROW_FINAL) {
                     uint32_t ra[4] = {0u, 0u, 0u, 0u}, rb[4], rc[4] = {0u, 0u, 0u, 0u};
-                    if (vA) tmem_ld4_nowait(lane_tm + (uint32_t)((iA % a.NS) * a.slot_cols), ra);
-                    tmem_ld4_nowait(lane_tm + (uint32_t)((iB % a.NS) * a.slot_cols), rb);
-                    if (vC) tmem_ld4_nowait(lane_tm + (uint32_t)((iC % a.NS) * a.slot_cols), rc);
+                    if (vA) tmem_ld4_nowait(lane_tm + (uint32_t)(slA * SLOT), ra);
+                    tmem_ld4_nowait(lane_tm + (uint32_t)(slB * SLOT), rb);
+                    if (vC) tmem_ld4_nowait(lane_tm + (uint32_t)(slC * SLOT), rc);
                     tmem_wait_ld();
                     tc_fence_before();
                     if (lane == 0) {
-                        if (vA) mbar_arrive_n(smem_u32(&hdr->acc_empty[iA % a.NS]), nA);
-                        mbar_arrive_n(smem_u32(&hdr->acc_empty[iB % a.NS]), nB);
-                        if (vC) mbar_arrive_n(smem_u32(&hdr->acc_empty[iC % a.NS]), nC);
+                        if (vA) mbar_arrive_n(smem_u32(&hdr->acc_empty[slA]), nA);
+                        mbar_arrive_n(smem_u32(&hdr->acc_empty[slB]), nB);
+                        if (vC) mbar_arrive_n(smem_u32(&hdr->acc_empty[slC]), nC);
                     }
+                    if (tr) tw[1] += clock64() - te0;
                     const float f = (__uint_as_float(ra[0]) + __uint_as_float(rb[1])) + __uint_as_float(rc[2]) + a.final_bias;
                     a.frames[((int64_t)s.n * a.H + y) * RW + m] = f;
                     continue;
                 }
-                float v[32];
-                {
-                    uint32_t r0[32], r1[32];
-                    tmem_ld32_nowait(lane_tm + (uint32_t)((iB % a.NS) * a.slot_cols + 32), r0);
-                    if (vA) tmem_ld32_nowait(lane_tm + (uint32_t)((iA % a.NS) * a.slot_cols), r1);
+                const uint32_t obuf = obuf0 + (uint32_t)(ob & 1) * kOutTile;
+                const uint32_t orow = obuf + (uint32_t)m * 64u;
+                const uint32_t rrow = rbuf0 + (uint32_t)(ob & 1) * kOutTile + (uint32_t)m * 64u;
+                if (RESID) mbar_wait(smem_u32(&hdr->res_full[e][ob & 1]), (uint32_t)(ob >> 1) & 1u);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t ra[16], rb[16], rc[16];
+                    tmem_ld16_nowait(lane_tm + (uint32_t)(slB * SLOT + 32 + half * 16), rb);
+                    if (vA) tmem_ld16_nowait(lane_tm + (uint32_t)(slA * SLOT + half * 16), ra);
+                    if (vC) tmem_ld16_nowait(lane_tm + (uint32_t)(slC * SLOT + 64 + half * 16), rc);
                     tmem_wait_ld();
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r0[i]) + (vA ? __uint_as_float(r1[i]) : 0.f);
-                    if (vC) {
-                        tmem_ld32_nowait(lane_tm + (uint32_t)((iC % a.NS) * a.slot_cols + 64), r0);
-                        tmem_wait_ld();
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] += __uint_as_float(r0[i]);
+                    if (half == 1) {   // all three slots fully read
+                        tc_fence_before();
+                        if (lane == 0) {
+                            if (vA) mbar_arrive_n(smem_u32(&hdr->acc_empty[slA]), nA);
+                            mbar_arrive_n(smem_u32(&hdr->acc_empty[slB]), nB);
+                            if (vC) mbar_arrive_n(smem_u32(&hdr->acc_empty[slC]), nC);
+                        }
                     }
-                }
-                tc_fence_before();
-                if (lane == 0) {
-                    if (vA) mbar_arrive_n(smem_u32(&hdr->acc_empty[iA % a.NS]), nA);
-                    mbar_arrive_n(smem_u32(&hdr->acc_empty[iB % a.NS]), nB);
-                    if (vC) mbar_arrive_n(smem_u32(&hdr->acc_empty[iC % a.NS]), nC);
-                }
+                    float v[16];
 #pragma unroll
-                for (int qd = 0; qd < 8; ++qd) {
-                    const uint4 u = lds128(addv_u32 + (uint32_t)qd * 16u);
-                    v[4 * qd + 0] += __uint_as_float(u.x); v[4 * qd + 1] += __uint_as_float(u.y);
-                    v[4 * qd + 2] += __uint_as_float(u.z); v[4 * qd + 3] += __uint_as_float(u.w);
-                }
-                const uint32_t obuf = obuf0 + (uint32_t)(a.NOUT == 2 ? (ob & 1) : 0) * kOutTile;
-                if (leader) {   // the TMA store that last read this staging buffer is done with it
-                    if (a.NOUT == 2) bulk_wait_read_1(); else bulk_wait_read_0();
-                }
-                if (has_res) {
-                    mbar_wait(smem_u32(&hdr->res_full[e][rq & 1]), (uint32_t)(rq >> 1) & 1u);
-                    const uint32_t rrow = rbuf0 + (uint32_t)(rq & 1) * kOutTile + (uint32_t)m * 64u;
+                    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rb[i]);
+                    if (vA) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] += __uint_as_float(ra[i]);
+                    }
+                    if (vC) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] += __uint_as_float(rc[i]);
+                    }
 #pragma unroll
                     for (int qd = 0; qd < 4; ++qd) {
-                        const uint4 u = lds128(rrow + (uint32_t)((qd ^ ((m >> 1) & 3)) << 4));
-                        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                        for (int kk = 0; kk < 4; ++kk) { v[8 * qd + 2 * kk] += bf16_lo(w[kk]); v[8 * qd + 2 * kk + 1] += bf16_hi(w[kk]); }
+                        const uint4 u = lds128(addv_u32 + (uint32_t)(half * 4 + qd) * 16u);
+                        v[4 * qd + 0] += __uint_as_float(u.x); v[4 * qd + 1] += __uint_as_float(u.y);
+                        v[4 * qd + 2] += __uint_as_float(u.z); v[4 * qd + 3] += __uint_as_float(u.w);
                     }
-                    ++rq;
-                }
-                group_bar(bar_id);   // staging buffer free (leader waited), residual buffer fully read by the whole group
-                if (has_res && leader) res_issue();
-                const uint32_t orow = obuf + (uint32_t)m * 64u;
+                    if (RESID) {
 #pragma unroll
-                for (int qd = 0; qd < 4; ++qd) {
-                    uint4 u;
-                    u.x = pack_bf16(v[8 * qd + 0], v[8 * qd + 1]); u.y = pack_bf16(v[8 * qd + 2], v[8 * qd + 3]);
-                    u.z = pack_bf16(v[8 * qd + 4], v[8 * qd + 5]); u.w = pack_bf16(v[8 * qd + 6], v[8 * qd + 7]);
-                    sts128(orow + (uint32_t)((qd ^ ((m >> 1) & 3)) << 4), u);
+                        for (int qd = 0; qd < 2; ++qd) {
+                            const uint4 u = lds128(rrow + ((((uint32_t)(half * 2 + qd)) ^ swz) << 4));
+                            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) { v[8 * qd + 2 * kk] += bf16_lo(w[kk]); v[8 * qd + 2 * kk + 1] += bf16_hi(w[kk]); }
+                        }
+                    }
+#pragma unroll
+                    for (int qd = 0; qd < 2; ++qd) {
+                        uint4 u;
+                        u.x = pack_bf16(v[8 * qd + 0], v[8 * qd + 1]); u.y = pack_bf16(v[8 * qd + 2], v[8 * qd + 3]);
+                        u.z = pack_bf16(v[8 * qd + 4], v[8 * qd + 5]); u.w = pack_bf16(v[8 * qd + 6], v[8 * qd + 7]);
+                        sts128(orow + ((((uint32_t)(half * 2 + qd)) ^ swz) << 4), u);
+                    }
                 }
+                if (tr) tw[1] += clock64() - te0;
                 fence_async_smem();
+                // every TMA store issued so far has finished reading its staging row (the newest was issued a whole row ago), so
+                // after the barrier the OTHER buffer is free for the next row: one barrier per row
+                const long long tw0 = tr ? clock64() : 0;
+                if (leader) bulk_wait_read_0();
+                const long long tg0 = tr ? clock64() : 0;
                 group_bar(bar_id);
+                if (tr) { tw[3] += tg0 - tw0; tw[2] += clock64() - tg0; }
+                const long long ts0 = tr ? clock64() : 0;
                 if (leader) {
                     tma_store_4d(&maps.out, obuf, 0, 0, y, s.n);
                     bulk_commit();
+                    if (RESID) res_issue();   // the residual buffer of this row is free: refill it for this group's row after next
                 }
+                if (tr) tw[4] += clock64() - ts0;
                 ++ob;
                 // column sums of the staged (rounded) row: 2 channels per lane, even / odd pixels per half-warp
                 {
@@ -287,6 +322,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const RowArgs 
                         s2a = fmaf(fx, fx, s2a); s2b = fmaf(fy, fy, s2b);
                     }
                 }
+                if (tr) tw[5] += clock64() - ts0;
                 if ((y & 15) >= 14) {   // this group's last row of the 16-row block: publish its partial, maybe finalise the sample
                     s1a += __shfl_xor_sync(0xffffffffu, s1a, 16); s1b += __shfl_xor_sync(0xffffffffu, s1b, 16);
                     s2a += __shfl_xor_sync(0xffffffffu, s2a, 16); s2b += __shfl_xor_sync(0xffffffffu, s2b, 16);
@@ -311,52 +347,51 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const RowArgs 
             }
         }
         if (leader) bulk_wait_all();
+        if (tr && leader) {
+            long long* o = a.trace + e * 8;
+            o[0] = clock64() - t_begin; o[1] = tw[0]; o[2] = tw[1]; o[3] = tw[2]; o[4] = tw[3]; o[5] = tw[4]; o[6] = tw[5]; o[7] = ob;
+        }
     } else if (warp == kMma) {
         // ============================== MMA issuer ==========================================================================
-        const uint32_t idesc = make_idesc(a.n_cols), idesc_res = make_idesc(32);
-        const uint32_t w_chunk = (uint32_t)a.n_cols * 32u;                    // bytes per (k16, kx) weight chunk: 2 halves x N rows x 16 B
+        const uint32_t idesc = make_idesc(NCOLS), idesc_res = make_idesc(32);
         const uint64_t a_desc0 = make_desc_nosw(base + a.off_a, (uint32_t)PLANE * 16u, 128u);
-        const uint64_t w_desc0 = make_desc_nosw(base + a.off_w, (uint32_t)a.n_cols * 16u, 128u);
-        const uint64_t wr_desc0 = make_desc_nosw(base + a.off_w + (uint32_t)(a.n_main * a.ksteps * 3) * w_chunk, 32u * 16u, 128u);
-        mbar_wait(smem_u32(&hdr->w_full), 0u);
+        const uint64_t w_desc0 = make_desc_nosw(base + a.off_w, (uint32_t)NCOLS * 16u, 128u);
+        const uint64_t wr_desc0 = make_desc_nosw(base + a.off_w + (uint32_t)(NMAIN * KSTEPS * 3) * W_CHUNK, 32u * 16u, 128u);
+        mbar_wait_t(smem_u32(&hdr->w_full), 0u, tr, tw[0]);
         tc_fence_after();
-        int it = 0, sa = 0;
+        int sa = 0;
         uint32_t pa = 0;
-        Seg s;
-        for (int k = 0; seg_at(a.H, b0, b1, k, s); ++k) {
-            for (int r = s.r0; r <= s.r1; ++r, ++it) {
-                const int slot = it % a.NS;
-                mbar_wait(smem_u32(&hdr->acc_empty[slot]), ((uint32_t)(it / a.NS) & 1u) ^ 1u);
+        for (int it = 0; it < nitems; ++it) {
+            const int slot = it % kNS;
+            mbar_wait_t(smem_u32(&hdr->acc_empty[slot]), ((uint32_t)(it / kNS) & 1u) ^ 1u, tr, tw[1]);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(slot * SLOT);
+#pragma unroll
+            for (int sl = 0; sl < NSLAB; ++sl) {
+                mbar_wait_t(smem_u32(&hdr->full_a[sa]), pa, tr, tw[2]);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(slot * a.slot_cols);
-                uint32_t acc = 0;
-                for (int sl = 0; sl < nslab; ++sl) {
-                    mbar_wait(smem_u32(&hdr->full_a[sa]), pa);
-                    tc_fence_after();
-                    const uint64_t adesc = a_desc0 + (uint64_t)((uint32_t)sa * (kAStage >> 4));
-                    if (elect_one()) {
-                        if (sl < a.n_main) {
-                            for (int h = 0; h < a.ksteps; ++h)
+                const uint64_t adesc = a_desc0 + (uint64_t)((uint32_t)sa * (kAStage >> 4));
+                if (elect_one()) {
+                    if (sl < NMAIN) {
 #pragma unroll
-                                for (int kx = 0; kx < 3; ++kx) {
-                                    umma(d_tmem, adesc + (uint64_t)(uint32_t)(h * 2 * PLANE + kx),
-                                         w_desc0 + (uint64_t)((uint32_t)((sl * a.ksteps + h) * 3 + kx) * (w_chunk >> 4)), idesc, acc);
-                                    acc = 1;
-                                }
-                        } else {   // 1x1 res_conv over the raw block input: centre tap, centre (ky = 1) columns
+                        for (int h = 0; h < KSTEPS; ++h)
 #pragma unroll
-                            for (int h = 0; h < 2; ++h)
-                                umma(d_tmem + 32u, adesc + (uint64_t)(uint32_t)(h * 2 * PLANE + 1),
-                                     wr_desc0 + (uint64_t)((uint32_t)((sl - a.n_main) * 2 + h) * (1024u >> 4)), idesc_res, 1u);
-                        }
-                        umma_commit(smem_u32(&hdr->empty_a[sa]));
+                            for (int kx = 0; kx < 3; ++kx)
+                                umma(d_tmem, adesc + (uint64_t)(uint32_t)(h * 2 * PLANE + kx),
+                                     w_desc0 + (uint64_t)((uint32_t)((sl * KSTEPS + h) * 3 + kx) * (W_CHUNK >> 4)), idesc, (sl | h | kx) ? 1u : 0u);
+                    } else {   // 1x1 res_conv over the raw block input: centre tap, centre (ky = 1) columns
+#pragma unroll
+                        for (int h = 0; h < 2; ++h)
+                            umma(d_tmem + 32u, adesc + (uint64_t)(uint32_t)(h * 2 * PLANE + 1),
+                                 wr_desc0 + (uint64_t)((uint32_t)((sl - NMAIN) * 2 + h) * (1024u >> 4)), idesc_res, 1u);
                     }
-                    acc = 1;
-                    if (++sa == a.NA) { sa = 0; pa ^= 1u; }
+                    umma_commit(smem_u32(&hdr->empty_a[sa]));
+                    if (sl == NSLAB - 1) umma_commit(smem_u32(&hdr->acc_full[slot]));
                 }
-                if (elect_one()) umma_commit(smem_u32(&hdr->acc_full[slot]));
+                if (++sa == kNA) { sa = 0; pa ^= 1u; }
             }
         }
+        if (tr && lane == 0) { long long* o = a.trace + 16; o[0] = clock64() - t_begin; o[1] = tw[0]; o[2] = tw[1]; o[3] = tw[2]; o[4] = nitems; }
     } else if (warp == kWld) {
         if (lane == 0) {   // weights: one bulk copy, resident for the whole CTA
             const uint32_t bar = smem_u32(&hdr->w_full);
@@ -371,111 +406,111 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const RowArgs 
             uint32_t pr = 0;
             Seg s;
             for (int k = 0; seg_at(a.H, b0, b1, k, s); ++k)
-                for (int r = s.r0; r <= s.r1; ++r)
-                    for (int sl = 0; sl < nslab; ++sl) {
+                for (int r = s.r0; r <= s.r1; ++r) {
+#pragma unroll
+                    for (int sl = 0; sl < NSLAB; ++sl) {
                         const uint32_t bar = smem_u32(&hdr->raw_full[rs]);
-                        mbar_wait(smem_u32(&hdr->raw_empty[rs]), pr ^ 1u);
+                        mbar_wait_t(smem_u32(&hdr->raw_empty[rs]), pr ^ 1u, tr, tw[0]);
                         const uint32_t dst = base + a.off_raw + (uint32_t)rs * kRawStage;
-                        if (a.stem) {
+                        if (KIND == ROW_STEM) {
                             mbar_expect_tx(bar, 1024u);
                             bulk_g2s(dst, a.cond + (int64_t)s.n * a.L + (int64_t)r * a.hop, 512u, bar);
                             bulk_g2s(dst + 512u, a.x_t + (int64_t)s.n * a.L + (int64_t)r * a.hop, 512u, bar);
-                        } else if (sl < a.n_main) {
+                        } else if (sl < NMAIN) {
                             const int cb = sl * 32, si = cb < a.C0 ? 0 : 1;
-                            const bool aff = a.affine != 0;
-                            mbar_expect_tx(bar, (a.up ? 4096u : 8192u) + (aff ? 256u : 0u));
-                            tma_load_4d(dst, &maps.src[si], cb - (si ? a.C0 : 0), 0, a.up ? (r >> 1) : r, s.n, bar);
-                            if (aff) {
+                            mbar_expect_tx(bar, (UP ? 4096u : 8192u) + (AFF ? 256u : 0u));
+                            tma_load_4d(dst, &maps.src[si], cb - (si ? a.C0 : 0), 0, UP ? (r >> 1) : r, s.n, bar);
+                            if (AFF) {
                                 bulk_g2s(dst + 8192u, a.scale + (int64_t)s.n * a.Cin + cb, 128u, bar);
                                 bulk_g2s(dst + 8192u + 128u, a.shift + (int64_t)s.n * a.Cin + cb, 128u, bar);
                             }
                         } else {
-                            const int cb = (sl - a.n_main) * 32, si = cb < a.rC0 ? 0 : 1;
+                            const int cb = (sl - NMAIN) * 32, si = cb < a.rC0 ? 0 : 1;
                             mbar_expect_tx(bar, 8192u);
                             tma_load_4d(dst, &maps.rsrc[si], cb - (si ? a.rC0 : 0), 0, r, s.n, bar);
                         }
-                        if (++rs == a.NR) { rs = 0; pr ^= 1u; }
+                        if (++rs == kNR) { rs = 0; pr ^= 1u; }
                     }
+                }
+            if (tr) { long long* o = a.trace + 21; o[0] = clock64() - t_begin; o[1] = tw[0]; }
         }
     } else if (warp >= kXf0 && warp < kXf0 + 8) {
         // ============================== transform: raw row slab -> bf16 operand row ========================================
-        // two groups of 128 threads take alternate slabs of the CTA's (row, slab) sequence
+        // two groups of 128 threads take alternate slabs of the CTA's (row, slab) sequence; no coordinates needed here
         const int gi = (warp - kXf0) >> 2, gt = tid - (kXf0 * 32 + gi * kGrp);
         const int j = gt & 3, px0 = gt >> 2;
-        int qn = 0;   // global slab counter
-        Seg s;
-        for (int k = 0; seg_at(a.H, b0, b1, k, s); ++k)
-            for (int r = s.r0; r <= s.r1; ++r)
-                for (int sl = 0; sl < nslab; ++sl, ++qn) {
-                    if ((qn & 1) != gi) continue;
-                    const int rs = qn % a.NR, sa = qn % a.NA;
-                    const uint32_t raw = base + a.off_raw + (uint32_t)rs * kRawStage;
-                    const uint32_t opd = base + a.off_a + (uint32_t)sa * kAStage;
-                    mbar_wait(smem_u32(&hdr->raw_full[rs]), (uint32_t)(qn / a.NR) & 1u);
-                    mbar_wait(smem_u32(&hdr->empty_a[sa]), ((uint32_t)(qn / a.NA) & 1u) ^ 1u);
-                    if (a.stem) {
-                        // K slots of plane 0: [cond hi, x_t hi, cond lo, x_t lo, 0, 0, 0, 0]
-                        const float c = lds32(raw + (uint32_t)gt * 4u), x = lds32(raw + 512u + (uint32_t)gt * 4u);
-                        const __nv_bfloat16 ch = __float2bfloat16_rn(c), xh = __float2bfloat16_rn(x);
-                        const float cl = c - __bfloat162float(ch), xl = x - __bfloat162float(xh);
-                        uint4 o;
-                        o.x = (uint32_t)__bfloat16_as_ushort(ch) | ((uint32_t)__bfloat16_as_ushort(xh) << 16);
-                        o.y = pack_bf16(cl, xl);
-                        o.z = 0u; o.w = 0u;
-                        sts128(opd + (uint32_t)(gt + 1) * 16u, o);
-                    } else {
-                        const bool aff = a.affine != 0 && sl < a.n_main;
-                        const bool up = a.up != 0 && sl < a.n_main;
-                        float sch[8], shh[8];
-                        if (aff) {   // halved: swish(y) = h + h tanh(h), h = y / 2
-                            const uint32_t ss = raw + 8192u + (uint32_t)j * 32u;
-                            const uint4 s0 = lds128(ss), s1 = lds128(ss + 16u), h0 = lds128(ss + 128u), h1 = lds128(ss + 144u);
-                            sch[0] = 0.5f * __uint_as_float(s0.x); sch[1] = 0.5f * __uint_as_float(s0.y); sch[2] = 0.5f * __uint_as_float(s0.z); sch[3] = 0.5f * __uint_as_float(s0.w);
-                            sch[4] = 0.5f * __uint_as_float(s1.x); sch[5] = 0.5f * __uint_as_float(s1.y); sch[6] = 0.5f * __uint_as_float(s1.z); sch[7] = 0.5f * __uint_as_float(s1.w);
-                            shh[0] = 0.5f * __uint_as_float(h0.x); shh[1] = 0.5f * __uint_as_float(h0.y); shh[2] = 0.5f * __uint_as_float(h0.z); shh[3] = 0.5f * __uint_as_float(h0.w);
-                            shh[4] = 0.5f * __uint_as_float(h1.x); shh[5] = 0.5f * __uint_as_float(h1.y); shh[6] = 0.5f * __uint_as_float(h1.z); shh[7] = 0.5f * __uint_as_float(h1.w);
-                        }
-                        const int rounds = up ? 2 : 4;
-                        uint4 rv[4];
-#pragma unroll
-                        for (int rd = 0; rd < 4; ++rd)
-                            if (rd < rounds) rv[rd] = lds128(raw + (uint32_t)(px0 + 32 * rd) * 64u + (uint32_t)j * 16u);
-#pragma unroll
-                        for (int rd = 0; rd < 4; ++rd) {
-                            if (rd >= rounds) break;
-                            uint4 o = rv[rd];
-                            if (aff) {
-                                const uint32_t w[4] = {o.x, o.y, o.z, o.w};
-                                uint32_t ow[4];
-#pragma unroll
-                                for (int kk = 0; kk < 4; ++kk) {
-                                    const float h0 = fmaf(bf16_lo(w[kk]), sch[2 * kk], shh[2 * kk]);
-                                    const float h1 = fmaf(bf16_hi(w[kk]), sch[2 * kk + 1], shh[2 * kk + 1]);
-                                    ow[kk] = pack_bf16(fmaf(h0, tanh_approx(h0), h0), fmaf(h1, tanh_approx(h1), h1));
-                                }
-                                o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-                            }
-                            const int px = px0 + 32 * rd;
-                            const uint32_t dstp = opd + (uint32_t)j * (uint32_t)PLANE * 16u;
-                            if (up) {
-                                sts128(dstp + (uint32_t)(2 * px + 1) * 16u, o);
-                                sts128(dstp + (uint32_t)(2 * px + 2) * 16u, o);
-                            } else {
-                                sts128(dstp + (uint32_t)(px + 1) * 16u, o);
-                            }
-                        }
-                    }
-                    fence_async_smem();
-                    mbar_arrive(smem_u32(&hdr->full_a[sa]));
-                    mbar_arrive(smem_u32(&hdr->raw_empty[rs]));
+        const int nslabs = nitems * NSLAB;
+        for (int qn = gi; qn < nslabs; qn += 2) {
+            const int rs = qn % kNR, sa = qn % kNA, sl = NSLAB == 1 ? 0 : qn % NSLAB;
+            const uint32_t raw = base + a.off_raw + (uint32_t)rs * kRawStage;
+            const uint32_t opd = base + a.off_a + (uint32_t)sa * kAStage;
+            mbar_wait_t(smem_u32(&hdr->raw_full[rs]), (uint32_t)(qn / kNR) & 1u, tr, tw[0]);
+            mbar_wait_t(smem_u32(&hdr->empty_a[sa]), ((uint32_t)(qn / kNA) & 1u) ^ 1u, tr, tw[1]);
+            const long long tx0 = tr ? clock64() : 0;
+            if (KIND == ROW_STEM) {
+                // K slots of plane 0: [cond hi, x_t hi, cond lo, x_t lo, 0, 0, 0, 0]
+                const float c = lds32(raw + (uint32_t)gt * 4u), x = lds32(raw + 512u + (uint32_t)gt * 4u);
+                const __nv_bfloat16 ch = __float2bfloat16_rn(c), xh = __float2bfloat16_rn(x);
+                const float cl = c - __bfloat162float(ch), xl = x - __bfloat162float(xh);
+                uint4 o;
+                o.x = (uint32_t)__bfloat16_as_ushort(ch) | ((uint32_t)__bfloat16_as_ushort(xh) << 16);
+                o.y = pack_bf16(cl, xl);
+                o.z = 0u; o.w = 0u;
+                sts128(opd + (uint32_t)(gt + 1) * 16u, o);
+            } else {
+                const bool is_main = sl < NMAIN;
+                const bool aff = AFF && is_main, up = UP && is_main;
+                float sch[8], shh[8];
+                if (aff) {   // halved: swish(y) = h + h tanh(h), h = y / 2
+                    const uint32_t ss = raw + 8192u + (uint32_t)j * 32u;
+                    const uint4 s0 = lds128(ss), s1 = lds128(ss + 16u), h0 = lds128(ss + 128u), h1 = lds128(ss + 144u);
+                    sch[0] = 0.5f * __uint_as_float(s0.x); sch[1] = 0.5f * __uint_as_float(s0.y); sch[2] = 0.5f * __uint_as_float(s0.z); sch[3] = 0.5f * __uint_as_float(s0.w);
+                    sch[4] = 0.5f * __uint_as_float(s1.x); sch[5] = 0.5f * __uint_as_float(s1.y); sch[6] = 0.5f * __uint_as_float(s1.z); sch[7] = 0.5f * __uint_as_float(s1.w);
+                    shh[0] = 0.5f * __uint_as_float(h0.x); shh[1] = 0.5f * __uint_as_float(h0.y); shh[2] = 0.5f * __uint_as_float(h0.z); shh[3] = 0.5f * __uint_as_float(h0.w);
+                    shh[4] = 0.5f * __uint_as_float(h1.x); shh[5] = 0.5f * __uint_as_float(h1.y); shh[6] = 0.5f * __uint_as_float(h1.z); shh[7] = 0.5f * __uint_as_float(h1.w);
                 }
+                const uint32_t dstp = opd + (uint32_t)j * (uint32_t)PLANE * 16u;
+                uint4 rv[4];
+#pragma unroll
+                for (int rd = 0; rd < 4; ++rd)
+                    if (!up || rd < 2) rv[rd] = lds128(raw + (uint32_t)(px0 + 32 * rd) * 64u + (uint32_t)j * 16u);
+#pragma unroll
+                for (int rd = 0; rd < 4; ++rd) {
+                    if (up && rd >= 2) break;
+                    uint4 o = rv[rd];
+                    if (aff) {
+                        const uint32_t w[4] = {o.x, o.y, o.z, o.w};
+                        uint32_t ow[4];
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            const float h0 = fmaf(bf16_lo(w[kk]), sch[2 * kk], shh[2 * kk]);
+                            const float h1 = fmaf(bf16_hi(w[kk]), sch[2 * kk + 1], shh[2 * kk + 1]);
+                            ow[kk] = pack_bf16(fmaf(h0, tanh_approx(h0), h0), fmaf(h1, tanh_approx(h1), h1));
+                        }
+                        o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                    }
+                    const int px = px0 + 32 * rd;
+                    if (up) {
+                        sts128(dstp + (uint32_t)(2 * px + 1) * 16u, o);
+                        sts128(dstp + (uint32_t)(2 * px + 2) * 16u, o);
+                    } else {
+                        sts128(dstp + (uint32_t)(px + 1) * 16u, o);
+                    }
+                }
+            }
+            fence_async_smem();
+            mbar_arrive(smem_u32(&hdr->full_a[sa]));
+            mbar_arrive(smem_u32(&hdr->raw_empty[rs]));
+            if (tr) tw[2] += clock64() - tx0;
+        }
+        if (tr && gt == 0) { long long* o = a.trace + 24 + 4 * gi; o[0] = clock64() - t_begin; o[1] = tw[0]; o[2] = tw[1]; o[3] = tw[2]; }
     }
 
     tc_fence_before();
     __syncthreads();
     if (warp == kMma) {
         __syncwarp();
-        tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
+        tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
@@ -493,6 +528,9 @@ int encode_rows(CUtensorMap* m, const void* basep, int B, int H, int W, int C, i
     if (r != CUDA_SUCCESS) { set_error("conv row: cuTensorMapEncodeTiled failed (%d) for [%d,%d,%d,%d]", (int)r, B, H, W, C); return SDDM_E_CUDA; }
     return SDDM_OK;
 }
+
+long long* g_row_trace = nullptr;   // device buffer [64 launches][32 counters], set by sddm_debug_row_trace
+int g_row_trace_launch = 0;
 
 int device_sms() {
     int dev = 0, n = 0;
@@ -521,33 +559,25 @@ bool conv_row_supported(const ConvP& p) {
     return true;
 }
 
-// shared-memory plan + tensor maps + launch
-static int launch_row(RowArgs a, RowMaps& maps, cudaStream_t st) {
+// shared-memory plan + launch of one instantiation
+template <int KIND, int NMAIN, int NRES, bool UP, bool AFF, bool RESID>
+static int launch_row_t(RowArgs a, const RowMaps& maps, cudaStream_t st) {
     a.nblocks = a.B * (a.H / 16);
-    a.slot_cols = a.final_out ? 32 : 96;
-    a.NS = 5;
-    a.tmem_cols = a.final_out ? 256 : 512;
-    a.NOUT = a.final_out ? 0 : 2;
-    a.NRES = a.res_identity ? 2 : 0;
     const size_t w_al = ((size_t)a.w_bytes + 1023) & ~(size_t)1023;
-    const size_t fixed = kHdr + w_al + (size_t)kEpi * (a.NOUT + a.NRES) * kOutTile;
-    a.NR = 4; a.NA = 4;
-    for (bool grew = true; grew;) {
-        grew = false;
-        if (a.NR < kMaxRing && fixed + (size_t)(a.NR + 1) * kRawStage + (size_t)a.NA * kAStage <= kSmemCap) { ++a.NR; grew = true; }
-        if (a.NA < kMaxRing && fixed + (size_t)a.NR * kRawStage + (size_t)(a.NA + 1) * kAStage <= kSmemCap) { ++a.NA; grew = true; }
-    }
-    if (fixed + (size_t)a.NR * kRawStage + (size_t)a.NA * kAStage > kSmemCap) { set_error("conv row: shared-memory plan does not fit"); return SDDM_E_INVALID; }
+    const int nout = KIND == ROW_FINAL ? 0 : 2, nres = RESID ? 2 : 0;
     a.off_w = kHdr;
     a.off_out = a.off_w + (uint32_t)w_al;                                     // 1024-aligned (swizzled TMA tiles)
-    a.off_res = a.off_out + (uint32_t)(kEpi * a.NOUT) * kOutTile;
-    a.off_raw = a.off_res + (uint32_t)(kEpi * a.NRES) * kOutTile;
-    a.off_a = a.off_raw + (uint32_t)a.NR * kRawStage;
-    const size_t smem = a.off_a + (size_t)a.NA * kAStage + 1024;
-    SDDM_CUDA_TRY(cudaFuncSetAttribute(conv_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemCap + 1024)));   // per device: set every time
+    a.off_res = a.off_out + (uint32_t)(kEpi * nout) * kOutTile;
+    a.off_raw = a.off_res + (uint32_t)(kEpi * nres) * kOutTile;
+    a.off_a = a.off_raw + (uint32_t)kNR * kRawStage;
+    const size_t smem = a.off_a + (size_t)kNA * kAStage + 1024;
+    if (smem > kSmemCap + 1024) { set_error("conv row: shared-memory plan does not fit (%zu bytes)", smem); return SDDM_E_INVALID; }
+    auto kern = conv_row_kernel<KIND, NMAIN, NRES, UP, AFF, RESID>;
+    SDDM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemCap + 1024)));   // per device: set every time
+    a.trace = g_row_trace ? g_row_trace + (size_t)(g_row_trace_launch++ % 64) * 32 : nullptr;
     const int sms = device_sms();
     const int grid = a.nblocks < sms ? a.nblocks : sms;
-    SDDM_CUDA_TRY(launch_pdl(conv_row_kernel, dim3(grid), dim3(kRowThreads), smem, st, a, maps));
+    SDDM_CUDA_TRY(launch_pdl(kern, dim3(grid), dim3(kRowThreads), smem, st, a, maps));
     SDDM_LAUNCH_CHECK();
     return SDDM_OK;
 }
@@ -559,33 +589,36 @@ int launch_conv_row(const ConvP& p, const __nv_bfloat16* w_row, uint32_t w_bytes
     RowMaps maps;
     memset(&maps, 0, sizeof(maps));
     a.B = p.B; a.H = p.Hout;
-    a.final_out = p.Cout == 1;
-    a.up = p.mode == CONV_UP;
-    a.n_main = p.Cin / 32;
-    a.ksteps = 2;
+    const bool final_out = p.Cout == 1, up = p.mode == CONV_UP, aff = p.src[0].scale != nullptr;
     const bool res_conv = p.res_Cin && !p.res_identity;
-    a.n_res = res_conv ? p.res_Cin / 32 : 0;
     a.C0 = p.src[0].C; a.rC0 = p.res_src[0].C;
     a.Cin = p.Cin;
-    a.affine = p.src[0].scale != nullptr;
     a.scale = p.src[0].scale; a.shift = p.src[0].shift;
     a.w = w_row; a.w_bytes = w_bytes;
-    a.n_cols = a.final_out ? 16 : 96;
     a.bias = p.bias; a.temb = p.temb; a.temb_stride = p.temb_stride; a.res_bias = p.res_bias;
-    a.res_identity = p.res_identity;
     a.parts = p.parts; a.nparts = p.nparts;
     a.frames = frames; a.final_bias = final_bias;
     a.gn_on = p.gn_on; a.gn = p.gn;
-    if (!a.final_out && (!p.parts || p.nparts != conv_row_nparts(p.Hout))) { set_error("conv row: nparts mismatch"); return SDDM_E_INVALID; }
+    if (!final_out && (!p.parts || p.nparts != conv_row_nparts(p.Hout))) { set_error("conv row: nparts mismatch"); return SDDM_E_INVALID; }
     int rc;
     for (int i = 0; i < p.nsrc; ++i)
-        if ((rc = encode_rows(&maps.src[i], p.src[i].x, p.B, p.Hin, p.Win, p.src[i].C, a.up ? 64 : 128, 0))) return rc;
+        if ((rc = encode_rows(&maps.src[i], p.src[i].x, p.B, p.Hin, p.Win, p.src[i].C, up ? 64 : 128, 0))) return rc;
     if (res_conv)
         for (int i = 0; i < p.res_nsrc; ++i)
             if ((rc = encode_rows(&maps.rsrc[i], p.res_src[i].x, p.B, p.Hout, RW, p.res_src[i].C, 128, 0))) return rc;
     if (p.res_identity && (rc = encode_rows(&maps.rsrc[0], p.res_src[0].x, p.B, p.Hout, RW, 32, 128, 64))) return rc;
-    if (!a.final_out && (rc = encode_rows(&maps.out, p.out, p.B, p.Hout, RW, 32, 128, 64))) return rc;
-    return launch_row(a, maps, st);
+    if (!final_out && (rc = encode_rows(&maps.out, p.out, p.B, p.Hout, RW, 32, 128, 64))) return rc;
+    // the seven layer shapes of a 128-wide level (config_unet.json: final Block, downs.1 block1 / block2, ups.13, ups.14 block1 / block2)
+    if (final_out && aff) return launch_row_t<ROW_FINAL, 1, 0, false, true, false>(a, maps, st);
+    if (up && p.Cin == 32 && !aff && !res_conv && !p.res_identity) return launch_row_t<ROW_ACT, 1, 0, true, false, false>(a, maps, st);
+    if (up && p.Cin == 32 && aff && !res_conv && !p.res_identity) return launch_row_t<ROW_ACT, 1, 0, true, true, false>(a, maps, st);
+    if (!up && p.Cin == 32 && !aff && !res_conv && !p.res_identity) return launch_row_t<ROW_ACT, 1, 0, false, false, false>(a, maps, st);
+    if (!up && p.Cin == 32 && aff && !res_conv && !p.res_identity) return launch_row_t<ROW_ACT, 1, 0, false, true, false>(a, maps, st);
+    if (!up && p.Cin == 32 && aff && p.res_identity) return launch_row_t<ROW_ACT, 1, 0, false, true, true>(a, maps, st);
+    if (!up && p.Cin == 32 && aff && res_conv) return launch_row_t<ROW_ACT, 1, 2, false, true, false>(a, maps, st);
+    if (!up && p.Cin == 64 && aff && !res_conv && !p.res_identity) return launch_row_t<ROW_ACT, 2, 0, false, true, false>(a, maps, st);
+    set_error("conv row: no instantiation for Cin=%d up=%d affine=%d res_conv=%d identity=%d final=%d", p.Cin, (int)up, (int)aff, (int)res_conv, p.res_identity, (int)final_out);
+    return SDDM_E_INVALID;
 }
 
 // stem: SignalToFrames x 2 + cat + conv3x3(2 -> 32)
@@ -596,18 +629,33 @@ int launch_stem_row(const StemP& p, const __nv_bfloat16* w_row, uint32_t w_bytes
     RowMaps maps;
     memset(&maps, 0, sizeof(maps));
     a.B = p.B; a.H = p.H;
-    a.stem = 1;
-    a.n_main = 1; a.ksteps = 1; a.n_res = 0;
     a.Cin = 2;
     a.w = w_row; a.w_bytes = w_bytes;
-    a.n_cols = 96;
     a.bias = p.bias;
     a.cond = p.cond; a.x_t = p.x_t; a.L = p.L; a.hop = p.hop;
     a.parts = p.parts; a.nparts = p.nparts;
     a.gn_on = p.gn_on; a.gn = p.gn;
     int rc;
     if ((rc = encode_rows(&maps.out, p.out, p.B, p.H, RW, 32, 128, 64))) return rc;
-    return launch_row(a, maps, st);
+    return launch_row_t<ROW_STEM, 1, 0, false, false, false>(a, maps, st);
 }
 
 }  // namespace sddm
+
+// debug: enable != 0 -> (re)start tracing: the next 64 conv_row launches record per-role wait cycles of CTA 0;
+// enable == 0 -> copy the [64][32] counters to host_out (may be null) and stop tracing.
+extern "C" SDDM_API int sddm_debug_row_trace(int enable, long long* host_out) {
+    using namespace sddm;
+    if (enable) {
+        if (!g_row_trace) SDDM_CUDA_TRY(cudaMalloc(&g_row_trace, 64 * 32 * sizeof(long long)));
+        SDDM_CUDA_TRY(cudaMemset(g_row_trace, 0, 64 * 32 * sizeof(long long)));
+        g_row_trace_launch = 0;
+        return SDDM_OK;
+    }
+    if (!g_row_trace) { set_error("tracing was not enabled"); return SDDM_E_STATE; }
+    SDDM_CUDA_TRY(cudaDeviceSynchronize());
+    if (host_out) SDDM_CUDA_TRY(cudaMemcpy(host_out, g_row_trace, 64 * 32 * sizeof(long long), cudaMemcpyDeviceToHost));
+    cudaFree(g_row_trace);
+    g_row_trace = nullptr;
+    return SDDM_OK;
+}
