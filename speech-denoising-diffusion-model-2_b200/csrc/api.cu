@@ -551,10 +551,9 @@ static int build_program(sddm_plan* p, Arena& a) {
         Op& g = p->ops[i];
         const Op& prev = p->ops[i - 1];
         if (g.kind != Op::GN || !want_tc) continue;
-        // Only the row kernels fuse: their CTAs own contiguous row runs, so a sample is finalised by one of <= 3 CTAs.  With the
-        // round-robin tile schedule of conv_tc.cu the CTA that finalises sample n falls behind and is then the last to arrive for
-        // sample n + 1, n + 2, ... too: all finalisations serialise on one CTA (measured: 57 -> 606 us for ups.10.conv).
-        const bool producer_ok = (prev.kind == Op::STEM || prev.kind == Op::CONV) && prev.use_row;
+        // (conv_tc.cu and conv_row.cu give every CTA a contiguous run of tiles / rows: with a round-robin schedule the CTA that
+        //  finalises sample n falls behind and is then the last arriver for every following sample - measured 57 -> 606 us)
+        const bool producer_ok = prev.kind == Op::STEM ? prev.use_row : (prev.kind == Op::CONV && prev.use_tc);
         bool small = true;   // the last-arriving CTA walks every partial of the sample: keep that walk short
         for (int k = 0; k < g.gn_nsrc; ++k) small = small && p->tensors[g.gn_src[k]].nparts <= 256;
         if (producer_ok && small && prev.out == g.gn_src[0]) { g.gn_fused = true; ++fused; }

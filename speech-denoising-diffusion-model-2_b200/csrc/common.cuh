@@ -34,6 +34,32 @@ void count_launch(int n = 1);
         }                                                                                            \
     } while (0)
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize applies per (kernel, DEVICE): set it once per device, not once per process
+// (one process may build plans on several GPUs).  Each expansion site owns its flags.
+#define SDDM_SET_MAX_SMEM(kernel, bytes)                                                                          \
+    do {                                                                                                         \
+        static bool _done[64] = {};                                                                              \
+        int _dev = 0;                                                                                            \
+        if (cudaGetDevice(&_dev) != cudaSuccess) _dev = -1;                                                      \
+        if (_dev < 0 || _dev >= 64 || !_done[_dev]) {                                                            \
+            SDDM_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+            if (_dev >= 0 && _dev < 64) _done[_dev] = true;                                                      \
+        }                                                                                                        \
+    } while (0)
+
+// SM count of the CURRENT device (cached per device)
+inline int device_sm_count() {
+    static int cache[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { cudaGetLastError(); return 148; }
+    if (cache[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) { cudaGetLastError(); n = 148; }
+        cache[dev] = n;
+    }
+    return cache[dev];
+}
+
 // ---------------------------------------------------------------------------------------------------
 // convolution op descriptor, shared by the CUDA-core fp32 kernel and the tcgen05 bf16 kernel.
 // Activations are NHWC fp32 (or bf16 when act16; the pointers below are then reinterpreted) ("raw", i.e. pre-GroupNorm); a source with scale != nullptr is consumed as

@@ -39,6 +39,10 @@
 namespace sddm {
 namespace {
 
+#ifndef SDDM_ROW_TRACE
+#define SDDM_ROW_TRACE 0
+#endif
+
 constexpr int RW = 128;                      // row width = MMA M
 constexpr int kRowThreads = 20 * 32;         // warps 0-3 / 4-7 epilogue groups, 8-15 transform groups, 16 MMA, 17 weights, 18 raw TMA
 constexpr int kEpi = 2, kGrp = 128;
@@ -159,7 +163,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const RowArgs 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = hdr->tmem_base;
-    const bool tr = a.trace != nullptr && blockIdx.x == 0;
+    const bool tr = SDDM_ROW_TRACE && a.trace != nullptr && blockIdx.x == 0;   // compiled out unless built with -DSDDM_ROW_TRACE=1
     long long tw[6] = {0, 0, 0, 0, 0, 0};
     const long long t_begin = tr ? clock64() : 0;
 
@@ -332,17 +336,22 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const RowArgs 
                         *dst = make_float4(s1a, s2a, s1b, s2b);
                     }
                     s1a = s1b = s2a = s2b = 0.f;
-                    if (a.gn_on) {
-                        __threadfence();
-                        group_bar(bar_id);
-                        if (leader) hdr->gn_last[e] = atomicAdd(a.gn.counter + s.n, 1u) == (unsigned)(a.gn.expect - 1) ? 1u : 0u;
-                        group_bar(bar_id);
-                        if (hdr->gn_last[e]) {
-                            __threadfence();
-                            gn_fused_finalize(a.gn, s.n, m, kGrp);
-                            if (leader) a.gn.counter[s.n] = 0u;
-                        }
-                    }
+                }
+            }
+            // one arrival per (segment, group) - an atomic round trip per block would cost ~1.5 us each: this group's rows of sample n
+            // are done and their partials published; the group that completes the sample's H rows finalises the consumer's GroupNorm
+            if (KIND != ROW_FINAL && a.gn_on) {
+                __threadfence();
+                group_bar(bar_id);
+                if (leader) {
+                    const unsigned add = (unsigned)((s.yb - s.ya) >> 1);
+                    hdr->gn_last[e] = atomicAdd(a.gn.counter + s.n, add) + add == (unsigned)a.gn.expect ? 1u : 0u;
+                }
+                group_bar(bar_id);
+                if (hdr->gn_last[e]) {
+                    __threadfence();
+                    gn_fused_finalize(a.gn, s.n, m, kGrp);
+                    if (leader) a.gn.counter[s.n] = 0u;
                 }
             }
         }
@@ -532,19 +541,12 @@ int encode_rows(CUtensorMap* m, const void* basep, int B, int H, int W, int C, i
 long long* g_row_trace = nullptr;   // device buffer [64 launches][32 counters], set by sddm_debug_row_trace
 int g_row_trace_launch = 0;
 
-int device_sms() {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
-        cudaGetLastError();
-        n = 148;
-    }
-    return n;
-}
+int device_sms() { return device_sm_count(); }
 
 }  // namespace
 
 int conv_row_nparts(int H) { return (H / 16) * 8; }
-int conv_row_arrivals(int H) { return (H / 16) * 2; }
+int conv_row_arrivals(int H) { return H; }   // the counter adds up completed rows
 
 bool conv_row_supported(const ConvP& p) {
     if (!p.act16 || p.Wout != RW || p.Hout % 16 || p.Hout < 16) return false;
@@ -573,7 +575,7 @@ static int launch_row_t(RowArgs a, const RowMaps& maps, cudaStream_t st) {
     const size_t smem = a.off_a + (size_t)kNA * kAStage + 1024;
     if (smem > kSmemCap + 1024) { set_error("conv row: shared-memory plan does not fit (%zu bytes)", smem); return SDDM_E_INVALID; }
     auto kern = conv_row_kernel<KIND, NMAIN, NRES, UP, AFF, RESID>;
-    SDDM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemCap + 1024)));   // per device: set every time
+    SDDM_SET_MAX_SMEM(kern, kSmemCap + 1024);
     a.trace = g_row_trace ? g_row_trace + (size_t)(g_row_trace_launch++ % 64) * 32 : nullptr;
     const int sms = device_sms();
     const int grid = a.nblocks < sms ? a.nblocks : sms;

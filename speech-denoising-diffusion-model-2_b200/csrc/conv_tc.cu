@@ -248,8 +248,9 @@ struct SmemHdr {
     uint32_t gn_last[kEpiGroups];
     uint32_t pad[13];
     float addv[kEpiGroups][256];
+    alignas(16) float red[kEpiGroups][4][32][2];   // per-warp (pixel quarter) column sums of one 32-channel block, combined to one partial per tile
 };
-constexpr uint32_t kHdrBytes = 3072;
+constexpr uint32_t kHdrBytes = 5120;
 static_assert(sizeof(SmemHdr) <= kHdrBytes, "header too large");
 
 struct TileCoord { int n, oy0, ox0, trem; };
@@ -279,6 +280,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
     const ConvP& p = a.p;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nA = a.n_main + a.n_res;
+    // contiguous tile run of this CTA (near-equal split): a sample is touched by few CTAs, so the GroupNorm finalisation of one
+    // sample (gn_fuse.cuh) cannot make the same CTA the last arriver of every following sample, and neighbouring tiles share L2 lines
+    const int tq = a.ntiles / (int)gridDim.x, trm = a.ntiles - tq * (int)gridDim.x;
+    const int tile0 = (int)blockIdx.x * tq + ((int)blockIdx.x < trm ? (int)blockIdx.x : trm);
+    const int tend = tile0 + tq + ((int)blockIdx.x < trm ? 1 : 0);
     pdl_launch_dependents();   // PDL: the next kernel's CTAs may be scheduled as soon as SMs free up
 
     if (tid == 0) {
@@ -325,11 +331,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
         const uint32_t addv_u32 = smem_u32(hdr->addv[e]);
         // tiles of this group: it = e, e + 2, ...
         int my_tiles = 0;
-        for (int it = e, tile = blockIdx.x + e * gridDim.x; tile < a.ntiles; tile += 2 * gridDim.x, it += 2) ++my_tiles;
+        for (int it = e, tile = tile0 + e; tile < tend; tile += 2, it += 2) ++my_tiles;
         const int total_blocks = my_tiles * nblk;
         auto issue_res = [&](int g) {   // leader: prefetch the identity-residual tile of this group's block g
             const int k = g / nblk, cb = g - k * nblk;
-            const TileCoord t = decode_tile(a, blockIdx.x + (e + 2 * k) * gridDim.x);
+            const TileCoord t = decode_tile(a, tile0 + (e + 2 * k));
             const int buf = g % a.NRES;
             const uint32_t bar = smem_u32(&hdr->res_full[e][buf]);
             mbar_expect_tx(bar, kOutTileBytes);
@@ -347,8 +353,27 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
         const int c2 = lane & 15, hrow = lane >> 4;
         int g = 0;
         uint32_t aph = 0;
-        for (int tile = blockIdx.x + e * gridDim.x; tile < a.ntiles; tile += 2 * gridDim.x, aph ^= 1u) {
+        // GroupNorm finalisation of the consumer (gn_fuse.cuh): the tiles of a CTA are contiguous, so this group counts its tiles of
+        // the current sample and arrives ONCE when it moves on (an atomic round trip per tile would cost ~1.5 us each); the group
+        // whose arrival completes the sample's tile count finalises it
+        int gn_n = -1;
+        unsigned gn_cnt = 0;
+        auto gn_flush = [&]() {
+            if (!p.gn_on || gn_cnt == 0) return;
+            __threadfence();
+            group_bar(bar_id);
+            if (leader) hdr->gn_last[e] = atomicAdd(p.gn.counter + gn_n, gn_cnt) + gn_cnt == (unsigned)p.gn.expect ? 1u : 0u;
+            group_bar(bar_id);
+            if (hdr->gn_last[e]) {
+                __threadfence();
+                gn_fused_finalize(p.gn, gn_n, m, kEpiGroupThreads);
+                if (leader) p.gn.counter[gn_n] = 0u;
+            }
+            gn_cnt = 0;
+        };
+        for (int tile = tile0 + e; tile < tend; tile += 2, aph ^= 1u) {
             const TileCoord t = decode_tile(a, tile);
+            if (t.n != gn_n) { gn_flush(); gn_n = t.n; }
             const bool valid = (t.oy0 + py) < p.Hout && (t.ox0 + px) < p.Wout;
             if (a.temb_per_row) {   // explicit per-row noise levels (sddm_eps with a noise_level vector)
                 group_bar(bar_id);
@@ -456,10 +481,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
                     }
                     s1a += __shfl_xor_sync(0xffffffffu, s1a, 16); s1b += __shfl_xor_sync(0xffffffffu, s1b, 16);
                     s2a += __shfl_xor_sync(0xffffffffu, s2a, 16); s2b += __shfl_xor_sync(0xffffffffu, s2b, 16);
-                    if (hrow == 0) {
-                        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float2*>(p.parts) + ((int64_t)t.n * p.nparts + t.trem * 4 + w4) * p.Cout + cb * 32 + 2 * c2);
-                        *dst = make_float4(s1a, s2a, s1b, s2b);
-                    }
+                    if (hrow == 0) *reinterpret_cast<float4*>(&hdr->red[e][w4][2 * c2][0]) = make_float4(s1a, s2a, s1b, s2b);
                 } else if (p.parts) {   // column sums of the staged tile: channel = lane, pixel quarter = warp
                     float s1 = 0.f, s2 = 0.f;
                     const uint32_t qbase = obuf + (uint32_t)(w4 * 32) * 128u;
@@ -469,22 +491,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
                         s1 += x;
                         s2 = fmaf(x, x, s2);
                     }
-                    float2* dst = reinterpret_cast<float2*>(p.parts) + ((int64_t)t.n * p.nparts + t.trem * 4 + w4) * p.Cout + cb * 32 + lane;
-                    *dst = make_float2(s1, s2);
+                    *reinterpret_cast<float2*>(&hdr->red[e][w4][lane][0]) = make_float2(s1, s2);
+                }
+                if (p.parts && !(a.skip & 1)) {   // one partial per tile: the four pixel quarters are added in a fixed order
+                    group_bar(bar_id);
+                    if (m < 32) {
+                        float2 acc = *reinterpret_cast<const float2*>(&hdr->red[e][0][m][0]);
+#pragma unroll
+                        for (int qq = 1; qq < 4; ++qq) {
+                            const float2 v2 = *reinterpret_cast<const float2*>(&hdr->red[e][qq][m][0]);
+                            acc.x += v2.x; acc.y += v2.y;
+                        }
+                        reinterpret_cast<float2*>(p.parts)[((int64_t)t.n * p.nparts + t.trem) * p.Cout + cb * 32 + m] = acc;
+                    }
                 }
             }
-            if (p.gn_on) {   // publish this tile's partials; the group that completes sample n finalises the consumer's GroupNorm
-                __threadfence();
-                group_bar(bar_id);
-                if (leader) hdr->gn_last[e] = atomicAdd(p.gn.counter + t.n, 1u) == (unsigned)(p.gn.expect - 1) ? 1u : 0u;
-                group_bar(bar_id);
-                if (hdr->gn_last[e]) {
-                    __threadfence();
-                    gn_fused_finalize(p.gn, t.n, m, kEpiGroupThreads);
-                    if (leader) p.gn.counter[t.n] = 0u;
-                }
-            }
+            ++gn_cnt;
         }
+        gn_flush();
         if (leader) bulk_wait_all();
         if (tr && leader) {
             long long* o = a.trace + (e == 0 ? 0 : 8);
@@ -513,7 +537,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
         auto skip_slabs = [&](int n) { sa += n; while (sa >= a.NA) { sa -= a.NA; pa ^= 1u; } };
         bool w_ready = false;   // resident weights: all chunks have landed (after this warp's first tile)
         if (mw < nmma) skip_slabs(mw * nA);
-        for (int it = mw, tile = blockIdx.x + mw * gridDim.x; mw < nmma && tile < a.ntiles; tile += nmma * gridDim.x, it += nmma) {
+        for (int it = mw, tile = tile0 + mw; mw < nmma && tile < tend; tile += nmma, it += nmma) {
             const int as = it & 1;
             const uint32_t aph = (uint32_t)(it >> 1) & 1u;
             mbar_wait_t(smem_u32(&hdr->tmem_empty[as]), aph ^ 1u, tr, tw[0]);
@@ -601,7 +625,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
             const uint32_t w_ring = base_u32 + a.off_w;
             int sw = 0;
             uint32_t pw = 0;
-            for (int it = 0, tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
+            for (int it = 0, tile = tile0; tile < tend; ++tile, ++it) {
                 if (a.resident && it > 0) break;
                 for (int c = 0; c < nchunks; ++c) {
                     const bool is_res = c >= a.n_main_chunks;
@@ -631,7 +655,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
             const uint32_t raw_ring = base_u32 + a.off_raw;
             int rs = 0;
             uint32_t pr = 0;
-            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+            for (int tile = tile0; tile < tend; ++tile) {
                 const TileCoord t = decode_tile(a, tile);
                 const int yo = org_of<MODE>(t.oy0), xo = org_of<MODE>(t.ox0);
                 for (int ai = 0; ai < nA; ++ai) {
@@ -696,13 +720,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
         };
 
         // this group's position in the CTA-wide (tile, slab) sequence and in the rings; it advances kXfGroups slabs at a time
-        int tile = blockIdx.x, ai = gi;
-        while (ai >= nA) { ai -= nA; tile += gridDim.x; }
+        int tile = tile0, ai = gi;
+        while (ai >= nA) { ai -= nA; tile += 1; }
         int rs = gi % a.NR, sa = gi % a.NA;
         uint32_t pr = (uint32_t)(gi / a.NR) & 1u, pa = (uint32_t)(gi / a.NA) & 1u;
         int cur_tile = -1;
         TileCoord t{0, 0, 0, 0};
-        while (tile < a.ntiles) {
+        while (tile < tend) {
             const long long ts0 = tr ? clock64() : 0;
             if (tile != cur_tile) { t = decode_tile(a, tile); cur_tile = tile; }
             const bool is_res = ai >= a.n_main;
@@ -842,7 +866,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
             if (tr) { tw[3] += ts2 - ts1; tw[4] += clock64() - ts2; }
             // advance by kXfGroups slabs
             ai += kXfGroups;
-            while (ai >= nA) { ai -= nA; tile += gridDim.x; }
+            while (ai >= nA) { ai -= nA; tile += 1; }
             rs += kXfGroups; if (rs >= a.NR) { rs -= a.NR; pr ^= 1u; }
             sa += kXfGroups; if (sa >= a.NA) { sa -= a.NA; pa ^= 1u; }
         }
@@ -951,17 +975,7 @@ __global__ void __launch_bounds__(128) umma_rate_kernel(int N, int reps, int nA,
     if (warp == 0) { __syncwarp(); tmem_dealloc(tmem, 256); }
 }
 
-int num_sms() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
-            cudaGetLastError();
-            n = 148;
-        }
-    }
-    return n;
-}
+int num_sms() { return device_sm_count(); }
 
 long long* g_trace = nullptr;   // device buffer [64 launches][48 counters], set by sddm_debug_tc_trace
 int g_trace_launch = 0;
@@ -1069,11 +1083,7 @@ int launch_mode(TcArgs a, cudaStream_t st) {
     if ((rc = encode_nhwc(&maps.out, p.out, p.B, p.Hout, p.Wout, p.Cout, 32, TW, TH, swz_tile, A16))) return rc;
     if (p.res_identity && (rc = encode_nhwc(&maps.res, p.res_src[0].x, p.B, p.Hout, p.Wout, p.Cout, 32, TW, TH, swz_tile, A16))) return rc;
 
-    static bool attr_set = false;
-    if (!attr_set) {
-        SDDM_CUDA_TRY(cudaFuncSetAttribute(conv3x3_tc_kernel<MODE, TPC, A16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
-        attr_set = true;
-    }
+    SDDM_SET_MAX_SMEM((conv3x3_tc_kernel<MODE, TPC, A16>), kSmemMax);
     { static int skip = -1; if (skip < 0) { const char* e = getenv("SDDM_TC_SKIP"); skip = e ? atoi(e) : 0; } a.skip = skip; }
     a.trace = g_trace ? g_trace + (size_t)(g_trace_launch++ % 64) * 48 : nullptr;
     const int grid = a.ntiles < num_sms() ? a.ntiles : num_sms();
@@ -1092,7 +1102,7 @@ bool conv_tc_supported(const ConvP& p) {
     return p.mode == CONV_S1 || p.mode == CONV_S2 || p.mode == CONV_UP;
 }
 
-int conv_tc_nparts(int Hout, int Wout) { return ((Hout + TH - 1) / TH) * ((Wout + TW - 1) / TW) * 4; }
+int conv_tc_nparts(int Hout, int Wout) { return ((Hout + TH - 1) / TH) * ((Wout + TW - 1) / TW); }
 int conv_tc_tiles(int Hout, int Wout) { return ((Hout + TH - 1) / TH) * ((Wout + TW - 1) / TW); }
 
 int launch_conv_tc(const ConvP& p, cudaStream_t st) {
@@ -1110,7 +1120,7 @@ int launch_conv_tc(const ConvP& p, cudaStream_t st) {
     a.ntiles = p.B * a.tiles_x * a.tiles_y;
     a.magic_per = (0x100000000ull + (unsigned long long)(a.tiles_x * a.tiles_y) - 1) / (unsigned long long)(a.tiles_x * a.tiles_y);
     a.magic_tx = (0x100000000ull + (unsigned long long)a.tiles_x - 1) / (unsigned long long)a.tiles_x;
-    if (p.parts && p.nparts != a.tiles_x * a.tiles_y * 4) { set_error("conv tc: nparts mismatch"); return SDDM_E_INVALID; }
+    if (p.parts && p.nparts != a.tiles_x * a.tiles_y) { set_error("conv tc: nparts mismatch"); return SDDM_E_INVALID; }
     a.n_res = has_res_conv ? p.res_Cin / 32 : 0;
     a.n_res_chunks = has_res_conv ? p.res_Cin / 32 : 0;
     a.acc_stride = p.Cout <= 32 ? 32 : (p.Cout <= 64 ? 64 : (p.Cout <= 128 ? 128 : 256));

@@ -462,11 +462,7 @@ __global__ void __launch_bounds__(192, 1) dw_cond_tc_kernel(const __grid_constan
 
 int launch_dw_layer_tc(const DwLayerTc& p, cudaStream_t st) {
     if (p.T % kTile) { set_error("diffwave tc: T must be a multiple of %d", kTile); return SDDM_E_INVALID; }
-    static bool attr = false;
-    if (!attr) {
-        SDDM_CUDA_TRY(cudaFuncSetAttribute(dw_layer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLayerSmem));
-        attr = true;
-    }
+    SDDM_SET_MAX_SMEM(dw_layer_tc_kernel, kLayerSmem);
     // tensor maps depend only on (buffers, shape): cache them (one sampling run re-launches the same 30 layers T_steps times)
     static std::map<std::tuple<const void*, const void*, const void*, const void*, const void*, int, int>, LayerMaps> cache;
     const auto key = std::make_tuple((const void*)p.x_in, (const void*)p.x_out, (const void*)p.cond, (const void*)p.zc, (const void*)p.w1, p.B, p.T);
@@ -492,11 +488,7 @@ int launch_dw_layer_tc(const DwLayerTc& p, cudaStream_t st) {
 
 int launch_dw_final_tc(const DwFinalTc& p, cudaStream_t st) {
     if (p.T % kTile) { set_error("diffwave tc: T must be a multiple of %d", kTile); return SDDM_E_INVALID; }
-    static bool attr = false;
-    if (!attr) {
-        SDDM_CUDA_TRY(cudaFuncSetAttribute(dw_final_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFinSmem));
-        attr = true;
-    }
+    SDDM_SET_MAX_SMEM(dw_final_tc_kernel, kFinSmem);
     static std::map<std::tuple<const void*, const void*, int, int, int>, FinalMaps> cache;
     const auto key = std::make_tuple((const void*)p.zc, (const void*)p.ws, p.L, p.B, p.T);
     auto it = cache.find(key);
@@ -517,11 +509,7 @@ int launch_dw_final_tc(const DwFinalTc& p, cudaStream_t st) {
 
 int launch_dw_cond_tc(const DwCondTc& p, cudaStream_t st) {
     if (p.T % kTile || p.KP % 64) { set_error("diffwave tc: T %% 128 and KP %% 64 must be 0"); return SDDM_E_INVALID; }
-    static bool attr = false;
-    if (!attr) {
-        SDDM_CUDA_TRY(cudaFuncSetAttribute(dw_cond_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCondSmem));
-        attr = true;
-    }
+    SDDM_SET_MAX_SMEM(dw_cond_tc_kernel, kCondSmem);
     CondMaps m;
     int rc = encode_bf16(&m.up, p.up, p.KP, p.KP, p.T, 0, 128);
     if (rc) return rc;

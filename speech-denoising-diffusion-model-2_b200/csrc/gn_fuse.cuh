@@ -27,20 +27,20 @@ __device__ __forceinline__ void gn_fused_finalize(const GnFuse& f, int n, int ti
             const int lo = c_lo > off ? c_lo : off, hi = (c_lo + cpg) < (off + C) ? (c_lo + cpg) : (off + C);
             const int w = hi - lo;                         // channels of this group inside source s
             if (w > 0) {
-                // flat (part, channel) walk with independent loads: 8 are in flight per thread (the walk is latency-bound)
+                // flat (part, channel) walk with independent loads: 16 are in flight per thread (the walk is latency-bound)
                 const float2* basep = reinterpret_cast<const float2*>(f.parts[s]) + (int64_t)n * np * C + (lo - off);
                 const int total = np * w;
 #pragma unroll 1
-                for (int i0 = sub; i0 < total; i0 += lanes * 8) {
-                    float2 v[8];
+                for (int i0 = sub; i0 < total; i0 += lanes * 16) {
+                    float2 v[16];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
+                    for (int u = 0; u < 16; ++u) {
                         const int i = i0 + u * lanes;
                         const int part = w == 1 ? i : i / w, j = w == 1 ? 0 : i - part * w;
                         v[u] = i < total ? __ldcg(basep + (int64_t)part * C + j) : make_float2(0.f, 0.f);
                     }
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) { sum += (double)v[u].x; sq += (double)v[u].y; }
+                    for (int u = 0; u < 16; ++u) { sum += (double)v[u].x; sq += (double)v[u].y; }
                 }
             }
             off += C;

@@ -581,11 +581,7 @@ int launch_final_conv(const FinalP& p, cudaStream_t st) {
     const int grid = ntiles < 148 * 4 ? ntiles : 148 * 4;
 #define SDDM_FINAL_LAUNCH(CC, FF, AA)                                                                                      \
     do {                                                                                                                  \
-        static bool attr = false;                                                                                         \
-        if (!attr) {                                                                                                      \
-            SDDM_CUDA_TRY(cudaFuncSetAttribute(final_conv_kernel<CC, FF, AA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 18 * 18 * CC * 4)); \
-            attr = true;                                                                                                  \
-        }                                                                                                                 \
+        SDDM_SET_MAX_SMEM((final_conv_kernel<CC, FF, AA>), 18 * 18 * CC * 4);                                           \
         final_conv_kernel<CC, FF, AA><<<grid, 4 * CC, smem, st>>>(p);                                                     \
     } while (0)
     if (p.act16 && !p.fast_math) { set_error("final conv: bf16 activations come with the tcgen05 path"); return SDDM_E_INVALID; }

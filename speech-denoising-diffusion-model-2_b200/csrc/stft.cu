@@ -209,11 +209,7 @@ extern "C" SDDM_API int sddm_stft_features(const float* wav, int B, int L, int n
     if (mel_fb && n_mels <= 0) { set_error("stft: n_mels must be positive with a filterbank"); return SDDM_E_INVALID; }
     StftP p{wav, window, mel_fb, mel_fb ? mel_lo : nullptr, mel_fb ? mel_hi : nullptr, out, B, L, hop, 1 + L / hop, mel_fb ? n_mels : 0, log_clamp, inv_norm};
     const size_t smem = (520 + 8 * ZPAD) * sizeof(float2) + (size_t)NFFT * sizeof(float) + (size_t)NBIN * TILE_LD * sizeof(float);
-    static bool attr = false;
-    if (!attr) {
-        SDDM_CUDA_TRY(cudaFuncSetAttribute(stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
-    }
+    SDDM_SET_MAX_SMEM(stft_kernel, smem);
     dim3 grid((p.frames + FPB - 1) / FPB, B);
     stft_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(p);
     SDDM_LAUNCH_CHECK();

@@ -239,16 +239,7 @@ int encode_bf16_view(CUtensorMap* m, const void* base, int cols, long long row_p
     return SDDM_OK;
 }
 
-int num_sms() {
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
-    }
-    return n;
-}
+int num_sms() { return device_sm_count(); }
 
 
 }  // namespace

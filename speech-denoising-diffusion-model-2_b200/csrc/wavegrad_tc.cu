@@ -203,11 +203,7 @@ __global__ void __launch_bounds__(kThreads, 1) wg_conv_tc_kernel(const __grid_co
 
 int launch_wg_conv_tc(const WgTcConv& p, cudaStream_t st) {
     if (p.Cin % 64 || p.H % 32 || p.Ntot != p.phases * p.H || p.ntaps < 1 || p.ntaps > 3) { set_error("wavegrad tc: unsupported conv shape (Cin=%d H=%d N=%d taps=%d)", p.Cin, p.H, p.Ntot, p.ntaps); return SDDM_E_INVALID; }
-    static bool attr = false;
-    if (!attr) {
-        SDDM_CUDA_TRY(cudaFuncSetAttribute(wg_conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
-        attr = true;
-    }
+    SDDM_SET_MAX_SMEM(wg_conv_tc_kernel, kSmem);
     static std::map<std::tuple<const void*, const void*, long long, long long, int, int, int, int>, WgMaps> cache;
     const auto key = std::make_tuple((const void*)p.a, (const void*)p.w, p.a_row_pitch, p.a_batch_pitch, p.rows, p.Cin, p.Ntot, p.B * 4 + p.ntaps);
     auto it = cache.find(key);

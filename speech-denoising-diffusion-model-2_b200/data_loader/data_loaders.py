@@ -40,15 +40,22 @@ def load_wave(path, sample_rate: int = None) -> torch.Tensor:
     return torch.from_numpy(np.ascontiguousarray(x)).reshape(1, -1)
 
 
-def save_wave(path, wave: torch.Tensor, sample_rate: int = 16000) -> None:
-    """float32 waveform [1, n] / [n] -> 16-bit PCM ``.wav`` (what torchaudio.save writes for float input), or ``.npy``."""
+def save_wave(path, wave: torch.Tensor, sample_rate: int = 16000, bits: int = 32) -> None:
+    """float32 waveform [1, n] / [n] -> ``.wav`` or ``.npy``.  bits=32 (default) writes IEEE-float WAV, which is what the
+    reference's torchaudio.save(path, float32 tensor, sr) produces (infer.py:115-120): no quantisation ahead of PESQ / SI-SNR
+    evaluation; bits=16 writes rounded, clipped 16-bit PCM."""
     x = wave.detach().to("cpu", torch.float32).reshape(-1).numpy()
     path = str(path)
     if path.endswith(".npy"):
         np.save(path, x)
         return
     from scipy.io import wavfile
-    wavfile.write(path, sample_rate, np.clip(np.round(x * 32768.0), -32768, 32767).astype(np.int16))
+    if bits == 32:
+        wavfile.write(path, sample_rate, np.ascontiguousarray(x, dtype=np.float32))
+    elif bits == 16:
+        wavfile.write(path, sample_rate, np.clip(np.round(x * 32768.0), -32768, 32767).astype(np.int16))
+    else:
+        raise ValueError("bits must be 32 (float) or 16 (PCM)")
 
 
 def chunk_waveform(wave: torch.Tensor, T: int) -> torch.Tensor:

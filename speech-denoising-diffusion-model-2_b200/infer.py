@@ -48,13 +48,30 @@ def enhance_batch(model, condition: torch.Tensor, **kw) -> torch.Tensor:
 
 
 @torch.no_grad()
-def enhance_utterances(model, waves: Sequence[torch.Tensor], batch_chunks: int = 64, seed: int = 0,
+def _resolve_seed(seed: Optional[int], world: int) -> int:
+    """seed=None: draw one from torch's CPU generator (so torch.manual_seed governs it, as it governs the reference's torch.randn
+    draws) and share rank 0's value, since the Philox stream is keyed by (seed, GLOBAL row)."""
+    if seed is not None:
+        return int(seed)
+    s = torch.randint(0, 2 ** 62, (1,), dtype=torch.int64)
+    if world > 1:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+            s = s.to(dev)
+            dist.broadcast(s, src=0)
+            s = s.cpu()
+    return int(s.item())
+
+
+def enhance_utterances(model, waves: Sequence[torch.Tensor], batch_chunks: int = 64, seed: Optional[int] = None,
                        rank: int = 0, world: int = 1) -> List[torch.Tensor]:
     """Chunk every utterance to [n_i,1,L] (InferDataset semantics), enhance the rows this rank owns in sub-batches,
     gather, and regroup to one waveform per utterance trimmed to its original length.  The Philox stream is keyed
     by the GLOBAL row id, so the result does not depend on `world` or `batch_chunks`."""
     L = model.noise_estimate_model.cfg["num_samples"]
     device = next(model.parameters()).device
+    seed = _resolve_seed(seed, world)
     ds = module_data.InferDataset([(None, w) for w in waves], T=L)
     _, rows, index = module_data.infer_data_collate([ds[i] for i in range(len(ds))])
     n = rows.shape[0]
@@ -68,12 +85,13 @@ def enhance_utterances(model, waves: Sequence[torch.Tensor], batch_chunks: int =
 
 
 @torch.no_grad()
-def generate_from_spectrograms(model, specs: Sequence[torch.Tensor], batch: int = 8, seed: int = 0, rank: int = 0,
+def generate_from_spectrograms(model, specs: Sequence[torch.Tensor], batch: int = 8, seed: Optional[int] = None, rank: int = 0,
                                world: int = 1) -> List[torch.Tensor]:
     """SDDM_spectrogram.infer over a list of [bins, frames] spectrograms: utterances are sharded contiguously over the ranks
     (no communication inside the loop), equal-length neighbours are batched, Philox is keyed by the GLOBAL utterance id.
     Returns this rank's waveforms ([1, hop * frames] each) in utterance order, with None for utterances of other ranks."""
     device = next(model.parameters()).device
+    seed = _resolve_seed(seed, world)
     lo, hi = shard_bounds(len(specs), world, rank)
     outs: List[Optional[torch.Tensor]] = [None] * len(specs)
     i = lo
@@ -89,7 +107,7 @@ def generate_from_spectrograms(model, specs: Sequence[torch.Tensor], batch: int 
     return outs
 
 
-def main(config, inputs: Sequence[str], out_dir: Optional[str] = None):
+def main(config, inputs: Sequence[str], out_dir: Optional[str] = None, seed: Optional[int] = None):
     import os
     import pathlib
     import numpy as np
@@ -109,10 +127,10 @@ def main(config, inputs: Sequence[str], out_dir: Optional[str] = None):
                 cfg = config.config.get("spectrogram", {"window_length": 1024, "hop_samples": 256})
                 tr = PS.Spectrogram(n_fft=cfg["window_length"], hop_length=cfg["hop_samples"], window_fn=torch.hamming_window, log_clamp=True)
                 specs.append(tr(module_data.load_wave(f, sr).to(device))[0].cpu())
-        outs = generate_from_spectrograms(model, specs, batch=bs)
+        outs = generate_from_spectrograms(model, specs, batch=bs, seed=seed)
     else:
         waves = [module_data.load_wave(f, sr).reshape(-1) for f in inputs]
-        outs = enhance_utterances(model, waves, batch_chunks=bs)
+        outs = enhance_utterances(model, waves, batch_chunks=bs, seed=seed)
     out_path = (config.save_dir / "samples" / "output") if out_dir is None else pathlib.Path(out_dir)
     out_path.mkdir(parents=True, exist_ok=True)
     for f, o in zip(inputs, outs):
@@ -130,5 +148,6 @@ if __name__ == "__main__":
     args.add_argument("--inputs", "--npy", nargs="+", default=[], dest="inputs",
                       help="noisy utterances (.wav / .npy waveforms) or, for SDDM_spectrogram, spectrograms (.npy [bins, frames])")
     args.add_argument("--out", default=None, type=str)
+    args.add_argument("--seed", default=None, type=int, help="Philox seed of the sampling noise (default: drawn from torch's generator)")
     parsed = args.parse_args()
-    main(ConfigParser.from_args(parsed), parsed.inputs, parsed.out)
+    main(ConfigParser.from_args(parsed), parsed.inputs, parsed.out, parsed.seed)

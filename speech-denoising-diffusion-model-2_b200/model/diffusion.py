@@ -108,6 +108,15 @@ class GaussianDiffusion(nn.Module):
             self._host = {k: getattr(self, k).detach().cpu().numpy().astype(np.float32) for k in _BUFFERS}
         return self._host
 
+    def tables_key(self) -> str:
+        """Content hash of the schedule tables: the plan caches of the denoisers key on it (an id() can be reused by a rebuilt dict
+        after a checkpoint load)."""
+        import hashlib
+        h = hashlib.sha1()
+        for k in _BUFFERS:
+            h.update(self.host_tables()[k].tobytes())
+        return h.hexdigest()
+
     def _load_from_state_dict(self, *a, **k):
         self._host = None
         return super()._load_from_state_dict(*a, **k)

@@ -164,8 +164,11 @@ class SDDM_spectrogram(SDDM):
         z = (lambda k: None) if noises is None else (lambda k: noises[k].reshape(B, 1, Ls))
         x_t = d._x_T("original", torch.empty(B, 1, Ls, device=condition.device), z(0), seed)      # pure-noise start (:216)
         samples = [condition]
+        if isinstance(net, DiffWave):
+            plan.condition(condition)          # step independent: evaluated once for this spectrogram, reused by every step below
         for t in range(T, 0, -1):
-            predicted = plan.eps(condition, x_t, t=t).reshape(x_t.shape)
+            predicted = (plan.eps(condition, x_t, t=t, reuse_condition=True) if isinstance(net, DiffWave)
+                         else plan.eps(condition, x_t, t=t)).reshape(x_t.shape)
             x_t = d.p_transition(x_t, t, predicted, noise=z(T + 1 - t) if t > 1 else None, seed=seed + t)
             if t % every == 0:
                 samples.append(x_t)

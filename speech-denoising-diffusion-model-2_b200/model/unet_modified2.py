@@ -130,7 +130,7 @@ class UNetModified2(nn.Module):
                                "there is no CPU fallback")
         prec = precision if precision is not None else (self.precision if self.precision is not None else default_precision())
         tables = diffusion.host_tables() if diffusion is not None else None
-        key = (id(tables), prec, str(dev), self._param_version())
+        key = (diffusion.tables_key() if diffusion is not None else None, prec, str(dev), self._param_version())
         plan = self._plans.get(key)
         if plan is None:
             self._plans = {k: v for k, v in self._plans.items() if k[3] == key[3]}   # drop plans of stale weights

@@ -232,7 +232,7 @@ class WaveGrad(nn.Module):
         prec = precision if precision is not None else (self.precision if self.precision is not None else default_precision())
         prec = _lib.PREC_FP32 if prec == _lib.PREC_FP32 else _lib.PREC_BF16      # bf16act == bf16 for this denoiser
         tables = diffusion.host_tables() if diffusion is not None else None
-        key = (id(tables), noise_condition, prec, str(dev), self._param_version())
+        key = (diffusion.tables_key() if diffusion is not None else None, noise_condition, prec, str(dev), self._param_version())
         plan = self._plans.get(key)
         if plan is None:
             self._plans = {k: v for k, v in self._plans.items() if k[4] == key[4]}
