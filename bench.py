@@ -279,7 +279,7 @@ def run_cfg3(args):
     torch.cuda.set_device(dev)
     torch.manual_seed(0)
     net = UNetModified2(**UNET)
-    net.precision = {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16act": PREC_BF16_ACT}[args.precision]
+    net.precision = {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16act": PREC_BF16_ACT, "bf16x3": 3}[args.precision]
     model = SDDM(GaussianDiffusion("linear", T_STEPS, 1e-6, 1e-3, device=dev), net, p_transition="condition_in").to(dev).eval()
     lengths = cfg3_lengths()
     g = torch.Generator().manual_seed(824)
@@ -698,7 +698,7 @@ def run_ours(args):
     torch.cuda.set_device(dev)
     torch.manual_seed(0)
     net = UNetModified2(**UNET)
-    net.precision = {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16act": PREC_BF16_ACT}[args.precision]
+    net.precision = {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16act": PREC_BF16_ACT, "bf16x3": 3}[args.precision]
     model = SDDM(GaussianDiffusion("linear", T_STEPS, 1e-6, 1e-3, device=dev), net, p_transition="condition_in").to(dev).eval()
     B = args.batch
     cond_host = synth_batch(B, 1000 + rank).pin_memory()
@@ -748,6 +748,20 @@ def run_ours(args):
         prof = plan.profile_report()
         plan.profile(False)
     ms_e2e = timed(step_e2e, args.steps)
+    lat = None
+    if rank == 0 and world == 1:
+        # BASELINE configs[0] (the reference's CPU-runnable case) on the GPU: ONE 2 s clip = 2 chunks, full 100 steps, end to end through
+        # the host-buffer C-ABI call; the latency a single-utterance caller sees (this size is launch / latency bound, not bandwidth bound)
+        clip = (0.05 * torch.randn(1, 32000, generator=torch.Generator().manual_seed(1)))
+        c2 = torch.nn.functional.pad(clip, (0, 2 * L - 32000)).view(2, 1, L).contiguous().pin_memory()
+        o2 = torch.empty_like(c2).pin_memory()
+        ts = []
+        for i in range(7):
+            t0 = time.perf_counter()
+            plan.enhance_host(c2, "condition_in", seed=i, row0=0, max_rows=2, out=o2)
+            ts.append(1e3 * (time.perf_counter() - t0))
+        lat = {"ms_median": statistics.median(ts[2:]), "ms_min": min(ts[2:]), "rows": 2, "clip_seconds": 2.0, "runs": 5, "warmup": 2,
+               "rtf": statistics.median(ts[2:]) / 1e3 / 2.0, "path": "sddm_enhance_host (H2D + 100 steps + D2H), wall clock"}
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -760,16 +774,19 @@ def run_ours(args):
     pk = peaks()
     line = {"metric": "utterances_per_sec", "value": value, "unit": "utt/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "fp32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+            "vs_baseline": None, "dtype": {"fp32": "fp32", "bf16x3": "bf16x3"}.get(args.precision, "bf16"), "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "reverse_steps": T_STEPS, "noise": "in-kernel Philox4x32-10",
                        "weights": "config-shaped random init (torch.manual_seed(0))", "precision": args.precision,
                        "l2": "per-step working set (20-40 MB of activations per chunk, x64 chunks) >> 126 MB L2; no flush needed",
-                       "activations": {"fp32": "fp32", "bf16": "fp32 in HBM, bf16 tensor-core operands", "bf16act": "bf16 in HBM, bf16 tensor-core operands, fp32 accumulate"}[args.precision],
+                       "activations": {"fp32": "fp32", "bf16": "fp32 in HBM, bf16 tensor-core operands", "bf16act": "bf16 in HBM, bf16 tensor-core operands, fp32 accumulate",
+                                       "bf16x3": "fp32 in HBM, split-bf16 (hi, lo) tensor-core operands, 3 products per MMA step, fp32 accumulate"}[args.precision],
                        "utterance": "one 16448-sample chunk (1.028 s); a 2 s clip is 2 chunks"},
             "rtf": 1.0 / (value * L / SR), "chunks_per_sec": value,
             "e2e": {"value": e2e, "unit": "utt/s", "h2d_bytes_per_step": B * L * 4, "d2h_bytes_per_step": B * L * 4,
                     "rtf": 1.0 / (e2e * L / SR)},
             "gpu_launches": int(launches), "clocks": clocks, "peaks": pk["source"]}
+    if lat:
+        line["cfg1_latency"] = lat
     if prof:
         tot = sum(o["ms"] for o in prof) or 1.0
         fam = {}
@@ -828,7 +845,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
     ap.add_argument("--batch", type=int, default=64)
-    ap.add_argument("--precision", default=os.environ.get("SDDM_B200_PRECISION", "bf16act"), choices=["bf16", "fp32", "bf16act"])
+    ap.add_argument("--precision", default=os.environ.get("SDDM_B200_PRECISION", "bf16act"), choices=["bf16", "fp32", "bf16act", "bf16x3"])
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the reference's CUDA-eager run (gpu_eager_baseline)")

@@ -41,6 +41,9 @@ extern "C" {
 #define SDDM_PREC_FP32 0        /* CUDA-core fp32 FMA (parity mode: eps_hat error ~1e-6) */
 #define SDDM_PREC_BF16 1        /* tcgen05 / TMEM implicit GEMM, bf16 operands, fp32 accumulate, fp32 activations in HBM */
 #define SDDM_PREC_BF16_ACT 2    /* same, and the UNet's intermediate activations are stored as bf16 in HBM */
+#define SDDM_PREC_BF16X3 3      /* tensor-core high-precision mode (north_star's "TF32 mode", stricter): fp32 activations, every conv
+                                 * operand split into a bf16 (hi, lo) pair, a.w = a_hi w_hi + a_hi w_lo + a_lo w_hi on tcgen05 with
+                                 * fp32 accumulation (operands carried to 2^-17); eps_hat error ~1e-5 vs the reference */
 
 /* posterior-update variants: SDDM.p_transition argument, model/model.py:17-26 */
 #define SDDM_VAR_ORIGINAL 0     /* diffusion.py:177-190, x_T = pure noise               */

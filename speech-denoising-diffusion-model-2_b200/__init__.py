@@ -8,7 +8,7 @@ reference ``state_dict`` key layout).  The device work is hand-written CUDA reac
 fallback: every compute entry point raises if the extension or a CUDA device is missing.
 """
 from . import _lib  # noqa: F401
-from ._lib import PREC_BF16, PREC_BF16_ACT, PREC_FP32, SddmError, library_path  # noqa: F401
+from ._lib import PREC_BF16, PREC_BF16_ACT, PREC_BF16X3, PREC_FP32, SddmError, library_path  # noqa: F401
 
-__all__ = ["_lib", "PREC_FP32", "PREC_BF16", "PREC_BF16_ACT", "SddmError", "library_path"]
+__all__ = ["_lib", "PREC_FP32", "PREC_BF16", "PREC_BF16_ACT", "PREC_BF16X3", "SddmError", "library_path"]
 __version__ = "0.1.0"

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 from typing import Optional
 
-PREC_FP32, PREC_BF16, PREC_BF16_ACT = 0, 1, 2
+PREC_FP32, PREC_BF16, PREC_BF16_ACT, PREC_BF16X3 = 0, 1, 2, 3
 VARIANTS = {"original": 0, "condition_in": 1, "sr3": 2, "supportive": 3, "conditional": 4}
 
 _HERE = os.path.dirname(os.path.abspath(__file__))

@@ -62,6 +62,7 @@ struct Op {
     int mode = CONV_S1;
     int out = -1;
     size_t w_off = 0, wtc_off = 0, bias_off = 0;
+    size_t wtc_lo_off = 0, reswtc_lo_off = 0;   // split-bf16 mode: lo weight images
     int temb_off = -1;
     int res_kind = 0;   // 0 none, 1 identity, 2 1x1 conv
     size_t resw_off = 0, reswtc_off = 0, resb_off = 0;
@@ -275,6 +276,13 @@ static std::vector<__nv_bfloat16> pack_stem_row(const std::vector<float>& w, int
     return o;
 }
 
+// w - float(bf16(w)): the part of the weights a bf16 image drops (its own bf16 image is the "lo" operand of the split-bf16 mode)
+static std::vector<float> bf16_residual(const std::vector<float>& w) {
+    std::vector<float> r(w.size());
+    for (size_t i = 0; i < w.size(); ++i) r[i] = w[i] - __bfloat162float(__float2bfloat16(w[i]));
+    return r;
+}
+
 static int new_tensor(sddm_plan* p, const std::string& name, int C, int H, int W) {
     TensorInfo t{name, C, H, W, 0, 0, 0};
     p->tensors.push_back(t);
@@ -286,7 +294,10 @@ static const std::vector<float>& W_(sddm_plan* p, const std::string& k) { return
 static void fill_conv_op(sddm_plan* p, Arena& a, Op& op, const std::string& wkey, int cout, int cin, bool tc_ok) {
     op.w_off = a.put(pack_conv_f32(W_(p, wkey + ".weight"), cout, cin, 9));
     op.bias_off = a.put(W_(p, wkey + ".bias"));
-    if (tc_ok && cin % 32 == 0) op.wtc_off = a.put_h(pack_conv_tc(W_(p, wkey + ".weight"), cout, cin, 9));
+    if (tc_ok && cin % 32 == 0) {
+        op.wtc_off = a.put_h(pack_conv_tc(W_(p, wkey + ".weight"), cout, cin, 9));
+        if (p->cfg.precision == SDDM_PREC_BF16X3) op.wtc_lo_off = a.put_h(pack_conv_tc(bf16_residual(W_(p, wkey + ".weight")), cout, cin, 9));
+    }
 }
 
 static int emit_gn(sddm_plan* p, Arena& a, std::vector<int> srcs, const std::string& gkey, size_t* ss_off_cursor) {
@@ -391,7 +402,10 @@ static int build_program(sddm_plan* p, Arena& a) {
             c2.res_kind = 2;
             c2.resw_off = a.put(pack_conv_f32(W_(p, nd.key + ".res_conv.weight"), nd.cout, nd.cin, 1));
             c2.resb_off = a.put(W_(p, nd.key + ".res_conv.bias"));
-            if (want_tc && nd.cin % 32 == 0) c2.reswtc_off = a.put_h(pack_conv_tc(W_(p, nd.key + ".res_conv.weight"), nd.cout, nd.cin, 1));
+            if (want_tc && nd.cin % 32 == 0) {
+                c2.reswtc_off = a.put_h(pack_conv_tc(W_(p, nd.key + ".res_conv.weight"), nd.cout, nd.cin, 1));
+                if (c.precision == SDDM_PREC_BF16X3) c2.reswtc_lo_off = a.put_h(pack_conv_tc(bf16_residual(W_(p, nd.key + ".res_conv.weight")), nd.cout, nd.cin, 1));
+            }
             // the residual reads the raw block input; record its sources in gn_src (unused by CONV otherwise)
             c2.gn_nsrc = (int)srcs.size();
             for (size_t i = 0; i < srcs.size(); ++i) c2.gn_src[i] = srcs[i];
@@ -683,6 +697,8 @@ static int run_unet(sddm_plan* p, const float* cond, const float* x_t, const flo
                 cp.Hout = o.H; cp.Wout = o.W; cp.Cout = o.C; cp.mode = op.mode;
                 cp.w = p->d_f32 + op.w_off;
                 cp.w_tc = p->d_bf16 ? p->d_bf16 + op.wtc_off : nullptr;
+                cp.x3 = c.precision == SDDM_PREC_BF16X3;
+                cp.w_tc_lo = (cp.x3 && p->d_bf16) ? p->d_bf16 + op.wtc_lo_off : nullptr;
                 cp.bias = p->d_f32 + op.bias_off;
                 if (op.temb_off >= 0) { cp.temb = temb + op.temb_off; cp.temb_stride = temb_stride; }
                 if (op.res_kind) {
@@ -699,6 +715,7 @@ static int run_unet(sddm_plan* p, const float* cond, const float* x_t, const flo
                     } else {
                         cp.res_w = p->d_f32 + op.resw_off;
                         cp.res_w_tc = p->d_bf16 ? p->d_bf16 + op.reswtc_off : nullptr;
+                        cp.res_w_tc_lo = (cp.x3 && p->d_bf16) ? p->d_bf16 + op.reswtc_lo_off : nullptr;
                         cp.res_bias = p->d_f32 + op.resb_off;
                     }
                 }
@@ -800,7 +817,7 @@ int sddm_plan_create(const sddm_config* cfg, sddm_plan** out) {
     if (c.num_samples % 4 || c.segment_len % 4 || c.segment_stride % 4) { set_error("num_samples, segment_len, segment_stride must be multiples of 4"); return SDDM_E_INVALID; }
     if (c.inner_channel != 32 && c.inner_channel != 64) { set_error("inner_channel must be 32 or 64"); return SDDM_E_INVALID; }
     if (c.norm_groups < 1 || c.inner_channel % c.norm_groups) { set_error("inner_channel must be divisible by norm_groups"); return SDDM_E_INVALID; }
-    if (c.precision != SDDM_PREC_FP32 && c.precision != SDDM_PREC_BF16 && c.precision != SDDM_PREC_BF16_ACT) { set_error("unknown precision %d", c.precision); return SDDM_E_INVALID; }
+    if (c.precision != SDDM_PREC_FP32 && c.precision != SDDM_PREC_BF16 && c.precision != SDDM_PREC_BF16_ACT && c.precision != SDDM_PREC_BF16X3) { set_error("unknown precision %d", c.precision); return SDDM_E_INVALID; }
     const int H = (c.num_samples - c.segment_len) / c.segment_stride + 1, W = c.segment_len;
     // every level must tile: the deepest (H/2^n x W/2^n) by 8x4, all others by 16x8
     if (H % (1 << c.n_mults) || W % (1 << c.n_mults) || (H >> c.n_mults) % 8 || (W >> c.n_mults) % 4) {

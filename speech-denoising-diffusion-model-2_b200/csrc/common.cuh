@@ -117,6 +117,9 @@ struct ConvP {
     int nparts;
     int B;
     int act16;     // activations (every src / res_src / out tensor) are bf16 in HBM instead of fp32 (tcgen05 path only)
+    int x3;        // tcgen05 path, fp32 activations: split-bf16 operands (hi, lo) and three products per MMA step (SDDM_PREC_BF16X3)
+    const __nv_bfloat16* w_tc_lo;      // bf16(w - bf16(w)) in the w_tc layout
+    const __nv_bfloat16* res_w_tc_lo;
     int gn_on;     // tcgen05 path: finalise the consumer's GroupNorm in this kernel (gn below), no gn_finalize launch
     GnFuse gn;
 };

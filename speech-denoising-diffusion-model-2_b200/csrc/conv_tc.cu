@@ -79,6 +79,11 @@ struct TcArgs {
     int temb_per_row;
     uint32_t off_out, off_res, off_raw, off_a, off_w;   // byte offsets from the 1024-aligned shared-memory base
     uint32_t raw_stage, a_stage, w_stage;
+    // split-bf16 high-precision mode (SDDM_PREC_BF16X3): every operand is a bf16 (hi, lo) pair, x = hi + lo to 2^-17, and
+    // a . w = a_hi w_hi + a_hi w_lo + a_lo w_hi on the tensor cores (fp32 accumulate); the lo images sit a_half / w_half bytes
+    // behind the hi images inside each operand / weight stage
+    int x3;
+    uint32_t a_half, w_half;
     int skip;                       // debug experiments: bit 0 no statistics pass, bit 1 no transform work, bit 2 no epilogue staging / store
     long long* trace;               // debug: per-role wait / busy cycle counters of CTA 0 (nullptr = off)
 };
@@ -568,9 +573,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
                             for (int tt = 0; tt < TPC; ++tt) {
                                 const int tap = q * TPC + tt, ky = tap / 3, kx = tap - 3 * ky;
                                 const int aslot = (MODE == CONV_S2) ? ky * G::PW + (kx == 1 ? G::EVEN_OFF : (kx >> 1)) : ky * G::PW + kx;
-                                umma(d_tmem, adesc + (uint64_t)(uint32_t)(h * 2 * G::PLANE + aslot), wdesc + (uint64_t)((uint32_t)tt * tap_step),
-                                     idesc, acc);
+                                const uint64_t ad = adesc + (uint64_t)(uint32_t)(h * 2 * G::PLANE + aslot), wd = wdesc + (uint64_t)((uint32_t)tt * tap_step);
+                                umma(d_tmem, ad, wd, idesc, acc);
                                 acc = 1;
+                                if (a.x3) {
+                                    umma(d_tmem, ad, wd + (uint64_t)(a.w_half >> 4), idesc, 1u);
+                                    umma(d_tmem, ad + (uint64_t)(a.a_half >> 4), wd, idesc, 1u);
+                                }
                             }
                             if (!a.resident) umma_commit(smem_u32(&hdr->empty_w[sw]));
                         }
@@ -603,8 +612,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
                 if (elect_one()) {
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        umma(d_tmem, adesc + (uint64_t)(uint32_t)(h * 2 * G::PLANE), wdesc + (uint64_t)((uint32_t)h * tap_step), idesc, acc);
+                        const uint64_t ad = adesc + (uint64_t)(uint32_t)(h * 2 * G::PLANE), wd = wdesc + (uint64_t)((uint32_t)h * tap_step);
+                        umma(d_tmem, ad, wd, idesc, acc);
                         acc = 1;
+                        if (a.x3) {
+                            umma(d_tmem, ad, wd + (uint64_t)(a.w_half >> 4), idesc, 1u);
+                            umma(d_tmem, ad + (uint64_t)(a.a_half >> 4), wd, idesc, 1u);
+                        }
                     }
                     if (!a.resident) umma_commit(smem_u32(&hdr->empty_w[sw]));
                     umma_commit(smem_u32(&hdr->empty_a[sa]));
@@ -641,8 +655,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
                         src = p.res_w_tc + (size_t)(c - a.n_main_chunks) * 32 * p.Cout;
                     }
                     const uint32_t bar = smem_u32(&hdr->full_w[wslot]);
-                    mbar_expect_tx(bar, bytes);
+                    mbar_expect_tx(bar, a.x3 ? 2u * bytes : bytes);
                     bulk_g2s(w_ring + (uint32_t)wslot * a.w_stage, src, bytes, bar);
+                    if (a.x3) {   // the lo image of the same chunk
+                        const void* src_lo = !is_res ? (const void*)(p.w_tc_lo + (size_t)c * 16 * TPC * p.Cout)
+                                                     : (const void*)(p.res_w_tc_lo + (size_t)(c - a.n_main_chunks) * 32 * p.Cout);
+                        bulk_g2s(w_ring + (uint32_t)wslot * a.w_stage + a.w_half, src_lo, bytes, bar);
+                    }
                     if (!a.resident && ++sw == a.NW) { sw = 0; pw ^= 1u; }
                 }
             }
@@ -692,6 +711,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
 
         // one 8-channel item: raw fp32 -> (affine, swish) -> masked -> packed bf16.   swish(y) = h + h * tanh(h), h = y / 2
         // raw loads: fp32 storage = two 16-byte chunks per item (u0, u1); bf16 storage = one chunk (u0) holding all 8 channels
+        const bool x3 = !A16 && a.x3 != 0;
+        uint4 o_lo = make_uint4(0u, 0u, 0u, 0u);   // lo halves of the last converted item (split-bf16 mode)
         auto convert = [&](auto aff_c, const uint4 u0, const uint4 u1, bool ok, const float (&sch)[8], const float (&shh)[8]) -> uint4 {
             constexpr bool AFF = decltype(aff_c)::value;
             float f[8];
@@ -707,16 +728,39 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
                 f[4] = __uint_as_float(u1.x); f[5] = __uint_as_float(u1.y); f[6] = __uint_as_float(u1.z); f[7] = __uint_as_float(u1.w);
             }
             if (AFF) {
+                if (x3) {   // high-precision Swish: y / (1 + 2^(-y log2 e)) with ex2.approx / rcp.approx (~1e-6), not tanh.approx (~5e-4)
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const float h = fmaf(f[k], sch[k], shh[k]);
-                    f[k] = fmaf(h, tanh_approx(h), h);
+                    for (int k = 0; k < 8; ++k) {
+                        const float y = 2.0f * fmaf(f[k], sch[k], shh[k]);
+                        f[k] = __fdividef(y, 1.0f + __expf(-y));
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float h = fmaf(f[k], sch[k], shh[k]);
+                        f[k] = fmaf(h, tanh_approx(h), h);
+                    }
                 }
             }
             uint4 o;
             o.x = ok ? pack_bf16(f[0], f[1]) : 0u; o.y = ok ? pack_bf16(f[2], f[3]) : 0u;
             o.z = ok ? pack_bf16(f[4], f[5]) : 0u; o.w = ok ? pack_bf16(f[6], f[7]) : 0u;
+            if (x3) {   // lo = bf16(x - hi): x = hi + lo to 2^-17
+                const uint32_t hw[4] = {o.x, o.y, o.z, o.w};
+                uint32_t lw[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float2 h2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw[k]));
+                    lw[k] = ok ? pack_bf16(f[2 * k] - h2.x, f[2 * k + 1] - h2.y) : 0u;
+                }
+                o_lo = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            }
             return o;
+        };
+        // operand store: the hi image, and in split-bf16 mode the lo image a_half bytes behind it
+        auto put = [&](uint32_t addr, const uint4 o) {
+            sts128(addr, o);
+            if (x3) sts128(addr + a.a_half, o_lo);
         };
 
         // this group's position in the CTA-wide (tile, slab) sequence and in the rings; it advances kXfGroups slabs at a time
@@ -793,7 +837,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
                             for (int dx = 0; dx < 2; ++dx) {
                                 const int hx = 2 * rx - 1 + dx;
                                 if (hx < 0 || hx >= G::PW) continue;
-                                sts128(opd + (uint32_t)(hy * G::PW + hx) * 16u, o);
+                                put(opd + (uint32_t)(hy * G::PW + hx) * 16u, o);
                             }
                         }
                     }
@@ -824,7 +868,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
                             const bool ok = hy >= ylo && hy < yhi && hx >= xlo && hx < xhi;
                             const uint4 o = convert(aff_c, rv[q][0], rv[q][1], ok, sch, shh);
                             const int slot = hy * G::PW + ((hx & 1) ? G::EVEN_OFF + (hx >> 1) : (hx >> 1));
-                            sts128(opd + (uint32_t)slot * 16u, o);
+                            put(opd + (uint32_t)slot * 16u, o);
                         }
                     }
                 } else {   // stride-1 halo (main conv of CONV_S1, res_conv slabs)
@@ -851,7 +895,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
                             const int hy = pix / 10, hx = pix - hy * 10;
                             const bool ok = hy >= ylo && hy < yhi && hx >= xlo && hx < xhi;
                             const uint4 o = convert(aff_c, rv[q][0], rv[q][1], ok, sch, shh);
-                            sts128(opd + (uint32_t)pix * 16u, o);
+                            put(opd + (uint32_t)pix * 16u, o);
                         }
                     }
                 }
@@ -1034,6 +1078,10 @@ int launch_mode(TcArgs a, cudaStream_t st) {
     a.a_stage = (uint32_t)align_up_sz((size_t)(G::SLAB / 8) * G::PLANE * 16, 128);
     if (a.n_res && a.a_stage < 4u * 182u * 16u) a.a_stage = (uint32_t)align_up_sz(4 * 182 * 16, 128);
     a.w_stage = 32u * TPC * (uint32_t)p.Cout;
+    a.x3 = (!A16 && p.x3) ? 1 : 0;
+    a.a_half = a.a_stage;
+    a.w_half = a.w_stage;
+    if (a.x3) { a.a_stage *= 2; a.w_stage *= 2; }   // (hi, lo) image pairs
     const int nchunks = a.n_main_chunks + a.n_res_chunks;
     const int nblk = p.Cout / 32;
     // shared-memory plan: header | out staging (per epilogue group) | residual ring (per group) | raw ring | operand ring |
@@ -1107,10 +1155,12 @@ int conv_tc_tiles(int Hout, int Wout) { return ((Hout + TH - 1) / TH) * ((Wout +
 
 int launch_conv_tc(const ConvP& p, cudaStream_t st) {
     if (!conv_tc_supported(p) || !p.w_tc) { set_error("conv tc: unsupported shape Cin=%d Cout=%d mode=%d", p.Cin, p.Cout, p.mode); return SDDM_E_INVALID; }
+    if (p.x3 && (p.act16 || !p.w_tc_lo)) { set_error("conv tc: the split-bf16 mode needs fp32 activations and the lo weight image"); return SDDM_E_INVALID; }
     const int ein_h = p.mode == CONV_S2 ? p.Hout * 2 : (p.mode == CONV_UP ? p.Hout / 2 : p.Hout);
     const int ein_w = p.mode == CONV_S2 ? p.Wout * 2 : (p.mode == CONV_UP ? p.Wout / 2 : p.Wout);
     if (ein_h != p.Hin || ein_w != p.Win) { set_error("conv tc: inconsistent spatial sizes"); return SDDM_E_INVALID; }
     const bool has_res_conv = p.res_Cin && !p.res_identity;
+    if (has_res_conv && p.x3 && !p.res_w_tc_lo) { set_error("conv tc: res_conv lo weight image missing"); return SDDM_E_INVALID; }
     if (has_res_conv && (!p.res_w_tc || p.mode != CONV_S1)) { set_error("conv tc: res_conv needs packed weights and stride 1"); return SDDM_E_INVALID; }
     if (p.mode == CONV_UP && ((p.Hout % TH) || (p.Wout % TW))) { set_error("conv tc: upsampled output must tile by 16x8"); return SDDM_E_INVALID; }
     TcArgs a{};
@@ -1130,7 +1180,11 @@ int launch_conv_tc(const ConvP& p, cudaStream_t st) {
 #define SDDM_TC_DISPATCH(M)                                                                                   \
     do {                                                                                                     \
         if (p.act16) { rc = launch_mode<M, 9, true>(a, st); if (rc == 1) rc = launch_mode<M, 3, true>(a, st); } \
-        else { rc = launch_mode<M, 9, false>(a, st); if (rc == 1) rc = launch_mode<M, 3, false>(a, st); }       \
+        else {                                                                                               \
+            rc = launch_mode<M, 9, false>(a, st);                                                            \
+            if (rc == 1) rc = launch_mode<M, 3, false>(a, st);                                               \
+            if (rc == 1) rc = launch_mode<M, 1, false>(a, st);   /* split-bf16 stride-2 layers: one tap per weight chunk */ \
+        }                                                                                                    \
     } while (0)
     switch (p.mode) {
         case CONV_S1: SDDM_TC_DISPATCH(CONV_S1); break;

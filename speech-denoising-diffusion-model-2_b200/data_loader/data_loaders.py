@@ -66,6 +66,50 @@ def chunk_waveform(wave: torch.Tensor, T: int) -> torch.Tensor:
     return F.pad(wave, (0, n_chunk * T - n), "constant", 0).view(n_chunk, 1, T)
 
 
+def chunk_counts(lengths: Sequence[int], T: int) -> List[int]:
+    """Rows each utterance contributes to the [N,1,T] batch: max(1, ceil(n / T)) (reference :112-118)."""
+    return [max(1, ceil(int(n) / T)) for n in lengths]
+
+
+def rows_of_range(waves: Sequence[torch.Tensor], T: int, lo: int, hi: int, out: torch.Tensor = None) -> torch.Tensor:
+    """Rows [lo, hi) of the batch InferDataset + infer_data_collate would build from `waves`, WITHOUT building the other rows:
+    a rank of a sharded run pads / copies only the chunks it owns.  `out` may be a (pinned) [hi - lo, 1, T] staging buffer."""
+    counts = chunk_counts([w.numel() for w in waves], T)
+    if out is None:
+        out = torch.zeros((hi - lo, 1, T), dtype=torch.float32)
+    else:
+        out.zero_()
+    flat = out.view(hi - lo, T)
+    row = 0
+    for w, c in zip(waves, counts):
+        a, b = max(row, lo), min(row + c, hi)
+        if a < b:
+            x = torch.as_tensor(w, dtype=torch.float32).reshape(-1)
+            s0, s1 = (a - row) * T, min((b - row) * T, x.numel())
+            if s1 > s0:
+                dst = flat[a - lo:b - lo].reshape(-1)
+                dst[: s1 - s0] = x[s0:s1]
+        row += c
+        if row >= hi:
+            break
+    return out
+
+
+def balanced_splits(n: int, limit: int) -> List[Tuple[int, int]]:
+    """[0, n) cut into ceil(n / limit) near-equal pieces (a 51-row tail behind four 64-row sub-batches costs almost a full
+    sub-batch of GPU time; five pieces of 61-62 rows do not)."""
+    if n <= 0:
+        return []
+    k = max(1, ceil(n / max(1, limit)))
+    base, extra = divmod(n, k)
+    out, lo = [], 0
+    for i in range(k):
+        hi = lo + base + (1 if i < extra else 0)
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
 class InferDataset(torch.utils.data.Dataset):
     """(clean, noisy) utterance pairs -> (clean_chunks, noisy_chunks, index) exactly as the reference yields them.
 

@@ -72,16 +72,19 @@ def enhance_utterances(model, waves: Sequence[torch.Tensor], batch_chunks: int =
     L = model.noise_estimate_model.cfg["num_samples"]
     device = next(model.parameters()).device
     seed = _resolve_seed(seed, world)
-    ds = module_data.InferDataset([(None, w) for w in waves], T=L)
-    _, rows, index = module_data.infer_data_collate([ds[i] for i in range(len(ds))])
-    n = rows.shape[0]
+    lengths = [int(w.numel()) for w in waves]
+    counts = module_data.chunk_counts(lengths, L)
+    n = int(sum(counts))
+    index = torch.repeat_interleave(torch.arange(len(waves)), torch.tensor(counts))
     lo, hi = shard_bounds(n, world, rank)
     out_local = torch.empty((hi - lo, 1, L), device=device)
-    for s in range(lo, hi, batch_chunks):
-        e = min(hi, s + batch_chunks)
-        out_local[s - lo:e - lo] = model.infer(rows[s:e].to(device, non_blocking=True), seed=seed, row0=s)
+    stage = torch.empty((min(batch_chunks, max(1, hi - lo)), 1, L), dtype=torch.float32).pin_memory() if hi > lo else None
+    for a, b in module_data.balanced_splits(hi - lo, batch_chunks):      # near-equal sub-batches: no short tail
+        rows = module_data.rows_of_range(waves, L, lo + a, lo + b, out=stage[: b - a])   # only this rank's chunks are padded / copied
+        out_local[a:b] = model.infer(rows.to(device, non_blocking=True), seed=seed, row0=lo + a)
+        torch.cuda.current_stream().synchronize()                       # the pinned staging buffer is reused by the next sub-batch
     full = gather_rows(out_local, n) if world > 1 else out_local
-    return module_data.regroup(full, index, [int(w.numel()) for w in waves])
+    return module_data.regroup(full, index, lengths)
 
 
 @torch.no_grad()

@@ -238,7 +238,7 @@ class DiffWave(nn.Module):
         if dev.type != "cuda":
             raise RuntimeError("DiffWave (sddm_b200) must live on a CUDA device: call .to('cuda') first; there is no CPU fallback")
         prec = precision if precision is not None else (self.precision if self.precision is not None else default_precision())
-        prec = _lib.PREC_FP32 if prec == _lib.PREC_FP32 else _lib.PREC_BF16      # bf16act == bf16 for this denoiser
+        prec = _lib.PREC_FP32 if prec in (_lib.PREC_FP32, _lib.PREC_BF16X3) else _lib.PREC_BF16      # bf16act == bf16, bf16x3 -> fp32 for this denoiser
         tables = diffusion.host_tables() if diffusion is not None else None
         key = (diffusion.tables_key() if diffusion is not None else None, noise_condition, prec, str(dev), self._param_version())
         plan = self._plans.get(key)

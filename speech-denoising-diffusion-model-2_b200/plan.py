@@ -21,7 +21,9 @@ def default_precision() -> int:
         return _lib.PREC_BF16
     if v in ("bf16act", "bf16_act", "2"):
         return _lib.PREC_BF16_ACT
-    raise ValueError("SDDM_B200_PRECISION must be fp32, bf16 or bf16act, got %r" % v)
+    if v in ("bf16x3", "tf32", "3"):
+        return _lib.PREC_BF16X3
+    raise ValueError("SDDM_B200_PRECISION must be fp32, bf16, bf16act or bf16x3, got %r" % v)
 
 
 def _ptr(t: Optional[torch.Tensor]):

@@ -175,3 +175,37 @@ def test_wave_io_roundtrip(tmp_path):
     ds = D.InferDataset([(None, str(tmp_path / "a.wav"))], T=2048)
     clean, noisy, idx = ds[0]
     assert noisy.shape == (3, 1, 2048) and torch.equal(clean, noisy) and idx.tolist() == [0, 0, 0]
+
+
+def test_dataset_edge_vs_reference_golden():
+    """Chunking / collation / regrouping against outputs of the reference's own InferDataset + infer_data_collate
+    and the regroup loop of infer.py:81-120 (tests/golden/make_golden_dataset.py), plus the sharded variants built on them."""
+    import numpy as np
+    from conftest import GOLDEN
+    from sddm_b200.data_loader import data_loaders as D
+    g = np.load(os.path.join(GOLDEN, "dataset.npz"))
+    T = int(g["T"])
+    order = [str(n).split(".")[0] for n in g["inventory"]]                     # the order the reference's glob produced
+    waves = [torch.from_numpy(g["wave." + n]) for n in order]
+    ds = D.InferDataset([(0.5 * w, w) for w in waves], T=T, names=order)
+    clean, noisy, index = D.infer_data_collate([ds[i] for i in range(len(ds))])
+    assert torch.equal(noisy, torch.from_numpy(g["noisy"])) and torch.equal(clean, torch.from_numpy(g["clean"]))
+    assert index.tolist() == g["index"].tolist()
+    assert [ds.getName(i) for i in range(len(ds))] == [str(n) for n in g["names"]]
+    # regrouping: every file, untrimmed, equals the reference's reshape(1, -1) of its rows
+    files = D.regroup(noisy, index)
+    assert len(files) == len(waves)
+    for k, f in enumerate(files):
+        assert int(g["file%d.index" % k]) == k and torch.equal(f, torch.from_numpy(g["file%d.signal" % k]))
+    assert int(g["n_flushed_by_reference_loop"]) == len(waves) - 1               # the reference loop never flushes the last file of a batch
+    # trimmed regrouping returns the original signals
+    lengths = [int(w.numel()) for w in waves]
+    for f, w in zip(D.regroup(noisy, index, lengths), waves):
+        assert torch.equal(f, w.reshape(1, -1))
+    # per-rank row ranges (no full-dataset chunking) and balanced sub-batches
+    n = noisy.shape[0]
+    assert D.chunk_counts(lengths, T) == [int((index == i).sum()) for i in range(len(waves))]
+    for lo, hi in ((0, n), (1, 5), (4, 5), (6, n), (0, 1)):
+        assert torch.equal(D.rows_of_range([w.reshape(-1) for w in waves], T, lo, hi), noisy[lo:hi])
+    assert D.balanced_splits(307, 64) == [(0, 62), (62, 124), (124, 185), (185, 246), (246, 307)]
+    assert D.balanced_splits(64, 64) == [(0, 64)] and D.balanced_splits(0, 64) == [] and D.balanced_splits(65, 64) == [(0, 33), (33, 65)]

@@ -21,7 +21,7 @@ def main():
     from sddm_b200.model.model import SDDM
     dev = torch.device("cuda:0")
     sd, net = seed0_state_dict()
-    net.precision = {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16act": PREC_BF16_ACT}[prec]
+    net.precision = {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16act": PREC_BF16_ACT, "bf16x3": 3}[prec]
     model = SDDM(GaussianDiffusion("linear", 100, 1e-6, 1e-3, device=dev), net, p_transition="condition_in").to(dev).eval()
     cond, noises = cfg2_inputs()
     cond, noises = cond[:rows].to(dev), noises[:, :rows].contiguous().to(dev)

@@ -13,7 +13,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--iters", type=int, default=2)
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "bf16act"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "bf16act", "bf16x3"])
     ap.add_argument("--trace", action="store_true", help="per-role wait-cycle trace of every tcgen05 conv launch of the last forward")
     args = ap.parse_args()
     import torch
@@ -26,7 +26,7 @@ def main():
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
     net = UNetModified2(num_samples=16448, res_blocks=1)
-    net.precision = {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16act": PREC_BF16_ACT}[args.precision]
+    net.precision = {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16act": PREC_BF16_ACT, "bf16x3": 3}[args.precision]
     model = SDDM(GaussianDiffusion("linear", 100, 1e-6, 1e-3, device=dev), net, p_transition="condition_in").to(dev).eval()
     plan = net.get_plan(model.diffusion)
     cond = (0.1 * torch.randn(args.batch, 1, 16448, generator=torch.Generator().manual_seed(1))).clamp(-1, 1).to(dev)

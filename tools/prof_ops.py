@@ -13,7 +13,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--iters", type=int, default=5)
-    ap.add_argument("--precision", default="bf16act", choices=["bf16", "fp32", "bf16act"])
+    ap.add_argument("--precision", default="bf16act", choices=["bf16", "fp32", "bf16act", "bf16x3"])
     ap.add_argument("--trace", action="store_true", help="per-role wait-cycle trace of the conv_row launches of one forward")
     args = ap.parse_args()
     import torch
@@ -26,7 +26,7 @@ def main():
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
     net = UNetModified2(num_samples=16448, res_blocks=1)
-    net.precision = {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16act": PREC_BF16_ACT}[args.precision]
+    net.precision = {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16act": PREC_BF16_ACT, "bf16x3": 3}[args.precision]
     model = SDDM(GaussianDiffusion("linear", 100, 1e-6, 1e-3, device=dev), net, p_transition="condition_in").to(dev).eval()
     plan = net.get_plan(model.diffusion)
     B = args.batch
