@@ -319,6 +319,17 @@ def run_cfg3(args):
     launches = _lib.launch_count() - launches0
     clocks = sampler.stop() if sampler else None
     ok = len(outs[0]) == len(lengths) and all(o.shape[-1] == int(n) for o, n in zip(outs[0], lengths))
+    phases = {}
+    sync_all()
+    t_ph = time.perf_counter()
+    enhance_utterances(model, waves, batch_chunks=args.batch, seed=0, rank=rank, world=world, timings=phases)   # one extra, untimed step with a phase timeline
+    sync_all()
+    phases["step_wall_ms"] = 1e3 * (time.perf_counter() - t_ph)
+    ph_all = [None] * world
+    if world > 1:
+        dist.all_gather_object(ph_all, phases)
+    else:
+        ph_all = [phases]
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -337,7 +348,9 @@ def run_cfg3(args):
             "rtf": (ms / args.steps / 1e3) / audio_s, "chunks_per_sec": n_chunks * args.steps / (ms / 1e3),
             "e2e": {"value": value, "unit": "utt/s", "h2d_bytes_per_step": n_chunks * L * 4 // world, "d2h_bytes_per_step": 0,
                     "note": "the timed step is already end to end from pinned host waveforms (chunking, H2D, enhancement, gather, regroup); outputs stay on the device"},
-            "gpu_launches": int(launches), "clocks": clocks, "outputs_ok": bool(ok)}
+            "gpu_launches": int(launches), "clocks": clocks, "outputs_ok": bool(ok),
+            "timeline": {"note": "one extra step with device syncs between phases, per rank (ms): host chunking of the rank's own rows, H2D + enhancement, "
+                                 "NCCL all-gather of the rows, per-utterance regroup", "per_rank": ph_all}}
     print(json.dumps(line))
     if world > 1:
         dist.barrier()

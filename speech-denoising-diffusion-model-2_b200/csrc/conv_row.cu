@@ -172,7 +172,10 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const RowArgs 
         pdl_wait();
         const int e = warp >> 2, w4 = warp & 3, m = tid & 127;
         const int bar_id = 1 + e;
-        const bool leader = m == 0;
+        // single-thread duties sit on the warps of scheduler partitions 3 and 2 (warp id % 4): partition 0 already hosts the MMA
+        // issuer and one warp of every other group, and the group advances at the pace of its slowest warp
+        const bool leader = m == 96;       // TMA stores (+ their bulk-group waits), GroupNorm arrival
+        const bool res_leader = m == 64;   // identity-residual prefetch (mbarrier based: any thread may wait on it)
         const uint32_t obuf0 = base + a.off_out + (uint32_t)(e * 2) * kOutTile;
         const uint32_t rbuf0 = base + a.off_res + (uint32_t)(e * 2) * kOutTile;
         const uint32_t addv_u32 = smem_u32(hdr->addv[e]);
@@ -201,7 +204,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const RowArgs 
             tma_load_4d(rbuf0 + (uint32_t)(pissued & 1) * kOutTile, &maps.rsrc[0], 0, 0, py, pn, bar);
             ++pissued;
         };
-        if (RESID && leader) { res_issue(); res_issue(); }
+        if (RESID && res_leader) { res_issue(); res_issue(); }
         int item_base = 0;
         Seg s;
         for (int k = 0; seg_at(a.H, b0, b1, k, s); item_base += s.r1 - s.r0 + 1, ++k) {
@@ -310,8 +313,8 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const RowArgs 
                 if (leader) {
                     tma_store_4d(&maps.out, obuf, 0, 0, y, s.n);
                     bulk_commit();
-                    if (RESID) res_issue();   // the residual buffer of this row is free: refill it for this group's row after next
                 }
+                if (RESID && res_leader) res_issue();   // the residual buffer of this row is free: refill it for this group's row after next
                 if (tr) tw[4] += clock64() - ts0;
                 ++ob;
                 // column sums of the staged (rounded) row: 2 channels per lane, even / odd pixels per half-warp

@@ -273,7 +273,7 @@ template <int MODE> __device__ __forceinline__ int org_of(int o0) {   // first i
 }
 
 // =====================================================================================================
-template <int MODE, int TPC, bool A16>
+template <int MODE, int TPC, bool A16, bool X3>
 __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a, const __grid_constant__ TcMaps maps) {
     using G = Geo<MODE>;
     constexpr uint32_t kOutTileBytes = OutTile<A16>::kBytes;
@@ -576,7 +576,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
                                 const uint64_t ad = adesc + (uint64_t)(uint32_t)(h * 2 * G::PLANE + aslot), wd = wdesc + (uint64_t)((uint32_t)tt * tap_step);
                                 umma(d_tmem, ad, wd, idesc, acc);
                                 acc = 1;
-                                if (a.x3) {
+                                if (X3) {
                                     umma(d_tmem, ad, wd + (uint64_t)(a.w_half >> 4), idesc, 1u);
                                     umma(d_tmem, ad + (uint64_t)(a.a_half >> 4), wd, idesc, 1u);
                                 }
@@ -615,7 +615,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
                         const uint64_t ad = adesc + (uint64_t)(uint32_t)(h * 2 * G::PLANE), wd = wdesc + (uint64_t)((uint32_t)h * tap_step);
                         umma(d_tmem, ad, wd, idesc, acc);
                         acc = 1;
-                        if (a.x3) {
+                        if (X3) {
                             umma(d_tmem, ad, wd + (uint64_t)(a.w_half >> 4), idesc, 1u);
                             umma(d_tmem, ad + (uint64_t)(a.a_half >> 4), wd, idesc, 1u);
                         }
@@ -655,9 +655,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
                         src = p.res_w_tc + (size_t)(c - a.n_main_chunks) * 32 * p.Cout;
                     }
                     const uint32_t bar = smem_u32(&hdr->full_w[wslot]);
-                    mbar_expect_tx(bar, a.x3 ? 2u * bytes : bytes);
+                    mbar_expect_tx(bar, X3 ? 2u * bytes : bytes);
                     bulk_g2s(w_ring + (uint32_t)wslot * a.w_stage, src, bytes, bar);
-                    if (a.x3) {   // the lo image of the same chunk
+                    if (X3) {   // the lo image of the same chunk
                         const void* src_lo = !is_res ? (const void*)(p.w_tc_lo + (size_t)c * 16 * TPC * p.Cout)
                                                      : (const void*)(p.res_w_tc_lo + (size_t)(c - a.n_main_chunks) * 32 * p.Cout);
                         bulk_g2s(w_ring + (uint32_t)wslot * a.w_stage + a.w_half, src_lo, bytes, bar);
@@ -711,7 +711,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
 
         // one 8-channel item: raw fp32 -> (affine, swish) -> masked -> packed bf16.   swish(y) = h + h * tanh(h), h = y / 2
         // raw loads: fp32 storage = two 16-byte chunks per item (u0, u1); bf16 storage = one chunk (u0) holding all 8 channels
-        const bool x3 = !A16 && a.x3 != 0;
+        constexpr bool x3 = X3;
         uint4 o_lo = make_uint4(0u, 0u, 0u, 0u);   // lo halves of the last converted item (split-bf16 mode)
         auto convert = [&](auto aff_c, const uint4 u0, const uint4 u1, bool ok, const float (&sch)[8], const float (&shh)[8]) -> uint4 {
             constexpr bool AFF = decltype(aff_c)::value;
@@ -1065,7 +1065,7 @@ int encode_nhwc(CUtensorMap* m, const float* base, int B, int H, int W, int C, i
 inline size_t align_up_sz(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // returns 1 when the shared-memory plan does not fit with TPC taps per weight chunk (the caller retries with smaller chunks)
-template <int MODE, int TPC, bool A16>
+template <int MODE, int TPC, bool A16, bool X3>
 int launch_mode(TcArgs a, cudaStream_t st) {
     using G = Geo<MODE>;
     constexpr uint32_t kOutTileBytes = OutTile<A16>::kBytes;
@@ -1078,7 +1078,7 @@ int launch_mode(TcArgs a, cudaStream_t st) {
     a.a_stage = (uint32_t)align_up_sz((size_t)(G::SLAB / 8) * G::PLANE * 16, 128);
     if (a.n_res && a.a_stage < 4u * 182u * 16u) a.a_stage = (uint32_t)align_up_sz(4 * 182 * 16, 128);
     a.w_stage = 32u * TPC * (uint32_t)p.Cout;
-    a.x3 = (!A16 && p.x3) ? 1 : 0;
+    a.x3 = X3 ? 1 : 0;
     a.a_half = a.a_stage;
     a.w_half = a.w_stage;
     if (a.x3) { a.a_stage *= 2; a.w_stage *= 2; }   // (hi, lo) image pairs
@@ -1131,11 +1131,11 @@ int launch_mode(TcArgs a, cudaStream_t st) {
     if ((rc = encode_nhwc(&maps.out, p.out, p.B, p.Hout, p.Wout, p.Cout, 32, TW, TH, swz_tile, A16))) return rc;
     if (p.res_identity && (rc = encode_nhwc(&maps.res, p.res_src[0].x, p.B, p.Hout, p.Wout, p.Cout, 32, TW, TH, swz_tile, A16))) return rc;
 
-    SDDM_SET_MAX_SMEM((conv3x3_tc_kernel<MODE, TPC, A16>), kSmemMax);
+    SDDM_SET_MAX_SMEM((conv3x3_tc_kernel<MODE, TPC, A16, X3>), kSmemMax);
     { static int skip = -1; if (skip < 0) { const char* e = getenv("SDDM_TC_SKIP"); skip = e ? atoi(e) : 0; } a.skip = skip; }
     a.trace = g_trace ? g_trace + (size_t)(g_trace_launch++ % 64) * 48 : nullptr;
     const int grid = a.ntiles < num_sms() ? a.ntiles : num_sms();
-    SDDM_CUDA_TRY(launch_pdl(conv3x3_tc_kernel<MODE, TPC, A16>, dim3(grid), dim3(kThreads), smem, st, a, maps));
+    SDDM_CUDA_TRY(launch_pdl(conv3x3_tc_kernel<MODE, TPC, A16, X3>, dim3(grid), dim3(kThreads), smem, st, a, maps));
     SDDM_LAUNCH_CHECK();
     return SDDM_OK;
 }
@@ -1179,11 +1179,12 @@ int launch_conv_tc(const ConvP& p, cudaStream_t st) {
     int rc;
 #define SDDM_TC_DISPATCH(M)                                                                                   \
     do {                                                                                                     \
-        if (p.act16) { rc = launch_mode<M, 9, true>(a, st); if (rc == 1) rc = launch_mode<M, 3, true>(a, st); } \
+        if (p.act16) { rc = launch_mode<M, 9, true, false>(a, st); if (rc == 1) rc = launch_mode<M, 3, true, false>(a, st); } \
+        else if (!p.x3) { rc = launch_mode<M, 9, false, false>(a, st); if (rc == 1) rc = launch_mode<M, 3, false, false>(a, st); } \
         else {                                                                                               \
-            rc = launch_mode<M, 9, false>(a, st);                                                            \
-            if (rc == 1) rc = launch_mode<M, 3, false>(a, st);                                               \
-            if (rc == 1) rc = launch_mode<M, 1, false>(a, st);   /* split-bf16 stride-2 layers: one tap per weight chunk */ \
+            rc = launch_mode<M, 9, false, true>(a, st);                                                      \
+            if (rc == 1) rc = launch_mode<M, 3, false, true>(a, st);                                         \
+            if (rc == 1) rc = launch_mode<M, 1, false, true>(a, st);   /* split-bf16 stride-2 layers: one tap per weight chunk */ \
         }                                                                                                    \
     } while (0)
     switch (p.mode) {

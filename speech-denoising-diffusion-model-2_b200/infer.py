@@ -65,13 +65,14 @@ def _resolve_seed(seed: Optional[int], world: int) -> int:
 
 
 def enhance_utterances(model, waves: Sequence[torch.Tensor], batch_chunks: int = 64, seed: Optional[int] = None,
-                       rank: int = 0, world: int = 1) -> List[torch.Tensor]:
+                       rank: int = 0, world: int = 1, timings: Optional[dict] = None) -> List[torch.Tensor]:
     """Chunk every utterance to [n_i,1,L] (InferDataset semantics), enhance the rows this rank owns in sub-batches,
     gather, and regroup to one waveform per utterance trimmed to its original length.  The Philox stream is keyed
     by the GLOBAL row id, so the result does not depend on `world` or `batch_chunks`."""
     L = model.noise_estimate_model.cfg["num_samples"]
     device = next(model.parameters()).device
     seed = _resolve_seed(seed, world)
+    import time
     lengths = [int(w.numel()) for w in waves]
     counts = module_data.chunk_counts(lengths, L)
     n = int(sum(counts))
@@ -79,12 +80,25 @@ def enhance_utterances(model, waves: Sequence[torch.Tensor], batch_chunks: int =
     lo, hi = shard_bounds(n, world, rank)
     out_local = torch.empty((hi - lo, 1, L), device=device)
     stage = torch.empty((min(batch_chunks, max(1, hi - lo)), 1, L), dtype=torch.float32).pin_memory() if hi > lo else None
+
+    def tick(name, t0):   # phase timeline for bench.py (adds device syncs; off by default)
+        if timings is not None:
+            torch.cuda.synchronize()
+            timings[name] = timings.get(name, 0.0) + 1e3 * (time.perf_counter() - t0)
+        return time.perf_counter()
+
+    t0 = time.perf_counter()
     for a, b in module_data.balanced_splits(hi - lo, batch_chunks):      # near-equal sub-batches: no short tail
         rows = module_data.rows_of_range(waves, L, lo + a, lo + b, out=stage[: b - a])   # only this rank's chunks are padded / copied
+        t0 = tick("chunk_host_ms", t0)
         out_local[a:b] = model.infer(rows.to(device, non_blocking=True), seed=seed, row0=lo + a)
         torch.cuda.current_stream().synchronize()                       # the pinned staging buffer is reused by the next sub-batch
+        t0 = tick("h2d_enhance_ms", t0)
     full = gather_rows(out_local, n) if world > 1 else out_local
-    return module_data.regroup(full, index, lengths)
+    t0 = tick("gather_ms", t0)
+    res = module_data.regroup(full, index, lengths)
+    tick("regroup_ms", t0)
+    return res
 
 
 @torch.no_grad()
