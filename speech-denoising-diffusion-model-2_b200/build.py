@@ -26,7 +26,7 @@ NVCC_FLAGS = [
 ]
 # per-file extras: the tensor-core kernel computes Swish with ex2.approx / rcp.approx and flushes denormals (its operands
 # are rounded to bf16 anyway); every other translation unit keeps IEEE arithmetic (bit-exact posterior update, fp32 parity mode)
-EXTRA_FLAGS = {"conv_tc.cu": ["-use_fast_math"], "conv_row.cu": ["-use_fast_math"]}
+EXTRA_FLAGS = {"conv_tc.cu": ["-use_fast_math"]}
 # debug builds: SDDM_NVCC_EXTRA="-DSDDM_ROW_TRACE=1" python -m sddm_b200.build  (per-role wait tracing of conv_row.cu, tools/prof_ops.py --trace)
 NVCC_FLAGS += [f for f in os.environ.get("SDDM_NVCC_EXTRA", "").split() if f]
 

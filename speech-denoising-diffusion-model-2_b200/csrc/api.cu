@@ -111,6 +111,7 @@ struct sddm_plan {
     size_t off_x = 0, off_frames = 0, off_temb_rows = 0, off_nl = 0;
     size_t floats_per_sample = 0;
     int launches_per_eps = 0;
+    bool post_fused = false;   // the final Block's row kernel also does the overlap-add + posterior update (no post_kernel launch)
     // internal arena for sddm_enhance_host
     cudaStream_t own_stream = nullptr;
     float* d_cond = nullptr;
@@ -572,7 +573,9 @@ static int build_program(sddm_plan* p, Arena& a) {
         for (int k = 0; k < g.gn_nsrc; ++k) small = small && p->tensors[g.gn_src[k]].nparts <= 256;
         if (producer_ok && small && prev.out == g.gn_src[0]) { g.gn_fused = true; ++fused; }
     }
-    p->launches_per_eps = (int)p->ops.size() - fused + 1;   // + the overlap-add / posterior kernel
+    const char* no_pf = getenv("SDDM_NO_POST_FUSE");   // A/B switch: keep the separate overlap-add / posterior kernel
+    p->post_fused = p->ops.back().kind == Op::FINAL && p->ops.back().use_row && 2 * c.segment_stride == c.segment_len && !(no_pf && no_pf[0] == '1');
+    p->launches_per_eps = (int)p->ops.size() - fused + (p->post_fused ? 0 : 1);   // + the overlap-add / posterior kernel unless the final Block does it
     return SDDM_OK;
 }
 
@@ -642,7 +645,7 @@ static void fill_gn_fuse(const sddm_plan* p, const Op& op, int B, void* ws, int 
 
 // one UNetModified2 forward up to the final conv frames (ws.frames); temb: device pointer, row stride
 static int run_unet(sddm_plan* p, const float* cond, const float* x_t, const float* temb, int temb_stride, int B, void* ws,
-                    cudaStream_t st) {
+                    cudaStream_t st, const PostP* post = nullptr, const float* post_k8 = nullptr, bool keep_frames = true) {
     const sddm_config& c = p->cfg;
     for (size_t oi = 0; oi < p->ops.size(); ++oi) {
         const Op& op = p->ops[oi];
@@ -725,7 +728,7 @@ static int run_unet(sddm_plan* p, const float* cond, const float* x_t, const flo
                 cp.B = B;
                 cp.act16 = c.precision == SDDM_PREC_BF16_ACT;
                 if (fuse) { cp.gn_on = 1; fill_gn_fuse(p, *fuse, B, ws, op.use_row ? conv_row_arrivals(o.H) : conv_tc_tiles(o.H, o.W), &cp.gn); }
-                if (op.use_row) rc = launch_conv_row(cp, p->d_bf16 + op.wrow_off, op.wrow_bytes, nullptr, 0.f, st);
+                if (op.use_row) rc = launch_conv_row(cp, p->d_bf16 + op.wrow_off, op.wrow_bytes, nullptr, 0.f, st, nullptr, nullptr);
                 else rc = op.use_tc ? launch_conv_tc(cp, st) : launch_conv_fp32(cp, st);
                 break;
             }
@@ -738,7 +741,9 @@ static int run_unet(sddm_plan* p, const float* cond, const float* x_t, const flo
                     cp.src[0].scale = sect(p, ws, op.in_ss_off, B);
                     cp.src[0].shift = cp.src[0].scale + (size_t)t.C * B;
                     cp.Hin = cp.Hout = t.H; cp.Win = cp.Wout = t.W; cp.mode = CONV_S1; cp.B = B; cp.act16 = 1;
-                    rc = launch_conv_row(cp, p->d_bf16 + op.wrow_off, op.wrow_bytes, sect(p, ws, p->off_frames, B), p->final_bias, st);
+                    // fused tail: overlap-add + posterior (or just eps_hat) in the epilogue; frames only for sddm_eps / debug fetch
+                    rc = launch_conv_row(cp, p->d_bf16 + op.wrow_off, op.wrow_bytes, (keep_frames || !p->post_fused) ? sect(p, ws, p->off_frames, B) : nullptr,
+                                         p->final_bias, st, p->post_fused ? post : nullptr, post_k8);
                     break;
                 }
                 FinalP f{};
@@ -966,7 +971,6 @@ int sddm_eps(sddm_plan* p, const float* cond, const float* x_t, const float* noi
         temb = p->d_temb_table + (size_t)t * p->E;
         stride = 0;
     }
-    if ((rc = run_unet(p, cond, x_t, temb, stride, B, ws, st))) return rc;
     PostP pp{};
     pp.frames = sect(p, ws, p->off_frames, B);
     pp.eps_out = eps_out;
@@ -974,6 +978,8 @@ int sddm_eps(sddm_plan* p, const float* cond, const float* x_t, const float* noi
     pp.B = B; pp.L = p->cfg.num_samples; pp.F = p->cfg.segment_len; pp.hop = p->cfg.segment_stride; pp.n_frames = p->H;
     pp.t = 1; pp.T = p->cfg.n_timestep;
     float k8[8] = {0};
+    if ((rc = run_unet(p, cond, x_t, temb, stride, B, ws, st, &pp, k8, true))) return rc;
+    if (p->post_fused) return SDDM_OK;   // the final Block's kernel wrote eps_hat (and the frames, for sddm_debug_fetch)
     return launch_post_coef(pp, k8, st);
 }
 
@@ -1057,7 +1063,6 @@ int sddm_sample(sddm_plan* p, int variant, const float* cond, const float* noise
     float* x = sect(p, ws, p->off_x, B);
     if ((rc = sddm_x_T(p, variant, cond, noises, seed, row0, x, B, stream))) return rc;
     for (int t = T; t >= 1; --t) {
-        if ((rc = run_unet(p, cond, x, p->d_temb_table + (size_t)t * p->E, 0, B, ws, st))) return rc;
         PostP pp{};
         pp.frames = sect(p, ws, p->off_frames, B);
         pp.eps_out = eps_trace ? eps_trace + (size_t)(T - t) * BL : nullptr;
@@ -1071,6 +1076,9 @@ int sddm_sample(sddm_plan* p, int variant, const float* cond, const float* noise
         pp.B = B; pp.L = L; pp.F = p->cfg.segment_len; pp.hop = p->cfg.segment_stride; pp.n_frames = p->H;
         float k8[8];
         step_coefs(p, variant, t, k8);
+        // one forward; with the row kernels its last launch also does the overlap-add + posterior update (frames / eps_hat stay on chip)
+        if ((rc = run_unet(p, cond, x, p->d_temb_table + (size_t)t * p->E, 0, B, ws, st, &pp, k8, false))) return rc;
+        if (p->post_fused) continue;
         if ((rc = prof_mark(p, (int)p->ops.size(), true, st))) return rc;
         if ((rc = launch_post_coef(pp, k8, st))) return rc;
         if ((rc = prof_mark(p, (int)p->ops.size(), false, st))) return rc;

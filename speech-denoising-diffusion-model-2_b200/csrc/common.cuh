@@ -134,7 +134,10 @@ int conv_tc_tiles(int Hout, int Wout);
 bool conv_row_supported(const ConvP& p);
 int conv_row_nparts(int H);      // partial-statistics slots per sample: (H / 16) blocks x 2 groups x 4 warps
 int conv_row_arrivals(int H);    // arrivals per sample of the fused GroupNorm finalisation
-int launch_conv_row(const ConvP& p, const __nv_bfloat16* w_row, uint32_t w_bytes, float* frames, float final_bias, cudaStream_t st);   // tiles per sample (= arrivals per sample of the fused GroupNorm finalisation)
+struct PostP;
+// post != nullptr (final Block only): fuse the overlap-add of the frames + the posterior update described by (post, k8) into the epilogue
+int launch_conv_row(const ConvP& p, const __nv_bfloat16* w_row, uint32_t w_bytes, float* frames, float final_bias, cudaStream_t st,
+                    const PostP* post, const float* k8);   // tiles per sample (= arrivals per sample of the fused GroupNorm finalisation)
 
 // ---------------------------------------------------------------------------------------------------
 // programmatic dependent launch (PDL): a kernel launched with launch_pdl() may start while its predecessor in the stream
@@ -179,20 +182,29 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
     return ctr;
 }
 
-// four N(0,1) samples from one Philox block (Box-Muller on (0,1] uniforms)
-__device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint32_t elem4, uint64_t row, uint32_t draw) {
-    uint4 r = philox4x32_10(make_uint4(elem4, (uint32_t)row, draw, (uint32_t)(row >> 32)),
-                            make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+// four N(0,1) samples from one Philox block (Box-Muller on (0,1] uniforms).  The transcendental parts use the hardware
+// approximations explicitly (lg2.approx / sin.approx / cos.approx: absolute error ~1e-6, far below what a Gaussian draw needs),
+// so every translation unit - whatever its math flags - produces the SAME stream for a given (seed, element, row, draw).
+__device__ __forceinline__ float2 box_muller_fast(uint32_t a, uint32_t b) {
     const float k = 2.3283064365386963e-10f;  // 2^-32
-    float u0 = ((float)r.x + 1.0f) * k, u1 = (float)r.y * k;
-    float u2 = ((float)r.z + 1.0f) * k, u3 = (float)r.w * k;
-    u0 = fminf(u0, 1.0f);
-    u2 = fminf(u2, 1.0f);
-    float m0 = sqrtf(-2.0f * logf(u0)), m1 = sqrtf(-2.0f * logf(u2));
-    float s0, c0, s1, c1;
-    sincospif(2.0f * u1, &s0, &c0);
-    sincospif(2.0f * u3, &s1, &c1);
-    return make_float4(m0 * c0, m0 * s0, m1 * c1, m1 * s1);
+    const float u0 = fminf(((float)a + 1.0f) * k, 1.0f), u1 = (float)b * k;
+    const float m = sqrtf(-2.0f * __logf(u0));
+    float s, c;
+    __sincosf(6.283185307179586f * u1, &s, &c);
+    return make_float2(m * c, m * s);
+}
+__device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint32_t elem4, uint64_t row, uint32_t draw) {
+    const uint4 r = philox4x32_10(make_uint4(elem4, (uint32_t)row, draw, (uint32_t)(row >> 32)),
+                                  make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const float2 p0 = box_muller_fast(r.x, r.y), p1 = box_muller_fast(r.z, r.w);
+    return make_float4(p0.x, p0.y, p1.x, p1.y);
+}
+// component `comp` (0..3) of philox_normal4 - only the Box-Muller pair that holds it is evaluated
+__device__ __forceinline__ float philox_normal1(uint64_t seed, uint32_t elem4, uint64_t row, uint32_t draw, int comp) {
+    const uint4 r = philox4x32_10(make_uint4(elem4, (uint32_t)row, draw, (uint32_t)(row >> 32)),
+                                  make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const float2 p = (comp & 2) ? box_muller_fast(r.z, r.w) : box_muller_fast(r.x, r.y);
+    return (comp & 1) ? p.y : p.x;
 }
 
 // Warp-wide column sums of 32 per-lane values with 31 shuffles (recursive halving):

@@ -71,7 +71,9 @@ struct RowArgs {
     const float* bias; const float* temb; int temb_stride; const float* res_bias;
     const float* cond; const float* x_t; int L, hop;   // stem
     float* parts; int nparts;   // [B][nparts][32][2]
-    float* frames; float final_bias;
+    float* frames; float final_bias;   // final Block: frames are written only when non-null (sddm_eps / debug fetch)
+    int post_on;                       // final Block: overlap-add of the frames + posterior update fused into the epilogue
+    PostP post; PostCoef pk;
     int gn_on; GnFuse gn;
     uint32_t off_w, off_raw, off_a, off_out, off_res;
     long long* trace;           // debug: per-role wait / busy cycle counters of CTA 0 (nullptr = off), 32 counters per launch
@@ -86,17 +88,24 @@ struct RowHdr {
     uint32_t tmem_base;
     uint32_t gn_last[kEpi];
     alignas(16) float addv[kEpi][32];
+    // final Block: positions 64..127 of frame row y wait here for the group that owns row y + 1 (overlap-add partner)
+    uint64_t f_full[4], f_empty[4];
+    alignas(16) float fup[4][64];
 };
-constexpr uint32_t kHdr = 1024;
+constexpr uint32_t kHdr = 2048;
 static_assert(sizeof(RowHdr) <= kHdr, "header too large");
 
 // the k-th sample segment of a CTA that owns the 16-row blocks [b0, b1): output rows [ya, yb) of sample n need input rows [r0, r1]
-struct Seg { int n, ya, yb, r0, r1; };
-__device__ __forceinline__ bool seg_at(int H, int b0, int b1, int k, Seg& s) {
+// yo = first row whose results this CTA publishes; ext (final Block with the fused overlap-add): the run also recomputes frame row
+// ya - 1, whose upper half the samples of row ya need (it belongs to the CTA above, which publishes it)
+struct Seg { int n, ya, yb, r0, r1, yo; };
+__device__ __forceinline__ bool seg_at(int H, int b0, int b1, int k, Seg& s, bool ext) {
     const int bps = H >> 4, n0 = b0 / bps;
     s.n = n0 + k;
     if (s.n * bps >= b1) return false;
     s.ya = k == 0 ? (b0 - n0 * bps) << 4 : 0;
+    s.yo = s.ya;
+    if (ext && s.ya > 0) s.ya -= 1;
     const int e = (b1 - s.n * bps) << 4;
     s.yb = e < H ? e : H;
     s.r0 = s.ya > 0 ? s.ya - 1 : 0;
@@ -130,6 +139,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const RowArgs 
     constexpr int SLOT = KIND == ROW_FINAL ? 32 : 96;                // TMEM columns per accumulator slot
     constexpr uint32_t TMEM_COLS = KIND == ROW_FINAL ? 256u : 512u;
     constexpr uint32_t W_CHUNK = (uint32_t)NCOLS * 32u;              // bytes per (k16, kx) weight chunk: 2 halves x N rows x 16 B
+    constexpr bool EXT = KIND == ROW_FINAL;                          // final Block: runs start one frame row early (overlap-add partner)
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t dyn = smem_u32(smem_dyn), base = (dyn + 1023u) & ~1023u;
     RowHdr* hdr = reinterpret_cast<RowHdr*>(smem_dyn + (base - dyn));
@@ -143,7 +153,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const RowArgs 
     int nitems = 0;
     {
         Seg s;
-        for (int k = 0; seg_at(a.H, b0, b1, k, s); ++k) nitems += s.r1 - s.r0 + 1;
+        for (int k = 0; seg_at(a.H, b0, b1, k, s, EXT); ++k) nitems += s.r1 - s.r0 + 1;
     }
 
     if (tid == 0) {
@@ -152,6 +162,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const RowArgs 
         for (int i = 0; i < kNS; ++i) { mbar_init(smem_u32(&hdr->acc_full[i]), 1); mbar_init(smem_u32(&hdr->acc_empty[i]), 12); }
         for (int e = 0; e < kEpi; ++e) for (int k = 0; k < 2; ++k) mbar_init(smem_u32(&hdr->res_full[e][k]), 1);
         mbar_init(smem_u32(&hdr->w_full), 1);
+        for (int i = 0; i < 4; ++i) { mbar_init(smem_u32(&hdr->f_full[i]), 2); mbar_init(smem_u32(&hdr->f_empty[i]), 2); }
         fence_barrier_init();
     }
     if (warp == kMma) tmem_alloc(smem_u32(&hdr->tmem_base), TMEM_COLS);
@@ -184,13 +195,14 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const RowArgs 
         const int c2 = lane & 15, hrow = lane >> 4;
         float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;   // statistics of this group's rows of the current block (2 channels per lane)
         int ob = 0;                                          // rows stored so far (staging / residual buffer parity)
+        uint32_t fwc[2] = {0u, 0u}, frc[2] = {0u, 0u};       // final Block: fills / reads so far of the two fup slots this group writes / reads
         // identity residual: TMA prefetch two rows ahead along this group's (n, y) sequence
         int pk = 0, py = -1, pn = 0, pend = 0, pissued = 0;
         Seg ps{};
         auto res_issue = [&]() {
             for (;;) {   // advance (pk, py) to this group's next output row
                 if (py < 0) {
-                    if (!seg_at(a.H, b0, b1, pk, ps)) return;
+                    if (!seg_at(a.H, b0, b1, pk, ps, EXT)) return;
                     py = ps.ya + ((ps.ya & 1) == e ? 0 : 1);
                     pend = ps.yb; pn = ps.n;
                 } else {
@@ -207,7 +219,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const RowArgs 
         if (RESID && res_leader) { res_issue(); res_issue(); }
         int item_base = 0;
         Seg s;
-        for (int k = 0; seg_at(a.H, b0, b1, k, s); item_base += s.r1 - s.r0 + 1, ++k) {
+        for (int k = 0; seg_at(a.H, b0, b1, k, s, EXT); item_base += s.r1 - s.r0 + 1, ++k) {
             if (KIND != ROW_FINAL) {
                 // per-channel additive term of this sample: bias (+ noise-level embedding row) (+ res_conv bias)
                 group_bar(bar_id);
@@ -223,6 +235,21 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const RowArgs 
                 const bool vA = y - 1 >= s.r0, vC = y + 1 <= s.r1;
                 const int iB = item_base + (y - s.r0), last = vC ? iB + 1 : iB;
                 const int slB = iB % kNS, slA = (iB + kNS - 1) % kNS, slC = (iB + 1) % kNS;
+                // final Block: the posterior update of this row's samples reads x_t (+ injected noise, + the condition) from HBM -
+                // issue those loads now, so their latency hides behind the accumulator wait
+                int p_sidx = -1;
+                float p_x = 0.f, p_z = 0.f, p_c = 0.f;
+                if (KIND == ROW_FINAL && a.post_on) {
+                    const PostP& q = a.post;
+                    if (w4 < 2) { if (y >= s.yo) p_sidx = y * (RW / 2) + m; }
+                    else if (y + 1 == a.H) p_sidx = a.H * (RW / 2) + (m - 64);
+                    if (p_sidx >= 0 && q.do_update) {
+                        const int64_t gi = (int64_t)s.n * q.L + p_sidx;
+                        p_x = q.x_in[gi];
+                        if (q.z && q.t > 1) p_z = q.z[gi];
+                        if (q.variant == SDDM_VAR_SUPPORTIVE || q.variant == SDDM_VAR_CONDITIONAL) p_c = q.cond[gi];
+                    }
+                }
                 mbar_wait_t(smem_u32(&hdr->acc_full[last % kNS]), (uint32_t)(last / kNS) & 1u, tr, tw[0]);
                 tc_fence_after();
                 // arrivals owed to the three accumulator slots: an input row r is read by the output rows r - 1, r, r + 1; those
@@ -244,7 +271,46 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const RowArgs 
                     }
                     if (tr) tw[1] += clock64() - te0;
                     const float f = (__uint_as_float(ra[0]) + __uint_as_float(rb[1])) + __uint_as_float(rc[2]) + a.final_bias;
-                    a.frames[((int64_t)s.n * a.H + y) * RW + m] = f;
+                    if (a.frames && y >= s.yo) a.frames[((int64_t)s.n * a.H + y) * RW + m] = f;
+                    if (!a.post_on) continue;
+                    // overlap-add (UNetModified2.py:30-41, hop = W / 2): eps[hop a + j] = frame[a - 1][j + hop] + frame[a][j], then the
+                    // posterior update of that sample (post_one, bit-exact) - frames / eps_hat never touch HBM in the sampling loop
+                    auto emit = [&](float ev) {
+                        const PostP& q = a.post;
+                        const int64_t gi = (int64_t)s.n * q.L + p_sidx;
+                        if (q.eps_out) q.eps_out[gi] = ev;
+                        if (!q.do_update) return;
+                        const bool add_noise = q.t > 1;
+                        float zv = p_z;
+                        if (add_noise && !q.z)
+                            zv = philox_normal1(q.seed, (uint32_t)(p_sidx >> 2), (uint64_t)(q.row0 + s.n), (uint32_t)(q.T + 1 - q.t), p_sidx & 3);
+                        const float o = post_one(q.variant, a.pk, p_x, ev, p_c, zv, add_noise);
+                        q.x_out[gi] = o;
+                        if (q.x_trace) q.x_trace[gi] = o;
+                    };
+                    if (w4 >= 2) {   // positions 64..127 belong to sample row y + 1
+                        if (y + 1 < s.yb) {
+                            const int slot = y & 3, ci = (y >> 1) & 1;
+                            mbar_wait(smem_u32(&hdr->f_empty[slot]), (fwc[ci] & 1u) ^ 1u);
+                            hdr->fup[slot][m - 64] = f;
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(smem_u32(&hdr->f_full[slot]));
+                            ++fwc[ci];
+                        } else if (y + 1 == a.H) {
+                            emit(f);                    // the last half frame of the sample has no partner
+                        }
+                    } else if (y >= s.yo) {   // positions 0..63: sample row y
+                        float ev = f;
+                        if (y > 0) {
+                            const int slot = (y - 1) & 3, ci = ((y - 1) >> 1) & 1;
+                            mbar_wait(smem_u32(&hdr->f_full[slot]), frc[ci] & 1u);
+                            ev = hdr->fup[slot][m] + f;      // ascending frame order, as the reference accumulates
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(smem_u32(&hdr->f_empty[slot]));
+                            ++frc[ci];
+                        }
+                        emit(ev);
+                    }
                     continue;
                 }
                 const uint32_t obuf = obuf0 + (uint32_t)(ob & 1) * kOutTile;
@@ -417,7 +483,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const RowArgs 
             int rs = 0;
             uint32_t pr = 0;
             Seg s;
-            for (int k = 0; seg_at(a.H, b0, b1, k, s); ++k)
+            for (int k = 0; seg_at(a.H, b0, b1, k, s, EXT); ++k)
                 for (int r = s.r0; r <= s.r1; ++r) {
 #pragma unroll
                     for (int sl = 0; sl < NSLAB; ++sl) {
@@ -588,7 +654,8 @@ static int launch_row_t(RowArgs a, const RowMaps& maps, cudaStream_t st) {
 }
 
 // ResnetBlock / Upsample convolutions (Cout = 32) and the final Block (Cout = 1, frames out) on a 128-wide level
-int launch_conv_row(const ConvP& p, const __nv_bfloat16* w_row, uint32_t w_bytes, float* frames, float final_bias, cudaStream_t st) {
+int launch_conv_row(const ConvP& p, const __nv_bfloat16* w_row, uint32_t w_bytes, float* frames, float final_bias, cudaStream_t st,
+                    const PostP* post, const float* k8) {
     if (!conv_row_supported(p) || !w_row) { set_error("conv row: unsupported shape Cin=%d Cout=%d mode=%d W=%d", p.Cin, p.Cout, p.mode, p.Wout); return SDDM_E_INVALID; }
     RowArgs a{};
     RowMaps maps;
@@ -603,6 +670,12 @@ int launch_conv_row(const ConvP& p, const __nv_bfloat16* w_row, uint32_t w_bytes
     a.bias = p.bias; a.temb = p.temb; a.temb_stride = p.temb_stride; a.res_bias = p.res_bias;
     a.parts = p.parts; a.nparts = p.nparts;
     a.frames = frames; a.final_bias = final_bias;
+    if (final_out && post) {
+        if (!k8 || post->L != (p.Hout + 1) * (RW / 2)) { set_error("conv row: fused overlap-add needs hop = W / 2 and L = (H + 1) hop"); return SDDM_E_INVALID; }
+        a.post_on = 1;
+        a.post = *post;
+        a.pk = PostCoef{k8[0], k8[1], k8[2], k8[3], k8[4], k8[5], k8[6], k8[7]};
+    }
     a.gn_on = p.gn_on; a.gn = p.gn;
     if (!final_out && (!p.parts || p.nparts != conv_row_nparts(p.Hout))) { set_error("conv row: nparts mismatch"); return SDDM_E_INVALID; }
     int rc;

@@ -1,6 +1,7 @@
 // Host-callable launchers of the non-convolution kernels (kernels_misc.cu).
 #pragma once
 #include "common.cuh"
+#include "../../include/sddm_b200.h"
 
 namespace sddm {
 
@@ -28,6 +29,28 @@ struct PostP {
 };
 // k8 = {c2, sqrt(alpha_t), noise std, gamma, 1-gamma, c_xt, c_yt, c_epst} of step t (host scalars)
 int launch_post_coef(const PostP& p, const float* k8, cudaStream_t st);
+
+struct PostCoef {  // scalars of step t, fetched on the host from the plan's host tables
+    float c2, sa, sig, gam, one_m_gam, cx, cy, ce;
+};
+
+// one sample of p_transition / _sr3 / _supportive / _conditional incl. the clamp: every product, sum and quotient rounded
+// separately, as the reference's eager ops do (diffusion.py:164-222)
+__device__ __forceinline__ float post_one(int variant, const PostCoef& k, float x, float e, float c, float z, bool add_noise) {
+    float r;
+    if (variant == SDDM_VAR_SUPPORTIVE) {
+        float mu = __fsub_rn(x, __fmul_rn(k.c2, e));
+        r = __fdiv_rn(__fadd_rn(__fmul_rn(k.one_m_gam, mu), __fmul_rn(k.gam, c)), k.sa);
+    } else if (variant == SDDM_VAR_CONDITIONAL) {
+        r = __fsub_rn(__fadd_rn(__fmul_rn(k.cx, x), __fmul_rn(k.cy, c)), __fmul_rn(k.ce, e));
+    } else {
+        r = __fdiv_rn(__fsub_rn(x, __fmul_rn(k.c2, e)), k.sa);
+    }
+    if (add_noise) r = __fadd_rn(r, __fmul_rn(k.sig, z));
+    return fminf(fmaxf(r, -1.0f), 1.0f);
+}
+
+
 
 // forward diffusion q(x_t | x_0) with per-row coefficients (diffusion.py:225-279); see q_sample_kernel
 int launch_q_sample(int mode, const float* coef, const float* x0, const float* y, const float* z, uint64_t seed, int64_t row0, float* x_t,

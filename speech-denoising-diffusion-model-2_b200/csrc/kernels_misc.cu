@@ -55,24 +55,6 @@ int launch_x_T_coef(int variant, float a, float b, const float* cond, const floa
 // posterior update (+ fused overlap-add)                reference: model/diffusion.py:164-222,
 //                                                                  model/UNetModified2.py:30-41
 // ===================================================================================================
-struct PostCoef {  // scalars of step t, fetched on the host from the plan's host tables
-    float c2, sa, sig, gam, one_m_gam, cx, cy, ce;
-};
-
-__device__ __forceinline__ float post_one(int variant, const PostCoef& k, float x, float e, float c, float z, bool add_noise) {
-    float r;
-    if (variant == SDDM_VAR_SUPPORTIVE) {
-        float mu = __fsub_rn(x, __fmul_rn(k.c2, e));
-        r = __fdiv_rn(__fadd_rn(__fmul_rn(k.one_m_gam, mu), __fmul_rn(k.gam, c)), k.sa);
-    } else if (variant == SDDM_VAR_CONDITIONAL) {
-        r = __fsub_rn(__fadd_rn(__fmul_rn(k.cx, x), __fmul_rn(k.cy, c)), __fmul_rn(k.ce, e));
-    } else {
-        r = __fdiv_rn(__fsub_rn(x, __fmul_rn(k.c2, e)), k.sa);
-    }
-    if (add_noise) r = __fadd_rn(r, __fmul_rn(k.sig, z));
-    return fminf(fmaxf(r, -1.0f), 1.0f);
-}
-
 __global__ void __launch_bounds__(256) post_kernel(PostP p, PostCoef k) {
     const int L4 = p.L / 4;
     const int64_t total = (int64_t)p.B * L4;
