@@ -804,14 +804,21 @@ def run_ours(args):
         tot = sum(o["ms"] for o in prof) or 1.0
         fam = {}
         for o in prof:
-            k = ("conv_tc" if o["tensor_cores"] else "conv_fp32") if o["label"].startswith("conv:") else o["label"].split(":")[0]
+            if not o["launches"]:
+                continue
+            k = o["kernel"] if o["kernel"] != "cuda_core" else o["label"].split(":")[0]
             f = fam.setdefault(k, dict(ms=0.0, flops=0.0, bytes=0.0, launches=0))
             f["ms"] += o["ms"]; f["launches"] += o["launches"]
             f["flops"] += o["flops_per_row"] * B * o["launches"]; f["bytes"] += o["bytes_per_row"] * B * o["launches"]
+        # per kernel FUNCTION: share of the step, average launch, algorithmic GB/s and TFLOP/s over all its launches, and both roofline fractions
         kernels = {k: {"share": f["ms"] / tot, "avg_us": 1e3 * f["ms"] / max(1, f["launches"]), "launches": f["launches"],
-                       "tflops": f["flops"] / (f["ms"] * 1e-3) / 1e12 if f["ms"] else 0.0,
-                       "gbs": f["bytes"] / (f["ms"] * 1e-3) / 1e9 if f["ms"] else 0.0} for k, f in fam.items()}
+                       "tflops": f["flops"] / (f["ms"] * 1e-3) / 1e12, "gbs": f["bytes"] / (f["ms"] * 1e-3) / 1e9,
+                       "frac_hbm": f["bytes"] / (f["ms"] * 1e-3) / 1e9 / pk["hbm"], "frac_bf16_sustained": f["flops"] / (f["ms"] * 1e-3) / 1e12 / pk["bf16_sustained"]}
+                   for k, f in fam.items()}
         line["kernels"] = kernels
+        line["ops"] = {o["label"]: {"us": 1e3 * o["ms"] / o["launches"], "kernel": o["kernel"], "gbs": o["bytes_per_row"] * B * o["launches"] / (o["ms"] * 1e-3) / 1e9,
+                                    "tflops": o["flops_per_row"] * B * o["launches"] / (o["ms"] * 1e-3) / 1e12} for o in prof if o["launches"]}
+        # roofline block: the dominant kernel = the single op with the largest share of the step (one launch per step)
         top = max((o for o in prof if o["launches"]), key=lambda o: o["ms"])
         dur = top["ms"] * 1e-3 / top["launches"]
         ai = top["flops_per_row"] / max(top["bytes_per_row"], 1.0)
@@ -828,11 +835,14 @@ def run_ours(args):
                 traffic = tj.get("dram_bytes_per_launch", {}).get(top["label"])
         except Exception:
             pass
-        line["roofline"] = {"kernel": top["label"], "bound": "hbm" if hbm_bound else "tensor", "achieved": ach, "peak": peak,
+        line["roofline"] = {"kernel": "%s (%s)" % (top["kernel"], top["label"]), "bound": "hbm" if hbm_bound else "tensor", "achieved": ach, "peak": peak,
                             "unit": unit, "frac": ach / peak, "traffic": traffic, "avg_launch_us": dur * 1e6,
                             "share_of_step": top["ms"] / tot, "arith_intensity_flop_per_byte": ai,
                             "algorithmic_bytes_per_launch": top["bytes_per_row"] * B,
-                            "algorithmic_flops_per_launch": top["flops_per_row"] * B}
+                            "algorithmic_flops_per_launch": top["flops_per_row"] * B,
+                            "family": kernels.get(top["kernel"]),
+                            "note": "one launch per step of the dominant kernel function; 'family' = the same figures over ALL launches of that function; "
+                                    "'kernels' lists every kernel function, 'ops' every launch of a step"}
     if world == 1 and not args.no_gpu_baseline:
         del model, plan
         torch.cuda.empty_cache()

@@ -537,7 +537,7 @@ static int build_program(sddm_plan* p, Arena& a) {
             op.wrow_bytes = (uint32_t)(img.size() * sizeof(__nv_bfloat16));
         }
         op.flops = 2.0 * 9.0 * C * p->H * p->W;
-        op.bytes = esz * (double)C * p->H * p->W + 4.0 * (double)p->H * p->W;
+        op.bytes = esz * (double)C * p->H * p->W + 4.0 * (double)p->H * p->W;   // activation in, frames (or, fused: x_t in + x_{t-1} out) 
         p->ops.push_back(op);
     }
     if (temb_cursor != p->E) { set_error("internal: embedding width mismatch"); return SDDM_E_INVALID; }
@@ -1152,7 +1152,7 @@ int sddm_profile_read(sddm_plan* p, int op, double* total_ms, int64_t* launches,
     if (flops_per_row) *flops_per_row = is_post ? 8.0 * L : p->ops[op].flops;
     // ola + posterior with in-kernel Philox: read frames (2 per sample) + x_t, write x_{t-1}
     if (bytes_per_row) *bytes_per_row = is_post ? 4.0 * (2.0 * L + 2.0 * L) : p->ops[op].bytes;
-    if (uses_tensor_cores) *uses_tensor_cores = is_post ? 0 : (p->ops[op].use_tc ? 1 : 0);
+    if (uses_tensor_cores) *uses_tensor_cores = is_post ? 0 : (p->ops[op].use_row ? 2 : (p->ops[op].use_tc ? 1 : 0));   // 2 = conv_row.cu, 1 = conv_tc.cu
     if (label && label_cap > 0) snprintf(label, (size_t)label_cap, "%s", is_post ? "ola_posterior" : p->ops[op].label.c_str());
     return SDDM_OK;
 }

@@ -157,8 +157,8 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const RowArgs 
     }
 
     if (tid == 0) {
-        for (int i = 0; i < kNR; ++i) { mbar_init(smem_u32(&hdr->raw_full[i]), 1); mbar_init(smem_u32(&hdr->raw_empty[i]), kGrp); }
-        for (int i = 0; i < kNA; ++i) { mbar_init(smem_u32(&hdr->full_a[i]), kGrp); mbar_init(smem_u32(&hdr->empty_a[i]), 1); }
+        for (int i = 0; i < kNR; ++i) { mbar_init(smem_u32(&hdr->raw_full[i]), 1); mbar_init(smem_u32(&hdr->raw_empty[i]), kGrp / 32); }
+        for (int i = 0; i < kNA; ++i) { mbar_init(smem_u32(&hdr->full_a[i]), kGrp / 32); mbar_init(smem_u32(&hdr->empty_a[i]), 1); }
         for (int i = 0; i < kNS; ++i) { mbar_init(smem_u32(&hdr->acc_full[i]), 1); mbar_init(smem_u32(&hdr->acc_empty[i]), 12); }
         for (int e = 0; e < kEpi; ++e) for (int k = 0; k < 2; ++k) mbar_init(smem_u32(&hdr->res_full[e][k]), 1);
         mbar_init(smem_u32(&hdr->w_full), 1);
@@ -576,9 +576,14 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const RowArgs 
                     }
                 }
             }
+            // one arrival per warp (32 same-address mbarrier arrivals serialise in the shared-memory pipe): every lane fences its
+            // own operand stores towards the async proxy, the warp converges, lane 0 publishes
             fence_async_smem();
-            mbar_arrive(smem_u32(&hdr->full_a[sa]));
-            mbar_arrive(smem_u32(&hdr->raw_empty[rs]));
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(smem_u32(&hdr->full_a[sa]));
+                mbar_arrive(smem_u32(&hdr->raw_empty[rs]));
+            }
             if (tr) tw[2] += clock64() - tx0;
         }
         if (tr && gt == 0) { long long* o = a.trace + 24 + 4 * gi; o[0] = clock64() - t_begin; o[1] = tw[0]; o[2] = tw[1]; o[3] = tw[2]; }

@@ -104,10 +104,10 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"   // suspend-time hint: fewer wake-ups / re-polls of a waiting warp
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(0x20000u)
         : "memory");
     return ok != 0;
 }
@@ -294,12 +294,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
 
     if (tid == 0) {
         for (int i = 0; i < kMaxRing; ++i) {
-            mbar_init(smem_u32(&hdr->raw_full[i]), 1); mbar_init(smem_u32(&hdr->raw_empty[i]), kXfGroupThreads);
-            mbar_init(smem_u32(&hdr->full_a[i]), kXfGroupThreads); mbar_init(smem_u32(&hdr->empty_a[i]), 1);
+            mbar_init(smem_u32(&hdr->raw_full[i]), 1); mbar_init(smem_u32(&hdr->raw_empty[i]), kXfGroupThreads / 32);
+            mbar_init(smem_u32(&hdr->full_a[i]), kXfGroupThreads / 32); mbar_init(smem_u32(&hdr->empty_a[i]), 1);
         }
         for (int i = 0; i < kMaxW; ++i) { mbar_init(smem_u32(&hdr->full_w[i]), 1); mbar_init(smem_u32(&hdr->empty_w[i]), 1); }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(smem_u32(&hdr->tmem_full[i]), 1); mbar_init(smem_u32(&hdr->tmem_empty[i]), kEpiGroupThreads);
+            mbar_init(smem_u32(&hdr->tmem_full[i]), 1); mbar_init(smem_u32(&hdr->tmem_empty[i]), kEpiGroupThreads / 32);
             for (int k = 0; k < 4; ++k) mbar_init(smem_u32(&hdr->res_full[i][k]), 1);
         }
         fence_barrier_init();
@@ -408,7 +408,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
                 if (tr) tw[4] += clock64() - te0;
                 if (cb == nblk - 1) {   // accumulator fully drained: hand the TMEM stage back to the MMA warp early
                     tc_fence_before();
-                    mbar_arrive(smem_u32(&hdr->tmem_empty[e]));
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&hdr->tmem_empty[e]));   // one arrival per warp: same-address arrivals serialise
                 }
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
@@ -905,8 +906,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
             }
             const long long ts2 = tr ? clock64() : 0;
             fence_async_smem();
-            mbar_arrive(smem_u32(&hdr->full_a[sa]));
-            mbar_arrive(smem_u32(&hdr->raw_empty[rs]));
+            __syncwarp();   // one arrival per warp (every lane has fenced its own operand stores above)
+            if (lane == 0) {
+                mbar_arrive(smem_u32(&hdr->full_a[sa]));
+                mbar_arrive(smem_u32(&hdr->raw_empty[rs]));
+            }
             if (tr) { tw[3] += ts2 - ts1; tw[4] += clock64() - ts2; }
             // advance by kXfGroups slabs
             ai += kXfGroups;

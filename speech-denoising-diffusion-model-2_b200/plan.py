@@ -185,7 +185,7 @@ class Plan:
                 _lib.check(lib.sddm_profile_read(self._h, i, C.byref(ms), C.byref(n), C.byref(fl), C.byref(by), C.byref(tc),
                                                  label, 128))
                 out.append(dict(label=label.value.decode(), ms=ms.value, launches=n.value, flops_per_row=fl.value,
-                                bytes_per_row=by.value, tensor_cores=bool(tc.value)))
+                                bytes_per_row=by.value, tensor_cores=bool(tc.value), kernel={0: "cuda_core", 1: "conv3x3_tc_kernel", 2: "conv_row_kernel"}.get(tc.value, "?")))
         return out
 
     def fetch(self, node: str, B: int) -> torch.Tensor:
