@@ -162,6 +162,18 @@ SDDM_API int sddm_sample(sddm_plan* plan, int variant, const float* cond, const 
 SDDM_API int sddm_enhance_host(sddm_plan* plan, int variant, const float* cond_host, float* out_host, int B,
                       uint64_t seed, int64_t row0, int max_rows_per_pass);
 
+/* ---- dataset edge on the device ------------------------------------------------------------------- */
+/* The utterances of a batch sit back to back in `flat` (device): utterance u = flat[sample_off[u] .. sample_off[u + 1]) and owns the rows
+ * row_off[u] .. row_off[u + 1] of the [N, 1, T] batch (ceil(len / T) rows, last one zero padded).  sample_off / row_off: device int64
+ * [n_utt + 1].  A rank of a sharded run converts only its own row range [row_lo, row_hi).
+ * replaces: InferDataset.__getitem__ (F.pad + view) + infer_data_collate (torch.cat), data_loader/data_loaders.py:101-155 */
+SDDM_API int sddm_chunk_rows(const float* flat, const int64_t* sample_off, const int64_t* row_off, int n_utt, int T, int64_t row_lo,
+                    int64_t row_hi, float* rows /* [row_hi - row_lo][T] */, void* stream);
+/* the inverse, trimmed to the utterance lengths (only samples of [row_lo, row_hi) are written).
+ * replaces: the per-file regroup loop of infer.py:81-120 (output[batch_index_temp].reshape(1, -1)) */
+SDDM_API int sddm_regroup_rows(const float* rows /* [row_hi - row_lo][T] */, const int64_t* sample_off, const int64_t* row_off, int n_utt, int T,
+                      int64_t row_lo, int64_t row_hi, float* flat_out, void* stream);
+
 /* ---- framing helpers (standalone; the sampler uses fused versions) -------------------------------- */
 /* replaces: SignalToFrames.forward (UNetModified2.py:23-28): [B,1,n] -> [B,1,n_frames,F]. */
 SDDM_API int sddm_frames(const float* sig, float* frames, int B, int n_samples, int frame_len, int stride, void* stream);

@@ -1127,6 +1127,26 @@ int sddm_overlap_add(const float* frames, float* sig, int B, int n, int F, int h
     return launch_overlap_add(frames, sig, B, n, F, hop, (cudaStream_t)stream);
 }
 
+static int check_rows_args(const void* a, const void* b, const int64_t* so, const int64_t* ro, int n_utt, int T, int64_t lo, int64_t hi) {
+    if (!a || !b || !so || !ro || n_utt <= 0 || T <= 0 || lo < 0 || hi < lo) { set_error("bad argument"); return SDDM_E_INVALID; }
+    if (hi - lo > 0x7fffffffLL) { set_error("too many rows in one call"); return SDDM_E_INVALID; }
+    return SDDM_OK;
+}
+
+int sddm_chunk_rows(const float* flat, const int64_t* sample_off, const int64_t* row_off, int n_utt, int T, int64_t row_lo, int64_t row_hi,
+                    float* rows, void* stream) {
+    int rc = check_rows_args(flat, rows, sample_off, row_off, n_utt, T, row_lo, row_hi);
+    if (rc) return rc;
+    return launch_chunk_rows(flat, sample_off, row_off, n_utt, T, row_lo, row_hi, rows, (cudaStream_t)stream);
+}
+
+int sddm_regroup_rows(const float* rows, const int64_t* sample_off, const int64_t* row_off, int n_utt, int T, int64_t row_lo, int64_t row_hi,
+                      float* flat_out, void* stream) {
+    int rc = check_rows_args(rows, flat_out, sample_off, row_off, n_utt, T, row_lo, row_hi);
+    if (rc) return rc;
+    return launch_regroup_rows(rows, sample_off, row_off, n_utt, T, row_lo, row_hi, flat_out, (cudaStream_t)stream);
+}
+
 int sddm_plan_num_ops(const sddm_plan* p) { return (p && p->finalized) ? (int)p->ops.size() + 1 : 0; }
 
 int sddm_profile_enable(sddm_plan* p, int on) {

@@ -110,6 +110,12 @@ struct FinalP {
 };
 int launch_final_conv(const FinalP& p, cudaStream_t st);
 
+// dataset edge on the device: utterances back to back in `flat` <-> rows of the [N, 1, T] batch (kernels_misc.cu)
+int launch_chunk_rows(const float* flat, const int64_t* sample_off, const int64_t* row_off, int n_utt, int T, int64_t row_lo, int64_t row_hi,
+                      float* rows, cudaStream_t st);
+int launch_regroup_rows(const float* rows, const int64_t* sample_off, const int64_t* row_off, int n_utt, int T, int64_t row_lo, int64_t row_hi,
+                        float* flat_out, cudaStream_t st);
+
 // debug / tests: bf16 -> fp32 copy of an activation tensor
 int launch_bf16_to_f32(const void* src, float* dst, size_t n, cudaStream_t st);
 

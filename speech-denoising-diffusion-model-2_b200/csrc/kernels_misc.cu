@@ -574,6 +574,63 @@ int launch_final_conv(const FinalP& p, cudaStream_t st) {
     return SDDM_OK;
 }
 
+// ===================================================================================================
+// dataset edge on the device                            reference: InferDataset.__getitem__ + infer_data_collate,
+//                                                       data_loader/data_loaders.py:101-155; regroup loop infer.py:81-120
+// The utterances of a batch sit back to back in `flat` (sample_off[u] .. sample_off[u + 1]); utterance u owns the rows
+// row_off[u] .. row_off[u + 1] of the [N, 1, T] batch (ceil(len / T) rows, the last one zero padded).
+//   chunk  : rows[r - row_lo][:] for r in [row_lo, row_hi)  <- flat            (pad + view + cat of the reference)
+//   regroup: flat_out[sample_off[u] + i] <- rows[...]  for i < len(u)          (reshape(1, -1) per file, trimmed to the input length)
+// One block per row; the owning utterance is found by bisection of row_off.
+// ===================================================================================================
+__device__ __forceinline__ int owner_of_row(const int64_t* __restrict__ row_off, int n_utt, int64_t r) {
+    int lo = 0, hi = n_utt - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (__ldg(row_off + mid) <= r) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256) chunk_rows_kernel(const float* __restrict__ flat, const int64_t* __restrict__ sample_off,
+                                                         const int64_t* __restrict__ row_off, int n_utt, int T, int64_t row_lo,
+                                                         float* __restrict__ rows) {
+    const int64_t r = row_lo + blockIdx.x;
+    const int u = owner_of_row(row_off, n_utt, r);
+    const int64_t s0 = __ldg(sample_off + u), len = __ldg(sample_off + u + 1) - s0;
+    const int64_t first = (r - __ldg(row_off + u)) * T;          // first sample of this row inside its utterance
+    float* dst = rows + (int64_t)blockIdx.x * T;
+    for (int i = threadIdx.x; i < T; i += blockDim.x) dst[i] = (first + i < len) ? __ldg(flat + s0 + first + i) : 0.f;
+}
+
+__global__ void __launch_bounds__(256) regroup_rows_kernel(const float* __restrict__ rows, const int64_t* __restrict__ sample_off,
+                                                           const int64_t* __restrict__ row_off, int n_utt, int T, int64_t row_lo,
+                                                           float* __restrict__ flat_out) {
+    const int64_t r = row_lo + blockIdx.x;
+    const int u = owner_of_row(row_off, n_utt, r);
+    const int64_t s0 = __ldg(sample_off + u), len = __ldg(sample_off + u + 1) - s0;
+    const int64_t first = (r - __ldg(row_off + u)) * T;
+    const float* src = rows + (int64_t)blockIdx.x * T;
+    for (int i = threadIdx.x; i < T; i += blockDim.x)
+        if (first + i < len) flat_out[s0 + first + i] = src[i];
+}
+
+int launch_chunk_rows(const float* flat, const int64_t* sample_off, const int64_t* row_off, int n_utt, int T, int64_t row_lo, int64_t row_hi,
+                      float* rows, cudaStream_t st) {
+    if (row_hi <= row_lo) return SDDM_OK;
+    chunk_rows_kernel<<<(unsigned)(row_hi - row_lo), 256, 0, st>>>(flat, sample_off, row_off, n_utt, T, row_lo, rows);
+    SDDM_LAUNCH_CHECK();
+    return SDDM_OK;
+}
+
+int launch_regroup_rows(const float* rows, const int64_t* sample_off, const int64_t* row_off, int n_utt, int T, int64_t row_lo, int64_t row_hi,
+                        float* flat_out, cudaStream_t st) {
+    if (row_hi <= row_lo) return SDDM_OK;
+    regroup_rows_kernel<<<(unsigned)(row_hi - row_lo), 256, 0, st>>>(rows, sample_off, row_off, n_utt, T, row_lo, flat_out);
+    SDDM_LAUNCH_CHECK();
+    return SDDM_OK;
+}
+
 __global__ void __launch_bounds__(256) bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, size_t n) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = __bfloat162float(src[i]);
 }

@@ -95,6 +95,64 @@ def rows_of_range(waves: Sequence[torch.Tensor], T: int, lo: int, hi: int, out: 
     return out
 
 
+class DeviceBatch:
+    """The dataset edge on the GPU (C ABI: sddm_chunk_rows / sddm_regroup_rows): the utterances of a run are uploaded ONCE, back to
+    back; any row range of the [N, 1, T] batch InferDataset + infer_data_collate would build is produced on the device, and enhanced
+    rows are scattered back into per-utterance waveforms trimmed to their input lengths (the regroup loop of reference infer.py:81-120)."""
+
+    def __init__(self, waves: Sequence[torch.Tensor], T: int, device, lo: int = 0, hi: int = None):
+        """Only the samples of the utterances that own rows [lo, hi) are uploaded (a rank of a sharded run passes its slice)."""
+        self.T, self.device = int(T), torch.device(device)
+        self.lengths = [int(torch.as_tensor(w).numel()) for w in waves]
+        counts = chunk_counts(self.lengths, T)
+        self.row_off = torch.zeros(len(waves) + 1, dtype=torch.int64)
+        self.row_off[1:] = torch.cumsum(torch.tensor(counts), 0)
+        self.n_rows = int(self.row_off[-1])
+        hi = self.n_rows if hi is None else hi
+        self.lo, self.hi = lo, hi
+        owns = [(int(self.row_off[u]) < hi and int(self.row_off[u + 1]) > lo) for u in range(len(waves))]
+        self.sample_off = torch.zeros(len(waves) + 1, dtype=torch.int64)
+        self.sample_off[1:] = torch.cumsum(torch.tensor([n if o else 0 for n, o in zip(self.lengths, owns)]), 0)
+        total = int(self.sample_off[-1])
+        host = torch.empty(max(total, 1), dtype=torch.float32).pin_memory()
+        for u, w in enumerate(waves):
+            if owns[u]:
+                host[int(self.sample_off[u]):int(self.sample_off[u + 1])] = torch.as_tensor(w, dtype=torch.float32).reshape(-1)
+        self.owns = owns
+        self.flat = host.to(self.device, non_blocking=True)
+        self.sample_off_d = self.sample_off.to(self.device)
+        self.row_off_d = self.row_off.to(self.device)
+
+    def _call(self, fn, a, b, lo, hi):
+        import ctypes as C
+        from .. import _lib
+        with torch.cuda.device(self.device):
+            st = torch.cuda.current_stream().cuda_stream
+            _lib.check(fn(C.c_void_p(a.data_ptr()), C.c_void_p(self.sample_off_d.data_ptr()), C.c_void_p(self.row_off_d.data_ptr()),
+                          len(self.lengths), self.T, int(lo), int(hi), C.c_void_p(b.data_ptr()), C.c_void_p(st)))
+
+    def rows(self, lo: int, hi: int) -> torch.Tensor:
+        """[hi - lo, 1, T] rows of the batch, built on the device."""
+        from .. import _lib
+        assert self.lo <= lo <= hi <= self.hi
+        out = torch.empty((hi - lo, 1, self.T), device=self.device)
+        self._call(_lib.lib().sddm_chunk_rows, self.flat, out, lo, hi)
+        return out
+
+    def regroup(self, rows: torch.Tensor, lo: int, hi: int, flat_out: torch.Tensor = None) -> torch.Tensor:
+        """Scatter enhanced rows [lo, hi) into the flat per-utterance layout (trimmed); returns the flat buffer."""
+        from .. import _lib
+        if flat_out is None:
+            flat_out = torch.zeros_like(self.flat)
+        self._call(_lib.lib().sddm_regroup_rows, rows.contiguous(), flat_out, lo, hi)
+        return flat_out
+
+    def split(self, flat_out: torch.Tensor) -> List[torch.Tensor]:
+        """Per-utterance [1, n_u] views of a flat buffer (None for utterances this batch does not own)."""
+        return [flat_out[int(self.sample_off[u]):int(self.sample_off[u + 1])].reshape(1, -1) if o else None
+                for u, o in enumerate(self.owns)]
+
+
 def balanced_splits(n: int, limit: int) -> List[Tuple[int, int]]:
     """[0, n) cut into ceil(n / limit) near-equal pieces (a 51-row tail behind four 64-row sub-batches costs almost a full
     sub-batch of GPU time; five pieces of 61-62 rows do not)."""

@@ -74,12 +74,8 @@ def enhance_utterances(model, waves: Sequence[torch.Tensor], batch_chunks: int =
     seed = _resolve_seed(seed, world)
     import time
     lengths = [int(w.numel()) for w in waves]
-    counts = module_data.chunk_counts(lengths, L)
-    n = int(sum(counts))
-    index = torch.repeat_interleave(torch.arange(len(waves)), torch.tensor(counts))
+    n = int(sum(module_data.chunk_counts(lengths, L)))
     lo, hi = shard_bounds(n, world, rank)
-    out_local = torch.empty((hi - lo, 1, L), device=device)
-    stage = torch.empty((min(batch_chunks, max(1, hi - lo)), 1, L), dtype=torch.float32).pin_memory() if hi > lo else None
 
     def tick(name, t0):   # phase timeline for bench.py (adds device syncs; off by default)
         if timings is not None:
@@ -88,17 +84,41 @@ def enhance_utterances(model, waves: Sequence[torch.Tensor], batch_chunks: int =
         return time.perf_counter()
 
     t0 = time.perf_counter()
-    for a, b in module_data.balanced_splits(hi - lo, batch_chunks):      # near-equal sub-batches: no short tail
-        rows = module_data.rows_of_range(waves, L, lo + a, lo + b, out=stage[: b - a])   # only this rank's chunks are padded / copied
-        t0 = tick("chunk_host_ms", t0)
-        out_local[a:b] = model.infer(rows.to(device, non_blocking=True), seed=seed, row0=lo + a)
-        torch.cuda.current_stream().synchronize()                       # the pinned staging buffer is reused by the next sub-batch
-        t0 = tick("h2d_enhance_ms", t0)
-    full = gather_rows(out_local, n) if world > 1 else out_local
+    # dataset edge on the device: one upload of the samples this rank owns, rows built / regrouped by sddm_chunk_rows / sddm_regroup_rows
+    batch = module_data.DeviceBatch(waves, L, device, lo, hi)
+    t0 = tick("upload_ms", t0)
+    if world == 1:
+        flat_out = torch.zeros_like(batch.flat)
+        for a, b in module_data.balanced_splits(hi - lo, batch_chunks):      # near-equal sub-batches: no short tail
+            out = model.infer(batch.rows(lo + a, lo + b), seed=seed, row0=lo + a)
+            batch.regroup(out, lo + a, lo + b, flat_out)
+        t0 = tick("chunk_enhance_regroup_ms", t0)
+        return batch.split(flat_out)
+    out_local = torch.empty((hi - lo, 1, L), device=device)
+    for a, b in module_data.balanced_splits(hi - lo, batch_chunks):
+        out_local[a:b] = model.infer(batch.rows(lo + a, lo + b), seed=seed, row0=lo + a)
+    t0 = tick("chunk_enhance_ms", t0)
+    full = gather_rows(out_local, n)                                         # every rank gets every enhanced row (reference: one process sees all)
     t0 = tick("gather_ms", t0)
-    res = module_data.regroup(full, index, lengths)
+    whole = module_data.DeviceBatch.__new__(module_data.DeviceBatch)         # index tables of the WHOLE set (no samples uploaded)
+    whole.T, whole.device, whole.lengths = L, device, lengths
+    counts = module_data.chunk_counts(lengths, L)
+    whole.row_off = torch.zeros(len(waves) + 1, dtype=torch.int64)
+    whole.row_off[1:] = torch.cumsum(torch.tensor(counts), 0)
+    whole.sample_off = torch.zeros(len(waves) + 1, dtype=torch.int64)
+    whole.sample_off[1:] = torch.cumsum(torch.tensor(lengths), 0)
+    whole.owns = [True] * len(waves)
+    whole.sample_off_d, whole.row_off_d = whole.sample_off.to(device), whole.row_off.to(device)
+    flat_out = torch.zeros(int(whole.sample_off[-1]), device=device)
+    whole._call(_lib_mod().sddm_regroup_rows, full, flat_out, 0, n)
+    res = whole.split(flat_out)
     tick("regroup_ms", t0)
     return res
+
+
+def _lib_mod():
+    from . import _lib
+    return _lib.lib()
 
 
 @torch.no_grad()

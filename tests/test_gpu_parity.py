@@ -313,3 +313,35 @@ def test_full_size_cfg2(dev, golden):
         per_row = torch.stack([O.sisnr(outs[prec][i:i + 1].cpu(), outs["fp32"][i:i + 1].cpu()) for i in range(64)])
         report(f"cfg2: {prec} vs fp32 SI-SNR per row: min {float(per_row.min()):.1f} dB, mean {float(per_row.mean()):.1f} dB")
         assert float(per_row.min()) >= SNR_BAR
+
+
+def test_device_dataset_edge_vs_reference_golden(dev):
+    """sddm_chunk_rows / sddm_regroup_rows (the dataset edge on the device) against outputs of the reference's own InferDataset +
+    infer_data_collate and the regroup loop of infer.py:81-120 (tests/golden/make_golden_dataset.py): bit-exact, for the whole batch
+    and for row ranges (what a rank of a sharded run converts)."""
+    import numpy as np
+    from conftest import GOLDEN
+    from sddm_b200.data_loader import data_loaders as D
+    g = np.load(os.path.join(GOLDEN, "dataset.npz"))
+    T = int(g["T"])
+    order = [str(n).split(".")[0] for n in g["inventory"]]
+    waves = [torch.from_numpy(g["wave." + n]).reshape(-1) for n in order]
+    noisy = torch.from_numpy(g["noisy"])
+    n = noisy.shape[0]
+    batch = D.DeviceBatch(waves, T, dev)
+    assert batch.n_rows == n
+    assert torch.equal(batch.rows(0, n).cpu(), noisy)
+    for lo, hi in ((1, 5), (4, 5), (6, n), (0, 1)):
+        part = D.DeviceBatch(waves, T, dev, lo, hi)
+        assert torch.equal(part.rows(lo, hi).cpu(), noisy[lo:hi]), (lo, hi)
+    # regroup: every file, trimmed to its length, equals its input (the reference's reshape(1, -1) of its rows, minus the padding)
+    flat = batch.regroup(batch.rows(0, n), 0, n)
+    for k, (f, w) in enumerate(zip(batch.split(flat), waves)):
+        assert torch.equal(f.cpu().reshape(-1), w)
+        ref = torch.from_numpy(g["file%d.signal" % k]).reshape(-1)
+        assert torch.equal(f.cpu().reshape(-1), ref[: w.numel()])
+    # piecewise regroup (sub-batches) gives the same flat buffer
+    flat2 = torch.zeros_like(flat)
+    for lo, hi in ((0, 3), (3, 4), (4, n)):
+        batch.regroup(batch.rows(lo, hi), lo, hi, flat2)
+    assert torch.equal(flat, flat2)

@@ -40,3 +40,39 @@ def test_two_rank_shard_and_gather():
             ret = mgr.dict()
             mp.spawn(_worker, args=(2, port, n_rows, ret), nprocs=2, join=True)
             assert dict(ret) == {0: True, 1: True}
+
+
+def _worker_utterances(rank, world, port, ret):
+    """The N>1 host path of infer.enhance_utterances on CPU: each rank builds ONLY the rows it owns from the utterance list
+    (rows_of_range), processes them in balanced sub-batches, all-gathers, and regroups per utterance."""
+    import sys
+    sys.path.insert(0, ROOT)
+    from sddm_b200.data_loader import data_loaders as D
+    from sddm_b200.sharding import gather_rows, shard_bounds
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    T = 16
+    g = torch.Generator().manual_seed(3)
+    waves = [torch.randn(n, generator=g) for n in (40, 16, 3, 70, 17, 1)]
+    lengths = [int(w.numel()) for w in waves]
+    counts = D.chunk_counts(lengths, T)
+    n = sum(counts)
+    index = torch.repeat_interleave(torch.arange(len(waves)), torch.tensor(counts))
+    lo, hi = shard_bounds(n, world, rank)
+    local = torch.empty(hi - lo, 1, T)
+    for a, b in D.balanced_splits(hi - lo, 3):
+        local[a:b] = D.rows_of_range(waves, T, lo + a, lo + b) * 2 + 1            # stand-in for the per-row enhancement
+    full = gather_rows(local, n)
+    outs = D.regroup(full, index, lengths)
+    ok = all(torch.equal(o.reshape(-1), w * 2 + 1) for o, w in zip(outs, waves)) and len(outs) == len(waves)
+    ret[rank] = bool(ok)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_utterance_path():
+    port = _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_worker_utterances, args=(2, port, ret), nprocs=2, join=True)
+        assert dict(ret) == {0: True, 1: True}
