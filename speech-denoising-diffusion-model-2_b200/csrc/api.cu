@@ -118,6 +118,9 @@ struct sddm_plan {
     float* d_out = nullptr;
     void* d_ws = nullptr;
     int arena_rows = 0;
+    unsigned long long* d_seed = nullptr;                 // {seed, row0} read by the graph-captured sampler
+    std::map<std::pair<int, int>, cudaGraphExec_t> graphs;   // (rows, variant) -> captured sddm_sample on the arena buffers
+    std::map<std::pair<int, int>, int> graph_calls;
     Prof prof;
 };
 
@@ -849,6 +852,8 @@ void sddm_plan_destroy(sddm_plan* p) {
     cudaFree(p->d_cond);
     cudaFree(p->d_out);
     cudaFree(p->d_ws);
+    cudaFree(p->d_seed);
+    for (auto& kv : p->graphs) cudaGraphExecDestroy(kv.second);
     if (p->own_stream) cudaStreamDestroy(p->own_stream);
     for (cudaEvent_t e : p->prof.ev) cudaEventDestroy(e);
     delete p;
@@ -983,8 +988,16 @@ int sddm_eps(sddm_plan* p, const float* cond, const float* x_t, const float* noi
     return launch_post_coef(pp, k8, st);
 }
 
+static int x_T_impl(sddm_plan* p, int variant, const float* cond, const float* z, uint64_t seed, int64_t row0, float* x_out, int B,
+                    void* stream, const unsigned long long* seed_dev);
+
 int sddm_x_T(sddm_plan* p, int variant, const float* cond, const float* z, uint64_t seed, int64_t row0, float* x_out, int B,
              void* stream) {
+    return x_T_impl(p, variant, cond, z, seed, row0, x_out, B, stream, nullptr);
+}
+
+static int x_T_impl(sddm_plan* p, int variant, const float* cond, const float* z, uint64_t seed, int64_t row0, float* x_out, int B,
+                    void* stream, const unsigned long long* seed_dev) {
     int rc = check_ready(p);
     if (rc) return rc;
     if ((rc = check_variant(variant))) return rc;
@@ -995,7 +1008,7 @@ int sddm_x_T(sddm_plan* p, int variant, const float* cond, const float* z, uint6
     volatile float om = 1.0f - sq;
     float b = sqrtf(om);                              // diffusion.py:297
     if (variant == SDDM_VAR_CONDITIONAL) b = p->sch[7][T];   // sqrt_delta[T], diffusion.py:317
-    return launch_x_T_coef(variant, a, b, cond, z, seed, row0, x_out, B, p->cfg.num_samples, (cudaStream_t)stream);
+    return launch_x_T_coef(variant, a, b, cond, z, seed, row0, x_out, B, p->cfg.num_samples, (cudaStream_t)stream, seed_dev);
 }
 
 int sddm_p_step(sddm_plan* p, int variant, float* x_t, const float* eps, const float* cond, const float* z, uint64_t seed,
@@ -1050,8 +1063,16 @@ int sddm_q_sample_raw(int mode, const float* coef, const float* x0, const float*
     return launch_q_sample(mode, coef, x0, y, noise, seed, row0, x_t, combined_noise, noise_out, B, L, (cudaStream_t)stream);
 }
 
+static int sample_impl(sddm_plan* p, int variant, const float* cond, const float* noises, uint64_t seed, int64_t row0, float* out,
+                       float* eps_trace, float* x_trace, int B, void* ws, size_t ws_bytes, void* stream, const unsigned long long* seed_dev);
+
 int sddm_sample(sddm_plan* p, int variant, const float* cond, const float* noises, uint64_t seed, int64_t row0, float* out,
                 float* eps_trace, float* x_trace, int B, void* ws, size_t ws_bytes, void* stream) {
+    return sample_impl(p, variant, cond, noises, seed, row0, out, eps_trace, x_trace, B, ws, ws_bytes, stream, nullptr);
+}
+
+static int sample_impl(sddm_plan* p, int variant, const float* cond, const float* noises, uint64_t seed, int64_t row0, float* out,
+                       float* eps_trace, float* x_trace, int B, void* ws, size_t ws_bytes, void* stream, const unsigned long long* seed_dev) {
     int rc = check_ready(p);
     if (rc) return rc;
     if ((rc = check_variant(variant))) return rc;
@@ -1061,7 +1082,7 @@ int sddm_sample(sddm_plan* p, int variant, const float* cond, const float* noise
     const int T = p->cfg.n_timestep, L = p->cfg.num_samples;
     const size_t BL = (size_t)B * L;
     float* x = sect(p, ws, p->off_x, B);
-    if ((rc = sddm_x_T(p, variant, cond, noises, seed, row0, x, B, stream))) return rc;
+    if ((rc = x_T_impl(p, variant, cond, noises, seed, row0, x, B, stream, seed_dev))) return rc;
     for (int t = T; t >= 1; --t) {
         PostP pp{};
         pp.frames = sect(p, ws, p->off_frames, B);
@@ -1071,7 +1092,7 @@ int sddm_sample(sddm_plan* p, int variant, const float* cond, const float* noise
         pp.x_trace = x_trace ? x_trace + (size_t)(T - t) * BL : nullptr;
         pp.cond = cond;
         pp.z = (noises && t > 1) ? noises + (size_t)(T + 1 - t) * BL : nullptr;
-        pp.seed = seed; pp.row0 = row0;
+        pp.seed = seed; pp.row0 = row0; pp.seed_dev = seed_dev;
         pp.variant = variant; pp.t = t; pp.T = T; pp.do_update = 1;
         pp.B = B; pp.L = L; pp.F = p->cfg.segment_len; pp.hop = p->cfg.segment_stride; pp.n_frames = p->H;
         float k8[8];
@@ -1098,17 +1119,53 @@ int sddm_enhance_host(sddm_plan* p, int variant, const float* cond_host, float* 
     if (p->arena_rows < R) {
         cudaFree(p->d_cond); cudaFree(p->d_out); cudaFree(p->d_ws);
         p->d_cond = p->d_out = nullptr; p->d_ws = nullptr; p->arena_rows = 0;
+        for (auto& kv : p->graphs) cudaGraphExecDestroy(kv.second);   // captured on the old buffers
+        p->graphs.clear();
+        p->graph_calls.clear();
         SDDM_CUDA_TRY(cudaMalloc(&p->d_cond, R * L * sizeof(float)));
         SDDM_CUDA_TRY(cudaMalloc(&p->d_out, R * L * sizeof(float)));
         SDDM_CUDA_TRY(cudaMalloc(&p->d_ws, sddm_workspace_bytes(p, R)));
         p->arena_rows = R;
     }
+    if (!p->d_seed) SDDM_CUDA_TRY(cudaMalloc(&p->d_seed, 2 * sizeof(unsigned long long)));
+    static int no_graph = -1;   // SDDM_NO_GRAPH=1: always enqueue the ~4400 launches of a sampling run one by one
+    if (no_graph < 0) { const char* ev = getenv("SDDM_NO_GRAPH"); no_graph = (ev && ev[0] == '1') ? 1 : 0; }
     for (int r0 = 0; r0 < B; r0 += R) {
         const int nb = (B - r0) < R ? (B - r0) : R;
         SDDM_CUDA_TRY(cudaMemcpyAsync(p->d_cond, cond_host + (size_t)r0 * L, nb * L * sizeof(float), cudaMemcpyHostToDevice, p->own_stream));
-        rc = sddm_sample(p, variant, p->d_cond, nullptr, seed, row0 + r0, p->d_out, nullptr, nullptr, nb, p->d_ws,
-                         sddm_workspace_bytes(p, p->arena_rows), p->own_stream);
-        if (rc) return rc;
+        // The whole sampling run of a sub-batch (x_T + T x 44 launches) on the plan's own buffers is captured ONCE per (rows, variant)
+        // into a CUDA graph and replayed afterwards: one launch instead of thousands (what a single-utterance caller is bound by);
+        // the Philox seed / first global row are read from device memory so that the same graph serves every call.
+        const std::pair<int, int> key(nb, variant);
+        // Small sub-batches only: measured on B200, replay beats stream launches at 2 rows (54.4 vs 57.2 ms per 2 s clip) but loses at 64
+        // rows (200.6 vs 184.7 ms), where the stream path's programmatic dependent launches overlap each kernel's prologue with its
+        // predecessor's tail and the graph's kernel-to-kernel edges do not.
+        const bool use_graph = !no_graph && nb <= 8 && !p->prof.on && p->graph_calls[key]++ >= 1;   // the first call of a shape runs eagerly (warm-up)
+        if (use_graph) {
+            const unsigned long long sr[2] = {(unsigned long long)seed, (unsigned long long)(row0 + r0)};
+            SDDM_CUDA_TRY(cudaMemcpyAsync(p->d_seed, sr, sizeof(sr), cudaMemcpyHostToDevice, p->own_stream));
+            auto it = p->graphs.find(key);
+            if (it == p->graphs.end()) {
+                cudaGraph_t g = nullptr;
+                SDDM_CUDA_TRY(cudaStreamBeginCapture(p->own_stream, cudaStreamCaptureModeThreadLocal));
+                rc = sample_impl(p, variant, p->d_cond, nullptr, 0, 0, p->d_out, nullptr, nullptr, nb, p->d_ws,
+                                 sddm_workspace_bytes(p, p->arena_rows), p->own_stream, p->d_seed);
+                const cudaError_t ce = cudaStreamEndCapture(p->own_stream, &g);
+                if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+                if (ce != cudaSuccess) { set_error("graph capture failed: %s", cudaGetErrorString(ce)); cudaGetLastError(); return SDDM_E_CUDA; }
+                cudaGraphExec_t ge = nullptr;
+                const cudaError_t ie = cudaGraphInstantiate(&ge, g, 0);
+                cudaGraphDestroy(g);
+                if (ie != cudaSuccess) { set_error("graph instantiation failed: %s", cudaGetErrorString(ie)); cudaGetLastError(); return SDDM_E_CUDA; }
+                it = p->graphs.emplace(key, ge).first;
+            }
+            SDDM_CUDA_TRY(cudaGraphLaunch(it->second, p->own_stream));
+            count_launch(1 + p->cfg.n_timestep * p->launches_per_eps);   // kernels inside the replayed graph
+        } else {
+            rc = sample_impl(p, variant, p->d_cond, nullptr, seed, row0 + r0, p->d_out, nullptr, nullptr, nb, p->d_ws,
+                             sddm_workspace_bytes(p, p->arena_rows), p->own_stream, nullptr);
+            if (rc) return rc;
+        }
         SDDM_CUDA_TRY(cudaMemcpyAsync(out_host + (size_t)r0 * L, p->d_out, nb * L * sizeof(float), cudaMemcpyDeviceToHost, p->own_stream));
     }
     SDDM_CUDA_TRY(cudaStreamSynchronize(p->own_stream));

@@ -283,7 +283,11 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const RowArgs 
                         const bool add_noise = q.t > 1;
                         float zv = p_z;
                         if (add_noise && !q.z)
-                            zv = philox_normal1(q.seed, (uint32_t)(p_sidx >> 2), (uint64_t)(q.row0 + s.n), (uint32_t)(q.T + 1 - q.t), p_sidx & 3);
+                        {
+                            const uint64_t sd = q.seed_dev ? q.seed_dev[0] : q.seed;
+                            const int64_t r0 = q.seed_dev ? (int64_t)q.seed_dev[1] : q.row0;
+                            zv = philox_normal1(sd, (uint32_t)(p_sidx >> 2), (uint64_t)(r0 + s.n), (uint32_t)(q.T + 1 - q.t), p_sidx & 3);
+                        }
                         const float o = post_one(q.variant, a.pk, p_x, ev, p_c, zv, add_noise);
                         q.x_out[gi] = o;
                         if (q.x_trace) q.x_trace[gi] = o;

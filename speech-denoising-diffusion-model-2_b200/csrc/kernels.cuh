@@ -6,8 +6,9 @@
 namespace sddm {
 
 // x_T = a * cond + b * z                       (diffusion.py:281-320); a, b are the step-T scalars
+// seed_dev (nullable): device {seed, row0} that overrides the by-value pair - a captured CUDA graph is replayed with new seeds
 int launch_x_T_coef(int variant, float a, float b, const float* cond, const float* z, uint64_t seed, int64_t row0,
-                    float* x_out, int B, int L, cudaStream_t st);
+                    float* x_out, int B, int L, cudaStream_t st, const unsigned long long* seed_dev = nullptr);
 
 // posterior update incl. clamp, optionally fused with the overlap-add of the final conv frames.
 //   frames != nullptr : eps[s] = frames[a][j] + frames[a-1][j+hop]   (UNetModified2.py:30-41)
@@ -24,6 +25,7 @@ struct PostP {
     const float* z;        // [B][L] injected noise or nullptr (Philox)
     uint64_t seed;
     int64_t row0;
+    const unsigned long long* seed_dev;   // nullable: device {seed, row0} overriding the two fields above (CUDA-graph replay)
     int variant, t, T, do_update;
     int B, L, F, hop, n_frames;
 };

@@ -12,7 +12,8 @@ namespace sddm {
 // ===================================================================================================
 __global__ void __launch_bounds__(256) x_T_kernel(int variant, float a, float b, const float4* __restrict__ cond,
                                                   const float4* __restrict__ z, uint64_t seed, int64_t row0,
-                                                  float4* __restrict__ out, int B, int L4) {
+                                                  float4* __restrict__ out, int B, int L4, const unsigned long long* __restrict__ seed_dev) {
+    if (seed_dev) { seed = seed_dev[0]; row0 = (int64_t)seed_dev[1]; }
     const int64_t total = (int64_t)B * L4;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int row = (int)(i / L4), e4 = (int)(i - (int64_t)row * L4);
@@ -43,10 +44,10 @@ static int grid_for(int64_t n_items, int block, int max_blocks = 148 * 16) {
 }
 
 int launch_x_T_coef(int variant, float a, float b, const float* cond, const float* z, uint64_t seed, int64_t row0,
-                    float* x_out, int B, int L, cudaStream_t st) {
+                    float* x_out, int B, int L, cudaStream_t st, const unsigned long long* seed_dev) {
     const int L4 = L / 4;
     x_T_kernel<<<grid_for((int64_t)B * L4, 256), 256, 0, st>>>(variant, a, b, (const float4*)cond, (const float4*)z,
-                                                              seed, row0, (float4*)x_out, B, L4);
+                                                              seed, row0, (float4*)x_out, B, L4, seed_dev);
     SDDM_LAUNCH_CHECK();
     return SDDM_OK;
 }
@@ -56,6 +57,7 @@ int launch_x_T_coef(int variant, float a, float b, const float* cond, const floa
 //                                                                  model/UNetModified2.py:30-41
 // ===================================================================================================
 __global__ void __launch_bounds__(256) post_kernel(PostP p, PostCoef k) {
+    if (p.seed_dev) { p.seed = p.seed_dev[0]; p.row0 = (int64_t)p.seed_dev[1]; }
     const int L4 = p.L / 4;
     const int64_t total = (int64_t)p.B * L4;
     const int K = (p.F + p.hop - 1) / p.hop;   // frames covering one sample
