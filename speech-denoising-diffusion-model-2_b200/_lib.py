@@ -13,6 +13,8 @@ VARIANTS = {"original": 0, "condition_in": 1, "sr3": 2, "supportive": 3, "condit
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "csrc", "libsddm_b200.so")
+if os.environ.get("SDDM_B200_LIB"):   # A/B runs: load another build of the same ABI (e.g. csrc/libsddm_b200_prev.so)
+    _LIB_PATH = os.path.abspath(os.environ["SDDM_B200_LIB"])
 _lib: Optional[C.CDLL] = None
 
 

@@ -337,21 +337,26 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const RowArgs 
                         }
                     }
                     float v[16];
+                    {   // tap sum + additive term on fp32 pairs (FADD2): same per-element order B + A + C + addv as scalar code
+                        float2 p[8];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rb[i]);
-                    if (vA) {
+                        for (int i = 0; i < 8; ++i) p[i] = make_float2(__uint_as_float(rb[2 * i]), __uint_as_float(rb[2 * i + 1]));
+                        if (vA) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] += __uint_as_float(ra[i]);
-                    }
-                    if (vC) {
+                            for (int i = 0; i < 8; ++i) p[i] = fadd2(p[i], make_float2(__uint_as_float(ra[2 * i]), __uint_as_float(ra[2 * i + 1])));
+                        }
+                        if (vC) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] += __uint_as_float(rc[i]);
-                    }
+                            for (int i = 0; i < 8; ++i) p[i] = fadd2(p[i], make_float2(__uint_as_float(rc[2 * i]), __uint_as_float(rc[2 * i + 1])));
+                        }
 #pragma unroll
-                    for (int qd = 0; qd < 4; ++qd) {
-                        const uint4 u = lds128(addv_u32 + (uint32_t)(half * 4 + qd) * 16u);
-                        v[4 * qd + 0] += __uint_as_float(u.x); v[4 * qd + 1] += __uint_as_float(u.y);
-                        v[4 * qd + 2] += __uint_as_float(u.z); v[4 * qd + 3] += __uint_as_float(u.w);
+                        for (int qd = 0; qd < 4; ++qd) {
+                            const uint4 u = lds128(addv_u32 + (uint32_t)(half * 4 + qd) * 16u);
+                            p[2 * qd] = fadd2(p[2 * qd], make_float2(__uint_as_float(u.x), __uint_as_float(u.y)));
+                            p[2 * qd + 1] = fadd2(p[2 * qd + 1], make_float2(__uint_as_float(u.z), __uint_as_float(u.w)));
+                        }
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) { v[2 * i] = p[i].x; v[2 * i + 1] = p[i].y; }
                     }
                     if (RESID) {
 #pragma unroll
@@ -542,14 +547,14 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const RowArgs 
             } else {
                 const bool is_main = sl < NMAIN;
                 const bool aff = AFF && is_main, up = UP && is_main;
-                float sch[8], shh[8];
-                if (aff) {   // halved: swish(y) = h + h tanh(h), h = y / 2
+                float2 sc2[4], sh2[4];   // (scale, shift) / 2 of this thread's 8 channels as fp32 pairs: swish(y) = h + h tanh(h), h = y / 2
+                if (aff) {
                     const uint32_t ss = raw + 8192u + (uint32_t)j * 32u;
                     const uint4 s0 = lds128(ss), s1 = lds128(ss + 16u), h0 = lds128(ss + 128u), h1 = lds128(ss + 144u);
-                    sch[0] = 0.5f * __uint_as_float(s0.x); sch[1] = 0.5f * __uint_as_float(s0.y); sch[2] = 0.5f * __uint_as_float(s0.z); sch[3] = 0.5f * __uint_as_float(s0.w);
-                    sch[4] = 0.5f * __uint_as_float(s1.x); sch[5] = 0.5f * __uint_as_float(s1.y); sch[6] = 0.5f * __uint_as_float(s1.z); sch[7] = 0.5f * __uint_as_float(s1.w);
-                    shh[0] = 0.5f * __uint_as_float(h0.x); shh[1] = 0.5f * __uint_as_float(h0.y); shh[2] = 0.5f * __uint_as_float(h0.z); shh[3] = 0.5f * __uint_as_float(h0.w);
-                    shh[4] = 0.5f * __uint_as_float(h1.x); shh[5] = 0.5f * __uint_as_float(h1.y); shh[6] = 0.5f * __uint_as_float(h1.z); shh[7] = 0.5f * __uint_as_float(h1.w);
+                    sc2[0] = make_float2(0.5f * __uint_as_float(s0.x), 0.5f * __uint_as_float(s0.y)); sc2[1] = make_float2(0.5f * __uint_as_float(s0.z), 0.5f * __uint_as_float(s0.w));
+                    sc2[2] = make_float2(0.5f * __uint_as_float(s1.x), 0.5f * __uint_as_float(s1.y)); sc2[3] = make_float2(0.5f * __uint_as_float(s1.z), 0.5f * __uint_as_float(s1.w));
+                    sh2[0] = make_float2(0.5f * __uint_as_float(h0.x), 0.5f * __uint_as_float(h0.y)); sh2[1] = make_float2(0.5f * __uint_as_float(h0.z), 0.5f * __uint_as_float(h0.w));
+                    sh2[2] = make_float2(0.5f * __uint_as_float(h1.x), 0.5f * __uint_as_float(h1.y)); sh2[3] = make_float2(0.5f * __uint_as_float(h1.z), 0.5f * __uint_as_float(h1.w));
                 }
                 const uint32_t dstp = opd + (uint32_t)j * (uint32_t)PLANE * 16u;
                 uint4 rv[4];
@@ -565,9 +570,9 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const RowArgs 
                         uint32_t ow[4];
 #pragma unroll
                         for (int kk = 0; kk < 4; ++kk) {
-                            const float h0 = fmaf(bf16_lo(w[kk]), sch[2 * kk], shh[2 * kk]);
-                            const float h1 = fmaf(bf16_hi(w[kk]), sch[2 * kk + 1], shh[2 * kk + 1]);
-                            ow[kk] = pack_bf16(fmaf(h0, tanh_approx(h0), h0), fmaf(h1, tanh_approx(h1), h1));
+                            const float2 h = ffma2(bf16x2_to_f32x2(w[kk]), sc2[kk], sh2[kk]);
+                            const float2 sw = ffma2(h, make_float2(tanh_approx(h.x), tanh_approx(h.y)), h);
+                            ow[kk] = pack_bf16(sw.x, sw.y);
                         }
                         o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
                     }

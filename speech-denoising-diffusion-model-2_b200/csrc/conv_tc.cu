@@ -236,6 +236,13 @@ __device__ __forceinline__ float lds32(uint32_t addr) {
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
     return v;
 }
+// packed fp32 pair fma (sm_100 FFMA2: one issue slot for two ordinary IEEE fmas)
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b),
+                       rc = *reinterpret_cast<unsigned long long*>(&c), rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2*>(&rd);
+}
 __device__ __forceinline__ float tanh_approx(float x) {
     float y;
     asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -737,9 +744,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
                     }
                 } else {
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const float h = fmaf(f[k], sch[k], shh[k]);
-                        f[k] = fmaf(h, tanh_approx(h), h);
+                    for (int k = 0; k < 4; ++k) {
+                        const float2 h = ffma2(make_float2(f[2 * k], f[2 * k + 1]), make_float2(sch[2 * k], sch[2 * k + 1]), make_float2(shh[2 * k], shh[2 * k + 1]));
+                        const float2 sw = ffma2(h, make_float2(tanh_approx(h.x), tanh_approx(h.y)), h);
+                        f[2 * k] = sw.x; f[2 * k + 1] = sw.y;
                     }
                 }
             }
