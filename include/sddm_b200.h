@@ -191,6 +191,14 @@ SDDM_API int sddm_stft_features(const float* wav, int B, int L, int n_fft, int h
                                 const float* mel_fb, const int32_t* mel_lo, const int32_t* mel_hi, int n_mels, int log_clamp,
                                 float* out, void* stream);
 
+/* overlap-add inverse STFT = torch.istft(spec, n_fft = 1024, hop, window = window, center = True, normalized = False, onesided = True,
+ * length = L): the inverse of the torch.stft inside the front-end above (north_star names it; the reference never inverts a spectrogram).
+ * spec_ri: device [B, 513, frames, 2] fp32 (torch.view_as_real of the complex spectrogram); window: device [1024]; wav_out: device [B, L];
+ * ws: device workspace of sddm_istft_workspace_bytes(B, frames) bytes (the windowed frames). */
+SDDM_API size_t sddm_istft_workspace_bytes(int B, int frames);
+SDDM_API int sddm_istft(const float* spec_ri, int B, int frames, int n_fft, int hop, const float* window, int L, float* wav_out,
+               void* ws, size_t ws_bytes, void* stream);
+
 /* ---- cfg 5: DiffWave denoiser + spectrogram-conditioned sampling loop --------------------------------- */
 /* replaces: DiffWave (model/diffwave.py:111-155) under SDDM_spectrogram.infer (model/model.py:206-257).
  * Device layout is time-major ([B][T][64] residual stream); the conditioner path (SpectrogramUpsampler + the 30

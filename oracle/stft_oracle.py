@@ -60,3 +60,19 @@ def mel_spectrogram(wav, n_fft, hop, n_mels, sample_rate, f_min=20.0, f_max=None
 
 def log_clamp(x: torch.Tensor) -> torch.Tensor:                   # prepare_spectrogram.py:41-44,50-53
     return torch.clamp((torch.log10(x) - 1 + 5) / 5, 0.0, 1.0)
+
+
+def istft(spec: torch.Tensor, n_fft: int, hop: int, win: torch.Tensor, length: int) -> torch.Tensor:
+    """Restatement of torch.istft(spec, n_fft, hop, window=win, center=True, normalized=False, onesided=True, length=length) for a complex
+    [B, n_fft/2+1, frames] spectrogram: irfft per frame, window, overlap-add in ascending frame order, division by the window
+    envelope, centre trim.  (torch's arithmetic: aten/src/ATen/native/SpectralOps.cpp istft; pinned by tests/golden/stft.npz 'istft.*')"""
+    B, _, frames = spec.shape
+    fr = torch.fft.irfft(spec, n=n_fft, dim=1) * win.reshape(1, -1, 1)                  # [B, n_fft, frames]
+    total = n_fft + hop * (frames - 1)
+    y = torch.zeros(B, total, dtype=fr.dtype)
+    env = torch.zeros(total, dtype=fr.dtype)
+    for m in range(frames):
+        y[:, m * hop:m * hop + n_fft] += fr[:, :, m]
+        env[m * hop:m * hop + n_fft] += win * win
+    out = y[:, n_fft // 2:] / env[n_fft // 2:].clamp_min(1e-11)
+    return out[:, :length]

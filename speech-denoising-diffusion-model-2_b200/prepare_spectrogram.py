@@ -107,6 +107,32 @@ class MelSpectrogram(Spectrogram):
         return self._run(waveform, self.fb, self.n_mels)
 
 
+def istft(spec: torch.Tensor, n_fft: int = 1024, hop_length: int = 256, window: Optional[torch.Tensor] = None,
+          length: Optional[int] = None) -> torch.Tensor:
+    """Overlap-add inverse STFT on the device = torch.istft(spec, n_fft, hop_length, window=window, center=True, length=length) for a
+    complex one-sided spectrogram [B, n_fft // 2 + 1, frames] (C ABI: sddm_istft).  CUDA tensors only: there is no CPU fallback."""
+    import ctypes as C
+    from . import _lib
+    if not spec.is_cuda:
+        raise RuntimeError("istft (sddm_b200) needs a CUDA tensor: there is no CPU fallback")
+    if not spec.is_complex() or spec.dim() != 3 or spec.shape[1] != n_fft // 2 + 1:
+        raise ValueError("spec must be complex [B, %d, frames], got %s %s" % (n_fft // 2 + 1, spec.dtype, tuple(spec.shape)))
+    dev = spec.device
+    B, _, frames = spec.shape
+    win = (torch.hann_window(n_fft) if window is None else window).to(dev, torch.float32).contiguous()
+    L = hop_length * (frames - 1) if length is None else int(length)
+    ri = torch.view_as_real(spec.to(torch.complex64).contiguous()).contiguous()
+    out = torch.empty((B, L), device=dev, dtype=torch.float32)
+    lib = _lib.lib()
+    nbytes = int(lib.sddm_istft_workspace_bytes(B, frames))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(lib.sddm_istft(C.c_void_p(ri.data_ptr()), B, frames, n_fft, hop_length, C.c_void_p(win.data_ptr()), L,
+                                  C.c_void_p(out.data_ptr()), C.c_void_p(ws.data_ptr()), nbytes, C.c_void_p(st)))
+    return out
+
+
 def features(audio: torch.Tensor, config) -> tuple:
     """Body of the reference's per-file loop (prepare_spectrogram.py:38-55) on a CUDA waveform [1, L] or [B, L]:
     returns (mel, spec) already log-compressed and clamped to [0, 1]."""

@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import ROOT
+from conftest import GOLDEN, ROOT
 
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import stft_oracle as SO  # noqa: E402
@@ -78,3 +78,38 @@ def test_stft_kernel_vs_goldens_and_oracle(golden, built_lib):
     assert int(S(tone.to(dev))[0, :, 30].argmax()) == 64                              # 1000 Hz / (16000 / 1024) = 64
     with pytest.raises(Exception):
         PS.Spectrogram(n_fft=512, hop_length=128)(x.to(dev))
+
+
+# ----------------------------------------------------------------------------------------------------
+# inverse STFT (north_star names it next to the front-end; torch.istft is the definition)
+# ----------------------------------------------------------------------------------------------------
+def _istft_cases():
+    g = np.load(os.path.join(GOLDEN, "istft.npz"))
+    for tag in ("hamming256", "hann128", "hann256"):
+        spec = torch.view_as_complex(torch.from_numpy(g[tag + ".spec"]).contiguous())
+        yield tag, spec, int(g[tag + ".hop"]), torch.from_numpy(g[tag + ".window"]), torch.from_numpy(g[tag + ".istft"]), \
+            torch.from_numpy(g[tag + ".wav"]), torch.view_as_complex(torch.from_numpy(g[tag + ".stft"]).contiguous())
+
+
+def test_istft_oracle_vs_torch_golden():
+    for tag, spec, hop, win, want, _, _ in _istft_cases():
+        got = SO.istft(spec, 1024, hop, win, want.shape[-1])
+        assert float((got - want).abs().max()) < 2e-6 * float(want.abs().max()) + 1e-7, tag
+
+
+@pytest.mark.gpu
+def test_istft_kernel_vs_torch_golden_and_round_trip(built_lib):
+    from sddm_b200 import prepare_spectrogram as PS
+    for tag, spec, hop, win, want, wav, stft in _istft_cases():
+        got = PS.istft(spec.cuda(), 1024, hop, win, want.shape[-1]).cpu()
+        err = float((got - want).abs().max() / want.abs().max())
+        assert err < 5e-6, (tag, err)
+        # perfect reconstruction: the inverse of a true STFT returns the signal (away from the last partial hop)
+        n = hop * (stft.shape[-1] - 1)
+        back = PS.istft(stft.cuda(), 1024, hop, win, n).cpu()
+        assert float((back - wav[:, :n]).abs().max()) < 2e-5, tag
+        # linearity
+        a = PS.istft((2.0 * spec).cuda(), 1024, hop, win, want.shape[-1]).cpu()
+        assert float((a - 2.0 * got).abs().max()) < 1e-5 * float(got.abs().max())
+    with pytest.raises(RuntimeError):
+        PS.istft(spec, 1024, hop, win)          # CPU tensor: no fallback
