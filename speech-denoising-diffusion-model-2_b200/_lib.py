@@ -124,6 +124,7 @@ SIGNATURES = {
     "sddm_debug_umma_probe": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "sddm_debug_tc_trace": (C.c_int, [C.c_int, C.c_void_p]),
     "sddm_debug_row_trace": (C.c_int, [C.c_int, C.c_void_p]),
+    "sddm_debug_hang": (C.c_int, [C.c_int, C.c_void_p]),
     "sddm_debug_umma_rate": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
 }
 

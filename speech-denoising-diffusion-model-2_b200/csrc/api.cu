@@ -335,8 +335,12 @@ static ConvP shape_probe(const sddm_plan* p, const Op& op) {
     for (int i = 0; i < op.nsrc; ++i) { c.src[i].C = p->tensors[op.src[i]].C; c.Cin += c.src[i].C; }
     c.res_identity = op.res_kind == 1;
     c.res_Cin = 0;   // channels of the raw block input read by the 1x1 res_conv
-    if (op.res_kind == 2)
-        for (int i = 0; i < op.gn_nsrc; ++i) c.res_Cin += p->tensors[op.gn_src[i]].C;
+    if (op.res_kind == 2) {
+        c.res_nsrc = op.gn_nsrc;
+        for (int i = 0; i < op.gn_nsrc; ++i) { c.res_src[i].C = p->tensors[op.gn_src[i]].C; c.res_Cin += c.res_src[i].C; }
+    }
+    static const float probe_affine = 0.f;   // shape probes carry no buffers: mark "input goes through GroupNorm + Swish" for conv_row_supported
+    if (op.in_gn) c.src[0].scale = &probe_affine;
     c.act16 = p->cfg.precision == SDDM_PREC_BF16_ACT;
     return c;
 }
@@ -363,7 +367,7 @@ static int build_program(sddm_plan* p, Arena& a) {
         op.use_tc = want_tc && conv_tc_supported(probe);
         op.use_row = want_tc && use_row_kernels && conv_row_supported(probe);
         if (act16 && !op.use_tc) act16_ok = false;
-        p->tensors[op.out].nparts = op.use_row ? conv_row_nparts(probe.Hout)
+        p->tensors[op.out].nparts = op.use_row ? conv_row_nparts(probe.Hout, probe.Wout)
                                                : (op.use_tc ? conv_tc_nparts(probe.Hout, probe.Wout) : conv_fp32_nparts(probe.Hout, probe.Wout));
     };
     // row-kernel weight image of a convolution op: main chunks, then the 1x1 res_conv chunks ([Cin/16][1][2][32][8] = pack_conv_tc with k = 1)
@@ -480,7 +484,7 @@ static int build_program(sddm_plan* p, Arena& a) {
                 Op op;
                 op.kind = Op::STEM;
                 op.use_row = use_row_kernels && W == 128 && H % 16 == 0 && nd.cout == 32;
-                p->tensors[cur].nparts = op.use_row ? conv_row_nparts(H) : stem_nparts(H, W);
+                p->tensors[cur].nparts = op.use_row ? conv_row_nparts(H, W) : stem_nparts(H, W);
                 if (op.use_row) {
                     const std::vector<__nv_bfloat16> img = pack_stem_row(w, nd.cout);
                     op.wrow_off = a.put_h(img);
@@ -574,7 +578,8 @@ static int build_program(sddm_plan* p, Arena& a) {
         const bool producer_ok = prev.kind == Op::STEM ? prev.use_row : (prev.kind == Op::CONV && prev.use_tc);
         bool small = true;   // the last-arriving CTA walks every partial of the sample: keep that walk short
         for (int k = 0; k < g.gn_nsrc; ++k) small = small && p->tensors[g.gn_src[k]].nparts <= 256;
-        if (producer_ok && small && prev.out == g.gn_src[0]) { g.gn_fused = true; ++fused; }
+        static const bool no_fuse = [] { const char* e = getenv("SDDM_NO_GN_FUSE"); return e && e[0] == '1'; }();   // A/B switch: separate GroupNorm finalisation kernels
+        if (producer_ok && small && prev.out == g.gn_src[0] && !no_fuse) { g.gn_fused = true; ++fused; }
     }
     const char* no_pf = getenv("SDDM_NO_POST_FUSE");   // A/B switch: keep the separate overlap-add / posterior kernel
     p->post_fused = p->ops.back().kind == Op::FINAL && p->ops.back().use_row && 2 * c.segment_stride == c.segment_len && !(no_pf && no_pf[0] == '1');
@@ -650,6 +655,7 @@ static void fill_gn_fuse(const sddm_plan* p, const Op& op, int B, void* ws, int 
 static int run_unet(sddm_plan* p, const float* cond, const float* x_t, const float* temb, int temb_stride, int B, void* ws,
                     cudaStream_t st, const PostP* post = nullptr, const float* post_k8 = nullptr, bool keep_frames = true) {
     const sddm_config& c = p->cfg;
+    static const bool sync_each = [] { const char* e = getenv("SDDM_SYNC_EACH_OP"); return e && e[0] == '1'; }();
     for (size_t oi = 0; oi < p->ops.size(); ++oi) {
         const Op& op = p->ops[oi];
         if (op.kind == Op::GN && op.gn_fused) continue;
@@ -765,6 +771,10 @@ static int run_unet(sddm_plan* p, const float* cond, const float* x_t, const flo
         }
         if (rc != SDDM_OK) return rc;
         if ((rc = prof_mark(p, (int)oi, false, st))) return rc;
+        if (sync_each) {   // debug: name the op whose kernel faults
+            const cudaError_t e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) { set_error("op %zu (%s) failed: %s", oi, op.label.c_str(), cudaGetErrorString(e)); return SDDM_E_CUDA; }
+        }
     }
     return SDDM_OK;
 }

@@ -132,7 +132,7 @@ int conv_tc_nparts(int Hout, int Wout);
 int conv_tc_tiles(int Hout, int Wout);
 // row-streaming tcgen05 kernel of the 128-wide level (conv_row.cu): bf16 activations, Cout = 32 (or 1: the final Block -> frames)
 bool conv_row_supported(const ConvP& p);
-int conv_row_nparts(int H);      // partial-statistics slots per sample: (H / 16) blocks x 2 groups x 4 warps
+int conv_row_nparts(int H, int W);   // partial-statistics slots per sample: (H / 16) blocks x 2 groups x 4 warps (64-wide level: (H / 4) x 2 x 2)
 int conv_row_arrivals(int H);    // arrivals per sample of the fused GroupNorm finalisation
 struct PostP;
 // post != nullptr (final Block only): fuse the overlap-add of the frames + the posterior update described by (post, k8) into the epilogue

@@ -34,6 +34,21 @@
 
 #include "gn_fuse.cuh"
 #include "kernels.cuh"
+
+// debug (sddm_debug_hang): a wait that times out notes (CTA, thread, barrier address, parity) in mapped host memory before it traps
+namespace sddm {
+__device__ unsigned* g_hang = nullptr;
+__device__ __noinline__ void hang_note(uint32_t bar, uint32_t parity) {
+    unsigned* g = g_hang;
+    if (!g) return;
+    // one slot per (CTA, warp), plain stores (no atomics towards host memory); [0] = 1 marks "some wait timed out"
+    const unsigned s = blockIdx.x * 20u + (threadIdx.x >> 5);
+    if (s < 4000u) { g[4 + 4 * s] = blockIdx.x + 1u; g[5 + 4 * s] = threadIdx.x; g[6 + 4 * s] = bar; g[7 + 4 * s] = parity; }
+    g[0] = 1u;
+    __threadfence_system();
+}
+}  // namespace sddm
+#define SDDM_MBAR_TIMEOUT_HOOK(bar, parity) ::sddm::hang_note(bar, parity)
 #include "tc_ptx.cuh"
 
 namespace sddm {
@@ -52,6 +67,11 @@ constexpr uint32_t kAStage = 4u * PLANE * 16u;            // 8576 B: one 32-chan
 constexpr uint32_t kRawStage = 8192u + 256u;              // bf16 row slab + scale / shift tail
 constexpr uint32_t kOutTile = 8192u;                      // 128 px x 32 ch bf16 staging row (64B swizzle)
 constexpr int kNR = 6, kNA = 6, kNS = 5;                  // ring depths: raw slabs, operand slabs, accumulator slots (compile time: cheap % and /)
+// PAIR variant (64-wide level): the M tile is one image row of TWO samples (64 + 64 pixels).  A shifted start address would pull the
+// neighbour sample's edge pixel across the seam, so the transform writes three operand copies per slab instead (kx = 0, 1, 2: shifted
+// by +1 / 0 / -1 slots, the seam slots stay zero); blocks are 4 rows (H = 128 rows give 148 CTAs ~7 blocks each)
+constexpr uint32_t kPairRawStage = 8192u + 512u;          // two samples' scale / shift behind the slab
+constexpr uint32_t kPairAStage = 3u * kAStage;
 constexpr size_t kSmemCap = 232448 - 1024;
 enum RowKind { ROW_ACT = 0, ROW_STEM = 1, ROW_FINAL = 2 };
 
@@ -62,7 +82,7 @@ struct alignas(64) RowMaps {
 };
 
 struct RowArgs {
-    int B, H, nblocks;          // 16-row blocks in the whole batch
+    int B, H, nblocks;          // 16-row blocks in the whole batch (PAIR: 4-row blocks of sample pairs)
     int C0, rC0;                // channels of source 0 (concat boundary) of the main / res inputs
     int Cin;
     const float* scale; const float* shift;     // [B][Cin] GroupNorm of the input
@@ -86,8 +106,8 @@ struct RowHdr {
     uint64_t res_full[kEpi][2];
     uint64_t w_full;
     uint32_t tmem_base;
-    uint32_t gn_last[kEpi];
-    alignas(16) float addv[kEpi][32];
+    uint32_t gn_last[kEpi][2];
+    alignas(16) float addv[kEpi][2][32];                  // [1] = second sample of a PAIR tile
     // final Block: positions 64..127 of frame row y wait here for the group that owns row y + 1 (overlap-add partner)
     uint64_t f_full[4], f_empty[4];
     alignas(16) float fup[4][64];
@@ -98,15 +118,17 @@ static_assert(sizeof(RowHdr) <= kHdr, "header too large");
 // the k-th sample segment of a CTA that owns the 16-row blocks [b0, b1): output rows [ya, yb) of sample n need input rows [r0, r1]
 // yo = first row whose results this CTA publishes; ext (final Block with the fused overlap-add): the run also recomputes frame row
 // ya - 1, whose upper half the samples of row ya need (it belongs to the CTA above, which publishes it)
+// (LG = log2 of the rows per block; PAIR: n counts sample pairs)
 struct Seg { int n, ya, yb, r0, r1, yo; };
+template <int LG = 4>
 __device__ __forceinline__ bool seg_at(int H, int b0, int b1, int k, Seg& s, bool ext) {
-    const int bps = H >> 4, n0 = b0 / bps;
+    const int bps = H >> LG, n0 = b0 / bps;
     s.n = n0 + k;
     if (s.n * bps >= b1) return false;
-    s.ya = k == 0 ? (b0 - n0 * bps) << 4 : 0;
+    s.ya = k == 0 ? (b0 - n0 * bps) << LG : 0;
     s.yo = s.ya;
     if (ext && s.ya > 0) s.ya -= 1;
-    const int e = (b1 - s.n * bps) << 4;
+    const int e = (b1 - s.n * bps) << LG;
     s.yb = e < H ? e : H;
     s.r0 = s.ya > 0 ? s.ya - 1 : 0;
     s.r1 = s.yb < H ? s.yb : H - 1;
@@ -130,9 +152,28 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[1
 
 // KIND: ROW_ACT (bf16 activation rows in, 32 channels out), ROW_STEM (waveform windows in), ROW_FINAL (1 channel out -> frames)
 // NMAIN / NRES: 32-channel slabs per input row of the 3x3 conv / the 1x1 res_conv; UP: nearest x2 of a [H/2][64] input;
-// AFF: GroupNorm-apply + Swish on the main slabs; RESID: identity residual added in the epilogue
-template <int KIND, int NMAIN, int NRES, bool UP, bool AFF, bool RESID>
+// AFF: GroupNorm-apply + Swish on the main slabs; RESID: identity residual added in the epilogue; PAIR: 64-wide level, two samples per tile
+template <int NMAIN, bool PAIR>
+struct RowRings {
+    // The raw ring depth must be EVEN: the two transform groups take alternate slabs, so a stage of an even ring always belongs to the
+    // same group.  On an odd ring the groups alternate on a stage; a group that runs ahead then polls raw_full[s] for use k + 1 while
+    // the other group's load of use k is still in flight (TMA loads complete out of order), the parity wait passes on the completed
+    // use k - 1, the group transforms the wrong slab and releases the stage early (seen as a Warp Illegal Instruction at the loader's
+    // next arrive.expect_tx on the unfinished phase).  The operand ring may be odd: the MMA warp consumes slabs in order, and a group
+    // reaches use k of a stage only after the MMA consumed the slab before its previous one, which is past use k - 2 of that stage.
+    static constexpr int NR = PAIR ? (NMAIN >= 4 ? 4 : 6) : kNR;
+    static constexpr int NA = PAIR ? (NMAIN >= 4 ? 3 : 4) : kNA;
+    static_assert(NR % 2 == 0, "raw ring depth must be even (two transform groups)");
+    static constexpr uint32_t RAW = PAIR ? kPairRawStage : kRawStage;
+    static constexpr uint32_t AST = PAIR ? kPairAStage : kAStage;
+    static constexpr int LG = PAIR ? 2 : 4;
+};
+template <int KIND, int NMAIN, int NRES, bool UP, bool AFF, bool RESID, bool PAIR = false>
 __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const RowArgs a, const __grid_constant__ RowMaps maps) {
+    static_assert(!PAIR || (KIND == ROW_ACT && !UP && !RESID), "the pair tile serves plain / res_conv ResnetBlock convolutions only");
+    using RR = RowRings<NMAIN, PAIR>;
+    constexpr int NR = RR::NR, NA = RR::NA, LG = RR::LG;
+    constexpr uint32_t RAWST = RR::RAW, AST = RR::AST;
     constexpr int NSLAB = NMAIN + NRES;
     constexpr int KSTEPS = KIND == ROW_STEM ? 1 : 2;                 // K16 steps per main slab
     constexpr int NCOLS = KIND == ROW_FINAL ? 16 : 96;               // N of the main MMAs
@@ -153,12 +194,12 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const RowArgs 
     int nitems = 0;
     {
         Seg s;
-        for (int k = 0; seg_at(a.H, b0, b1, k, s, EXT); ++k) nitems += s.r1 - s.r0 + 1;
+        for (int k = 0; seg_at<LG>(a.H, b0, b1, k, s, EXT); ++k) nitems += s.r1 - s.r0 + 1;
     }
 
     if (tid == 0) {
-        for (int i = 0; i < kNR; ++i) { mbar_init(smem_u32(&hdr->raw_full[i]), 1); mbar_init(smem_u32(&hdr->raw_empty[i]), kGrp / 32); }
-        for (int i = 0; i < kNA; ++i) { mbar_init(smem_u32(&hdr->full_a[i]), kGrp / 32); mbar_init(smem_u32(&hdr->empty_a[i]), 1); }
+        for (int i = 0; i < NR; ++i) { mbar_init(smem_u32(&hdr->raw_full[i]), 1); mbar_init(smem_u32(&hdr->raw_empty[i]), kGrp / 32); }
+        for (int i = 0; i < NA; ++i) { mbar_init(smem_u32(&hdr->full_a[i]), kGrp / 32); mbar_init(smem_u32(&hdr->empty_a[i]), 1); }
         for (int i = 0; i < kNS; ++i) { mbar_init(smem_u32(&hdr->acc_full[i]), 1); mbar_init(smem_u32(&hdr->acc_empty[i]), 12); }
         for (int e = 0; e < kEpi; ++e) for (int k = 0; k < 2; ++k) mbar_init(smem_u32(&hdr->res_full[e][k]), 1);
         mbar_init(smem_u32(&hdr->w_full), 1);
@@ -166,14 +207,16 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const RowArgs 
         fence_barrier_init();
     }
     if (warp == kMma) tmem_alloc(smem_u32(&hdr->tmem_base), TMEM_COLS);
-    // operand ring: zero once - the x halo slots (0 and 129) of every plane are never written again (stem: plane 1 stays zero too)
-    for (uint32_t i = (uint32_t)tid; i < (uint32_t)kNA * kAStage / 16u; i += kRowThreads)
+    // operand ring: zero once - the x halo slots (0 and 129; PAIR: the seam slots of the shifted copies) of every plane are never
+    // written again (stem: plane 1 stays zero too)
+    for (uint32_t i = (uint32_t)tid; i < (uint32_t)NA * AST / 16u; i += kRowThreads)
         sts128(base + a.off_a + i * 16u, make_uint4(0u, 0u, 0u, 0u));
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = hdr->tmem_base;
+    if (g_hang && tid == 0 && blockIdx.x == 0) { g_hang[1] = base; g_hang[2] = (unsigned)nitems; g_hang[3] = (unsigned)(NSLAB * 100 + NA * 10 + NR); }
     const bool tr = SDDM_ROW_TRACE && a.trace != nullptr && blockIdx.x == 0;   // compiled out unless built with -DSDDM_ROW_TRACE=1
     long long tw[6] = {0, 0, 0, 0, 0, 0};
     const long long t_begin = tr ? clock64() : 0;
@@ -189,7 +232,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const RowArgs 
         const bool res_leader = m == 64;   // identity-residual prefetch (mbarrier based: any thread may wait on it)
         const uint32_t obuf0 = base + a.off_out + (uint32_t)(e * 2) * kOutTile;
         const uint32_t rbuf0 = base + a.off_res + (uint32_t)(e * 2) * kOutTile;
-        const uint32_t addv_u32 = smem_u32(hdr->addv[e]);
+        const uint32_t addv_u32 = smem_u32(hdr->addv[e][PAIR ? (m >> 6) : 0]);
         const uint32_t lane_tm = tmem_base + ((uint32_t)(w4 * 32) << 16);
         const uint32_t swz = (uint32_t)((m >> 1) & 3);       // 64B swizzle of this thread's staging / residual row
         const int c2 = lane & 15, hrow = lane >> 4;
@@ -202,7 +245,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const RowArgs 
         auto res_issue = [&]() {
             for (;;) {   // advance (pk, py) to this group's next output row
                 if (py < 0) {
-                    if (!seg_at(a.H, b0, b1, pk, ps, EXT)) return;
+                    if (!seg_at<LG>(a.H, b0, b1, pk, ps, EXT)) return;
                     py = ps.ya + ((ps.ya & 1) == e ? 0 : 1);
                     pend = ps.yb; pn = ps.n;
                 } else {
@@ -219,15 +262,18 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const RowArgs 
         if (RESID && res_leader) { res_issue(); res_issue(); }
         int item_base = 0;
         Seg s;
-        for (int k = 0; seg_at(a.H, b0, b1, k, s, EXT); item_base += s.r1 - s.r0 + 1, ++k) {
+        for (int k = 0; seg_at<LG>(a.H, b0, b1, k, s, EXT); item_base += s.r1 - s.r0 + 1, ++k) {
             if (KIND != ROW_FINAL) {
                 // per-channel additive term of this sample: bias (+ noise-level embedding row) (+ res_conv bias)
                 group_bar(bar_id);
-                if (m < 32) {
-                    float v = __ldg(a.bias + m);
-                    if (a.temb) v += __ldg(a.temb + (int64_t)s.n * a.temb_stride + m);
-                    if (NRES) v += __ldg(a.res_bias + m);
-                    hdr->addv[e][m] = v;
+                if (m < (PAIR ? 64 : 32)) {
+                    const int c = m & 31;
+                    int nn = s.n;
+                    if (PAIR) { nn = 2 * s.n + (m >> 5); if (nn >= a.B) nn = a.B - 1; }
+                    float v = __ldg(a.bias + c);
+                    if (a.temb) v += __ldg(a.temb + (int64_t)nn * a.temb_stride + c);
+                    if (NRES) v += __ldg(a.res_bias + c);
+                    hdr->addv[e][m >> 5][c] = v;
                 }
                 group_bar(bar_id);
             }
@@ -386,7 +432,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const RowArgs 
                 if (tr) { tw[3] += tg0 - tw0; tw[2] += clock64() - tg0; }
                 const long long ts0 = tr ? clock64() : 0;
                 if (leader) {
-                    tma_store_4d(&maps.out, obuf, 0, 0, y, s.n);
+                    tma_store_4d(&maps.out, obuf, 0, 0, y, PAIR ? 2 * s.n : s.n);   // PAIR: box of two samples, the odd tail is clipped
                     bulk_commit();
                 }
                 if (RESID && res_leader) res_issue();   // the residual buffer of this row is free: refill it for this group's row after next
@@ -405,12 +451,14 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const RowArgs 
                     }
                 }
                 if (tr) tw[5] += clock64() - ts0;
-                if ((y & 15) >= 14) {   // this group's last row of the 16-row block: publish its partial, maybe finalise the sample
+                if ((y & ((1 << LG) - 1)) >= (1 << LG) - 2) {   // this group's last row of the block: publish its partial
                     s1a += __shfl_xor_sync(0xffffffffu, s1a, 16); s1b += __shfl_xor_sync(0xffffffffu, s1b, 16);
                     s2a += __shfl_xor_sync(0xffffffffu, s2a, 16); s2b += __shfl_xor_sync(0xffffffffu, s2b, 16);
-                    if (hrow == 0) {
-                        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float2*>(a.parts) +
-                                                                ((int64_t)s.n * a.nparts + (y >> 4) * 8 + e * 4 + w4) * 32 + 2 * c2);
+                    // PAIR: warps 0-1 hold the first sample of the pair, warps 2-3 the second (absent behind an odd batch)
+                    const int pn_ = PAIR ? 2 * s.n + (w4 >> 1) : s.n;
+                    const int slot = PAIR ? (y >> LG) * 4 + e * 2 + (w4 & 1) : (y >> LG) * 8 + e * 4 + w4;
+                    if (hrow == 0 && pn_ < a.B) {
+                        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float2*>(a.parts) + ((int64_t)pn_ * a.nparts + slot) * 32 + 2 * c2);
                         *dst = make_float4(s1a, s2a, s1b, s2b);
                     }
                     s1a = s1b = s2a = s2b = 0.f;
@@ -423,14 +471,21 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const RowArgs 
                 group_bar(bar_id);
                 if (leader) {
                     const unsigned add = (unsigned)((s.yb - s.ya) >> 1);
-                    hdr->gn_last[e] = atomicAdd(a.gn.counter + s.n, add) + add == (unsigned)a.gn.expect ? 1u : 0u;
+#pragma unroll
+                    for (int hh = 0; hh < (PAIR ? 2 : 1); ++hh) {
+                        const int nn = PAIR ? 2 * s.n + hh : s.n;
+                        hdr->gn_last[e][hh] = nn < a.B && atomicAdd(a.gn.counter + nn, add) + add == (unsigned)a.gn.expect ? 1u : 0u;
+                    }
                 }
                 group_bar(bar_id);
-                if (hdr->gn_last[e]) {
-                    __threadfence();
-                    gn_fused_finalize(a.gn, s.n, m, kGrp);
-                    if (leader) a.gn.counter[s.n] = 0u;
-                }
+#pragma unroll
+                for (int hh = 0; hh < (PAIR ? 2 : 1); ++hh)
+                    if (hdr->gn_last[e][hh]) {
+                        const int nn = PAIR ? 2 * s.n + hh : s.n;
+                        __threadfence();
+                        gn_fused_finalize(a.gn, nn, m, kGrp);
+                        if (leader) a.gn.counter[nn] = 0u;
+                    }
             }
         }
         if (leader) bulk_wait_all();
@@ -457,25 +512,25 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const RowArgs 
             for (int sl = 0; sl < NSLAB; ++sl) {
                 mbar_wait_t(smem_u32(&hdr->full_a[sa]), pa, tr, tw[2]);
                 tc_fence_after();
-                const uint64_t adesc = a_desc0 + (uint64_t)((uint32_t)sa * (kAStage >> 4));
+                const uint64_t adesc = a_desc0 + (uint64_t)((uint32_t)sa * (AST >> 4));
                 if (elect_one()) {
                     if (sl < NMAIN) {
 #pragma unroll
                         for (int h = 0; h < KSTEPS; ++h)
 #pragma unroll
                             for (int kx = 0; kx < 3; ++kx)
-                                umma(d_tmem, adesc + (uint64_t)(uint32_t)(h * 2 * PLANE + kx),
+                                umma(d_tmem, adesc + (uint64_t)(PAIR ? (uint32_t)kx * (kAStage >> 4) + (uint32_t)(h * 2 * PLANE) : (uint32_t)(h * 2 * PLANE + kx)),
                                      w_desc0 + (uint64_t)((uint32_t)((sl * KSTEPS + h) * 3 + kx) * (W_CHUNK >> 4)), idesc, (sl | h | kx) ? 1u : 0u);
                     } else {   // 1x1 res_conv over the raw block input: centre tap, centre (ky = 1) columns
 #pragma unroll
                         for (int h = 0; h < 2; ++h)
-                            umma(d_tmem + 32u, adesc + (uint64_t)(uint32_t)(h * 2 * PLANE + 1),
+                            umma(d_tmem + 32u, adesc + (uint64_t)(PAIR ? (kAStage >> 4) + (uint32_t)(h * 2 * PLANE) : (uint32_t)(h * 2 * PLANE + 1)),
                                  wr_desc0 + (uint64_t)((uint32_t)((sl - NMAIN) * 2 + h) * (1024u >> 4)), idesc_res, 1u);
                     }
                     umma_commit(smem_u32(&hdr->empty_a[sa]));
                     if (sl == NSLAB - 1) umma_commit(smem_u32(&hdr->acc_full[slot]));
                 }
-                if (++sa == kNA) { sa = 0; pa ^= 1u; }
+                if (++sa == NA) { sa = 0; pa ^= 1u; }
             }
         }
         if (tr && lane == 0) { long long* o = a.trace + 16; o[0] = clock64() - t_begin; o[1] = tw[0]; o[2] = tw[1]; o[3] = tw[2]; o[4] = nitems; }
@@ -492,31 +547,37 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const RowArgs 
             int rs = 0;
             uint32_t pr = 0;
             Seg s;
-            for (int k = 0; seg_at(a.H, b0, b1, k, s, EXT); ++k)
+            for (int k = 0; seg_at<LG>(a.H, b0, b1, k, s, EXT); ++k)
                 for (int r = s.r0; r <= s.r1; ++r) {
 #pragma unroll
                     for (int sl = 0; sl < NSLAB; ++sl) {
                         const uint32_t bar = smem_u32(&hdr->raw_full[rs]);
                         mbar_wait_t(smem_u32(&hdr->raw_empty[rs]), pr ^ 1u, tr, tw[0]);
-                        const uint32_t dst = base + a.off_raw + (uint32_t)rs * kRawStage;
+                        const uint32_t dst = base + a.off_raw + (uint32_t)rs * RAWST;
                         if (KIND == ROW_STEM) {
                             mbar_expect_tx(bar, 1024u);
                             bulk_g2s(dst, a.cond + (int64_t)s.n * a.L + (int64_t)r * a.hop, 512u, bar);
                             bulk_g2s(dst + 512u, a.x_t + (int64_t)s.n * a.L + (int64_t)r * a.hop, 512u, bar);
                         } else if (sl < NMAIN) {
                             const int cb = sl * 32, si = cb < a.C0 ? 0 : 1;
-                            mbar_expect_tx(bar, (UP ? 4096u : 8192u) + (AFF ? 256u : 0u));
-                            tma_load_4d(dst, &maps.src[si], cb - (si ? a.C0 : 0), 0, UP ? (r >> 1) : r, s.n, bar);
+                            mbar_expect_tx(bar, (UP ? 4096u : 8192u) + (AFF ? (PAIR ? 512u : 256u) : 0u));
+                            tma_load_4d(dst, &maps.src[si], cb - (si ? a.C0 : 0), 0, UP ? (r >> 1) : r, PAIR ? 2 * s.n : s.n, bar);   // PAIR: box of two samples, zero fill behind an odd batch
                             if (AFF) {
-                                bulk_g2s(dst + 8192u, a.scale + (int64_t)s.n * a.Cin + cb, 128u, bar);
-                                bulk_g2s(dst + 8192u + 128u, a.shift + (int64_t)s.n * a.Cin + cb, 128u, bar);
+                                const int n0 = PAIR ? 2 * s.n : s.n;
+                                bulk_g2s(dst + 8192u, a.scale + (int64_t)n0 * a.Cin + cb, 128u, bar);
+                                bulk_g2s(dst + 8192u + 128u, a.shift + (int64_t)n0 * a.Cin + cb, 128u, bar);
+                                if (PAIR) {
+                                    const int n1 = n0 + 1 < a.B ? n0 + 1 : n0;
+                                    bulk_g2s(dst + 8192u + 256u, a.scale + (int64_t)n1 * a.Cin + cb, 128u, bar);
+                                    bulk_g2s(dst + 8192u + 384u, a.shift + (int64_t)n1 * a.Cin + cb, 128u, bar);
+                                }
                             }
                         } else {
                             const int cb = (sl - NMAIN) * 32, si = cb < a.rC0 ? 0 : 1;
                             mbar_expect_tx(bar, 8192u);
-                            tma_load_4d(dst, &maps.rsrc[si], cb - (si ? a.rC0 : 0), 0, r, s.n, bar);
+                            tma_load_4d(dst, &maps.rsrc[si], cb - (si ? a.rC0 : 0), 0, r, PAIR ? 2 * s.n : s.n, bar);
                         }
-                        if (++rs == kNR) { rs = 0; pr ^= 1u; }
+                        if (++rs == NR) { rs = 0; pr ^= 1u; }
                     }
                 }
             if (tr) { long long* o = a.trace + 21; o[0] = clock64() - t_begin; o[1] = tw[0]; }
@@ -528,11 +589,11 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const RowArgs 
         const int j = gt & 3, px0 = gt >> 2;
         const int nslabs = nitems * NSLAB;
         for (int qn = gi; qn < nslabs; qn += 2) {
-            const int rs = qn % kNR, sa = qn % kNA, sl = NSLAB == 1 ? 0 : qn % NSLAB;
-            const uint32_t raw = base + a.off_raw + (uint32_t)rs * kRawStage;
-            const uint32_t opd = base + a.off_a + (uint32_t)sa * kAStage;
-            mbar_wait_t(smem_u32(&hdr->raw_full[rs]), (uint32_t)(qn / kNR) & 1u, tr, tw[0]);
-            mbar_wait_t(smem_u32(&hdr->empty_a[sa]), ((uint32_t)(qn / kNA) & 1u) ^ 1u, tr, tw[1]);
+            const int rs = qn % NR, sa = qn % NA, sl = NSLAB == 1 ? 0 : qn % NSLAB;
+            const uint32_t raw = base + a.off_raw + (uint32_t)rs * RAWST;
+            const uint32_t opd = base + a.off_a + (uint32_t)sa * AST;
+            mbar_wait_t(smem_u32(&hdr->raw_full[rs]), (uint32_t)(qn / NR) & 1u, tr, tw[0]);
+            mbar_wait_t(smem_u32(&hdr->empty_a[sa]), ((uint32_t)(qn / NA) & 1u) ^ 1u, tr, tw[1]);
             const long long tx0 = tr ? clock64() : 0;
             if (KIND == ROW_STEM) {
                 // K slots of plane 0: [cond hi, x_t hi, cond lo, x_t lo, 0, 0, 0, 0]
@@ -548,14 +609,14 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const RowArgs 
                 const bool is_main = sl < NMAIN;
                 const bool aff = AFF && is_main, up = UP && is_main;
                 float2 sc2[4], sh2[4];   // (scale, shift) / 2 of this thread's 8 channels as fp32 pairs: swish(y) = h + h tanh(h), h = y / 2
-                if (aff) {
-                    const uint32_t ss = raw + 8192u + (uint32_t)j * 32u;
+                auto load_aff = [&](uint32_t ss) {
                     const uint4 s0 = lds128(ss), s1 = lds128(ss + 16u), h0 = lds128(ss + 128u), h1 = lds128(ss + 144u);
                     sc2[0] = make_float2(0.5f * __uint_as_float(s0.x), 0.5f * __uint_as_float(s0.y)); sc2[1] = make_float2(0.5f * __uint_as_float(s0.z), 0.5f * __uint_as_float(s0.w));
                     sc2[2] = make_float2(0.5f * __uint_as_float(s1.x), 0.5f * __uint_as_float(s1.y)); sc2[3] = make_float2(0.5f * __uint_as_float(s1.z), 0.5f * __uint_as_float(s1.w));
                     sh2[0] = make_float2(0.5f * __uint_as_float(h0.x), 0.5f * __uint_as_float(h0.y)); sh2[1] = make_float2(0.5f * __uint_as_float(h0.z), 0.5f * __uint_as_float(h0.w));
                     sh2[2] = make_float2(0.5f * __uint_as_float(h1.x), 0.5f * __uint_as_float(h1.y)); sh2[3] = make_float2(0.5f * __uint_as_float(h1.z), 0.5f * __uint_as_float(h1.w));
-                }
+                };
+                if (aff) load_aff(raw + 8192u + (uint32_t)j * 32u);
                 const uint32_t dstp = opd + (uint32_t)j * (uint32_t)PLANE * 16u;
                 uint4 rv[4];
 #pragma unroll
@@ -564,6 +625,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const RowArgs 
 #pragma unroll
                 for (int rd = 0; rd < 4; ++rd) {
                     if (up && rd >= 2) break;
+                    if (PAIR && aff && rd == 2) load_aff(raw + 8192u + 256u + (uint32_t)j * 32u);   // pixels 64..127: the pair's second sample
                     uint4 o = rv[rd];
                     if (aff) {
                         const uint32_t w[4] = {o.x, o.y, o.z, o.w};
@@ -577,7 +639,14 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const RowArgs 
                         o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
                     }
                     const int px = px0 + 32 * rd;
-                    if (up) {
+                    if (PAIR) {   // copy kx holds pixel px + kx - 1 of the same sample at tile row px (seam slots stay zero)
+                        const uint32_t d1 = dstp + kAStage + (uint32_t)px * 16u;
+                        sts128(d1, o);
+                        if (is_main) {
+                            if ((px & 63) != 63) sts128(d1 - kAStage + 16u, o);
+                            if ((px & 63) != 0) sts128(d1 + kAStage - 16u, o);
+                        }
+                    } else if (up) {
                         sts128(dstp + (uint32_t)(2 * px + 1) * 16u, o);
                         sts128(dstp + (uint32_t)(2 * px + 2) * 16u, o);
                     } else {
@@ -606,13 +675,13 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const RowArgs 
     }
 }
 
-// NHWC bf16 tensor [B][H][W][C] as a 4-D tensor map (C innermost) with box (32, bw, 1, 1); swz 0 / 64
-int encode_rows(CUtensorMap* m, const void* basep, int B, int H, int W, int C, int bw, int swz) {
+// NHWC bf16 tensor [B][H][W][C] as a 4-D tensor map (C innermost) with box (32, bw, 1, bn); swz 0 / 64
+int encode_rows(CUtensorMap* m, const void* basep, int B, int H, int W, int C, int bw, int swz, int bn = 1) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) { set_error("conv row: cuTensorMapEncodeTiled is unavailable"); return SDDM_E_CUDA; }
     const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-    const cuuint32_t box[4] = {32, (cuuint32_t)bw, 1, 1};
+    const cuuint32_t box[4] = {32, (cuuint32_t)bw, 1, (cuuint32_t)bn};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(basep), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           swz == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -628,10 +697,25 @@ int device_sms() { return device_sm_count(); }
 
 }  // namespace
 
-int conv_row_nparts(int H) { return (H / 16) * 8; }
+int conv_row_nparts(int H, int W) { return W == RW ? (H / 16) * 8 : (H / 4) * 4; }   // (block, group, warp [, sample of the pair])
 int conv_row_arrivals(int H) { return H; }   // the counter adds up completed rows
 
+// 64-wide level: ResnetBlock convolutions with Cout = 32 on the pair tile (GroupNorm input, optional 1x1 res_conv)
+static bool pair_supported(const ConvP& p) {
+    static const bool off = [] { const char* e = getenv("SDDM_NO_ROW_PAIR"); return e && e[0] == '1'; }();   // A/B switch: 64-wide level stays on conv_tc.cu
+    if (off) return false;
+    if (!p.act16 || p.Wout != RW / 2 || p.Hout % 4 || p.Hout < 4 || p.Cout != 32 || p.mode != CONV_S1 || p.res_identity) return false;
+    if (!p.src[0].scale) return false;
+    for (int i = 0; i < p.nsrc; ++i)
+        if (p.src[i].C % 32) return false;
+    for (int i = 0; i < p.res_nsrc; ++i)
+        if (p.res_Cin && p.res_src[i].C % 32) return false;
+    const int cin = p.Cin, rc = p.res_Cin;
+    return (cin == 128 && rc == 0) || (cin == 64 && rc == 0) || (cin == 32 && rc == 0) || (cin == 32 && rc == 128) || (cin == 32 && rc == 64);
+}
+
 bool conv_row_supported(const ConvP& p) {
+    if (pair_supported(p)) return true;
     if (!p.act16 || p.Wout != RW || p.Hout % 16 || p.Hout < 16) return false;
     if (p.Cout != 32 && !(p.Cout == 1)) return false;
     if (p.mode != CONV_S1 && p.mode != CONV_UP) return false;
@@ -645,19 +729,20 @@ bool conv_row_supported(const ConvP& p) {
 }
 
 // shared-memory plan + launch of one instantiation
-template <int KIND, int NMAIN, int NRES, bool UP, bool AFF, bool RESID>
+template <int KIND, int NMAIN, int NRES, bool UP, bool AFF, bool RESID, bool PAIR = false>
 static int launch_row_t(RowArgs a, const RowMaps& maps, cudaStream_t st) {
-    a.nblocks = a.B * (a.H / 16);
+    using RR = RowRings<NMAIN, PAIR>;
+    a.nblocks = PAIR ? ((a.B + 1) / 2) * (a.H >> RR::LG) : a.B * (a.H >> RR::LG);
     const size_t w_al = ((size_t)a.w_bytes + 1023) & ~(size_t)1023;
     const int nout = KIND == ROW_FINAL ? 0 : 2, nres = RESID ? 2 : 0;
     a.off_w = kHdr;
     a.off_out = a.off_w + (uint32_t)w_al;                                     // 1024-aligned (swizzled TMA tiles)
     a.off_res = a.off_out + (uint32_t)(kEpi * nout) * kOutTile;
     a.off_raw = a.off_res + (uint32_t)(kEpi * nres) * kOutTile;
-    a.off_a = a.off_raw + (uint32_t)kNR * kRawStage;
-    const size_t smem = a.off_a + (size_t)kNA * kAStage + 1024;
+    a.off_a = a.off_raw + (uint32_t)RR::NR * RR::RAW;
+    const size_t smem = a.off_a + (size_t)RR::NA * RR::AST + 1024;
     if (smem > kSmemCap + 1024) { set_error("conv row: shared-memory plan does not fit (%zu bytes)", smem); return SDDM_E_INVALID; }
-    auto kern = conv_row_kernel<KIND, NMAIN, NRES, UP, AFF, RESID>;
+    auto kern = conv_row_kernel<KIND, NMAIN, NRES, UP, AFF, RESID, PAIR>;
     SDDM_SET_MAX_SMEM(kern, kSmemCap + 1024);
     a.trace = g_row_trace ? g_row_trace + (size_t)(g_row_trace_launch++ % 64) * 32 : nullptr;
     const int sms = device_sms();
@@ -691,8 +776,24 @@ int launch_conv_row(const ConvP& p, const __nv_bfloat16* w_row, uint32_t w_bytes
         a.pk = PostCoef{k8[0], k8[1], k8[2], k8[3], k8[4], k8[5], k8[6], k8[7]};
     }
     a.gn_on = p.gn_on; a.gn = p.gn;
-    if (!final_out && (!p.parts || p.nparts != conv_row_nparts(p.Hout))) { set_error("conv row: nparts mismatch"); return SDDM_E_INVALID; }
+    if (!final_out && (!p.parts || p.nparts != conv_row_nparts(p.Hout, p.Wout))) { set_error("conv row: nparts mismatch"); return SDDM_E_INVALID; }
     int rc;
+    if (p.Wout == RW / 2) {   // 64-wide level: tiles of two samples (ups.11 / ups.12 of config_unet.json)
+        for (int i = 0; i < p.nsrc; ++i)
+            if ((rc = encode_rows(&maps.src[i], p.src[i].x, p.B, p.Hin, p.Win, p.src[i].C, 64, 0, 2))) return rc;
+        if (res_conv)
+            for (int i = 0; i < p.res_nsrc; ++i)
+                if ((rc = encode_rows(&maps.rsrc[i], p.res_src[i].x, p.B, p.Hout, p.Wout, p.res_src[i].C, 64, 0, 2))) return rc;
+        if ((rc = encode_rows(&maps.out, p.out, p.B, p.Hout, p.Wout, 32, 64, 64, 2))) return rc;
+        const int rcin = res_conv ? p.res_Cin : 0;
+        if (p.Cin == 128 && !rcin) return launch_row_t<ROW_ACT, 4, 0, false, true, false, true>(a, maps, st);
+        if (p.Cin == 64 && !rcin) return launch_row_t<ROW_ACT, 2, 0, false, true, false, true>(a, maps, st);
+        if (p.Cin == 32 && !rcin) return launch_row_t<ROW_ACT, 1, 0, false, true, false, true>(a, maps, st);
+        if (p.Cin == 32 && rcin == 128) return launch_row_t<ROW_ACT, 1, 4, false, true, false, true>(a, maps, st);
+        if (p.Cin == 32 && rcin == 64) return launch_row_t<ROW_ACT, 1, 2, false, true, false, true>(a, maps, st);
+        set_error("conv row: no pair instantiation for Cin=%d res_conv=%d", p.Cin, rcin);
+        return SDDM_E_INVALID;
+    }
     for (int i = 0; i < p.nsrc; ++i)
         if ((rc = encode_rows(&maps.src[i], p.src[i].x, p.B, p.Hin, p.Win, p.src[i].C, up ? 64 : 128, 0))) return rc;
     if (res_conv)
@@ -716,7 +817,7 @@ int launch_conv_row(const ConvP& p, const __nv_bfloat16* w_row, uint32_t w_bytes
 // stem: SignalToFrames x 2 + cat + conv3x3(2 -> 32)
 int launch_stem_row(const StemP& p, const __nv_bfloat16* w_row, uint32_t w_bytes, cudaStream_t st) {
     if (!p.act16 || p.W != RW || p.H % 16 || p.CO != 32 || !w_row) { set_error("stem row: unsupported shape"); return SDDM_E_INVALID; }
-    if (p.nparts != conv_row_nparts(p.H)) { set_error("stem row: nparts mismatch"); return SDDM_E_INVALID; }
+    if (p.nparts != conv_row_nparts(p.H, RW)) { set_error("stem row: nparts mismatch"); return SDDM_E_INVALID; }
     RowArgs a{};
     RowMaps maps;
     memset(&maps, 0, sizeof(maps));
@@ -749,5 +850,25 @@ extern "C" SDDM_API int sddm_debug_row_trace(int enable, long long* host_out) {
     if (host_out) SDDM_CUDA_TRY(cudaMemcpy(host_out, g_row_trace, 64 * 32 * sizeof(long long), cudaMemcpyDeviceToHost));
     cudaFree(g_row_trace);
     g_row_trace = nullptr;
+    return SDDM_OK;
+}
+
+// debug: enable != 0 -> waits of the row kernel that time out leave a note (CTA, thread, barrier, parity) in a mapped host buffer;
+// enable == 0 -> copy the 16384 words to host_out (valid even after the trap killed the context)
+extern "C" SDDM_API int sddm_debug_hang(int enable, unsigned* host_out) {
+    using namespace sddm;
+    static unsigned* h_buf = nullptr;
+    if (enable) {
+        if (!h_buf) {
+            SDDM_CUDA_TRY(cudaHostAlloc(&h_buf, 16384 * sizeof(unsigned), cudaHostAllocMapped));
+            unsigned* d = nullptr;
+            SDDM_CUDA_TRY(cudaHostGetDevicePointer(&d, h_buf, 0));
+            SDDM_CUDA_TRY(cudaMemcpyToSymbol(g_hang, &d, sizeof(d)));
+        }
+        memset(h_buf, 0, 16384 * sizeof(unsigned));
+        return SDDM_OK;
+    }
+    if (!h_buf) { set_error("hang notes were not enabled"); return SDDM_E_STATE; }
+    if (host_out) memcpy(host_out, h_buf, 16384 * sizeof(unsigned));
     return SDDM_OK;
 }

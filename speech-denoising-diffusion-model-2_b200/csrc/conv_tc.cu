@@ -1112,10 +1112,15 @@ int launch_mode(TcArgs a, cudaStream_t st) {
         a.NW = a.resident ? nchunks : (TPC == 9 ? 2 : 4);
         if (!a.resident && total() > cap) a.NW = 2;   // last resort: a two-deep chunk ring
         if (total() > cap) continue;
+        // Ring depths stay EVEN: the two transform groups take alternate slabs, so with an even depth a stage always belongs to the
+        // same group.  With an odd depth the groups alternate on a stage, and a group that runs ahead can poll raw_full[s] for use
+        // k + 1 while the load of use k (the other group's, TMA loads complete out of order) is still in flight: mbarrier waits only
+        // see the phase parity, the wait passes on the completed use k - 1, the group transforms the wrong slab and releases the
+        // stage early - silent corruption, then a second arrive.expect_tx on an unfinished phase (Warp Illegal Instruction).
         for (bool grew = true; grew;) {   // spend what is left on deeper rings
             grew = false;
-            if (a.NR < kMaxRing) { ++a.NR; if (total() <= cap) grew = true; else --a.NR; }
-            if (a.NA < kMaxRing && a.NA < a.NR) { ++a.NA; if (total() <= cap) grew = true; else --a.NA; }
+            if (a.NR + 2 <= kMaxRing) { a.NR += 2; if (total() <= cap) grew = true; else a.NR -= 2; }
+            if (a.NA + 2 <= kMaxRing && a.NA + 2 <= a.NR) { a.NA += 2; if (total() <= cap) grew = true; else a.NA -= 2; }
             if (!a.resident && a.NW < 12 && a.NW < nchunks) { ++a.NW; if (total() <= cap) grew = true; else --a.NW; }
         }
         const int score = (a.NR < 4 ? a.NR : 4) * 100 + (a.NA < 4 ? a.NA : 4) * 10 + (2 - k);

@@ -37,8 +37,15 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
 // bounded wait: a pipeline bug must surface as a trap (CUDA error), never as a hung GPU
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t spins = 0;
-    while (!mbar_try(bar, parity))
-        if (++spins > 40000000u) __trap();
+    while (!mbar_try(bar, parity)) {
+        ++spins;
+#ifdef SDDM_MBAR_TIMEOUT_HOOK
+        if (spins == 40000000u) SDDM_MBAR_TIMEOUT_HOOK(bar, parity);   // debug: note who waits on what, give the other waiters time to do the same
+        if (spins > 42000000u) __trap();
+#else
+        if (spins > 40000000u) __trap();
+#endif
+    }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

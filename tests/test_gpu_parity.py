@@ -159,7 +159,7 @@ def test_unet_nodes_vs_oracle(dev, prec):
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16x3", "bf16", "bf16act"])
-@pytest.mark.parametrize("shape", ["two_levels_two_resblocks", "three_levels_wide", "batch_of_one"])
+@pytest.mark.parametrize("shape", ["two_levels_two_resblocks", "three_levels_wide", "batch_of_one", "odd_batch"])
 def test_other_unet_configs_vs_oracle(dev, prec, shape):
     """Shapes other than config_unet.json (different depth, res_blocks, channel widths, frame grid, batch sizes 1 / 3 / 5):
     the op program, tile masks, ring plans and weight residency are all derived from the config."""
@@ -171,6 +171,9 @@ def test_other_unet_configs_vs_oracle(dev, prec, shape):
     elif shape == "three_levels_wide":
         cfg = dict(num_samples=128 + 63 * 64, in_channel=2, out_channel=1, inner_channel=64, norm_groups=32, channel_mults=(1, 2, 4),
                    res_blocks=1, dropout=0, segment_len=128, segment_stride=64)
+        B = 5
+    elif shape == "odd_batch":   # the 64-wide level tiles two samples per MMA: the last pair is half empty
+        cfg = dict(UNET_CFG)
         B = 5
     else:
         cfg = dict(UNET_CFG)
