@@ -280,6 +280,25 @@ def test_batch_invariance_determinism_and_host_api(dev):
     assert all(torch.equal(a, b) for a, b in zip(outs, outs2))
 
 
+def test_back_to_back_forwards(dev):
+    """Pipeline stress at the bench size: 400 denoiser forwards of a 64-chunk batch back to back (every persistent CTA runs through
+    many ring wraps with the previous kernel's data still in L2).  A ring-parity race of the tcgen05 kernels (DESIGN.md section
+    4.2a) showed up only here, once in 30 - 500 forwards, as a launch failure; the result must also stay bit-identical."""
+    model, _ = make_model(dev)
+    net = model.noise_estimate_model
+    net.precision = prec_id("bf16act")
+    plan = net.get_plan(model.diffusion)
+    g = torch.Generator().manual_seed(31)
+    cond = (0.1 * torch.randn(64, 1, L, generator=g)).clamp(-1, 1).to(dev)
+    x = torch.randn(64, 1, L, generator=g).to(dev)
+    first = plan.eps(cond, x, t=37).clone()
+    for it in range(400):
+        out = plan.eps(cond, x, t=37)
+    torch.cuda.synchronize()
+    assert torch.equal(out, first)
+    report("stress: 400 back-to-back forwards at B=64 (bf16act): no fault, bit-identical results")
+
+
 def test_full_size_cfg2(dev, golden):
     """BASELINE cfg 2: 64 chunks, full 100-step schedule, every persistent CTA working through many tiles.
     Pinned to the REFERENCE: rows 0 / 31 / 63 of the batch were run through the reference's SDDM.infer with the same injected
