@@ -35,20 +35,7 @@
 #include "gn_fuse.cuh"
 #include "kernels.cuh"
 
-// debug (sddm_debug_hang): a wait that times out notes (CTA, thread, barrier address, parity) in mapped host memory before it traps
-namespace sddm {
-__device__ unsigned* g_hang = nullptr;
-__device__ __noinline__ void hang_note(uint32_t bar, uint32_t parity) {
-    unsigned* g = g_hang;
-    if (!g) return;
-    // one slot per (CTA, warp), plain stores (no atomics towards host memory); [0] = 1 marks "some wait timed out"
-    const unsigned s = blockIdx.x * 20u + (threadIdx.x >> 5);
-    if (s < 4000u) { g[4 + 4 * s] = blockIdx.x + 1u; g[5 + 4 * s] = threadIdx.x; g[6 + 4 * s] = bar; g[7 + 4 * s] = parity; }
-    g[0] = 1u;
-    __threadfence_system();
-}
-}  // namespace sddm
-#define SDDM_MBAR_TIMEOUT_HOOK(bar, parity) ::sddm::hang_note(bar, parity)
+#define SDDM_MBAR_TIMEOUT_NOTES 1   // waits of this file that time out leave a note (sddm_debug_hang)
 #include "tc_ptx.cuh"
 
 namespace sddm {
@@ -135,12 +122,6 @@ __device__ __forceinline__ bool seg_at(int H, int b0, int b1, int k, Seg& s, boo
     return true;
 }
 
-__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, bool tr, long long& acc) {
-    if (!tr) { mbar_wait(bar, parity); return; }
-    const long long t0 = clock64();
-    mbar_wait(bar, parity);
-    acc += clock64() - t0;
-}
 __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -863,7 +844,7 @@ extern "C" SDDM_API int sddm_debug_hang(int enable, unsigned* host_out) {
             SDDM_CUDA_TRY(cudaHostAlloc(&h_buf, 16384 * sizeof(unsigned), cudaHostAllocMapped));
             unsigned* d = nullptr;
             SDDM_CUDA_TRY(cudaHostGetDevicePointer(&d, h_buf, 0));
-            SDDM_CUDA_TRY(cudaMemcpyToSymbol(g_hang, &d, sizeof(d)));
+            SDDM_CUDA_TRY(set_hang_buffer(d));
         }
         memset(h_buf, 0, 16384 * sizeof(unsigned));
         return SDDM_OK;

@@ -33,6 +33,7 @@
 
 #include "common.cuh"
 #include "gn_fuse.cuh"
+#include "tc_ptx.cuh"
 #include "../../include/sddm_b200.h"
 
 namespace sddm {
@@ -88,168 +89,6 @@ struct TcArgs {
     long long* trace;               // debug: per-role wait / busy cycle counters of CTA 0 (nullptr = off)
 };
 
-// ---- PTX wrappers -----------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"   // suspend-time hint: fewer wake-ups / re-polls of a waiting warp
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity), "r"(0x20000u)
-        : "memory");
-    return ok != 0;
-}
-__device__ unsigned long long g_dead = 0ull;   // first watchdog victim: (blockIdx << 40) | (warp << 32) | (parity << 24) | barrier offset
-// Bounded wait: a pipeline bug must surface as a trap (CUDA error), never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t spins = 0;
-    while (!mbar_try(bar, parity)) {
-#ifdef SDDM_TC_DEADLOCK_DEBUG
-        if (++spins > 2000000u) {
-            atomicCAS(&g_dead, 0ull, ((unsigned long long)blockIdx.x << 40) | ((unsigned long long)(threadIdx.x >> 5) << 32) | ((unsigned long long)parity << 24) | (unsigned long long)(bar & 0xFFFFFFu));
-            return;
-        }
-#else
-        if (++spins > 40000000u) __trap();
-#endif
-    }
-}
-// wait + (when tracing) accumulate the cycles spent into acc
-__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, bool trace, long long& acc) {
-    if (!trace) { mbar_wait(bar, parity); return; }
-    const long long t0 = clock64();
-    mbar_wait(bar, parity);
-    acc += clock64() - t0;
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
-}
-__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
-    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
-                 "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read_0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-
-// shared-memory matrix descriptor, SWIZZLE_NONE, K-major: core matrix = 8 rows x 16 B (128 contiguous bytes);
-// LBO = byte distance between the two K halves (8 elements each) of one MMA K step, SBO = byte distance between
-// consecutive 8-row groups along M / N.  Bit 46 = descriptor version 1 (sm_100).
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
-           ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
-}
-// instruction descriptor, kind::f16: D = fp32, A = B = bf16, both K-major, M = 128, N = n
-__device__ __forceinline__ uint32_t make_idesc(int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-}
-__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// 32 lanes x 32 consecutive fp32 columns: thread i of the warp receives row (lane base + i)
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// one lane of the (converged) warp; the same lane every time, so commits track the MMAs issued under earlier elections
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "elect.sync _|p, 0xffffffff;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(pred));
-    return pred != 0;
-}
-__device__ __forceinline__ void group_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
-
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
-}
-__device__ __forceinline__ uint4 lds128(uint32_t addr) {
-    uint4 v;
-    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-__device__ __forceinline__ float lds32(uint32_t addr) {
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
-    return v;
-}
-// packed fp32 pair fma (sm_100 FFMA2: one issue slot for two ordinary IEEE fmas)
-__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
-    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b),
-                       rc = *reinterpret_cast<unsigned long long*>(&c), rd;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
-    return *reinterpret_cast<float2*>(&rd);
-}
-__device__ __forceinline__ float tanh_approx(float x) {
-    float y;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-
-// shared-memory header (at the 1024-aligned base)
 struct SmemHdr {
     uint64_t raw_full[kMaxRing], raw_empty[kMaxRing];
     uint64_t full_a[kMaxRing], empty_a[kMaxRing];
@@ -539,8 +378,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
         const uint32_t idesc = make_idesc(p.Cout);
         const uint32_t b_lbo = (uint32_t)p.Cout * 16u, b_sbo = 128u;
         const uint32_t a_lbo = (uint32_t)G::PLANE * 16u, a_sbo = (uint32_t)G::SBO;
-        const uint64_t a_desc0 = make_desc(base_u32 + a.off_a, a_lbo, a_sbo);
-        const uint64_t w_desc0 = make_desc(base_u32 + a.off_w, b_lbo, b_sbo);
+        const uint64_t a_desc0 = make_desc_nosw(base_u32 + a.off_a, a_lbo, a_sbo);
+        const uint64_t w_desc0 = make_desc_nosw(base_u32 + a.off_w, b_lbo, b_sbo);
         const uint32_t a_step = a.a_stage >> 4, w_step = a.w_stage >> 4, tap_step = 2u * (uint32_t)p.Cout;   // in 16-byte units
         // (mbarrier waits only see the phase PARITY: a warp that starts a tile may wait on operand stage s only if the
         // previous use of s is known to be filled, which holds when the ring is deeper than one tile: NA >= nA + 1.)
@@ -968,8 +807,8 @@ __global__ void __launch_bounds__(128) umma_probe_kernel(const __nv_bfloat16* __
         const uint32_t idesc = make_idesc(N);
         for (int ks = 0; ks < K / 16; ++ks) {
             const uint32_t aa = sA + a_off + (uint32_t)ks * 2u * a_lbo, bb = sA + b_off + (uint32_t)ks * 2u * b_lbo;
-            const uint64_t da = swap_fields ? make_desc(aa, a_sbo, a_lbo) : make_desc(aa, a_lbo, a_sbo);
-            const uint64_t db = swap_fields ? make_desc(bb, b_sbo, b_lbo) : make_desc(bb, b_lbo, b_sbo);
+            const uint64_t da = swap_fields ? make_desc_nosw(aa, a_sbo, a_lbo) : make_desc_nosw(aa, a_lbo, a_sbo);
+            const uint64_t db = swap_fields ? make_desc_nosw(bb, b_sbo, b_lbo) : make_desc_nosw(bb, b_lbo, b_sbo);
             umma(tmem, da, db, idesc, ks > 0 ? 1u : 0u);
         }
         umma_commit(smem_u32(&bar));
@@ -1006,8 +845,8 @@ __global__ void __launch_bounds__(128) umma_rate_kernel(int N, int reps, int nA,
     const uint32_t tmem = tbase;
     if (warp == 0) {
         const uint32_t idesc = make_idesc(N);
-        const uint64_t db = make_desc(sA + b_off, (uint32_t)N * 16u, 128);
-        const uint64_t da0 = geo == 1 ? make_desc(sA, 182u * 16u, 160u) : (geo == 2 ? make_desc(sA, 2304u + 128u, 128u) : make_desc(sA, 2048, 128));
+        const uint64_t db = make_desc_nosw(sA + b_off, (uint32_t)N * 16u, 128);
+        const uint64_t da0 = geo == 1 ? make_desc_nosw(sA, 182u * 16u, 160u) : (geo == 2 ? make_desc_nosw(sA, 2304u + 128u, 128u) : make_desc_nosw(sA, 2048, 128));
         long long t0 = 0;
         if (elect_one()) {
             t0 = clock64();
@@ -1031,30 +870,11 @@ __global__ void __launch_bounds__(128) umma_rate_kernel(int N, int reps, int nA,
     if (warp == 0) { __syncwarp(); tmem_dealloc(tmem, 256); }
 }
 
-int num_sms() { return device_sm_count(); }
 
 long long* g_trace = nullptr;   // device buffer [64 launches][48 counters], set by sddm_debug_tc_trace
 int g_trace_launch = 0;
 
 constexpr size_t kSmemMax = 232448;   // 227 KB opt-in limit per CTA on sm_100
-
-// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void* f = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !f) {
-            cudaGetLastError();
-            return nullptr;
-        }
-        fn = reinterpret_cast<EncodeTiledFn>(f);
-    }
-    return fn;
-}
 
 // NHWC tensor [B][H][W][C] (fp32, or bf16 when a16) as a 4-D tensor map (C innermost) with box (bc, bw, bh, 1);
 // swz: 0 none, 64 / 128 = CU_TENSOR_MAP_SWIZZLE_64B / 128B
@@ -1305,10 +1125,3 @@ extern "C" SDDM_API int sddm_debug_umma_rate(int N, int reps, int nA, int geo, f
     return SDDM_OK;
 }
 
-#ifdef SDDM_TC_DEADLOCK_DEBUG
-extern "C" SDDM_API unsigned long long sddm_debug_dead(void) {
-    unsigned long long v = 0;
-    cudaMemcpyFromSymbol(&v, sddm::g_dead, sizeof(v));
-    return v;
-}
-#endif

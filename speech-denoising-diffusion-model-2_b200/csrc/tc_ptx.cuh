@@ -34,18 +34,41 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// bounded wait: a pipeline bug must surface as a trap (CUDA error), never as a hung GPU
+// Bounded wait: a pipeline bug must surface as a trap (CUDA error), never as a hung GPU.
+// A kernel file compiled with SDDM_MBAR_TIMEOUT_NOTES defined before this header also reports WHO timed out on WHAT (sddm_debug_hang):
+// one copy of the note pointer per translation unit (the library is built without -rdc), an out-of-line call on the cold path only
+// (inlining the note at every wait site cost 6 % of the step: the polling loops fall out of the instruction cache).
+#ifdef SDDM_MBAR_TIMEOUT_NOTES
+__device__ unsigned* g_hang = nullptr;
+__device__ __noinline__ void hang_note(uint32_t bar, uint32_t parity) {
+    unsigned* g = g_hang;
+    if (!g) return;
+    // one slot per (CTA, warp), plain stores (no atomics towards host memory); [0] = 1 marks "some wait timed out"
+    const unsigned s = blockIdx.x * 20u + (threadIdx.x >> 5);
+    if (s < 4000u) { g[4 + 4 * s] = blockIdx.x + 1u; g[5 + 4 * s] = threadIdx.x; g[6 + 4 * s] = bar; g[7 + 4 * s] = parity; }
+    g[0] = 1u;
+    __threadfence_system();
+}
+inline cudaError_t set_hang_buffer(unsigned* dev_ptr) { return cudaMemcpyToSymbol(g_hang, &dev_ptr, sizeof(dev_ptr)); }
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try(bar, parity)) {
+#ifdef SDDM_MBAR_TIMEOUT_NOTES
         ++spins;
-#ifdef SDDM_MBAR_TIMEOUT_HOOK
-        if (spins == 40000000u) SDDM_MBAR_TIMEOUT_HOOK(bar, parity);   // debug: note who waits on what, give the other waiters time to do the same
+        if (spins == 40000000u) hang_note(bar, parity);   // then give the other waiters time to leave their notes
         if (spins > 42000000u) __trap();
 #else
-        if (spins > 40000000u) __trap();
+        if (++spins > 40000000u) __trap();
 #endif
     }
+}
+// wait + (when tracing) accumulate the cycles spent into acc
+__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, bool trace, long long& acc) {
+    if (!trace) { mbar_wait(bar, parity); return; }
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    acc += clock64() - t0;
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
