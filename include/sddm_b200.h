@@ -298,6 +298,24 @@ SDDM_API int sddm_plan_num_ops(const sddm_plan* plan);
 SDDM_API int sddm_profile_enable(sddm_plan* plan, int on);   /* also resets the accumulated totals */
 SDDM_API int sddm_profile_read(sddm_plan* plan, int op, double* total_ms, int64_t* launches, double* flops_per_row,
                       double* bytes_per_row, int* uses_tensor_cores, char* label, int label_cap);
+/* ---- SNR-adaptive diffusion (diffusion half) -------------------------------------------------------------------
+ * reference: VariableGaussianDiffusion, model/diffusion.py:329-446.  Frames x [B][N][L] fp32 (the reference's [B, 1, N, L]),
+ * snr [B][N] fp32 (dB, one estimate per frame), T = n_timestep, scale = snr_estimate_scale.  Every frame has its own linear beta
+ * schedule (end value from its SNR); the kernels recompute the few schedule terms they need per frame - the reference rebuilds the
+ * whole [B, 1, N, T + 1] schedule with numpy on the host in every call.  z == NULL: in-kernel Philox4x32-10 normals keyed by the global
+ * frame id (row0 + b) * N + n.  The two networks of that variant (SNREstimator, UNetModified2_withVariableNoiseLevel) are not built. */
+/* get_beta_schedule (:345-359): betas, alpha_bar [B][N][T + 1] */
+SDDM_API int sddm_var_schedule(const float* snr, int B, int N, int T, float scale, float* betas, float* alpha_bar, void* stream);
+/* get_noise_level (:438-444): out[b][n] = sqrt(alpha_bar_t) */
+SDDM_API int sddm_var_noise_level(const float* snr, int B, int N, int T, float scale, int t, float* out, void* stream);
+/* get_x_T (:417-435, t = T, x = condition) and q_stochastic with an integer step (:394-415, x = x_0, z = the noise):
+ * out = s x + sqrt(1 - s^2) z with s = sqrt(alpha_bar_t) of the frame; noise_level (may be NULL) receives s, [B][N] */
+SDDM_API int sddm_var_mix(const float* x, const float* snr, const float* z, uint64_t seed, int64_t row0, int B, int N, int L, int T, float scale,
+                          int t, float* out, float* noise_level, void* stream);
+/* p_transition (:373-391): out = clamp((x_t - beta_t / sqrt(1 - ab_t) eps) / sqrt(1 - beta_t) [+ sigma_t z if t > 1], -1, 1) */
+SDDM_API int sddm_var_posterior(const float* x_t, const float* eps, const float* snr, const float* z, uint64_t seed, int64_t row0, int B, int N,
+                                int L, int T, float scale, int t, float* out, void* stream);
+
 /* copies the NHWC activation of a named UNet node ("downs.3", "mid.0", "ups.7", ...) produced by the last
  * sddm_eps call on this workspace into out (device, [B,H,W,C] fp32); returns C*H*W via *chw. */
 SDDM_API int sddm_debug_fetch(sddm_plan* plan, const char* node, void* ws, int B, float* out, int64_t* chw, void* stream);

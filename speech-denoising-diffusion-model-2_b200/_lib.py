@@ -121,6 +121,12 @@ SIGNATURES = {
     "sddm_profile_read": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double),
                                     C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_char_p, C.c_int]),
     "sddm_debug_fetch": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]),
+    "sddm_var_schedule": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sddm_var_noise_level": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p]),
+    "sddm_var_mix": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
+                               C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sddm_var_posterior": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.c_float, C.c_int, C.c_void_p, C.c_void_p]),
     "sddm_debug_umma_probe": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "sddm_debug_tc_trace": (C.c_int, [C.c_int, C.c_void_p]),
     "sddm_debug_row_trace": (C.c_int, [C.c_int, C.c_void_p]),

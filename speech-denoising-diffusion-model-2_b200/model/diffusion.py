@@ -247,6 +247,104 @@ class GaussianDiffusion(nn.Module):
         return out + (z.reshape(x_0.shape),) if return_noise else out
 
 
+class VariableGaussianDiffusion(nn.Module):
+    """Mirror of the reference's SNR-adaptive diffusion (model/diffusion.py:329-446): every frame n of a row carries its own linear
+    beta schedule whose end value follows from the estimated SNR of that frame.  Same constructor arguments and method names; tensors
+    are frames ``[B, 1, N, L]`` and ``snr_estimate [B, N]`` (dB).  The reference rebuilds the whole ``[B, 1, N, T + 1]`` schedule with
+    numpy on the host inside every call; here each kernel recomputes the terms it needs per frame (csrc/var_diffusion.cu).
+    Extensions (keyword-only): injected ``noise`` for tests, ``seed`` / ``row0`` for the in-kernel Philox stream.
+    The two networks of that variant (SNREstimator, UNetModified2_withVariableNoiseLevel) are not built - SURVEY section 8f row 4."""
+
+    def __init__(self, n_timestep=100, snr_estimate_scale=100, device="cuda"):
+        super().__init__()
+        self.num_timesteps = int(n_timestep)
+        self.snr_estimate_scale = float(snr_estimate_scale)
+        self.device = device
+        self.linear_start = 1e-6
+
+    def _frames(self, x, snr):
+        x = _prep(x)
+        snr = _prep(snr)
+        _need_cuda(x, snr)
+        if x.ndim != 4 or x.shape[1] != 1:
+            raise ValueError("frames must be [B, 1, N, L], got %s" % (tuple(x.shape),))
+        B, _, N, L = x.shape
+        snr = snr.reshape(B, -1)
+        if snr.shape[1] != N:
+            raise ValueError("snr_estimate must hold one value per frame: [%d, %d], got %s" % (B, N, tuple(snr.shape)))
+        return x, snr.contiguous(), B, N, L
+
+    @torch.no_grad()
+    def get_beta_schedule(self, snr_estimate):
+        """reference :345-359 -> (betas, alpha_bar), both [B, 1, N, T + 1]"""
+        snr = _prep(snr_estimate)
+        _need_cuda(snr)
+        B, N = snr.shape
+        T = self.num_timesteps
+        betas = torch.empty(B, N, T + 1, device=snr.device)
+        ab = torch.empty_like(betas)
+        with torch.cuda.device(snr.device):
+            st = torch.cuda.current_stream().cuda_stream
+            _lib.check(_lib.lib().sddm_var_schedule(_ptr(snr), B, N, T, self.snr_estimate_scale, _ptr(betas), _ptr(ab), C.c_void_p(st)))
+        return betas.unsqueeze(1), ab.unsqueeze(1)
+
+    @torch.no_grad()
+    def get_noise_level(self, t, snr_estimate):
+        """reference :438-444 -> sqrt(alpha_bar_t) per frame, [B, 1, N, 1]"""
+        snr = _prep(snr_estimate)
+        _need_cuda(snr)
+        B, N = snr.shape
+        out = torch.empty(B, N, device=snr.device)
+        with torch.cuda.device(snr.device):
+            st = torch.cuda.current_stream().cuda_stream
+            _lib.check(_lib.lib().sddm_var_noise_level(_ptr(snr), B, N, self.num_timesteps, self.snr_estimate_scale, int(t), _ptr(out), C.c_void_p(st)))
+        return out.reshape(B, 1, N, 1)
+
+    def _mix(self, x, snr_estimate, t, noise, seed, row0):
+        x, snr, B, N, L = self._frames(x, snr_estimate)
+        z = _prep(noise)
+        _need_cuda(z)
+        out = torch.empty_like(x)
+        level = torch.empty(B, N, device=x.device)
+        with torch.cuda.device(x.device):
+            st = torch.cuda.current_stream().cuda_stream
+            _lib.check(_lib.lib().sddm_var_mix(_ptr(x), _ptr(snr), _ptr(z), _seed(seed), int(row0), B, N, L, self.num_timesteps,
+                                               self.snr_estimate_scale, int(t), _ptr(out), _ptr(level), C.c_void_p(st)))
+        return out, level.reshape(B, 1, N, 1)
+
+    @torch.no_grad()
+    def get_x_T(self, condition, snr_estimate, *, noise=None, seed=None, row0=0):
+        """reference :417-435"""
+        return self._mix(condition, snr_estimate, self.num_timesteps, noise, seed, row0)[0]
+
+    @torch.no_grad()
+    def q_stochastic(self, x_0, noise, snr_estimate, t_is_integer=True, *, t=None, seed=None, row0=0):
+        """reference :394-415 -> (x_t, sqrt_alpha_bar_sample [B, 1, N, 1], t); one t for the whole batch, as there"""
+        if not t_is_integer:
+            raise NotImplementedError   # as the reference
+        if t is None:
+            t = torch.randint(1, self.num_timesteps + 1, [1])
+        t = torch.as_tensor(t).reshape(1)
+        x_t, level = self._mix(x_0, snr_estimate, int(t.item()), noise, seed, row0)
+        return x_t, level, t.to(x_t.device)
+
+    @torch.no_grad()
+    def p_transition(self, x_t, t, snr_estimate, predicted, *, noise=None, seed=None, row0=0):
+        """reference :373-391"""
+        x, snr, B, N, L = self._frames(x_t, snr_estimate)
+        eps = _prep(predicted)
+        z = _prep(noise)
+        _need_cuda(eps, z)
+        if eps.shape != x.shape:
+            raise ValueError("predicted must have the shape of x_t")
+        out = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            st = torch.cuda.current_stream().cuda_stream
+            _lib.check(_lib.lib().sddm_var_posterior(_ptr(x), _ptr(eps), _ptr(snr), _ptr(z), _seed(seed), int(row0), B, N, L, self.num_timesteps,
+                                                     self.snr_estimate_scale, int(t), _ptr(out), C.c_void_p(st)))
+        return out
+
+
 def _seed(seed):
     if seed is None:   # draw from torch's CPU generator so torch.manual_seed governs reproducibility
         seed = int(torch.randint(0, 2 ** 62, (1,)).item())
