@@ -948,6 +948,7 @@ int launch_mode(TcArgs a, cudaStream_t st) {
     }
     if (best_score < 0) return 1;
     a = best;
+    if ((a.NR | a.NA) & 1) { set_error("conv tc: internal: odd ring depth %d / %d (two transform groups need even rings)", a.NR, a.NA); return SDDM_E_INVALID; }
     a.off_out = kHdrBytes;
     a.off_res = a.off_out + (uint32_t)(kEpiGroups * a.NOUT) * kOutTileBytes;
     a.off_raw = a.off_res + (uint32_t)(kEpiGroups * a.NRES) * kOutTileBytes;
