@@ -56,6 +56,20 @@ def main():
         t0 = time.perf_counter()
         plan.enhance_host(c2, "condition_in", seed=i, row0=0, max_rows=2, out=o2)
         ts.append(1e3 * (time.perf_counter() - t0))
+    if os.environ.get("PROBE_REALLOC") == "1":   # does the mode follow the placement of the plan's arena? (a larger batch re-allocates it)
+        res = []
+        for R in (2, 3, 4, 5, 6, 7, 8, 2, 3, 2):
+            cR = (0.05 * torch.randn(R, 1, L, generator=torch.Generator().manual_seed(1))).pin_memory()
+            oR = torch.empty_like(cR).pin_memory()
+            if R == 2:   # force a re-allocation for the repeated sizes too: grow first, which frees the arena
+                plan.enhance_host(torch.zeros(9, 1, L).pin_memory(), "condition_in", seed=0, row0=0, max_rows=9, out=torch.zeros(9, 1, L).pin_memory())
+            tt = []
+            for i in range(5):
+                t0 = time.perf_counter()
+                plan.enhance_host(cR, "condition_in", seed=i, row0=0, max_rows=R, out=oR)
+                tt.append(1e3 * (time.perf_counter() - t0))
+            res.append("%d:%.1f" % (R, min(tt[2:])))
+        print("rows:latency after re-allocating the arena:", " ".join(res))
     n_more = int(os.environ.get("PROBE_CLIPS", "0"))
     if n_more:   # does the clip latency drift while the GPU only sees this light load?
         more, clk = [], []
