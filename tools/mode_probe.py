@@ -19,11 +19,20 @@ def main():
     from sddm_b200.model.model import SDDM
     from sddm_b200.model.network import UNetModified2
     dev = torch.device("cuda:0")
+    L = 16448
+    pre = os.environ.get("PROBE_PRE", "")        # allocations made BEFORE the plan exists (bench.py makes both)
+    keep = []
+    if "pin" in pre:
+        keep.append(torch.zeros(64, 1, L).pin_memory())
+        keep.append(torch.zeros(64, 1, L).pin_memory())
+    if "dev" in pre:
+        keep.append(torch.zeros(64, 1, L, device=dev))
+    if "big" in pre:
+        keep.append(torch.zeros(int(os.environ.get("PROBE_BIG_MB", "64")) * 262144, device=dev))
     net = UNetModified2(num_samples=16448, res_blocks=1)
     net.precision = PREC_BF16_ACT
     model = SDDM(GaussianDiffusion("linear", 100, 1e-6, 1e-3, device=dev), net, p_transition="condition_in").to(dev).eval()
     plan = net.get_plan(model.diffusion)
-    L = 16448
     cond = (0.1 * torch.randn(64, 1, L, generator=torch.Generator().manual_seed(1))).clamp(-1, 1).to(dev)
     x = cond.clone()
     for _ in range(3):
