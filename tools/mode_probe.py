@@ -35,16 +35,29 @@ def main():
     plan = net.get_plan(model.diffusion)
     cond = (0.1 * torch.randn(64, 1, L, generator=torch.Generator().manual_seed(1))).clamp(-1, 1).to(dev)
     x = cond.clone()
-    for _ in range(3):
-        plan.eps(cond, x, t=50)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(20):
-        plan.eps(cond, x, t=50)
-    e1.record()
-    torch.cuda.synchronize()
-    fwd = e0.elapsed_time(e1) / 20
+    if os.environ.get("PROBE_ARENA_FIRST") == "1":   # bench.py's order: warm-up forwards, then the host-buffer call at 64 rows, then the timed loops
+        for i in range(3):
+            model.infer(cond, seed=i, row0=0)
+        c64 = cond.cpu().pin_memory()
+        plan.enhance_host(c64, "condition_in", seed=0, row0=0, max_rows=64, out=torch.empty_like(c64).pin_memory())
+    import contextlib
+    side = torch.cuda.Stream() if os.environ.get("PROBE_STREAM") == "1" else None      # a non-default stream instead of the legacy stream 0
+    with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+        for _ in range(3):
+            plan.eps(cond, x, t=50)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            plan.eps(cond, x, t=50)
+        e1.record()
+        torch.cuda.synchronize()
+        fwd = e0.elapsed_time(e1) / 20
+        t0 = time.perf_counter()
+        for i in range(3):
+            model.infer(cond, seed=i, row0=0)
+        torch.cuda.synchronize()
+        print("infer x3 (B = 64, 100 steps): %.1f ms each" % ((time.perf_counter() - t0) * 1e3 / 3))
     if os.environ.get("PROBE_INFER") == "1":     # bench.py's resident step: the whole 100-step loop inside the library
         for i in range(3):
             model.infer(cond, seed=i, row0=0)
