@@ -1,6 +1,14 @@
 #!/usr/bin/env python
 """Which of the two per-kernel latency modes does this process run in, and does it correlate with anything
-observable?  Prints the per-forward time at B = 64, the graph-replay latency of a 2-chunk clip, device addresses and clocks."""
+observable?  Prints the per-forward time at B = 64, the time of a full 100-step run, the graph-replay latency of a 2-chunk clip,
+device addresses and clocks.  Variants (environment):
+  PROBE_PRE=pin|dev|big   allocations made before the plan exists (pinned host / device / PROBE_BIG_MB MB of device memory)
+  PROBE_ARENA_FIRST=1     bench.py's order: warm-up runs, the host-buffer call at 64 rows, then the timed loops
+  PROBE_STREAM=1          timed loops on a side stream instead of the legacy default stream
+  PROBE_INFER=1, PROBE_PROFILE=1, PROBE_ARENA64=1   extra phases before the clip (full runs, the per-op profiling pass, a 64-row arena)
+  PROBE_REALLOC=1         re-allocate the plan's arena ten times and time the clip after each
+  PROBE_CLIPS=n           n more clips (drift?), a heavy burst, the clip again
+Result of round 2 (40+ processes, with and without ASLR): this script is always in the slow mode; bench.py is not - see DESIGN.md."""
 import os
 import subprocess
 import sys
