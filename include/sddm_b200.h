@@ -330,10 +330,11 @@ SDDM_API int sddm_debug_tc_trace(int enable, long long* host_out);
  * [16..20] MMA warp: total, wait weights, wait acc_empty, wait full_a, rows; [21..22] raw loader: total, wait raw_empty;
  * [24..27] / [28..31] transform group 0 / 1: total, wait raw_full, wait empty_a, work */
 SDDM_API int sddm_debug_row_trace(int enable, long long* host_out);
-/* debug: enable != 0 -> a wait of the row kernel that times out (pipeline bug; the kernel then traps) first notes
- * (CTA, thread, shared-memory address of the barrier, parity) in mapped host memory; enable == 0 -> copy the 16384 words out:
- * [0] 1 = some wait timed out, [1] shared-memory base of the CTA header, [2] rows of CTA 0, [3] slabs * 100 + operand ring * 10 + raw ring,
- * [4 + 4 (20 cta + warp) ..] = (cta + 1, thread, barrier address, parity) of a warp that timed out */
+/* debug: enable != 0 -> a wait of the row kernel (and, in a build with -DSDDM_TC_HANG_NOTES=1, of conv3x3_tc_kernel) that times out
+ * (pipeline bug; the kernel then traps) first notes who waits on what in mapped host memory; enable == 0 -> copy the 65536 words out:
+ * [0] 1 = some wait timed out, [1] shared-memory base of the CTA header, [2], [3] plan of the last launch that started,
+ * [4 + 4 (3000 (launch id mod 4) + 20 cta + warp) ..] = (cta + 1, thread, barrier address, parity | launch id << 1) of a warp that timed out,
+ * [60000 + 8 (launch id mod 4) ..] = (launch id, header base, ring depths, slab counts, Cin, Cout, Hout, grid) of the conv3x3_tc launches */
 SDDM_API int sddm_debug_hang(int enable, unsigned* host_out);
 /* issue-rate microbenchmark: average cycles per back-to-back tcgen05.mma (M 128, K 16, bf16, shared-memory operands) */
 SDDM_API int sddm_debug_umma_rate(int N, int reps, int nA, int geo, float* cycles_per_mma);

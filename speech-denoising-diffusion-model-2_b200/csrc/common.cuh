@@ -126,6 +126,7 @@ struct ConvP {
 
 int launch_conv_fp32(const ConvP& p, cudaStream_t st);
 int launch_conv_tc(const ConvP& p, cudaStream_t st);   // tcgen05 path; requires Hout%16==0, Wout%8==0, C%32==0
+cudaError_t conv_tc_set_hang_buffer(unsigned* dev_ptr);   // debug notes of timed-out waits (sddm_debug_hang); no-op in a normal build
 bool conv_tc_supported(const ConvP& p);
 int conv_fp32_nparts(int Hout, int Wout);
 int conv_tc_nparts(int Hout, int Wout);

@@ -835,21 +835,22 @@ extern "C" SDDM_API int sddm_debug_row_trace(int enable, long long* host_out) {
 }
 
 // debug: enable != 0 -> waits of the row kernel that time out leave a note (CTA, thread, barrier, parity) in a mapped host buffer;
-// enable == 0 -> copy the 16384 words to host_out (valid even after the trap killed the context)
+// enable == 0 -> copy the 65536 words to host_out (valid even after the trap killed the context)
 extern "C" SDDM_API int sddm_debug_hang(int enable, unsigned* host_out) {
     using namespace sddm;
     static unsigned* h_buf = nullptr;
     if (enable) {
         if (!h_buf) {
-            SDDM_CUDA_TRY(cudaHostAlloc(&h_buf, 16384 * sizeof(unsigned), cudaHostAllocMapped));
+            SDDM_CUDA_TRY(cudaHostAlloc(&h_buf, 65536 * sizeof(unsigned), cudaHostAllocMapped));
             unsigned* d = nullptr;
             SDDM_CUDA_TRY(cudaHostGetDevicePointer(&d, h_buf, 0));
             SDDM_CUDA_TRY(set_hang_buffer(d));
+            SDDM_CUDA_TRY(conv_tc_set_hang_buffer(d));
         }
-        memset(h_buf, 0, 16384 * sizeof(unsigned));
+        memset(h_buf, 0, 65536 * sizeof(unsigned));
         return SDDM_OK;
     }
     if (!h_buf) { set_error("hang notes were not enabled"); return SDDM_E_STATE; }
-    if (host_out) memcpy(host_out, h_buf, 16384 * sizeof(unsigned));
+    if (host_out) memcpy(host_out, h_buf, 65536 * sizeof(unsigned));
     return SDDM_OK;
 }

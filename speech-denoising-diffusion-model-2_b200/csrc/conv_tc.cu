@@ -33,6 +33,9 @@
 
 #include "common.cuh"
 #include "gn_fuse.cuh"
+#ifdef SDDM_TC_HANG_NOTES   // debug build (SDDM_NVCC_EXTRA="-DSDDM_TC_HANG_NOTES=1"): waits of this file that time out leave a note (sddm_debug_hang)
+#define SDDM_MBAR_TIMEOUT_NOTES 1
+#endif
 #include "tc_ptx.cuh"
 #include "../../include/sddm_b200.h"
 
@@ -151,6 +154,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
         fence_barrier_init();
     }
     if (warp == kMmaWarp) tmem_alloc(smem_u32(&hdr->tmem_base), (uint32_t)a.tmem_cols);
+#ifdef SDDM_TC_HANG_NOTES
+    if (g_hang && tid == 0 && blockIdx.x == 0) {   // the plan of the launch that is running when a wait times out
+        unsigned long long gid;
+        asm volatile("mov.u64 %0, %%gridid;" : "=l"(gid));
+        unsigned* o = g_hang + 60000 + 8 * (unsigned)(gid & 3ull);
+        o[0] = (unsigned)gid; o[1] = base_u32;
+        o[2] = ((unsigned)a.NR << 24) | ((unsigned)a.NA << 16) | ((unsigned)a.NW << 8) | (unsigned)(a.resident ? 1 : 0);
+        o[3] = 0x80000000u | ((unsigned)a.n_main << 20) | ((unsigned)a.n_res << 16) | ((unsigned)(tend - tile0) << 8) | (unsigned)(MODE * 64 + TPC * 4 + (A16 ? 2 : 0) + (X3 ? 1 : 0));
+        o[4] = (unsigned)p.Cin; o[5] = (unsigned)p.Cout; o[6] = (unsigned)p.Hout; o[7] = gridDim.x;
+        g_hang[1] = base_u32; g_hang[2] = o[2]; g_hang[3] = o[3];
+    }
+#endif
     if (warp < 8 && !a.temb_per_row) {   // per-channel additive term of the epilogue (same for every row of the batch)
         for (int c = tid & 127; c < p.Cout; c += 128) {
             float v = __ldg(p.bias + c);
@@ -381,9 +396,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const TcArgs a,
         const uint64_t a_desc0 = make_desc_nosw(base_u32 + a.off_a, a_lbo, a_sbo);
         const uint64_t w_desc0 = make_desc_nosw(base_u32 + a.off_w, b_lbo, b_sbo);
         const uint32_t a_step = a.a_stage >> 4, w_step = a.w_stage >> 4, tap_step = 2u * (uint32_t)p.Cout;   // in 16-byte units
-        // (mbarrier waits only see the phase PARITY: a warp that starts a tile may wait on operand stage s only if the
-        // previous use of s is known to be filled, which holds when the ring is deeper than one tile: NA >= nA + 1.)
-        const int mw = warp == kMmaWarp ? 0 : 1, nmma = (a.resident && a.NA >= nA + 1) ? 2 : 1;
+        // ONE issuing warp.  Two warps on alternate tiles (the round-1 design, enabled when the weights were resident and NA >= nA + 1)
+        // are not safe: mbarrier waits only see the phase PARITY, and a warp that waits on operand stage s for use k needs use k - 1
+        // of s to be filled already.  The other warp's slabs do not give it that: the two transform groups fill alternate slabs
+        // independently, so slab 3 (group 1) can be ready while slab 0 (group 0, same stage as slab 4) is not - the wait for slab 4
+        // then passes on the phase before slab 0, the warp multiplies an unfilled stage and releases it, and the pipeline wedges
+        // (seen as a timed-out wait, once in ~10 full-size runs of the fp32-activation modes; tools/diag_hang.py --precision bf16
+        // --infer on a build with -DSDDM_TC_HANG_NOTES=1).  A single warp consumes in order, so its own previous wait on the stage
+        // orders the phases.  (To get the second warp back: one full_a barrier set per issuing warp.)
+        const int mw = warp == kMmaWarp ? 0 : 1, nmma = 1;
         int sa = 0, sw = 0;
         uint32_t pa = 0, pw = 0;
         auto skip_slabs = [&](int n) { sa += n; while (sa >= a.NA) { sa -= a.NA; pa ^= 1u; } };
@@ -986,6 +1007,16 @@ bool conv_tc_supported(const ConvP& p) {
         if (p.src[i].C % 32) return false;
     if (p.res_Cin % 32) return false;
     return p.mode == CONV_S1 || p.mode == CONV_S2 || p.mode == CONV_UP;
+}
+
+// debug: timed-out waits of conv3x3_tc_kernel leave their notes in the same buffer as conv_row.cu's (no-op unless built with SDDM_TC_HANG_NOTES)
+cudaError_t conv_tc_set_hang_buffer(unsigned* dev_ptr) {
+#ifdef SDDM_TC_HANG_NOTES
+    return set_hang_buffer(dev_ptr);
+#else
+    (void)dev_ptr;
+    return cudaSuccess;
+#endif
 }
 
 int conv_tc_nparts(int Hout, int Wout) { return ((Hout + TH - 1) / TH) * ((Wout + TW - 1) / TW); }

@@ -43,9 +43,12 @@ __device__ unsigned* g_hang = nullptr;
 __device__ __noinline__ void hang_note(uint32_t bar, uint32_t parity) {
     unsigned* g = g_hang;
     if (!g) return;
-    // one slot per (CTA, warp), plain stores (no atomics towards host memory); [0] = 1 marks "some wait timed out"
-    const unsigned s = blockIdx.x * 20u + (threadIdx.x >> 5);
-    if (s < 4000u) { g[4 + 4 * s] = blockIdx.x + 1u; g[5 + 4 * s] = threadIdx.x; g[6 + 4 * s] = bar; g[7 + 4 * s] = parity; }
+    // one slot per (launch mod 4, CTA, warp) - a kernel and its programmatic successor are resident together and use the same CTA
+    // numbers; plain stores (no atomics towards host memory); [0] = 1 marks "some wait timed out"
+    unsigned long long gid;
+    asm volatile("mov.u64 %0, %%gridid;" : "=l"(gid));
+    const unsigned s = (unsigned)(gid & 3ull) * 3000u + blockIdx.x * 20u + (threadIdx.x >> 5);
+    if (blockIdx.x < 150u) { g[4 + 4 * s] = blockIdx.x + 1u; g[5 + 4 * s] = threadIdx.x; g[6 + 4 * s] = bar; g[7 + 4 * s] = (parity & 1u) | ((unsigned)gid << 1); }
     g[0] = 1u;
     __threadfence_system();
 }
