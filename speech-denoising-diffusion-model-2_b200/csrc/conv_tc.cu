@@ -20,8 +20,8 @@
 //
 // Warp roles (640 threads, persistent CTA, static tile schedule):
 //   warps 0-3 / 4-7 epilogue groups 0 / 1 (group e drains accumulator stage e; TMEM lane quarter = warp id % 4)
-//   warp 8 MMA issuer + TMEM owner | warp 9 weight loader | warp 10 raw-slab TMA issuer | warp 11 idle
-//   warps 12-15 / 16-19 transform groups 0 / 1 (alternate slabs, so two slabs are converted concurrently)
+//   warps 8-11 / 12-15 transform groups 0 / 1 (alternate slabs, so two slabs are converted concurrently; ring depths are even)
+//   warp 16 MMA issuer + TMEM owner | warp 17 weight loader | warp 18 raw-slab TMA issuer | warp 19 idle (round 1's second issuer)
 //
 // reference: Block / ResnetBlock / Downsample / Upsample, model/UNetModified2.py:93-142
 #include <cuda.h>
