@@ -28,6 +28,12 @@
 //               accumulate in registers over the 8 rows a group owns of a 16-row block; the last (block, group) of a sample
 //               finalises the consumer's GroupNorm (gn_fuse.cuh).  Final Block: 3 scalars per pixel -> frames.
 //
+// PAIR variant (64-wide level, Cout = 32 ResnetBlock convolutions): the M tile is one image row of TWO samples; see RowRings and the
+// transform for the three kx-shifted operand copies that keep the seam between the samples zero.
+//
+// Ring rule: the two transform groups take alternate slabs, so the raw ring depth is EVEN (a stage always belongs to one group); with an
+// odd depth a group could pass a parity wait on a stage whose current use - the other group's - was still loading.
+//
 // reference: Block / ResnetBlock / Upsample / stem / final_conv, model/UNetModified2.py:93-142,177-178,235
 #include <cstdlib>
 #include <cstring>
