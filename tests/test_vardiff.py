@@ -49,6 +49,21 @@ def test_oracle_steps_bit_exact(gold):
         assert torch.equal(x_t, gold["q_t%d.x_t" % t]) and torch.equal(s, gold["q_t%d.noise_level" % t])
 
 
+def test_host_mirror_has_no_cpu_fallback(gold):
+    """The product path runs on CUDA tensors only: CPU tensors raise, shapes are checked before anything is launched."""
+    from sddm_b200.model.diffusion import VariableGaussianDiffusion
+    d = VariableGaussianDiffusion(n_timestep=100, snr_estimate_scale=100, device="cpu")
+    snr, cond = gold["snr"], gold["cond"]
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        d.get_beta_schedule(snr)
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        d.get_x_T(cond, snr)
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        d.p_transition(cond, 5, snr, cond)
+    with pytest.raises(NotImplementedError):
+        d.q_stochastic(cond, cond, snr, t_is_integer=False)
+
+
 # ----------------------------------------------------------------------------------------------------
 # CUDA kernels through the C ABI (host mirror VariableGaussianDiffusion)
 # ----------------------------------------------------------------------------------------------------
