@@ -1,0 +1,151 @@
+"""Executable model of the mbarrier hand-offs of the two tcgen05 convolution kernels (csrc/conv_row.cu, csrc/conv_tc.cu).
+
+Roles, as in the kernels: ONE loader thread issues the raw-slab loads in slab order (the loads complete in ANY order, as TMA loads do),
+TWO transform groups take alternate slabs (raw stage -> operand stage), one or two MMA-issuing warps consume operand stages (two warps:
+alternate tiles of `slabs_per_tile` slabs each).  Every wait is a PARITY wait: `test(P)` is true iff the barrier's current phase has the
+other parity, i.e. "the phase with parity P has completed" - a waiter that polls while the barrier is still one use behind passes on
+the phase before it.  The model runs random schedules and reports the first of
+
+  * wrong slab   - a role consumed a stage that does not hold the slab it was waiting for (silent corruption in the kernel),
+  * over-arrival - an arrive on a barrier whose phase has no arrival left (in the kernel: Warp Illegal Instruction at the loader's
+                   next arrive.expect_tx - how the odd raw ring showed up),
+  * deadlock     - nobody can move (in the kernel: a timed-out wait - how the two issuing warps showed up).
+
+It is an argument about the PROTOCOL, kept next to the tests so that ring depths and role counts cannot be
+changed without re-running it; it does not execute the kernels."""
+import random
+
+
+class Violation(Exception):
+    pass
+
+
+class Barrier:
+    def __init__(self, count):
+        self.count, self.pending, self.tx, self.phase = count, count, 0, 0
+
+    def _maybe_complete(self):
+        if self.pending == 0 and self.tx == 0:
+            self.phase += 1
+            self.pending = self.count
+
+    def arrive(self, tx=0):
+        if self.pending == 0:
+            raise Violation("over-arrival")
+        self.pending -= 1
+        self.tx += tx
+        self._maybe_complete()
+
+    def complete_tx(self, tx):
+        self.tx -= tx
+        self._maybe_complete()
+
+    def test(self, parity):
+        return (self.phase & 1) != parity
+
+
+def simulate(nr, na, slabs, slabs_per_tile=1, issuers=1, rng=None, max_steps=200000):
+    """One random schedule of `slabs` slabs through a raw ring of depth nr and an operand ring of depth na.  Raises Violation."""
+    rng = rng or random.Random(0)
+    raw_full = [Barrier(1) for _ in range(nr)]
+    raw_empty = [Barrier(1) for _ in range(nr)]      # one arrival per consuming GROUP (4 warps in the kernel)
+    full_a = [Barrier(1) for _ in range(na)]
+    empty_a = [Barrier(1) for _ in range(na)]
+    raw_content, a_content = [None] * nr, [None] * na
+    in_flight = []                                   # issued loads that have not landed yet: (stage, slab)
+    st = {"loader": 0, "xf": [0, 1], "xf_stage": [0, 0], "mma": [0] * issuers, "mma_tile": list(range(issuers))}
+    done = {"loader": False, "xf": [False, False], "mma": [False] * issuers}
+    # per-trial speeds: some roles (or the landing of loads) are much slower than others in some trials
+    speed = {k: rng.choice([1, 1, 1, 5, 25]) for k in ("loader", "land", "xf0", "xf1", "mma0", "mma1")}
+    tiles = (slabs + slabs_per_tile - 1) // slabs_per_tile
+
+    def step_loader():
+        q = st["loader"]
+        if q >= slabs:
+            done["loader"] = True
+            return False
+        s, k = q % nr, q // nr
+        if not raw_empty[s].test((k & 1) ^ 1):
+            return False
+        raw_full[s].arrive(tx=1)                     # arrive.expect_tx, then the load is in flight
+        in_flight.append((s, q))
+        st["loader"] = q + 1
+        return True
+
+    def step_land():
+        if not in_flight:
+            return False
+        s, q = in_flight.pop(rng.randrange(len(in_flight)))   # loads complete out of order
+        raw_content[s] = q
+        raw_full[s].complete_tx(1)
+        return True
+
+    def step_xf(g):
+        q = st["xf"][g]
+        if q >= slabs:
+            done["xf"][g] = True
+            return False
+        s, sa = q % nr, q % na
+        if st["xf_stage"][g] == 0:                   # wait raw_full, then (a separate poll, possibly much later) empty_a
+            if not raw_full[s].test((q // nr) & 1):
+                return False
+            st["xf_stage"][g] = 1
+            return True
+        if not empty_a[sa].test(((q // na) & 1) ^ 1):
+            return False
+        if raw_content[s] != q:
+            raise Violation("wrong slab in raw stage %d: transform group %d wanted %d, found %s" % (s, g, q, raw_content[s]))
+        a_content[sa] = q
+        full_a[sa].arrive()
+        raw_empty[s].arrive()
+        st["xf"][g], st["xf_stage"][g] = q + 2, 0
+        return True
+
+    def step_mma(w):
+        t = st["mma_tile"][w]
+        if t >= tiles:
+            done["mma"][w] = True
+            return False
+        q = t * slabs_per_tile + st["mma"][w]
+        if q >= slabs:
+            done["mma"][w] = True
+            return False
+        sa = q % na
+        if not full_a[sa].test((q // na) & 1):
+            return False
+        if a_content[sa] != q:
+            raise Violation("wrong slab in operand stage %d: issuing warp %d wanted %d, found %s" % (sa, w, q, a_content[sa]))
+        empty_a[sa].arrive()                         # tcgen05.commit
+        st["mma"][w] += 1
+        if st["mma"][w] == slabs_per_tile:
+            st["mma"][w], st["mma_tile"][w] = 0, t + issuers
+        return True
+
+    agents = [("loader", step_loader), ("land", step_land), ("xf0", lambda: step_xf(0)), ("xf1", lambda: step_xf(1))]
+    agents += [("mma%d" % w, (lambda w=w: step_mma(w))) for w in range(issuers)]
+    idle = 0
+    for _ in range(max_steps):
+        if done["loader"] and all(done["xf"]) and all(done["mma"]) and not in_flight:
+            return
+        name, fn = agents[rng.randrange(len(agents))]
+        if rng.randrange(speed[name]) != 0:          # slow roles skip most of their turns
+            continue
+        if fn():
+            idle = 0
+        else:
+            idle += 1
+            if idle > 4000 and not any(f() for _, f in agents):
+                if done["loader"] and all(done["xf"]) and all(done["mma"]) and not in_flight:
+                    return
+                raise Violation("deadlock")
+    raise Violation("no progress within %d steps" % max_steps)
+
+
+def first_violation(nr, na, slabs=48, slabs_per_tile=1, issuers=1, trials=400, seed=0):
+    """None, or the message of the first violation found over `trials` random schedules."""
+    for i in range(trials):
+        try:
+            simulate(nr, na, slabs, slabs_per_tile, issuers, random.Random(seed * 100003 + i))
+        except Violation as v:
+            return "trial %d: %s" % (i, v)
+    return None

@@ -1,0 +1,43 @@
+"""The mbarrier hand-off protocol of conv_row.cu / conv_tc.cu under random schedules (tests/ring_model.py): the ring depths and role
+counts the kernels ship with are free of parity-wait hazards, and the two configurations that were not (an odd
+raw ring under two transform groups; two MMA-issuing warps on alternate tiles) are caught by the same model."""
+import os
+import re
+
+import pytest
+
+from ring_model import first_violation
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "speech-denoising-diffusion-model-2_b200", "csrc")
+
+
+def _src(name):
+    with open(os.path.join(CSRC, name)) as f:
+        return f.read()
+
+
+def test_sources_still_say_what_the_model_assumes():
+    row, tc = _src("conv_row.cu"), _src("conv_tc.cu")
+    assert re.search(r"constexpr int kNR = 6, kNA = 6, kNS = 5;", row)
+    assert "static constexpr int NR = PAIR ? (NMAIN >= 4 ? 4 : 6) : kNR;" in row
+    assert "static constexpr int NA = PAIR ? (NMAIN >= 4 ? 3 : 4) : kNA;" in row
+    assert 'static_assert(NR % 2 == 0' in row
+    assert "a.NR = 2; a.NA = 2;" in tc and "a.NR += 2" in tc and "a.NA += 2" in tc     # conv_tc ring depths: 2, 4, 6
+    assert "nmma = 1;" in tc                                                          # one MMA-issuing warp
+    assert "odd ring depth" in tc
+
+
+@pytest.mark.parametrize("nr,na,per_tile", [(6, 6, 1), (6, 6, 3),            # conv_row_kernel, 128-wide level (1 - 3 slabs per row)
+                                            (4, 3, 4), (6, 4, 5), (6, 4, 2),  # pair tile: 128 -> 32, 32 -> 32 + res 128, 64 -> 32
+                                            (2, 2, 5), (4, 2, 3), (4, 4, 3), (6, 4, 4), (6, 6, 10)])   # conv3x3_tc_kernel plans
+def test_shipped_rings_are_hazard_free(nr, na, per_tile):
+    assert first_violation(nr, na, slabs=12 * per_tile, slabs_per_tile=per_tile, issuers=1, trials=150) is None
+
+
+@pytest.mark.parametrize("nr,na,per_tile,issuers,what", [(5, 4, 5, 1, "the first pair-tile build"), (3, 3, 2, 1, "a conv_tc plan of round 1"),
+                                                         (4, 4, 3, 2, "two issuing warps, ups.14.block2 in the bf16 mode")])
+def test_the_two_races_of_round_2_are_caught(nr, na, per_tile, issuers, what):
+    v = first_violation(nr, na, slabs=12 * per_tile, slabs_per_tile=per_tile, issuers=issuers, trials=300)
+    assert v is not None, what
+    assert "wrong slab" in v or "over-arrival" in v or "deadlock" in v
