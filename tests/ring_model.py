@@ -149,3 +149,70 @@ def first_violation(nr, na, slabs=48, slabs_per_tile=1, issuers=1, trials=400, s
         except Violation as v:
             return "trial %d: %s" % (i, v)
     return None
+
+
+def simulate_acc(ns, rows, rng=None, max_steps=200000):
+    """Accumulator hand-off of conv_row_kernel: the MMA warp fills one TMEM slot per INPUT row (ring of ns slots), two epilogue groups
+    own the even / odd OUTPUT rows; output row y reads the slots of input rows y - 1, y, y + 1 and waits only for the last of them.
+    A slot is handed back through a barrier that counts 3 arrivals per use (one per reading output row); the first / last row of
+    the run arrives for the rows that never come.  Raises Violation."""
+    rng = rng or random.Random(0)
+    acc_full = [Barrier(1) for _ in range(ns)]
+    acc_empty = [Barrier(3) for _ in range(ns)]
+    content = [None] * ns
+    st = {"mma": 0, "epi": [0, 1]}
+    speed = {k: rng.choice([1, 1, 4, 20]) for k in ("mma", "epi0", "epi1")}
+
+    def step_mma():
+        j = st["mma"]
+        if j >= rows:
+            return False
+        s = j % ns
+        if not acc_empty[s].test(((j // ns) & 1) ^ 1):
+            return False
+        content[s] = j
+        acc_full[s].arrive()                         # tcgen05.commit
+        st["mma"] = j + 1
+        return True
+
+    def step_epi(e):
+        y = st["epi"][e]
+        if y >= rows:
+            return False
+        last = min(y + 1, rows - 1)
+        if not acc_full[last % ns].test((last // ns) & 1):
+            return False
+        first, lastrow = y == 0, y == rows - 1
+        for j, n in ((y - 1, 3 if first else 1), (y, 1 + first + lastrow), (y + 1, 3 if lastrow else 1)):
+            if 0 <= j < rows:
+                if content[j % ns] != j:
+                    raise Violation("wrong accumulator in slot %d: output row %d wanted input row %d, found %s" % (j % ns, y, j, content[j % ns]))
+                for _ in range(n):
+                    acc_empty[j % ns].arrive()
+        st["epi"][e] = y + 2
+        return True
+
+    agents = [("mma", step_mma), ("epi0", lambda: step_epi(0)), ("epi1", lambda: step_epi(1))]
+    idle = 0
+    for _ in range(max_steps):
+        if st["mma"] >= rows and st["epi"][0] >= rows and st["epi"][1] >= rows:
+            return
+        name, fn = agents[rng.randrange(3)]
+        if rng.randrange(speed[name]) != 0:
+            continue
+        if fn():
+            idle = 0
+        else:
+            idle += 1
+            if idle > 2000 and not any(f() for _, f in agents):
+                raise Violation("deadlock")
+    raise Violation("no progress within %d steps" % max_steps)
+
+
+def first_acc_violation(ns, rows=40, trials=300, seed=0):
+    for i in range(trials):
+        try:
+            simulate_acc(ns, rows, random.Random(seed * 100003 + i))
+        except Violation as v:
+            return "trial %d: %s" % (i, v)
+    return None

@@ -6,7 +6,7 @@ import re
 
 import pytest
 
-from ring_model import first_violation
+from ring_model import first_acc_violation, first_violation
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "speech-denoising-diffusion-model-2_b200", "csrc")
@@ -41,3 +41,14 @@ def test_the_two_races_of_round_2_are_caught(nr, na, per_tile, issuers, what):
     v = first_violation(nr, na, slabs=12 * per_tile, slabs_per_tile=per_tile, issuers=issuers, trials=300)
     assert v is not None, what
     assert "wrong slab" in v or "over-arrival" in v or "deadlock" in v
+
+
+@pytest.mark.parametrize("rows", [3, 4, 5, 17, 18, 113])
+def test_accumulator_slots_of_the_row_kernel(rows):
+    """Five TMEM slots, one per input row; even / odd output rows on two epilogue groups; three arrivals hand a slot back, the first /
+    last row of a run arrives for the rows that never come (conv_row.cu: kNS = 5, acc_empty counts 12 = 3 rows x 4 warps)."""
+    assert first_acc_violation(5, rows=rows, trials=120) is None
+
+
+def test_accumulator_model_has_teeth():
+    assert first_acc_violation(2, rows=20, trials=50) is not None     # an output row needs three slots at once
