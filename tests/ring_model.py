@@ -44,12 +44,15 @@ class Barrier:
         return (self.phase & 1) != parity
 
 
-def simulate(nr, na, slabs, slabs_per_tile=1, issuers=1, rng=None, max_steps=200000):
-    """One random schedule of `slabs` slabs through a raw ring of depth nr and an operand ring of depth na.  Raises Violation."""
+def simulate(nr, na, slabs, slabs_per_tile=1, issuers=1, rng=None, max_steps=200000, per_warp_full=False):
+    """One random schedule of `slabs` slabs through a raw ring of depth nr and an operand ring of depth na.  Raises Violation.
+    per_warp_full: one full_a barrier set per issuing warp (the transform arrives on the set of the warp that owns the slab's tile, each
+    warp counts its own uses of a stage) - the way to have two issuing warps without the parity hazard; not what the kernels do today."""
     rng = rng or random.Random(0)
     raw_full = [Barrier(1) for _ in range(nr)]
     raw_empty = [Barrier(1) for _ in range(nr)]      # one arrival per consuming GROUP (4 warps in the kernel)
-    full_a = [Barrier(1) for _ in range(na)]
+    full_a = [[Barrier(1) for _ in range(na)] for _ in range(issuers if per_warp_full else 1)]
+    uses = [[0] * na for _ in range(issuers)]        # per_warp_full: how often warp w has consumed stage s
     empty_a = [Barrier(1) for _ in range(na)]
     raw_content, a_content = [None] * nr, [None] * na
     in_flight = []                                   # issued loads that have not landed yet: (stage, slab)
@@ -96,7 +99,7 @@ def simulate(nr, na, slabs, slabs_per_tile=1, issuers=1, rng=None, max_steps=200
         if raw_content[s] != q:
             raise Violation("wrong slab in raw stage %d: transform group %d wanted %d, found %s" % (s, g, q, raw_content[s]))
         a_content[sa] = q
-        full_a[sa].arrive()
+        full_a[(q // slabs_per_tile) % issuers if per_warp_full else 0][sa].arrive()
         raw_empty[s].arrive()
         st["xf"][g], st["xf_stage"][g] = q + 2, 0
         return True
@@ -111,7 +114,11 @@ def simulate(nr, na, slabs, slabs_per_tile=1, issuers=1, rng=None, max_steps=200
             done["mma"][w] = True
             return False
         sa = q % na
-        if not full_a[sa].test((q // na) & 1):
+        if per_warp_full:
+            if not full_a[w][sa].test(uses[w][sa] & 1):
+                return False
+            uses[w][sa] += 1
+        elif not full_a[0][sa].test((q // na) & 1):
             return False
         if a_content[sa] != q:
             raise Violation("wrong slab in operand stage %d: issuing warp %d wanted %d, found %s" % (sa, w, q, a_content[sa]))
@@ -141,11 +148,11 @@ def simulate(nr, na, slabs, slabs_per_tile=1, issuers=1, rng=None, max_steps=200
     raise Violation("no progress within %d steps" % max_steps)
 
 
-def first_violation(nr, na, slabs=48, slabs_per_tile=1, issuers=1, trials=400, seed=0):
+def first_violation(nr, na, slabs=48, slabs_per_tile=1, issuers=1, trials=400, seed=0, per_warp_full=False):
     """None, or the message of the first violation found over `trials` random schedules."""
     for i in range(trials):
         try:
-            simulate(nr, na, slabs, slabs_per_tile, issuers, random.Random(seed * 100003 + i))
+            simulate(nr, na, slabs, slabs_per_tile, issuers, random.Random(seed * 100003 + i), per_warp_full=per_warp_full)
         except Violation as v:
             return "trial %d: %s" % (i, v)
     return None

@@ -52,3 +52,11 @@ def test_accumulator_slots_of_the_row_kernel(rows):
 
 def test_accumulator_model_has_teeth():
     assert first_acc_violation(2, rows=20, trials=50) is not None     # an output row needs three slots at once
+
+
+@pytest.mark.parametrize("nr,na,per_tile", [(4, 4, 3), (6, 6, 5), (2, 2, 3), (6, 4, 10)])
+def test_two_issuing_warps_are_safe_with_one_full_barrier_set_each(nr, na, per_tile):
+    """The design DESIGN.md section 4.2a names for bringing the second MMA-issuing warp back (not in the kernels today): the transform
+    arrives on the full_a set of the warp that owns the slab's tile and every warp counts its own uses of a stage."""
+    assert first_violation(nr, na, slabs=16 * per_tile, slabs_per_tile=per_tile, issuers=2, trials=150, per_warp_full=True) is None
+    assert first_violation(nr, na, slabs=16 * per_tile, slabs_per_tile=per_tile, issuers=2, trials=150) is not None     # shared set: the race
