@@ -223,3 +223,82 @@ def first_acc_violation(ns, rows=40, trials=300, seed=0):
         except Violation as v:
             return "trial %d: %s" % (i, v)
     return None
+
+
+def explore(nr, na, slabs, slabs_per_tile=1, issuers=1, max_states=2000000):
+    """EXHAUSTIVE search over every interleaving of the roles of `simulate` (shared full_a set) for a small number of slabs.
+    Returns (None, states visited) or (violation message, states visited)."""
+    tiles = (slabs + slabs_per_tile - 1) // slabs_per_tile
+    # a barrier is (pending, tx, phase); count is 1 everywhere in this part of the protocol
+    def arrive(b, tx=0):
+        pending, t, ph = b
+        if pending == 0:
+            raise Violation("over-arrival")
+        pending, t = pending - 1, t + tx
+        return (1, 0, ph + 1) if pending == 0 and t == 0 else (pending, t, ph)
+
+    def complete(b):
+        pending, t, ph = b
+        t -= 1
+        return (1, 0, ph + 1) if pending == 0 and t == 0 else (pending, t, ph)
+
+    def test(b, parity):
+        return (b[2] & 1) != parity
+
+    def put(tup, i, v):
+        return tup[:i] + (v,) + tup[i + 1:]
+
+    fresh = (1, 0, 0)
+    # state: loader, in_flight (sorted tuple of (stage, slab)), xf (q0, stage0, q1, stage1), mma ((tile, idx) per warp),
+    #        raw_full, raw_empty, full_a, empty_a, raw_content, a_content
+    init = (0, (), (0, 0, 1, 0), tuple((w, 0) for w in range(issuers)), (fresh,) * nr, (fresh,) * nr, (fresh,) * na, (fresh,) * na,
+            (None,) * nr, (None,) * na)
+    seen, stack = {init}, [init]
+    while stack:
+        state = stack.pop()
+        ld, fl, xf, mma, rf, re_, fa, ea, rc, ac = state
+        succ = []
+        try:
+            if ld < slabs:                                             # loader
+                s, k = ld % nr, ld // nr
+                if test(re_[s], (k & 1) ^ 1):
+                    succ.append((ld + 1, tuple(sorted(fl + ((s, ld),))), xf, mma, put(rf, s, arrive(rf[s], 1)), re_, fa, ea, rc, ac))
+            for i, (s, q) in enumerate(fl):                            # any load in flight may land next
+                succ.append((ld, fl[:i] + fl[i + 1:], xf, mma, put(rf, s, complete(rf[s])), re_, fa, ea, put(rc, s, q), ac))
+            for g in (0, 1):                                           # transform groups
+                q, stg = xf[2 * g], xf[2 * g + 1]
+                if q >= slabs:
+                    continue
+                s, sa = q % nr, q % na
+                if stg == 0:
+                    if test(rf[s], (q // nr) & 1):
+                        succ.append((ld, fl, put(xf, 2 * g + 1, 1), mma, rf, re_, fa, ea, rc, ac))
+                elif test(ea[sa], ((q // na) & 1) ^ 1):
+                    if rc[s] != q:
+                        raise Violation("wrong slab in raw stage %d: transform group %d wanted %d, found %s" % (s, g, q, rc[s]))
+                    nxf = put(put(xf, 2 * g, q + 2), 2 * g + 1, 0)
+                    succ.append((ld, fl, nxf, mma, rf, put(re_, s, arrive(re_[s])), put(fa, sa, arrive(fa[sa])), ea, rc, put(ac, sa, q)))
+            for w in range(issuers):                                   # issuing warps
+                t, i = mma[w]
+                q = t * slabs_per_tile + i
+                if t >= tiles or q >= slabs:
+                    continue
+                sa = q % na
+                if test(fa[sa], (q // na) & 1):
+                    if ac[sa] != q:
+                        raise Violation("wrong slab in operand stage %d: issuing warp %d wanted %d, found %s" % (sa, w, q, ac[sa]))
+                    nm = (t, i + 1) if i + 1 < slabs_per_tile else (t + issuers, 0)
+                    succ.append((ld, fl, xf, put(mma, w, nm), rf, re_, fa, put(ea, sa, arrive(ea[sa])), rc, ac))
+        except Violation as v:
+            return str(v), len(seen)
+        finished = ld >= slabs and not fl and xf[0] >= slabs and xf[2] >= slabs and all(
+            t >= tiles or t * slabs_per_tile + i >= slabs for t, i in mma)
+        if not succ and not finished:
+            return "deadlock", len(seen)
+        for n in succ:
+            if n not in seen:
+                if len(seen) >= max_states:
+                    raise RuntimeError("state space larger than %d" % max_states)
+                seen.add(n)
+                stack.append(n)
+    return None, len(seen)

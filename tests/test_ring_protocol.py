@@ -6,7 +6,7 @@ import re
 
 import pytest
 
-from ring_model import first_acc_violation, first_violation
+from ring_model import explore, first_acc_violation, first_violation
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "speech-denoising-diffusion-model-2_b200", "csrc")
@@ -60,3 +60,18 @@ def test_two_issuing_warps_are_safe_with_one_full_barrier_set_each(nr, na, per_t
     arrives on the full_a set of the warp that owns the slab's tile and every warp counts its own uses of a stage."""
     assert first_violation(nr, na, slabs=16 * per_tile, slabs_per_tile=per_tile, issuers=2, trials=150, per_warp_full=True) is None
     assert first_violation(nr, na, slabs=16 * per_tile, slabs_per_tile=per_tile, issuers=2, trials=150) is not None     # shared set: the race
+
+
+@pytest.mark.parametrize("nr,na,slabs,per_tile", [(6, 6, 36, 1), (6, 6, 39, 3), (4, 3, 32, 4), (6, 4, 40, 5), (6, 4, 30, 2),
+                                                  (2, 2, 30, 5), (4, 2, 30, 3), (4, 4, 30, 3), (6, 4, 32, 4), (6, 6, 40, 10)])
+def test_shipped_rings_exhaustively(nr, na, slabs, per_tile):
+    """EVERY interleaving of loader / out-of-order load completion / two transform groups / one issuing warp over 5 - 15 ring wraps:
+    no wrong slab, no over-arrival, no deadlock (10^3 - 10^5 reachable states each)."""
+    violation, states = explore(nr, na, slabs, per_tile, issuers=1)
+    assert violation is None, (violation, states)
+
+
+@pytest.mark.parametrize("nr,na,slabs,per_tile,issuers", [(5, 4, 15, 5, 1), (3, 3, 8, 1, 1), (5, 5, 12, 1, 1), (4, 4, 12, 3, 2), (6, 6, 20, 5, 2)])
+def test_known_bad_shapes_exhaustively(nr, na, slabs, per_tile, issuers):
+    violation, _ = explore(nr, na, slabs, per_tile, issuers=issuers)
+    assert violation is not None
